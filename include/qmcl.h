@@ -1,0 +1,200 @@
+/*
+ * qmcl.h — C ABI of the B200-native Monte Carlo localisation core.
+ *
+ * This is the drop-in boundary for QuickMCL's particle-filter hot path: the
+ * entry points are what an FFI for quickmcl::Map (include/quickmcl/map.h:31-62)
+ * and quickmcl::IParticleFilter (include/quickmcl/i_particle_filter.h:30-85)
+ * would bind.  Plain pointers and sizes only; every function returns a
+ * qmcl_status (0 = ok).  All host pointers are ordinary (pageable or pinned)
+ * host memory unless a parameter is named dev_*.
+ *
+ * There is no CPU fallback behind this ABI: every entry point that computes
+ * runs hand-written sm_100a kernels, and fails with QMCL_ERR_NO_DEVICE when no
+ * CUDA device is present.
+ *
+ * Reference file:line citations are relative to the QuickMCL 0.5.0 tree.
+ */
+#ifndef QMCL_H
+#define QMCL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum qmcl_status {
+  QMCL_OK = 0,
+  QMCL_ERR_INVALID_ARG = 1,
+  QMCL_ERR_NO_DEVICE = 2,
+  QMCL_ERR_CUDA = 3,
+  QMCL_ERR_NO_MAP = 4,
+  /* get_estimate met a particle whose bin has no cluster: the reference
+   * abort()s here (particle_filter.cpp:375-379). */
+  QMCL_ERR_INVALID_CLUSTER = 5,
+  QMCL_ERR_CAPACITY = 6
+} qmcl_status;
+
+/* quickmcl::WeightedParticle (particle.h:32-47): Pose2D<float> + double. */
+typedef struct qmcl_particle {
+  float x, y, theta;
+  float pad_;
+  double weight;
+} qmcl_particle;
+
+/* Parameters::LikelihoodMap (parameters.h:90-113). */
+typedef struct qmcl_likelihood_params {
+  float z_hit;
+  float z_rand;
+  int32_t num_beams; /* 0 = use every point */
+  float max_laser_distance;
+  float max_obstacle_distance;
+  float sigma_hit;
+} qmcl_likelihood_params;
+
+/* ResampleType (parameters.h:28-35). */
+enum { QMCL_RESAMPLE_LOW_VARIANCE = 0, QMCL_RESAMPLE_ADAPTIVE = 1, QMCL_RESAMPLE_KLD = 2 };
+
+/* Parameters::ParticleFilter (parameters.h:55-85). */
+typedef struct qmcl_pf_params {
+  int32_t resample_type;
+  int32_t particle_count_min;
+  int32_t particle_count_max;
+  int32_t resample_count;
+  double alpha_fast;
+  double alpha_slow;
+  double kld_epsilon;
+  double kld_z;
+  float res_xy;    /* space_partitioning_resolution_xy */
+  float res_theta; /* space_partitioning_resolution_theta */
+} qmcl_pf_params;
+
+typedef struct qmcl_map qmcl_map;
+typedef struct qmcl_filter qmcl_filter;
+
+const char *qmcl_version(void);
+const char *qmcl_last_error(void);
+/* Number of kernels this library has launched so far in this process. */
+uint64_t qmcl_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ Map ----
+ * quickmcl::Map / MapLikelihood (map.h:31-62, map_likelihood.h:35-93). */
+
+/* create_likelihood_map() (map_factory.h:29). device < 0 = current device. */
+qmcl_status qmcl_map_create(int device, qmcl_map **out);
+qmcl_status qmcl_map_destroy(qmcl_map *map);
+/* All work of this map (and of filters created on it) is enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
+qmcl_status qmcl_map_set_stream(qmcl_map *map, void *cuda_stream);
+
+/* Map::set_parameters (map_likelihood.cpp:40-49). z_hit/z_rand/num_beams/
+ * max_laser_distance act on the next sensor update; sigma_hit and
+ * max_obstacle_distance on the next qmcl_map_load (map.h:36-39). */
+qmcl_status qmcl_map_set_params(qmcl_map *map, const qmcl_likelihood_params *p);
+
+/* Map::new_map (map_base.cpp:30-56, map_likelihood.cpp:51-61):
+ * occupancy (row-major [y][x], nav_msgs/OccupancyGrid values) -> tri-state
+ * map, free-cell list, distance field, Gaussian table.  The distance field is
+ * the exact clipped Euclidean distance transform (north_star); the reference's
+ * brushfire (distance_calculator.cpp:103-182) is an approximation of it. */
+qmcl_status qmcl_map_load(qmcl_map *map, const int8_t *occ, uint32_t width,
+                          uint32_t height, float resolution, double origin_x,
+                          double origin_y);
+/* Parity hook: install a likelihood field and state map computed elsewhere
+ * (e.g. the reference's own brushfire field) instead of building one. */
+qmcl_status qmcl_map_load_field(qmcl_map *map, const float *field,
+                                const int8_t *state, uint32_t width,
+                                uint32_t height, float resolution,
+                                double origin_x, double origin_y);
+qmcl_status qmcl_map_size(const qmcl_map *map, uint32_t *width, uint32_t *height);
+qmcl_status qmcl_map_copy_field(const qmcl_map *map, float *out);
+qmcl_status qmcl_map_copy_distance(const qmcl_map *map, float *out);
+qmcl_status qmcl_map_copy_state(const qmcl_map *map, int8_t *out);
+qmcl_status qmcl_map_num_free_cells(const qmcl_map *map, uint64_t *out);
+qmcl_status qmcl_map_copy_free_cells(const qmcl_map *map, int32_t *xy_out);
+/* Map::get_map_state_at (map_base.cpp:66-77). */
+qmcl_status qmcl_map_state_at(const qmcl_map *map, float x, float y, int8_t *out);
+/* Map::get_likelihood_as_gridmap (map_likelihood.cpp:132-146). */
+qmcl_status qmcl_map_likelihood_grid(const qmcl_map *map, int8_t *out);
+/* Map::update_importance on a host particle vector (map_likelihood.cpp:63-130):
+ * H2D, kernel, D2H.  total_out receives the pre-penalty total weight. */
+qmcl_status qmcl_map_update_importance(qmcl_map *map, const float *cloud_xy,
+                                       size_t n_points, qmcl_particle *particles,
+                                       size_t n_particles, double *total_out);
+/* Map::generate_random_pose (map_base.cpp:58-64) for draw `index` of the
+ * shared RNG contract (Philox key `seed`, counter (index, step, GLOBAL)). */
+qmcl_status qmcl_map_generate_random_pose(const qmcl_map *map, uint64_t seed,
+                                          uint32_t step, uint64_t index,
+                                          float pose_out[3]);
+
+/* --------------------------------------------------------------- Filter ----
+ * quickmcl::IParticleFilter (i_particle_filter.h:30-85). */
+
+/* create_particle_filter(map) (particle_filter_factory.h:30-31). */
+qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out);
+qmcl_status qmcl_filter_destroy(qmcl_filter *f);
+/* Particle sharding (north_star / SURVEY §8e): this handle owns the
+ * contiguous global slice [first, first+count) of a filter of `global_count`
+ * particles.  Defaults: one shard holding everything. */
+qmcl_status qmcl_filter_set_shard(qmcl_filter *f, int shard_rank, int n_shards);
+
+/* IParticleFilter::set_parameters (particle_filter.cpp:177-184). */
+qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p);
+/* IParticleFilter::initialise (particle_filter.cpp:41-69). cov row-major. */
+qmcl_status qmcl_filter_initialise(qmcl_filter *f, const float pose[3],
+                                   const float cov[9]);
+/* Same, with the 3x3 factor V*sqrt(Lambda) (random.h:60-62) supplied. */
+qmcl_status qmcl_filter_initialise_factor(qmcl_filter *f, const float pose[3],
+                                          const float factor[9]);
+/* IParticleFilter::global_localization (particle_filter.cpp:71-83). */
+qmcl_status qmcl_filter_global_localization(qmcl_filter *f);
+/* IParticleFilter::handle_odometry (particle_filter.cpp:85-93,
+ * odometry.cpp:44-102). */
+qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double odom_new[3],
+                                        const double odom_old[3],
+                                        const float alpha[4]);
+/* IParticleFilter::update_importance_from_observations
+ * (particle_filter.cpp:95-136). cloud_xy = n_points x {float x, y}. */
+qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy,
+                                      size_t n_points);
+/* Device-resident variant for benchmarking the kernel alone: the cloud is
+ * already in HBM (dev_cloud_xy), nothing is copied to the host. */
+qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
+                                          size_t n_points);
+/* IParticleFilter::resample_and_cluster (particle_filter.cpp:138-161). */
+qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f);
+/* IParticleFilter::cluster (particle_filter.cpp:163-175). */
+qmcl_status qmcl_filter_cluster(qmcl_filter *f);
+/* IParticleFilter::get_estimated_pose (particle_filter.cpp:186-212).
+ * *valid = 1 and pose/cov written when a cluster has weight, else 0. */
+qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3],
+                                     double cov[9], int *valid);
+/* IParticleFilter::num_particles / get_particles (AoS copy). */
+qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out);
+qmcl_status qmcl_filter_copy_particles(const qmcl_filter *f, qmcl_particle *out,
+                                       size_t cap);
+
+/* ---- test hooks (not part of the reference interface) ---- */
+qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n);
+qmcl_status qmcl_filter_set_rng(qmcl_filter *f, uint64_t seed, uint32_t step);
+/* Pre-penalty total weight of the last sensor update. */
+qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out);
+/* Source index per output slot of the last resampling (-1 = injected). */
+qmcl_status qmcl_filter_copy_resample_indices(const qmcl_filter *f, int64_t *out,
+                                              size_t cap, size_t *n_out);
+/* Occupied bins as (kx, ky, ktheta, count), lexicographically sorted, with a
+ * canonical cluster label per bin (index of the first bin of its component). */
+qmcl_status qmcl_filter_num_bins(const qmcl_filter *f, size_t *out);
+qmcl_status qmcl_filter_copy_bins(const qmcl_filter *f, int32_t *keys4,
+                                  int32_t *labels, size_t cap, size_t *n_out);
+qmcl_status qmcl_filter_num_clusters(const qmcl_filter *f, size_t *out);
+qmcl_status qmcl_filter_get_lowpass(const qmcl_filter *f, double out[2]);
+qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast);
+/* Wait for everything enqueued by this filter. */
+qmcl_status qmcl_filter_synchronize(qmcl_filter *f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMCL_H */

@@ -1,0 +1,335 @@
+// filter.cu — particle filter handle, particle I/O, sensor update + normalise.
+//
+// Replaces quickmcl::ParticleFilter's container handling and
+// update_importance_from_observations (src/quickmcl/particle_filter.cpp:95-136)
+// and the weight helpers of src/quickmcl/particle.cpp:41-64.
+
+#include "filter.cuh"
+#include "sensor.cuh"
+
+namespace qmcl {
+
+// ------------------------------------------------------------------ kernels
+
+// AoS (the reference's 24-byte WeightedParticle) <-> SoA.
+__global__ void aos_to_soa_kernel(const qmcl_particle *__restrict__ in, size_t n,
+                                  float *__restrict__ x, float *__restrict__ y,
+                                  float *__restrict__ t, double *__restrict__ w) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const qmcl_particle p = in[i];
+  x[i] = p.x;
+  y[i] = p.y;
+  t[i] = p.theta;
+  w[i] = p.weight;
+}
+
+__global__ void soa_to_aos_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                  const float *__restrict__ t, const double *__restrict__ w,
+                                  size_t n, qmcl_particle *__restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  qmcl_particle p;
+  p.x = x[i];
+  p.y = y[i];
+  p.theta = t[i];
+  p.pad_ = 0.f;
+  p.weight = w[i];
+  out[i] = p;
+}
+
+// K8: particle.cpp:50-64 as used by particle_filter.cpp:101-120 — divide by the
+// pre-penalty total when it is positive, otherwise equalise to 1/N.
+__global__ void normalise_by_total_kernel(double *__restrict__ w, size_t n,
+                                          const FilterScalars *__restrict__ sc) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double total = sc->total_weight;
+  w[i] = (total > 0) ? __ddiv_rn(w[i], total) : __ddiv_rn(1.0, static_cast<double>(n));
+}
+
+qmcl_status launch_aos_to_soa(cudaStream_t s, const qmcl_particle *dev_in, size_t n, float *x,
+                              float *y, float *t, double *w) {
+  if (!n) return QMCL_OK;
+  aos_to_soa_kernel<<<div_up(n, 256), 256, 0, s>>>(dev_in, n, x, y, t, w);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+qmcl_status launch_soa_to_aos(cudaStream_t s, const float *x, const float *y, const float *t,
+                              const double *w, size_t n, qmcl_particle *dev_out) {
+  if (!n) return QMCL_OK;
+  soa_to_aos_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, w, n, dev_out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out) {
+  QMCL_TRY(f->scratch.ensure(bytes));
+  *out = f->scratch.ptr;
+  return QMCL_OK;
+}
+
+// low_pass_filter.h:39-50
+static void lowpass_update(double *value, double alpha, double x) {
+  if (*value == 0) *value = x;
+  else *value = *value + alpha * (x - *value);
+}
+
+// Runs K7 + K8 on the current set with the beams already in f->beams.
+static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
+  qmcl_map *m = f->map;
+  ParticleSet &ps = f->cur();
+  cudaStream_t s = m->stream;
+  if (ps.n == 0) {
+    f->last_total = 0.0;
+    return QMCL_OK;
+  }
+  QMCL_TRY(f->partials.ensure(sensor_grid(ps.n)));
+  SensorLaunch a;
+  a.x = ps.x.ptr;
+  a.y = ps.y.ptr;
+  a.t = ps.t.ptr;
+  a.w = ps.w.ptr;
+  a.n = ps.n;
+  a.beams = f->beams.ptr;
+  a.n_beams = n_used;
+  a.partials = f->partials.ptr;
+  a.scalars = f->scalars.ptr;
+  QMCL_TRY(launch_sensor(m, a));
+  normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+  QMCL_LAUNCHED();
+  // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
+  // total: one 8-byte read back per scan.
+  QMCL_CUDA(cudaMemcpyAsync(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double),
+                            cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  const double total = f->h_scalars.ptr[0];
+  f->last_total = total;
+  if (total > 0) {
+    const double avg = total / static_cast<double>(ps.n);
+    lowpass_update(&f->w_slow, f->params.alpha_slow, avg);
+    lowpass_update(&f->w_fast, f->params.alpha_fast, avg);
+  }
+  f->clusters_valid = false;
+  return QMCL_OK;
+}
+
+}  // namespace qmcl
+
+using namespace qmcl;
+
+extern "C" {
+
+qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) {
+  if (!map || !out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(map));
+  qmcl_filter *f = new qmcl_filter();
+  f->map = map;
+  f->seed = seed;
+  QMCL_TRY(f->scalars.ensure(1));
+  QMCL_CUDA(cudaMemsetAsync(f->scalars.ptr, 0, sizeof(FilterScalars), map->stream));
+  QMCL_TRY(f->h_scalars.ensure(16));
+  qmcl_filter_set_params(f, &f->params);
+  *out = f;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  cudaSetDevice(f->map->device);
+  cudaStreamSynchronize(f->map->stream);
+  for (auto &s : f->sets) {
+    s.x.release();
+    s.y.release();
+    s.t.release();
+    s.w.release();
+  }
+  f->beams.release();
+  f->cloud.release();
+  f->partials.release();
+  f->scalars.release();
+  f->h_beams.release();
+  f->h_scalars.release();
+  f->cdf.release();
+  f->src_index.release();
+  f->scratch.release();
+  f->bin_keys.release();
+  f->bin_unique.release();
+  f->bin_count.release();
+  f->bin_label.release();
+  delete f;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_set_shard(qmcl_filter *f, int shard_rank, int n_shards) {
+  if (!f || n_shards < 1 || shard_rank < 0 || shard_rank >= n_shards) return QMCL_ERR_INVALID_ARG;
+  f->shard_rank = shard_rank;
+  f->n_shards = n_shards;
+  return QMCL_OK;
+}
+
+// particle_filter.cpp:177-184 + space_partitioning.cpp:23-37
+qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p) {
+  if (!f || !p) return QMCL_ERR_INVALID_ARG;
+  if (!(p->res_xy > 0) || !(p->res_theta > 0)) return QMCL_ERR_INVALID_ARG;
+  f->params = *p;
+  // theta_range: world_to_map of (float)(-pi+0.001) and (float)(pi-0.001):
+  // float division then truncation (scaled_map.h:43-48).
+  f->theta_lo = static_cast<int>(static_cast<float>(-kPi + 0.001) / p->res_theta);
+  f->theta_hi = static_cast<int>(static_cast<float>(kPi - 0.001) / p->res_theta);
+  f->n_bins = 0;
+  f->n_clusters = 0;
+  f->clusters_valid = false;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_set_rng(qmcl_filter *f, uint64_t seed, uint32_t step) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  f->seed = seed;
+  f->step = step;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  *out = f->cur().n;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n) {
+  if (!f || (!p && n)) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  ParticleSet &ps = f->cur();
+  QMCL_TRY(ps.ensure(n));
+  ps.n = n;
+  f->clusters_valid = false;
+  if (!n) return QMCL_OK;
+  void *stage = nullptr;
+  QMCL_TRY(filter_scratch(f, n * sizeof(qmcl_particle), &stage));
+  QMCL_CUDA(cudaMemcpyAsync(stage, p, n * sizeof(qmcl_particle), cudaMemcpyHostToDevice, s));
+  QMCL_TRY(launch_aos_to_soa(s, static_cast<const qmcl_particle *>(stage), n, ps.x.ptr, ps.y.ptr,
+                             ps.t.ptr, ps.w.ptr));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_copy_particles(const qmcl_filter *fc, qmcl_particle *out, size_t cap) {
+  if (!fc || (!out && cap)) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  const ParticleSet &ps = f->cur();
+  const size_t n = ps.n < cap ? ps.n : cap;
+  if (!n) return QMCL_OK;
+  void *stage = nullptr;
+  QMCL_TRY(filter_scratch(f, n * sizeof(qmcl_particle), &stage));
+  QMCL_TRY(launch_soa_to_aos(s, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, n,
+                             static_cast<qmcl_particle *>(stage)));
+  QMCL_CUDA(cudaMemcpyAsync(out, stage, n * sizeof(qmcl_particle), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, size_t n_points) {
+  if (!f || (!cloud_xy && n_points)) return QMCL_ERR_INVALID_ARG;
+  if (!f->map->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  QMCL_TRY(f->cloud.ensure(2 * n_points + 2));
+  QMCL_TRY(f->beams.ensure(2 * n_points + 2));
+  QMCL_TRY(f->h_beams.ensure(2 * n_points + 2));
+  // stage through pinned memory so the H2D copy is a true async DMA
+  std::memcpy(f->h_beams.ptr, cloud_xy, 2 * n_points * sizeof(float));
+  QMCL_CUDA(cudaMemcpyAsync(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+  int n_used = 0;
+  QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
+  return sensor_update_common(f, n_used);
+}
+
+qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
+                                          size_t n_points) {
+  if (!f || (!dev_cloud_xy && n_points)) return QMCL_ERR_INVALID_ARG;
+  if (!f->map->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(f->map));
+  QMCL_TRY(f->beams.ensure(2 * n_points + 2));
+  int n_used = 0;
+  QMCL_TRY(launch_subsample(f->map, dev_cloud_xy, n_points, f->beams.ptr, &n_used));
+  return sensor_update_common(f, n_used);
+}
+
+qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  *out = f->last_total;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_get_lowpass(const qmcl_filter *f, double out[2]) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  out[0] = f->w_slow;
+  out[1] = f->w_fast;
+  return QMCL_OK;
+}
+qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  f->w_slow = w_slow;
+  f->w_fast = w_fast;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_synchronize(qmcl_filter *f) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  return QMCL_OK;
+}
+
+// Map::update_importance on a host vector (map_likelihood.cpp:63-130): the
+// reference's own Map interface, kept for API completeness.  H2D, K7, D2H.
+qmcl_status qmcl_map_update_importance(qmcl_map *m, const float *cloud_xy, size_t n_points,
+                                       qmcl_particle *particles, size_t n, double *total_out) {
+  if (!m || (!cloud_xy && n_points) || (!particles && n)) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(m));
+  cudaStream_t s = m->stream;
+  if (total_out) *total_out = 0.0;
+  if (!n) return QMCL_OK;
+  QMCL_TRY(m->tmp_x.ensure(n));
+  QMCL_TRY(m->tmp_y.ensure(n));
+  QMCL_TRY(m->tmp_t.ensure(n));
+  QMCL_TRY(m->tmp_w.ensure(n + sensor_grid(n) + 8));
+  QMCL_TRY(m->tmp_aos.ensure(n * sizeof(qmcl_particle)));
+  QMCL_TRY(m->tmp_cloud.ensure(4 * n_points + 4));
+  QMCL_TRY(m->tmp_scalars.ensure(1));
+  qmcl_particle *d_aos = reinterpret_cast<qmcl_particle *>(m->tmp_aos.ptr);
+  QMCL_CUDA(cudaMemsetAsync(m->tmp_scalars.ptr, 0, sizeof(FilterScalars), s));
+  QMCL_CUDA(cudaMemcpyAsync(d_aos, particles, n * sizeof(qmcl_particle), cudaMemcpyHostToDevice, s));
+  QMCL_CUDA(cudaMemcpyAsync(m->tmp_cloud.ptr, cloud_xy, 2 * n_points * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+  QMCL_TRY(launch_aos_to_soa(s, d_aos, n, m->tmp_x.ptr, m->tmp_y.ptr, m->tmp_t.ptr, m->tmp_w.ptr));
+  float *d_beams = m->tmp_cloud.ptr + 2 * n_points + 2;
+  int n_used = 0;
+  QMCL_TRY(launch_subsample(m, m->tmp_cloud.ptr, n_points, d_beams, &n_used));
+  SensorLaunch a;
+  a.x = m->tmp_x.ptr;
+  a.y = m->tmp_y.ptr;
+  a.t = m->tmp_t.ptr;
+  a.w = m->tmp_w.ptr;
+  a.n = n;
+  a.beams = d_beams;
+  a.n_beams = n_used;
+  a.partials = m->tmp_w.ptr + n;
+  a.scalars = m->tmp_scalars.ptr;
+  QMCL_TRY(launch_sensor(m, a));
+  QMCL_TRY(launch_soa_to_aos(s, a.x, a.y, a.t, a.w, n, d_aos));
+  QMCL_CUDA(cudaMemcpyAsync(particles, d_aos, n * sizeof(qmcl_particle), cudaMemcpyDeviceToHost, s));
+  double total = 0.0;
+  QMCL_CUDA(cudaMemcpyAsync(&total, &m->tmp_scalars.ptr->total_weight, sizeof(double),
+                            cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  if (total_out) *total_out = total;
+  return QMCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+// filter.cuh — internal launch helpers shared by the filter translation units.
+#pragma once
+
+#include "state.cuh"
+
+namespace qmcl {
+
+qmcl_status launch_aos_to_soa(cudaStream_t s, const qmcl_particle *dev_in, size_t n, float *x,
+                              float *y, float *t, double *w);
+qmcl_status launch_soa_to_aos(cudaStream_t s, const float *x, const float *y, const float *t,
+                              const double *w, size_t n, qmcl_particle *dev_out);
+// Grow-only byte scratch of the filter (contents are not preserved).
+qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out);
+
+}  // namespace qmcl

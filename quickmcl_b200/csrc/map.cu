@@ -1,0 +1,510 @@
+// map.cu — likelihood-field map on the device.
+//
+// Replaces quickmcl::MapBase / MapLikelihood / distance_calculator
+// (src/quickmcl/map_base.cpp, map_likelihood.cpp, distance_calculator.cpp).
+// Field build = K1 tri-state map, K2 exact clipped Euclidean distance
+// transform (separable, integer d^2), K3 Gaussian table through a d^2 LUT,
+// K4 free-cell compaction.  All HBM-bound; see DESIGN.md for the byte counts.
+
+#include "state.cuh"
+
+#include <string>
+#include <vector>
+
+namespace qmcl {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+qmcl_status use_device(const qmcl_map *m) {
+  QMCL_CUDA(cudaSetDevice(m->device));
+  return QMCL_OK;
+}
+
+// ------------------------------------------------------------------ kernels
+
+constexpr int kEdtInf = 0x3fff;  // "no obstacle within reach" marker for g (u16)
+constexpr int kSegLen = 128;     // rows per column segment in pass 1
+
+// K1 + K2 pass 1.  One thread per (column, row segment).  The clipped
+// transform only needs obstacles within R rows, so a segment is exact after
+// sweeping [y0-R, y1+R).  Down sweep writes g and the tri-state map
+// (distance_calculator.cpp:184-209: -1 -> Unknown, <35 -> Free, >65 ->
+// Occupied, else Unknown); up sweep folds in the distance from below.
+// Warp lanes are adjacent columns, so every load/store is coalesced.
+__global__ void __launch_bounds__(128)
+edt_columns_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
+                   uint16_t *__restrict__ g, int w, int h, int R) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  const int y0 = blockIdx.y * kSegLen;
+  const int y1 = min(h, y0 + kSegLen);
+  int d = kEdtInf;
+  for (int y = max(0, y0 - R); y < y1; ++y) {
+    const int8_t v = __ldg(occ + static_cast<size_t>(y) * w + x);
+    d = (v > 65) ? 0 : min(d + 1, kEdtInf);
+    if (y >= y0) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      g[i] = static_cast<uint16_t>(d);
+      int8_t s;
+      if (v == -1) s = 2;
+      else if (v < 35) s = 0;
+      else if (v > 65) s = 1;
+      else s = 2;
+      state[i] = s;
+    }
+  }
+  d = kEdtInf;
+  for (int y = min(h, y1 + R) - 1; y >= y0; --y) {
+    const int8_t v = __ldg(occ + static_cast<size_t>(y) * w + x);
+    d = (v > 65) ? 0 : min(d + 1, kEdtInf);
+    if (y < y1) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      const int cur = g[i];
+      if (d < cur) g[i] = static_cast<uint16_t>(d);
+    }
+  }
+}
+
+// Tri-state map only (used by load_field's callers that bring their own).
+// d^2 -> (distance, likelihood) table.  distance_calculator.cpp:150-157 for
+// the clipping, map_likelihood.cpp:60 for the Gaussian.  The last entry is the
+// "nothing within range" cell.  exp is evaluated in double and rounded once
+// (the correctly rounded float; Eigen's packet exp is 1-2 ulp off it).
+__global__ void edt_lut_kernel(float *__restrict__ lut_dist, float *__restrict__ lut_field,
+                               int n_entries, float res, float max_dist, float z_hit_pre) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_entries) return;
+  float d = max_dist;
+  if (k < n_entries - 1) {
+    const float cand = __fmul_rn(sqrtf(static_cast<float>(k)), res);
+    if (!(cand > max_dist)) d = cand;
+  }
+  lut_dist[k] = d;
+  const float arg = __fdiv_rn(-__fmul_rn(d, d), z_hit_pre);
+  lut_field[k] = static_cast<float>(exp(static_cast<double>(arg)));
+}
+
+// K2 pass 2 + K3.  One block per (row, 256-column chunk): G = g^2 of the chunk
+// plus an R-cell halo is staged in shared memory; each thread takes the
+// minimum of dx^2 + G[x+dx] over the window.  Chunks with no obstacle in reach
+// skip the search.  The result indexes the LUT, so no per-cell sqrt/exp.
+constexpr int kRowChunk = 256;
+__global__ void __launch_bounds__(kRowChunk)
+edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_dist,
+                const float *__restrict__ lut_field, float *__restrict__ distance,
+                float *__restrict__ field, int w, int h, int R, int kmax) {
+  extern __shared__ int sG[];  // kRowChunk + 2R entries
+  const int y = blockIdx.y;
+  const int x0 = blockIdx.x * kRowChunk;
+  const int span = kRowChunk + 2 * R;
+  const int big = 1 << 28;
+  int any = 0;
+  for (int i = threadIdx.x; i < span; i += kRowChunk) {
+    const int xx = x0 - R + i;
+    int v = big;
+    if (xx >= 0 && xx < w) {
+      const int gy = g[static_cast<size_t>(y) * w + xx];
+      if (gy <= R) {
+        v = gy * gy;
+        any = 1;
+      }
+    }
+    sG[i] = v;
+  }
+  any = __syncthreads_or(any);
+  const int x = x0 + threadIdx.x;
+  if (x >= w) return;
+  int best = big;
+  if (any) {
+    const int *c = sG + threadIdx.x + R;  // centre of this thread's window
+    for (int dx = -R; dx <= R; ++dx) best = min(best, c[dx] + dx * dx);
+  }
+  const int k = (best > kmax) ? (kmax + 1) : best;
+  const size_t i = static_cast<size_t>(y) * w + x;
+  field[i] = __ldg(lut_field + k);
+  distance[i] = __ldg(lut_dist + k);
+}
+
+// K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
+// Phase A: per-block count.  Phase B: single-block exclusive scan of the
+// counts.  Phase C: in-block scan + scatter.
+constexpr int kCompactBlock = 256;
+constexpr int kCompactItems = 16;  // contiguous cells per thread
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int *total) {
+  __shared__ int warp_tot[kCompactBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int offset = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < kCompactBlock / 32; ++i) {
+    const int t = warp_tot[i];
+    if (i < wid) offset += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return offset + incl - v;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+free_count_kernel(const int8_t *__restrict__ state, size_t n, uint32_t *__restrict__ counts) {
+  const size_t base =
+      (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < kCompactItems; ++i)
+    if (base + i < n && state[base + i] == 0) ++c;
+  int total;
+  block_exclusive_scan_256(c, &total);
+  if (threadIdx.x == 0) counts[blockIdx.x] = static_cast<uint32_t>(total);
+}
+
+// Exclusive scan of `n` uint32 in place by ONE block; grand total -> out_total.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(uint32_t *__restrict__ counts, size_t n, unsigned long long *out_total) {
+  __shared__ unsigned long long warp_excl[32];
+  __shared__ unsigned long long chunk_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long carry = 0;
+  for (size_t base = 0; base < n; base += 1024) {
+    const size_t i = base + threadIdx.x;
+    const unsigned long long v = (i < n) ? counts[i] : 0;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_excl[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const unsigned long long t = warp_excl[lane];
+      unsigned long long ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += up;
+      }
+      warp_excl[lane] = ti - t;
+      if (lane == 31) chunk_total = ti;
+    }
+    __syncthreads();
+    if (i < n) counts[i] = static_cast<uint32_t>(carry + warp_excl[wid] + incl - v);
+    carry += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && out_total) *out_total = carry;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+free_scatter_kernel(const int8_t *__restrict__ state, size_t n, int w,
+                    const uint32_t *__restrict__ block_offsets, int32_t *__restrict__ out_xy) {
+  const size_t base =
+      (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
+  unsigned mask = 0;
+#pragma unroll
+  for (int i = 0; i < kCompactItems; ++i)
+    if (base + i < n && state[base + i] == 0) mask |= 1u << i;
+  int total;
+  size_t pos = block_offsets[blockIdx.x] + block_exclusive_scan_256(__popc(mask), &total);
+#pragma unroll
+  for (int i = 0; i < kCompactItems; ++i)
+    if (mask & (1u << i)) {
+      const size_t cell = base + i;
+      out_xy[2 * pos] = static_cast<int32_t>(cell % w);
+      out_xy[2 * pos + 1] = static_cast<int32_t>(cell / w);
+      ++pos;
+    }
+}
+
+// map_likelihood.cpp:132-146: int8(100 * p + 0.5f)
+__global__ void likelihood_grid_kernel(const float *__restrict__ field, size_t n,
+                                       int8_t *__restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<int8_t>(__fadd_rn(__fmul_rn(100.f, field[i]), 0.5f));
+}
+
+// map_base.cpp:66-77 for one query point.
+__global__ void state_at_kernel(const int8_t *__restrict__ state, MapGeom g, float x, float y,
+                                int8_t *out) {
+  const int ix = cell_index(x, g.ox, g.res), iy = cell_index(y, g.oy, g.res);
+  *out = in_map(ix, iy, g) ? state[static_cast<size_t>(iy) * g.w + ix] : int8_t(2);
+}
+
+__global__ void random_pose_kernel(const int32_t *__restrict__ free_xy, unsigned long long n_free,
+                                   MapGeom g, uint64_t seed, uint32_t step, uint64_t index,
+                                   float *out) {
+  uint32_t r[4];
+  rng_draw(seed, step, P_GLOBAL, index, r);
+  random_free_pose(free_xy, n_free, g, r, out, out + 1, out + 2);
+}
+
+// ---------------------------------------------------------------- host side
+
+static qmcl_status rebuild_free_cells(qmcl_map *m) {
+  const size_t n = static_cast<size_t>(m->geom.w) * m->geom.h;
+  const unsigned blocks = div_up(n, static_cast<size_t>(kCompactBlock) * kCompactItems);
+  QMCL_TRY(m->scan_tmp.ensure(blocks + 4));
+  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
+      m->scan_tmp.ptr + ((blocks + 1) & ~1u));
+  free_count_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(m->state.ptr, n, m->scan_tmp.ptr);
+  QMCL_LAUNCHED();
+  scan_counts_kernel<<<1, 1024, 0, m->stream>>>(m->scan_tmp.ptr, blocks, d_total);
+  QMCL_LAUNCHED();
+  unsigned long long total = 0;
+  QMCL_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, m->stream));
+  QMCL_CUDA(cudaStreamSynchronize(m->stream));
+  m->n_free = total;
+  QMCL_TRY(m->free_cells.ensure(2 * total + 2));
+  if (total) {
+    free_scatter_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(
+        m->state.ptr, n, static_cast<int>(m->geom.w), m->scan_tmp.ptr, m->free_cells.ptr);
+    QMCL_LAUNCHED();
+  }
+  return QMCL_OK;
+}
+
+static void set_geometry(qmcl_map *m, uint32_t w, uint32_t h, float res, double ox, double oy) {
+  // map_base.cpp:37-40: offset = (float)origin, res = (float)resolution
+  m->geom.w = w;
+  m->geom.h = h;
+  m->geom.res = res;
+  m->geom.ox = static_cast<float>(ox);
+  m->geom.oy = static_cast<float>(oy);
+}
+
+}  // namespace qmcl
+
+using namespace qmcl;
+
+// ==================================================================== C ABI
+extern "C" {
+
+const char *qmcl_version(void) { return "quickmcl_b200 0.1 (sm_100a)"; }
+const char *qmcl_last_error(void) { return qmcl::g_error.c_str(); }
+uint64_t qmcl_kernel_launch_count(void) { return g_launches.load(); }
+
+qmcl_status qmcl_map_create(int device, qmcl_map **out) {
+  if (!out) return QMCL_ERR_INVALID_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    set_error("no CUDA device: this library has no CPU fallback");
+    return QMCL_ERR_NO_DEVICE;
+  }
+  if (device < 0) QMCL_CUDA(cudaGetDevice(&device));
+  if (device >= count) return QMCL_ERR_INVALID_ARG;
+  qmcl_map *m = new qmcl_map();
+  m->device = device;
+  QMCL_CUDA(cudaSetDevice(device));
+  qmcl_map_set_params(m, &m->params);
+  *out = m;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_destroy(qmcl_map *m) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  m->field.release();
+  m->distance.release();
+  m->state.release();
+  m->free_cells.release();
+  m->occ.release();
+  m->edt_g.release();
+  m->scan_tmp.release();
+  m->lut.release();
+  m->tmp_x.release();
+  m->tmp_y.release();
+  m->tmp_t.release();
+  m->tmp_w.release();
+  m->tmp_aos.release();
+  m->tmp_cloud.release();
+  m->tmp_scalars.release();
+  delete m;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_set_stream(qmcl_map *m, void *cuda_stream) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  m->stream = static_cast<cudaStream_t>(cuda_stream);
+  return QMCL_OK;
+}
+
+// map_likelihood.cpp:40-49.  All float arithmetic as in the reference; the one
+// exp is the correctly rounded float (computed in double, rounded once).
+qmcl_status qmcl_map_set_params(qmcl_map *m, const qmcl_likelihood_params *p) {
+  if (!m || !p) return QMCL_ERR_INVALID_ARG;
+  m->params = *p;
+  m->z_hit_pre = 2 * p->sigma_hit * p->sigma_hit;
+  const float arg = -(p->max_obstacle_distance * p->max_obstacle_distance) / m->z_hit_pre;
+  m->max_distance_probability = static_cast<float>(exp(static_cast<double>(arg)));
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32_t height,
+                          float resolution, double origin_x, double origin_y) {
+  if (!m || !occ || width == 0 || height == 0 || !(resolution > 0)) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(m));
+  const size_t n = static_cast<size_t>(width) * height;
+  const float max_dist = m->params.max_obstacle_distance;
+  // Clipping radius in cells: one more than distance_calculator.cpp:89's
+  // cache size so that every cell with d <= max_dist is inside the window.
+  const long Rl = static_cast<long>(max_dist / resolution) + 1;
+  if (Rl < 1 || Rl > 8000) {
+    set_error("max_obstacle_distance / resolution = %ld cells is out of range", Rl);
+    return QMCL_ERR_INVALID_ARG;
+  }
+  const int R = static_cast<int>(Rl);
+  const int kmax = 2 * R * R;
+  set_geometry(m, width, height, resolution, origin_x, origin_y);
+  QMCL_TRY(m->occ.ensure(n));
+  QMCL_TRY(m->state.ensure(n));
+  QMCL_TRY(m->field.ensure(n));
+  QMCL_TRY(m->distance.ensure(n));
+  QMCL_TRY(m->edt_g.ensure((n + 1) / 2));
+  QMCL_TRY(m->lut.ensure(2 * static_cast<size_t>(kmax + 2)));
+  QMCL_CUDA(cudaMemcpyAsync(m->occ.ptr, occ, n, cudaMemcpyHostToDevice, m->stream));
+  uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
+  float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
+
+  edt_lut_kernel<<<div_up(kmax + 2, 256), 256, 0, m->stream>>>(lut_dist, lut_field, kmax + 2,
+                                                               resolution, max_dist, m->z_hit_pre);
+  QMCL_LAUNCHED();
+  dim3 grid1(div_up(width, 128), div_up(height, kSegLen));
+  edt_columns_kernel<<<grid1, 128, 0, m->stream>>>(m->occ.ptr, m->state.ptr, g,
+                                                   static_cast<int>(width),
+                                                   static_cast<int>(height), R);
+  QMCL_LAUNCHED();
+  dim3 grid2(div_up(width, kRowChunk), height);
+  const size_t smem = (kRowChunk + 2 * static_cast<size_t>(R)) * sizeof(int);
+  if (smem > 200 * 1024) return QMCL_ERR_INVALID_ARG;
+  if (smem > 48 * 1024)
+    QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  edt_rows_kernel<<<grid2, kRowChunk, smem, m->stream>>>(g, lut_dist, lut_field, m->distance.ptr,
+                                                         m->field.ptr, static_cast<int>(width),
+                                                         static_cast<int>(height), R, kmax);
+  QMCL_LAUNCHED();
+  QMCL_TRY(rebuild_free_cells(m));
+  m->has_map = true;
+  m->has_distance = true;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *state,
+                                uint32_t width, uint32_t height, float resolution,
+                                double origin_x, double origin_y) {
+  if (!m || !field || !state || width == 0 || height == 0 || !(resolution > 0))
+    return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(m));
+  const size_t n = static_cast<size_t>(width) * height;
+  set_geometry(m, width, height, resolution, origin_x, origin_y);
+  QMCL_TRY(m->state.ensure(n));
+  QMCL_TRY(m->field.ensure(n));
+  QMCL_CUDA(cudaMemcpyAsync(m->field.ptr, field, n * sizeof(float), cudaMemcpyHostToDevice,
+                            m->stream));
+  QMCL_CUDA(cudaMemcpyAsync(m->state.ptr, state, n, cudaMemcpyHostToDevice, m->stream));
+  QMCL_TRY(rebuild_free_cells(m));
+  m->has_map = true;
+  m->has_distance = false;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_size(const qmcl_map *m, uint32_t *width, uint32_t *height) {
+  if (!m || !width || !height) return QMCL_ERR_INVALID_ARG;
+  *width = m->geom.w;
+  *height = m->geom.h;
+  return QMCL_OK;
+}
+
+static qmcl_status copy_out(const qmcl_map *m, const void *src, void *dst, size_t bytes) {
+  if (!m || !dst) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(m));
+  QMCL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->stream));
+  QMCL_CUDA(cudaStreamSynchronize(m->stream));
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_copy_field(const qmcl_map *m, float *out) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  return copy_out(m, m->field.ptr, out, sizeof(float) * m->geom.w * m->geom.h);
+}
+qmcl_status qmcl_map_copy_distance(const qmcl_map *m, float *out) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_distance) return QMCL_ERR_NO_MAP;
+  return copy_out(m, m->distance.ptr, out, sizeof(float) * m->geom.w * m->geom.h);
+}
+qmcl_status qmcl_map_copy_state(const qmcl_map *m, int8_t *out) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  return copy_out(m, m->state.ptr, out, static_cast<size_t>(m->geom.w) * m->geom.h);
+}
+qmcl_status qmcl_map_num_free_cells(const qmcl_map *m, uint64_t *out) {
+  if (!m || !out) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map) return QMCL_ERR_NO_MAP;
+  *out = m->n_free;
+  return QMCL_OK;
+}
+qmcl_status qmcl_map_copy_free_cells(const qmcl_map *m, int32_t *xy_out) {
+  if (!m) return QMCL_ERR_INVALID_ARG;
+  if (m->n_free == 0) return m->has_map ? QMCL_OK : QMCL_ERR_NO_MAP;
+  return copy_out(m, m->free_cells.ptr, xy_out, sizeof(int32_t) * 2 * m->n_free);
+}
+
+qmcl_status qmcl_map_state_at(const qmcl_map *m, float x, float y, int8_t *out) {
+  if (!m || !out) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(m));
+  qmcl_map *mm = const_cast<qmcl_map *>(m);
+  QMCL_TRY(mm->scan_tmp.ensure(8));
+  int8_t *d_out = reinterpret_cast<int8_t *>(mm->scan_tmp.ptr);
+  state_at_kernel<<<1, 1, 0, m->stream>>>(m->state.ptr, m->geom, x, y, d_out);
+  QMCL_LAUNCHED();
+  return copy_out(m, d_out, out, 1);
+}
+
+qmcl_status qmcl_map_likelihood_grid(const qmcl_map *m, int8_t *out) {
+  if (!m || !out) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(m));
+  qmcl_map *mm = const_cast<qmcl_map *>(m);
+  const size_t n = static_cast<size_t>(m->geom.w) * m->geom.h;
+  QMCL_TRY(mm->occ.ensure(n));
+  likelihood_grid_kernel<<<div_up(n, 256), 256, 0, m->stream>>>(m->field.ptr, n, mm->occ.ptr);
+  QMCL_LAUNCHED();
+  return copy_out(m, mm->occ.ptr, out, n);
+}
+
+qmcl_status qmcl_map_generate_random_pose(const qmcl_map *m, uint64_t seed, uint32_t step,
+                                          uint64_t index, float pose_out[3]) {
+  if (!m || !pose_out) return QMCL_ERR_INVALID_ARG;
+  if (!m->has_map || m->n_free == 0) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(m));
+  qmcl_map *mm = const_cast<qmcl_map *>(m);
+  QMCL_TRY(mm->scan_tmp.ensure(8));
+  float *d_out = reinterpret_cast<float *>(mm->scan_tmp.ptr);
+  random_pose_kernel<<<1, 1, 0, m->stream>>>(m->free_cells.ptr, m->n_free, m->geom, seed, step,
+                                             index, d_out);
+  QMCL_LAUNCHED();
+  return copy_out(m, d_out, pose_out, 3 * sizeof(float));
+}
+
+}  // extern "C"

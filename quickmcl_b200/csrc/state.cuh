@@ -1,0 +1,114 @@
+// state.cuh — the two opaque handles behind the C ABI.
+#pragma once
+
+#include "common.cuh"
+
+// Device-resident scalars of one filter.
+struct FilterScalars {
+  double total_weight;   // pre-penalty total of the last sensor update
+  double post_total;     // sum of weights used by normalise()
+  unsigned int blocks_done;
+  unsigned int pad0;
+  unsigned long long n_out;  // KLD output size
+};
+
+// quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)
+struct qmcl_map {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  qmcl_likelihood_params params{0.5f, 0.5f, 30, 14.0f, 2.0f, 0.01f};
+  // map_likelihood.cpp:45-48, refreshed by set_params
+  float z_hit_pre = 2 * 0.01f * 0.01f;
+  double max_distance_probability = 0.0;
+
+  bool has_map = false;
+  bool has_distance = false;
+  qmcl::MapGeom geom{0, 0, 0.f, 0.f, 0.f};
+
+  // HBM layout (row-major [y][x], as map_types.h:27-32):
+  //   field    float32  W*H   likelihood table exp(-d^2 / 2 sigma^2)
+  //   distance float32  W*H   clipped distance in metres (only after load())
+  //   state    int8     W*H   0 free / 1 occupied / 2 unknown (map_state.h)
+  //   free     int32x2  nfree cells with state free, row-major order
+  qmcl::DevBuf<float> field;
+  qmcl::DevBuf<float> distance;
+  qmcl::DevBuf<int8_t> state;
+  qmcl::DevBuf<int32_t> free_cells;
+  uint64_t n_free = 0;
+
+  // scratch for load()
+  qmcl::DevBuf<int8_t> occ;
+  qmcl::DevBuf<int32_t> edt_g;
+  qmcl::DevBuf<uint32_t> scan_tmp;
+  qmcl::DevBuf<float> lut;  // d^2 -> distance | likelihood
+
+  // scratch for the host-vector update_importance overload
+  qmcl::DevBuf<float> tmp_x, tmp_y, tmp_t;
+  qmcl::DevBuf<double> tmp_w;
+  qmcl::DevBuf<uint8_t> tmp_aos;
+  qmcl::DevBuf<float> tmp_cloud;
+  qmcl::DevBuf<FilterScalars> tmp_scalars;
+};
+
+struct ParticleSet {
+  // SoA in HBM: 12 B pose + 8 B weight per particle.
+  qmcl::DevBuf<float> x, y, t;
+  qmcl::DevBuf<double> w;
+  size_t n = 0;
+  qmcl_status ensure(size_t cap) {
+    QMCL_TRY(x.ensure(cap));
+    QMCL_TRY(y.ensure(cap));
+    QMCL_TRY(t.ensure(cap));
+    QMCL_TRY(w.ensure(cap));
+    return QMCL_OK;
+  }
+};
+
+// quickmcl::ParticleFilter (particle_filter.h)
+struct qmcl_filter {
+  qmcl_map *map = nullptr;
+  qmcl_pf_params params{QMCL_RESAMPLE_KLD, 100, 5000, 2, 0.1, 0.001, 0.01, 0.01, 0.5f,
+                        0.17453292f};
+  uint64_t seed = 0;
+  uint32_t step = 0;
+  int shard_rank = 0, n_shards = 1;
+
+  ParticleSet sets[2];
+  int current = 0;
+
+  // low_pass_filter.h: two host scalars
+  double w_slow = 0.0, w_fast = 0.0;
+  double last_total = 0.0;
+
+  // space_partitioning.cpp:34-35
+  int theta_lo = -17, theta_hi = 17;
+
+  qmcl::DevBuf<float> cloud;        // the scan as received, float2
+  qmcl::DevBuf<float> beams;        // compacted used beams, float2
+  qmcl::DevBuf<double> partials;    // per-block partial sums
+  qmcl::DevBuf<FilterScalars> scalars;
+  qmcl::PinnedBuf<float> h_beams;
+  qmcl::PinnedBuf<double> h_scalars;
+
+  // resampling scratch
+  qmcl::DevBuf<double> cdf;
+  qmcl::DevBuf<int64_t> src_index;
+  size_t n_src_index = 0;
+  qmcl::DevBuf<uint8_t> scratch;
+
+  // bins / clusters (sorted unique keys)
+  qmcl::DevBuf<unsigned long long> bin_keys;    // packed key per particle / per bin
+  qmcl::DevBuf<unsigned long long> bin_unique;
+  qmcl::DevBuf<int32_t> bin_count;
+  qmcl::DevBuf<int32_t> bin_label;
+  size_t n_bins = 0, n_clusters = 0;
+  bool clusters_valid = false;
+
+  ParticleSet &cur() { return sets[current]; }
+  const ParticleSet &cur() const { return sets[current]; }
+};
+
+namespace qmcl {
+qmcl_status use_device(const qmcl_map *m);
+}
