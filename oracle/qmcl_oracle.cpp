@@ -264,37 +264,59 @@ struct Bins {
     return limit_for(cells.size(), eps2, kld_z, nmin, nmax);
   }
 
-  // space_partitioning.cpp:89-128, with an explicit stack instead of the
-  // reference's recursion (which overflows on million-bin components) and a
-  // canonical component order (sorted keys) instead of unordered_map order.
+  // space_partitioning.cpp:89-128.  The reference labels connected components
+  // by a recursive flood fill over the neighbour relation "theta +-1 with
+  // wrap, x +-1, y +-1".  Restated as union-find over the same edges (no
+  // recursion: the reference overflows its stack on million-bin components),
+  // with components numbered in sorted-key order instead of unordered_map
+  // order (ids are not canonical in the reference, only the partition is).
+  // Deviation: for theta bins outside [t_lo, t_hi] (a heading of exactly
+  // +-pi as a float) the reference's relation is not symmetric and its result
+  // depends on hash-map iteration order; the symmetric closure is used here.
   void assign_clusters() {
-    for (auto &kv : cells) kv.second.label = -1;
-    cluster_count = 0;
-    std::vector<std::map<BinKey, Val>::iterator> stack;
+    std::vector<std::map<BinKey, Val>::iterator> its;
+    its.reserve(cells.size());
+    int32_t idx = 0;
     for (auto it = cells.begin(); it != cells.end(); ++it) {
-      if (it->second.label != -1) continue;
-      int32_t id = static_cast<int32_t>(cluster_count++);
-      it->second.label = id;
-      stack.push_back(it);
-      while (!stack.empty()) {
-        auto cur = stack.back();
-        stack.pop_back();
-        for (int dt = -1; dt <= 1; ++dt) {
-          int t = cur->first.t + dt;
-          if (t < t_lo) t = t_hi;
-          else if (t > t_hi) t = t_lo;
-          for (int dx = -1; dx <= 1; ++dx)
-            for (int dy = -1; dy <= 1; ++dy) {
-              auto nb = cells.find(
-                  BinKey{cur->first.x + dx, cur->first.y + dy, t});
-              if (nb != cells.end() && nb->second.label == -1) {
-                nb->second.label = id;
-                stack.push_back(nb);
-              }
-            }
-        }
+      it->second.label = idx++;  // temporarily: own sorted index
+      its.push_back(it);
+    }
+    std::vector<int32_t> parent(its.size());
+    for (size_t i = 0; i < parent.size(); ++i) parent[i] = static_cast<int32_t>(i);
+    auto find = [&](int32_t v) {
+      while (parent[v] != v) {
+        parent[v] = parent[parent[v]];
+        v = parent[v];
+      }
+      return v;
+    };
+    for (size_t i = 0; i < its.size(); ++i) {
+      const BinKey &k = its[i]->first;
+      for (int dt = -1; dt <= 1; ++dt) {
+        int t = k.t + dt;
+        if (t < t_lo) t = t_hi;
+        else if (t > t_hi) t = t_lo;
+        for (int dx = -1; dx <= 1; ++dx)
+          for (int dy = -1; dy <= 1; ++dy) {
+            auto nb = cells.find(BinKey{k.x + dx, k.y + dy, t});
+            if (nb == cells.end()) continue;
+            int32_t a = find(static_cast<int32_t>(i)), b = find(nb->second.label);
+            if (a == b) continue;
+            if (a < b) parent[b] = a;
+            else parent[a] = b;
+          }
       }
     }
+    // number components by their smallest sorted index
+    std::vector<int32_t> id_of_root(its.size(), -1);
+    cluster_count = 0;
+    std::vector<int32_t> labels(its.size());
+    for (size_t i = 0; i < its.size(); ++i) {
+      int32_t r = find(static_cast<int32_t>(i));
+      if (id_of_root[r] < 0) id_of_root[r] = static_cast<int32_t>(cluster_count++);
+      labels[i] = id_of_root[r];
+    }
+    for (size_t i = 0; i < its.size(); ++i) its[i]->second.label = labels[i];
   }
   int32_t cluster_of(float x, float y, float t) const {  // :76-87
     auto it = cells.find(key_of(x, y, t));

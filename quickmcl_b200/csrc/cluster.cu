@@ -1,0 +1,558 @@
+// cluster.cu — K13 (bins + connected components) and K14 (cluster moments and
+// pose estimate).
+//
+// Replaces SpacePartitioning (src/quickmcl/space_partitioning.cpp:39-128),
+// ParticleFilter::cluster / compute_cluster_statistics / get_estimated_pose
+// (src/quickmcl/particle_filter.cpp:163-212, :366-391) and
+// ParticleCloudStatistics (src/quickmcl/statistics.cpp:23-79).
+//
+// The reference keeps occupied bins in an unordered_map.  Here the bin grid is
+// a DENSE int32 table over the bounding box of the particles' bin coordinates
+// (x-major, then y, then theta — i.e. lexicographic key order): marking is an
+// atomicAdd, the occupied-bin list is a stream compaction of the table (so it
+// comes out sorted), neighbour lookups are direct loads, and connected
+// components are a lock-free union-find whose roots are the smallest bin index
+// of each component, which is also the canonical label the oracle reports.
+
+#include "cluster.cuh"
+
+#include "scan.cuh"
+
+namespace qmcl {
+
+constexpr size_t kMaxTableCells = size_t(1) << 28;  // 1 GiB of int32
+
+struct BinParams {
+  float res_xy, res_t;
+  int theta_lo, theta_hi;
+};
+
+// space_partitioning.cpp:45-50 via scaled_map.h:43-48: float division, then
+// truncation toward zero, no offset.
+__device__ __forceinline__ void bin_key(float x, float y, float t, const BinParams &bp, int *kx,
+                                        int *ky, int *kt) {
+  *kx = cell_index_inf(x, bp.res_xy);
+  *ky = cell_index_inf(y, bp.res_xy);
+  *kt = cell_index_inf(t, bp.res_t);
+}
+
+__device__ __forceinline__ long long grid_index(const BinGrid &g, int kx, int ky, int kt) {
+  const long long ix = static_cast<long long>(kx) - g.x0;
+  const long long iy = static_cast<long long>(ky) - g.y0;
+  const long long it = static_cast<long long>(kt) - g.t0;
+  if (ix < 0 || iy < 0 || it < 0 || ix >= g.nx || iy >= g.ny || it >= g.nt) return -1;
+  return (ix * g.ny + iy) * g.nt + it;
+}
+
+// bbox[0..2] = min (x,y,t), bbox[3..5] = max.
+__global__ void __launch_bounds__(256)
+bin_bbox_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                const float *__restrict__ t, size_t n, BinParams bp, int *__restrict__ bbox) {
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int k[3];
+    bin_key(x[i], y[i], t[i], bp, &k[0], &k[1], &k[2]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = min(mn[d], k[d]);
+      mx[d] = max(mx[d], k[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(bbox + d, mn[d]);
+      atomicMax(bbox + 3 + d, mx[d]);
+    }
+  }
+}
+
+__global__ void bbox_init_kernel(int *bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = INT_MIN;
+}
+
+// SpacePartitioning::add_point for every particle: table[idx] counts members.
+__global__ void __launch_bounds__(256)
+bin_mark_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                const float *__restrict__ t, size_t n, BinParams bp, BinGrid g,
+                int32_t *__restrict__ table) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int kx, ky, kt;
+  bin_key(x[i], y[i], t[i], bp, &kx, &ky, &kt);
+  const long long idx = grid_index(g, kx, ky, kt);
+  if (idx >= 0) atomicAdd(table + idx, 1);
+}
+
+struct OccupiedFlag {
+  const int32_t *table;
+  __device__ uint32_t operator()(size_t i) const { return table[i] > 0 ? 1u : 0u; }
+};
+// Writes the compacted bin list and turns the table into cell -> bin id + 1.
+struct EmitBin {
+  int32_t *table;
+  int32_t *bin_cell;
+  int32_t *bin_count;
+  int32_t *parent;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+    if (!flag) return;
+    bin_cell[pos] = static_cast<int32_t>(i);
+    bin_count[pos] = table[i];
+    parent[pos] = static_cast<int32_t>(pos);
+    table[i] = static_cast<int32_t>(pos) + 1;
+  }
+};
+
+__device__ __forceinline__ int uf_find(int32_t *parent, int v) {
+  int p = parent[v];
+  while (p != v) {
+    const int gp = parent[p];
+    if (gp != p) parent[v] = gp;  // path halving (benign race)
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int tmp = a;
+      a = b;
+      b = tmp;
+    }
+    // hook the larger root under the smaller one: roots end up being the
+    // smallest bin index of their component
+    if (atomicCAS(parent + a, a, b) == a) return;
+  }
+}
+
+// SpacePartitioning::do_cluster's neighbour relation (space_partitioning.cpp:
+// 102-128): theta' = theta + {-1,0,1} wrapped with "< lo -> hi, > hi -> lo",
+// then (x+dx, y+dy) for dx,dy in {-1,0,1}.  One thread per (bin, theta step).
+__global__ void __launch_bounds__(256)
+cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bin_cell,
+               size_t n_bins, BinGrid g, BinParams bp, int32_t *__restrict__ parent) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tid >= n_bins * 3) return;
+  const int b = static_cast<int>(tid / 3);
+  const int dt = static_cast<int>(tid % 3) - 1;
+  const int cell = bin_cell[b];
+  const int it = cell % g.nt;
+  const int iy = (cell / g.nt) % g.ny;
+  const int ix = cell / (g.nt * g.ny);
+  int kt = it + g.t0 + dt;
+  if (kt < bp.theta_lo) kt = bp.theta_hi;
+  else if (kt > bp.theta_hi) kt = bp.theta_lo;
+  const int jt = kt - g.t0;
+  if (jt < 0 || jt >= g.nt) return;
+  for (int dx = -1; dx <= 1; ++dx) {
+    const int jx = ix + dx;
+    if (jx < 0 || jx >= g.nx) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int jy = iy + dy;
+      if (jy < 0 || jy >= g.ny) continue;
+      const int v = table[(static_cast<size_t>(jx) * g.ny + jy) * g.nt + jt];
+      if (v > 0 && v - 1 != b) uf_union(parent, b, v - 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cc_flatten_kernel(int32_t *__restrict__ parent, size_t n_bins) {
+  const size_t b = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= n_bins) return;
+  parent[b] = uf_find(parent, static_cast<int>(b));
+}
+
+struct RootFlag {
+  const int32_t *label;
+  __device__ uint32_t operator()(size_t b) const {
+    return label[b] == static_cast<int32_t>(b) ? 1u : 0u;
+  }
+};
+struct EmitRootId {
+  int32_t *cluster_of_root;
+  __device__ void operator()(size_t b, uint32_t pos, uint32_t flag) const {
+    if (flag) cluster_of_root[b] = static_cast<int32_t>(pos);
+  }
+};
+
+// K14 accumulation.  Slots per cluster:
+// 0 W, 1..4 S = w*(x, y, sin, cos), 5..8 C = (w*d_i)*d_j (i,j<2), 9 count.
+constexpr int kAccSlots = 10;
+
+__device__ __forceinline__ double block_sum_256(double v, double *smem) {
+  v = warp_sum_xor(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t = __dadd_rn(t, smem[i]);
+  }
+  __syncthreads();
+  return t;
+}
+
+// statistics.cpp:23-41 for every particle, into its cluster's slots.  Blocks
+// (then warps) whose particles all share one cluster reduce first and issue a
+// single set of atomics; mixed warps fall back to per-lane atomics.
+__global__ void __launch_bounds__(256)
+moments_kernel(const float *__restrict__ x, const float *__restrict__ y,
+               const float *__restrict__ t, const double *__restrict__ w, size_t n, BinParams bp,
+               BinGrid g, const int32_t *__restrict__ table, const int32_t *__restrict__ label,
+               const int32_t *__restrict__ cluster_of_root, double *__restrict__ acc,
+               int *__restrict__ invalid_flag) {
+  __shared__ double smem[8];
+  __shared__ int s_first;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int cid = -1;
+  double v[kAccSlots];
+#pragma unroll
+  for (int k = 0; k < kAccSlots; ++k) v[k] = 0.0;
+  const bool active = i < n;
+  if (active) {
+    const float px = x[i], py = y[i], pt = t[i];
+    int kx, ky, kt;
+    bin_key(px, py, pt, bp, &kx, &ky, &kt);
+    const long long idx = grid_index(g, kx, ky, kt);
+    const int b = idx >= 0 ? table[idx] - 1 : -1;
+    if (b < 0) {
+      atomicExch(invalid_flag, 1);  // particle_filter.cpp:375-379
+    } else {
+      cid = cluster_of_root[label[b]];
+      const double wi = w[i];
+      double sn, cs;
+      sincos(static_cast<double>(pt), &sn, &cs);
+      const double d0 = static_cast<double>(px), d1 = static_cast<double>(py);
+      v[0] = wi;
+      v[1] = wi * d0;
+      v[2] = wi * d1;
+      v[3] = wi * sn;
+      v[4] = wi * cs;
+      v[5] = (wi * d0) * d0;
+      v[6] = (wi * d0) * d1;
+      v[7] = (wi * d1) * d0;
+      v[8] = (wi * d1) * d1;
+      v[9] = 1.0;
+    }
+  }
+  if (threadIdx.x == 0) s_first = cid;
+  __syncthreads();
+  const int first = s_first;
+  const bool same = (cid == first) || !active || cid < 0;
+  if (__syncthreads_and(same) && first >= 0) {
+#pragma unroll
+    for (int k = 0; k < kAccSlots; ++k) {
+      const double s = block_sum_256(v[k], smem);
+      if (threadIdx.x == 0) atomicAdd(acc + static_cast<size_t>(first) * kAccSlots + k, s);
+    }
+    return;
+  }
+  // warp level
+  const int wfirst = __shfl_sync(0xffffffffu, cid, 0);
+  const bool wsame = (cid == wfirst) || cid < 0;
+  if (__all_sync(0xffffffffu, wsame) && wfirst >= 0) {
+#pragma unroll
+    for (int k = 0; k < kAccSlots; ++k) {
+      const double s = warp_sum_xor(v[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(acc + static_cast<size_t>(wfirst) * kAccSlots + k, s);
+    }
+    return;
+  }
+  if (cid >= 0) {
+#pragma unroll
+    for (int k = 0; k < kAccSlots; ++k) atomicAdd(acc + static_cast<size_t>(cid) * kAccSlots + k, v[k]);
+  }
+}
+
+// statistics.cpp:50-79 + particle_filter.cpp:186-212: global = sum of the
+// clusters (in canonical cluster order), finalise, pick the first strict
+// maximum of total weight.  out = {valid, pose[3], cov[9]}.
+__global__ void __launch_bounds__(256)
+estimate_finalise_kernel(const double *__restrict__ acc, size_t n_clusters,
+                         double *__restrict__ out) {
+  __shared__ double s_best_w[256];
+  __shared__ long long s_best_i[256];
+  // best cluster: max W, ties -> smallest id (== "first strict maximum")
+  double bw = -1.0;
+  long long bi = -1;
+  for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x) {
+    const double wv = acc[c * kAccSlots];
+    if (wv > bw) {
+      bw = wv;
+      bi = static_cast<long long>(c);
+    }
+  }
+  s_best_w[threadIdx.x] = bw;
+  s_best_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double ow = s_best_w[threadIdx.x + o];
+      const long long oi = s_best_i[threadIdx.x + o];
+      if (oi >= 0 && (ow > s_best_w[threadIdx.x] ||
+                      (ow == s_best_w[threadIdx.x] && (s_best_i[threadIdx.x] < 0 || oi < s_best_i[threadIdx.x])))) {
+        s_best_w[threadIdx.x] = ow;
+        s_best_i[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  // global statistics = sum of the clusters (statistics.cpp:50-57); summed as
+  // a strided tree here, which differs from the sequential order by rounding only
+  __shared__ double s_g[kAccSlots];
+  __shared__ double s_red[8];
+  for (int k = 0; k < kAccSlots; ++k) {
+    double part = 0.0;
+    for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x)
+      part = __dadd_rn(part, acc[c * kAccSlots + k]);
+    const double tot = block_sum_256(part, s_red);
+    if (threadIdx.x == 0) s_g[k] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double *gsum = s_g;
+  const long long best = s_best_i[0];
+  const double best_w = s_best_w[0];
+  for (int k = 0; k < 13; ++k) out[k] = 0.0;
+  if (best < 0 || !(best_w > 0)) return;
+  const double *b = acc + static_cast<size_t>(best) * kAccSlots;
+  out[0] = 1.0;
+  out[1] = b[1] / b[0];
+  out[2] = b[2] / b[0];
+  out[3] = atan2(b[3], b[4]);
+  const double W = gsum[0];
+  const double m0 = gsum[1] / W, m1 = gsum[2] / W;
+  double *cov = out + 4;
+  cov[0] = gsum[5] / W - m0 * m0;
+  cov[1] = gsum[6] / W - m0 * m1;
+  cov[3] = gsum[7] / W - m1 * m0;
+  cov[4] = gsum[8] / W - m1 * m1;
+  const double R = sqrt(gsum[3] * gsum[3] + gsum[4] * gsum[4]);  // un-normalised, as the reference
+  cov[8] = 1 - R;
+}
+
+__global__ void decode_bins_kernel(const int32_t *__restrict__ bin_cell,
+                                   const int32_t *__restrict__ bin_count,
+                                   const int32_t *__restrict__ label, size_t n_bins, BinGrid g,
+                                   int32_t *__restrict__ keys4, int32_t *__restrict__ labels) {
+  const size_t b = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= n_bins) return;
+  const int cell = bin_cell[b];
+  keys4[4 * b + 0] = cell / (g.nt * g.ny) + g.x0;
+  keys4[4 * b + 1] = (cell / g.nt) % g.ny + g.y0;
+  keys4[4 * b + 2] = cell % g.nt + g.t0;
+  keys4[4 * b + 3] = bin_count[b];
+  labels[b] = label ? label[b] : -1;
+}
+
+static BinParams bin_params(const qmcl_filter *f) {
+  BinParams bp;
+  bp.res_xy = f->params.res_xy;
+  bp.res_t = f->params.res_theta;
+  bp.theta_lo = f->theta_lo;
+  bp.theta_hi = f->theta_hi;
+  return bp;
+}
+
+// SpacePartitioning::reset + add_point for x/y/t[0..n): bbox, dense table,
+// sorted occupied-bin list.  Leaves parent[b] = b.
+qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n) {
+  cudaStream_t s = f->map->stream;
+  f->n_bins = 0;
+  f->n_clusters = 0;
+  f->bins_built = false;
+  f->clusters_valid = false;
+  if (n == 0) {
+    f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+    f->bins_built = true;
+    return QMCL_OK;
+  }
+  const BinParams bp = bin_params(f);
+  QMCL_TRY(f->bbox.ensure(8));
+  bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
+  QMCL_LAUNCHED();
+  const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
+  bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
+  QMCL_LAUNCHED();
+  int hb[6];
+  QMCL_CUDA(cudaMemcpyAsync(hb, f->bbox.ptr, sizeof(hb), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  BinGrid g;
+  g.x0 = hb[0];
+  g.y0 = hb[1];
+  g.t0 = hb[2];
+  const long long nx = static_cast<long long>(hb[3]) - hb[0] + 1;
+  const long long ny = static_cast<long long>(hb[4]) - hb[1] + 1;
+  const long long nt = static_cast<long long>(hb[5]) - hb[2] + 1;
+  if (nx <= 0 || ny <= 0 || nt <= 0 ||
+      static_cast<double>(nx) * ny * nt > static_cast<double>(kMaxTableCells)) {
+    set_error("bin grid %lld x %lld x %lld exceeds the dense-table capacity", nx, ny, nt);
+    return QMCL_ERR_CAPACITY;
+  }
+  g.nx = static_cast<int>(nx);
+  g.ny = static_cast<int>(ny);
+  g.nt = static_cast<int>(nt);
+  const size_t cells = static_cast<size_t>(nx) * ny * nt;
+  f->grid = g;
+  QMCL_TRY(f->table.ensure(cells));
+  QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0, cells * sizeof(int32_t), s));
+  bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);
+  QMCL_LAUNCHED();
+  const size_t max_bins = std::min(n, cells);
+  QMCL_TRY(f->bin_cell.ensure(max_bins));
+  QMCL_TRY(f->bin_count.ensure(max_bins));
+  QMCL_TRY(f->bin_label.ensure(max_bins));
+  QMCL_TRY(f->bin_cluster.ensure(max_bins));
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(cells) + 4));
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(cells) + 1) & ~1u));
+  QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
+                       EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
+                       cells, f->scan_tmp.ptr, d_total));
+  unsigned long long nb = 0;
+  QMCL_CUDA(cudaMemcpyAsync(&nb, d_total, sizeof(nb), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  f->n_bins = nb;
+  f->bins_built = true;
+  return QMCL_OK;
+}
+
+// SpacePartitioning::assign_clusters on the current bin list.
+qmcl_status label_clusters(qmcl_filter *f) {
+  cudaStream_t s = f->map->stream;
+  f->n_clusters = 0;
+  if (f->n_bins == 0) {
+    f->clusters_valid = true;
+    return QMCL_OK;
+  }
+  const BinParams bp = bin_params(f);
+  cc_hook_kernel<<<div_up(f->n_bins * 3, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, f->n_bins,
+                                                            f->grid, bp, f->bin_label.ptr);
+  QMCL_LAUNCHED();
+  cc_flatten_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->bin_label.ptr, f->n_bins);
+  QMCL_LAUNCHED();
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(f->n_bins) + 4));
+  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
+      f->scan_tmp.ptr + ((scan_blocks(f->n_bins) + 1) & ~1u));
+  QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr}, EmitRootId{f->bin_cluster.ptr}, f->n_bins,
+                       f->scan_tmp.ptr, d_total));
+  unsigned long long nc = 0;
+  QMCL_CUDA(cudaMemcpyAsync(&nc, d_total, sizeof(nc), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  f->n_clusters = nc;
+  f->clusters_valid = true;
+  return QMCL_OK;
+}
+
+}  // namespace qmcl
+
+using namespace qmcl;
+
+extern "C" {
+
+// particle_filter.cpp:163-175
+qmcl_status qmcl_filter_cluster(qmcl_filter *f) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  const ParticleSet &ps = f->cur();
+  QMCL_TRY(build_bins(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
+  return label_clusters(f);
+}
+
+qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[9], int *valid) {
+  if (!f || !pose || !cov || !valid) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  *valid = 0;
+  const ParticleSet &ps = f->cur();
+  if (ps.n == 0 && f->n_clusters == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
+  if (ps.n > 0 && (!f->bins_built || f->n_clusters == 0)) {
+    set_error("get_estimate: particles have no cluster (call cluster() or resample first)");
+    return QMCL_ERR_INVALID_CLUSTER;
+  }
+  const BinParams bp = bin_params(f);
+  QMCL_TRY(f->cluster_acc.ensure(f->n_clusters * kAccSlots + 16));
+  double *acc = f->cluster_acc.ptr;
+  double *d_out = acc + f->n_clusters * kAccSlots;
+  QMCL_CUDA(cudaMemsetAsync(acc, 0, (f->n_clusters * kAccSlots + 16) * sizeof(double), s));
+  int *d_flag = reinterpret_cast<int *>(d_out + 14);
+  if (ps.n) {
+    moments_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n,
+                                                     bp, f->grid, f->table.ptr, f->bin_label.ptr,
+                                                     f->bin_cluster.ptr, acc, d_flag);
+    QMCL_LAUNCHED();
+  }
+  estimate_finalise_kernel<<<1, 256, 0, s>>>(acc, f->n_clusters, d_out);
+  QMCL_LAUNCHED();
+  double h[16];
+  QMCL_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  int flag;
+  std::memcpy(&flag, &h[14], sizeof(int));
+  if (flag) {
+    set_error("get_estimate: a particle's bin has no cluster (reference abort()s here)");
+    return QMCL_ERR_INVALID_CLUSTER;
+  }
+  if (h[0] != 0.0) {
+    *valid = 1;
+    pose[0] = h[1];
+    pose[1] = h[2];
+    pose[2] = h[3];
+    for (int k = 0; k < 9; ++k) cov[k] = h[4 + k];
+  }
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_num_bins(const qmcl_filter *f, size_t *out) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  *out = f->n_bins;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_num_clusters(const qmcl_filter *f, size_t *out) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  *out = f->n_clusters;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_copy_bins(const qmcl_filter *fc, int32_t *keys4, int32_t *labels,
+                                  size_t cap, size_t *n_out) {
+  if (!fc) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  if (n_out) *n_out = f->n_bins;
+  const size_t n = f->n_bins < cap ? f->n_bins : cap;
+  if (!n || !keys4 || !labels) return QMCL_OK;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  void *stage = nullptr;
+  QMCL_TRY(filter_scratch(f, n * 5 * sizeof(int32_t), &stage));
+  int32_t *d_keys = static_cast<int32_t *>(stage);
+  int32_t *d_labels = d_keys + 4 * n;
+  decode_bins_kernel<<<div_up(n, 256), 256, 0, s>>>(
+      f->bin_cell.ptr, f->bin_count.ptr, f->clusters_valid ? f->bin_label.ptr : nullptr, n, f->grid,
+      d_keys, d_labels);
+  QMCL_LAUNCHED();
+  QMCL_CUDA(cudaMemcpyAsync(keys4, d_keys, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaMemcpyAsync(labels, d_labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  return QMCL_OK;
+}
+
+}  // extern "C"

@@ -151,12 +151,18 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->h_beams.release();
   f->h_scalars.release();
   f->cdf.release();
+  f->pos.release();
+  f->incl.release();
   f->src_index.release();
   f->scratch.release();
-  f->bin_keys.release();
-  f->bin_unique.release();
+  f->bbox.release();
+  f->table.release();
+  f->bin_cell.release();
   f->bin_count.release();
   f->bin_label.release();
+  f->bin_cluster.release();
+  f->scan_tmp.release();
+  f->cluster_acc.release();
   delete f;
   return QMCL_OK;
 }
@@ -203,6 +209,8 @@ qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, si
   ParticleSet &ps = f->cur();
   QMCL_TRY(ps.ensure(n));
   ps.n = n;
+  f->global_first = 0;
+  f->global_n = n;
   f->clusters_valid = false;
   if (!n) return QMCL_OK;
   void *stage = nullptr;

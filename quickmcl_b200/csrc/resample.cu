@@ -1,0 +1,502 @@
+// resample.cu — K9-K12: CDF, low-variance / adaptive / KLD resampling, gather.
+//
+// Replaces ParticleFilter::resample_and_cluster, resample_low_variance,
+// resample_adaptive, resample_kld (src/quickmcl/particle_filter.cpp:138-161,
+// :214-348), ParticlesRunningSum (src/quickmcl/particle.cpp:66-82,
+// include/quickmcl/particle.h:99-107), SpacePartitioning::limit
+// (src/quickmcl/space_partitioning.cpp:52-74) and normalise_particle_weights
+// (src/quickmcl/particle.cpp:41-56).
+//
+// Bit-exactness: the reference's CDF is a *sequential* double running sum and
+// every resampling decision compares a draw against it, so the CDF here is the
+// same sequence of correctly rounded additions (see prefix.cu), not a
+// reassociated parallel sum.  Given that array, every step below is exact
+// comparison logic and the resulting indices / KLD bin counts are bit-exact.
+
+#include "cluster.cuh"
+#include "prefix.cuh"
+#include "scan.cuh"
+
+#include <cmath>
+
+namespace qmcl {
+
+// ---------------------------------------------------------------- low variance
+// particle_filter.cpp:225-238: U = r + m * minv (two rounded double ops), walk
+// to the first i with c_i >= U.  Deviation: i is clamped to
+// M-1 where the reference's .at(i) would throw.
+__global__ void __launch_bounds__(256)
+lv_select_kernel(const double *__restrict__ cdf, size_t M, double r, double minv,
+                 int64_t *__restrict__ src) {
+  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const double U = __dadd_rn(r, __dmul_rn(static_cast<double>(m), minv));
+  // first i with !(U > c_i)
+  size_t lo = 0, hi = M;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (U > cdf[mid]) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo > M - 1) lo = M - 1;
+  src[m] = static_cast<int64_t>(lo);
+}
+
+// K12: copy pose and weight of the selected source (particle_filter.cpp:237).
+__global__ void __launch_bounds__(256)
+gather_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
+              const float *__restrict__ it, const double *__restrict__ iw,
+              const int64_t *__restrict__ src, size_t n_out, float *__restrict__ ox,
+              float *__restrict__ oy, float *__restrict__ ot, double *__restrict__ ow) {
+  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= n_out) return;
+  const int64_t s = src[m];
+  if (s < 0) return;  // injected slot, already written
+  ox[m] = ix[s];
+  oy[m] = iy[s];
+  ot[m] = it[s];
+  ow[m] = iw[s];
+}
+
+// ------------------------------------------------------ running-sum lookup
+struct PositiveFlag {
+  const double *w;
+  __device__ uint32_t operator()(size_t i) const { return w[i] > 0 ? 1u : 0u; }
+};
+// pos[t] = original index of the t-th positive-weight particle and
+// incl[t] = running sum after it (= key of the next record).
+struct EmitPositive {
+  const double *cdf;
+  int64_t *pos;
+  double *incl;
+  __device__ void operator()(size_t i, uint32_t t, uint32_t flag) const {
+    if (!flag) return;
+    pos[t] = static_cast<int64_t>(i);
+    incl[t] = cdf[i];
+  }
+};
+
+// ParticlesRunningSum::lookup_index (particle.h:99-107) over the records
+// (key_t = running sum before positive particle t): the record with the
+// largest key <= r; among records sharing a key the first inserted wins
+// (std::map::insert keeps the existing entry, particle.cpp:77).
+__device__ __forceinline__ size_t running_sum_lookup(const double *__restrict__ incl, size_t P,
+                                                     double r) {
+  // t* = number of t in [1, P) with key_t = incl[t-1] <= r
+  size_t lo = 0, hi = P - 1;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (incl[mid] <= r) lo = mid + 1;
+    else hi = mid;
+  }
+  const size_t tstar = lo;
+  if (tstar == 0) return 0;
+  const double K = incl[tstar - 1];
+  // first t with key_t == K, i.e. 1 + first j with incl[j] >= K
+  lo = 0;
+  hi = tstar - 1;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (incl[mid] < K) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo + 1;
+}
+
+// One adaptive / KLD slot per thread (particle_filter.cpp:261-276, :313-327).
+__global__ void __launch_bounds__(256)
+draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
+            const float *__restrict__ it, const double *__restrict__ iw,
+            const int64_t *__restrict__ pos, const double *__restrict__ incl, size_t P,
+            double w_diff, size_t n_draws, const int32_t *__restrict__ free_xy,
+            unsigned long long n_free, MapGeom g, uint64_t seed, uint32_t step,
+            float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ ot,
+            double *__restrict__ ow, int64_t *__restrict__ src) {
+  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= n_draws) return;
+  uint32_t r[4];
+  rng_draw(seed, step, P_DRAW, m, r);
+  const double p = uniform53(r[0], r[1]);
+  if (p < w_diff) {
+    uint32_t q[4];
+    rng_draw(seed, step, P_INJECT, m, q);
+    float x, y, t;
+    random_free_pose(free_xy, n_free, g, q, &x, &y, &t);
+    ox[m] = x;
+    oy[m] = y;
+    ot[m] = t;
+    ow[m] = 0.0;  // no influence on the estimate until the next update
+    src[m] = -1;
+    return;
+  }
+  const double rr = uniform53(r[2], r[3]);
+  const int64_t s = pos[running_sum_lookup(incl, P, rr)];
+  ox[m] = ix[s];
+  oy[m] = iy[s];
+  ot[m] = it[s];
+  ow[m] = iw[s];
+  src[m] = s;
+}
+
+// ------------------------------------------------------------------------ KLD
+struct KldParams {
+  float res_xy, res_t;
+  double eps2, z;
+  int32_t nmin, nmax;
+};
+
+// space_partitioning.cpp:52-74, the same double expressions in the same order.
+__device__ __forceinline__ unsigned long long kld_limit(unsigned long long k, const KldParams &kp) {
+  if (k < 2) return static_cast<unsigned long long>(kp.nmax);
+  const double common = 2.0 / static_cast<double>(9 * (k - 1));
+  const double to_be_cubed = 1 - common - sqrt(common) * kp.z;
+  const double result =
+      (static_cast<double>(k - 1) / kp.eps2) * to_be_cubed * to_be_cubed * to_be_cubed;
+  const double c = ceil(result);
+  int32_t fin;
+  if (c >= 2147483647.0) fin = 2147483647;
+  else if (c <= -2147483648.0) fin = static_cast<int32_t>(-2147483647 - 1);
+  else fin = static_cast<int32_t>(c);
+  if (fin < kp.nmin) return static_cast<unsigned long long>(kp.nmin);
+  if (fin > kp.nmax) return static_cast<unsigned long long>(kp.nmax);
+  return static_cast<unsigned long long>(fin);
+}
+
+__device__ __forceinline__ long long kld_cell(float x, float y, float t, const KldParams &kp,
+                                              const BinGrid &g) {
+  const long long ix = static_cast<long long>(cell_index_inf(x, kp.res_xy)) - g.x0;
+  const long long iy = static_cast<long long>(cell_index_inf(y, kp.res_xy)) - g.y0;
+  const long long it = static_cast<long long>(cell_index_inf(t, kp.res_t)) - g.t0;
+  return (ix * g.ny + iy) * g.nt + it;
+}
+
+// table[cell] = smallest draw index that fell into the cell.
+__global__ void __launch_bounds__(256)
+kld_first_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                 const float *__restrict__ t, size_t n, KldParams kp, BinGrid g,
+                 int32_t *__restrict__ table) {
+  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  atomicMin(table + kld_cell(x[m], y[m], t[m], kp, g), static_cast<int32_t>(m));
+}
+
+// flag(m) = draw m opened a new bin.
+struct NewBinFlag {
+  const float *x, *y, *t;
+  KldParams kp;
+  BinGrid g;
+  const int32_t *table;
+  __device__ uint32_t operator()(size_t m) const {
+    return table[kld_cell(x[m], y[m], t[m], kp, g)] == static_cast<int32_t>(m) ? 1u : 0u;
+  }
+};
+// After draw m there are k = prefix + flag bins; the loop stops at the first m
+// with m >= limit(k) (particle_filter.cpp:329-334).
+struct StopRule {
+  KldParams kp;
+  unsigned long long *first_stop;
+  __device__ void operator()(size_t m, uint32_t before, uint32_t flag) const {
+    const unsigned long long k = static_cast<unsigned long long>(before) + flag;
+    if (m >= kld_limit(k, kp)) atomicMin(first_stop, static_cast<unsigned long long>(m));
+  }
+};
+
+// ------------------------------------------------------------------ normalise
+// particle.cpp:41-56: total = sum of weights, w /= total.  The sum is a fixed
+// tree (deterministic); it differs from the sequential sum by rounding only.
+__global__ void __launch_bounds__(256)
+weight_sum_kernel(const double *__restrict__ w, size_t n, double *__restrict__ partials,
+                  FilterScalars *__restrict__ sc) {
+  __shared__ double s_warp[8];
+  __shared__ bool s_last;
+  double t = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    t = __dadd_rn(t, w[i]);
+  t = warp_sum_xor(t);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b = __dadd_rn(b, s_warp[i]);
+    partials[blockIdx.x] = b;
+    __threadfence();
+    s_last = atomicAdd(&sc->blocks_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    a = __dadd_rn(a, __ldcg(partials + i));
+  a = warp_sum_xor(a);
+  __syncthreads();
+  if (lane == 0) s_warp[wid] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot = __dadd_rn(tot, s_warp[i]);
+    sc->post_total = tot;
+    sc->blocks_done = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+divide_by_post_total_kernel(double *__restrict__ w, size_t n, const FilterScalars *__restrict__ sc) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = __ddiv_rn(w[i], sc->post_total);
+}
+
+static qmcl_status normalise_current(qmcl_filter *f) {
+  ParticleSet &ps = f->cur();
+  if (!ps.n) return QMCL_OK;
+  cudaStream_t s = f->map->stream;
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(div_up(ps.n, 256 * 4), 4 * kSMs));
+  QMCL_TRY(f->partials.ensure(blocks));
+  weight_sum_kernel<<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
+  QMCL_LAUNCHED();
+  divide_by_post_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+__global__ void fill_default_kernel(float *x, float *y, float *t, double *w, size_t from,
+                                    size_t to) {
+  const size_t i = from + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= to) return;
+  x[i] = 0.f;
+  y[i] = 0.f;
+  t[i] = 0.f;
+  w[i] = 1.0;  // WeightedParticle's default weight (particle.h:46)
+}
+
+// ------------------------------------------------------------------ host side
+
+// particle_filter.cpp:214-239
+static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, ParticleSet &out) {
+  cudaStream_t s = f->map->stream;
+  const size_t M = in.n;
+  QMCL_TRY(out.ensure(M));
+  out.n = M;
+  f->n_src_index = M;
+  if (M == 0) return QMCL_OK;
+  QMCL_TRY(f->cdf.ensure(M));
+  QMCL_TRY(f->src_index.ensure(M));
+  QMCL_TRY(sequential_prefix(f, in.w.ptr, M, f->cdf.ptr));
+  const double minv = static_cast<double>(1.0f / static_cast<float>(M));
+  uint32_t r4[4];
+  rng_draw(f->seed, f->step, P_LV_OFFSET, 0, r4);
+  const double r = uniform53(r4[0], r4[1]) * minv;
+  lv_select_kernel<<<div_up(M, 256), 256, 0, s>>>(f->cdf.ptr, M, r, minv, f->src_index.ptr);
+  QMCL_LAUNCHED();
+  gather_kernel<<<div_up(M, 256), 256, 0, s>>>(in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr,
+                                               f->src_index.ptr, M, out.x.ptr, out.y.ptr, out.t.ptr,
+                                               out.w.ptr);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// Builds the running-sum records of `in`; *P_out = number of records,
+// *total_out = ParticlesRunningSum::get_total_weight().
+static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size_t *P_out,
+                                     double *total_out) {
+  cudaStream_t s = f->map->stream;
+  *P_out = 0;
+  *total_out = 0.0;
+  if (in.n == 0) return QMCL_OK;
+  QMCL_TRY(f->cdf.ensure(in.n));
+  QMCL_TRY(f->pos.ensure(in.n));
+  QMCL_TRY(f->incl.ensure(in.n));
+  QMCL_TRY(sequential_prefix(f, in.w.ptr, in.n, f->cdf.ptr));
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(in.n) + 4));
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(in.n) + 1) & ~1u));
+  QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
+                       in.n, f->scan_tmp.ptr, d_total));
+  unsigned long long P = 0;
+  double total = 0.0;
+  QMCL_CUDA(cudaMemcpyAsync(&P, d_total, sizeof(P), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaMemcpyAsync(&total, f->cdf.ptr + (in.n - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  *P_out = P;
+  *total_out = total;
+  return QMCL_OK;
+}
+
+static double adaptiveness(const qmcl_filter *f) {
+  // particle_filter.cpp:246: std::max(0.0, NaN) is 0.0
+  return std::max(0.0, 1.0 - f->w_fast / f->w_slow);
+}
+
+static qmcl_status launch_draws(qmcl_filter *f, const ParticleSet &in, ParticleSet &out, size_t P,
+                                double w_diff, size_t n_draws) {
+  cudaStream_t s = f->map->stream;
+  if (w_diff > 0 && f->map->n_free == 0) {
+    set_error("adaptive injection needs a map with free cells");
+    return QMCL_ERR_NO_MAP;
+  }
+  QMCL_TRY(f->src_index.ensure(n_draws));
+  draw_kernel<<<div_up(n_draws, 256), 256, 0, s>>>(
+      in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr, f->pos.ptr, f->incl.ptr, P, w_diff, n_draws,
+      f->map->free_cells.ptr, f->map->n_free, f->map->geom, f->seed, f->step, out.x.ptr, out.y.ptr,
+      out.t.ptr, out.w.ptr, f->src_index.ptr);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// particle_filter.cpp:241-291
+static qmcl_status resample_adaptive(qmcl_filter *f, const ParticleSet &in, ParticleSet &out) {
+  cudaStream_t s = f->map->stream;
+  const double w_diff = adaptiveness(f);
+  const size_t n_out = static_cast<size_t>(f->params.particle_count_min);
+  // output_particles->resize(output_size): keeps what the buffer held, new
+  // slots are default particles
+  const size_t old_n = out.n;
+  QMCL_TRY(out.x.ensure_keep(n_out, old_n, s));
+  QMCL_TRY(out.y.ensure_keep(n_out, old_n, s));
+  QMCL_TRY(out.t.ensure_keep(n_out, old_n, s));
+  QMCL_TRY(out.w.ensure_keep(n_out, old_n, s));
+  if (n_out > old_n) {
+    fill_default_kernel<<<div_up(n_out - old_n, 256), 256, 0, s>>>(out.x.ptr, out.y.ptr, out.t.ptr,
+                                                                   out.w.ptr, old_n, n_out);
+    QMCL_LAUNCHED();
+  }
+  out.n = n_out;
+  f->n_src_index = 0;
+  size_t P;
+  double total;
+  QMCL_TRY(build_running_sum(f, in, &P, &total));
+  if (!(total > 0)) return QMCL_OK;  // "No particles have any weights! Failing to resample"
+  if (n_out) QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_out));
+  f->n_src_index = n_out;
+  if (w_diff > 0.0) {
+    f->w_fast = 0;
+    f->w_slow = 0;
+  }
+  return QMCL_OK;
+}
+
+// particle_filter.cpp:293-348.  All particle_count_max candidate draws are
+// made at once (counter-based RNG: draw m does not depend on draw m-1); the
+// sequential stop rule "first m with m >= limit(bins after m)" becomes a
+// first-occurrence mark per bin, a prefix count and a min-reduction.
+static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleSet &out,
+                                bool *clustered) {
+  cudaStream_t s = f->map->stream;
+  *clustered = false;
+  const double w_diff = adaptiveness(f);
+  const size_t n_max = static_cast<size_t>(f->params.particle_count_max);
+  out.n = 0;  // output_set->particles.clear()
+  f->n_src_index = 0;
+  f->n_bins = 0;  // space_partitioning.reset()
+  f->n_clusters = 0;
+  f->bins_built = true;
+  f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+  size_t P;
+  double total;
+  QMCL_TRY(build_running_sum(f, in, &P, &total));
+  if (!(total > 0)) return QMCL_OK;
+  if (n_max == 0) return QMCL_OK;
+  if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
+  QMCL_TRY(out.ensure(n_max));
+  QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_max));
+  // bins of all candidates
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max));
+  const BinGrid g = f->grid;
+  const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
+  KldParams kp;
+  kp.res_xy = f->params.res_xy;
+  kp.res_t = f->params.res_theta;
+  kp.eps2 = 2 * f->params.kld_epsilon;  // space_partitioning.cpp:31
+  kp.z = f->params.kld_z;
+  kp.nmin = f->params.particle_count_min;
+  kp.nmax = f->params.particle_count_max;
+  QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0x7f, cells * sizeof(int32_t), s));
+  kld_first_kernel<<<div_up(n_max, 256), 256, 0, s>>>(out.x.ptr, out.y.ptr, out.t.ptr, n_max, kp, g,
+                                                      f->table.ptr);
+  QMCL_LAUNCHED();
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(n_max) + 8));
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(n_max) + 1) & ~1u));
+  unsigned long long *d_stop = d_total + 1;
+  QMCL_CUDA(cudaMemsetAsync(d_stop, 0xff, sizeof(unsigned long long), s));
+  QMCL_TRY(device_scan(s, NewBinFlag{out.x.ptr, out.y.ptr, out.t.ptr, kp, g, f->table.ptr},
+                       StopRule{kp, d_stop}, n_max, f->scan_tmp.ptr, d_total));
+  unsigned long long stop = 0;
+  QMCL_CUDA(cudaMemcpyAsync(&stop, d_stop, sizeof(stop), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  const size_t n_out = (stop >= n_max) ? n_max : static_cast<size_t>(stop) + 1;
+  out.n = n_out;
+  f->n_src_index = n_out;
+  if (w_diff > 0.0) {
+    f->w_fast = 0;
+    f->w_slow = 0;
+  }
+  // the bins the reference holds at this point are those of the kept draws
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_out));
+  QMCL_TRY(label_clusters(f));
+  *clustered = true;
+  return QMCL_OK;
+}
+
+}  // namespace qmcl
+
+using namespace qmcl;
+
+extern "C" {
+
+// particle_filter.cpp:138-161
+qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
+  if (!f) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  const ParticleSet &in = f->sets[f->current];
+  ParticleSet &out = f->sets[(f->current + 1) % 2];
+  f->current = (f->current + 1) % 2;
+  f->clusters_valid = false;
+  bool clustered = false;
+  switch (f->params.resample_type) {
+  case QMCL_RESAMPLE_LOW_VARIANCE:
+    QMCL_TRY(resample_low_variance(f, in, out));
+    break;
+  case QMCL_RESAMPLE_ADAPTIVE:
+    QMCL_TRY(resample_adaptive(f, in, out));
+    break;
+  case QMCL_RESAMPLE_KLD:
+    QMCL_TRY(resample_kld(f, in, out, &clustered));
+    break;
+  default:
+    return QMCL_ERR_INVALID_ARG;
+  }
+  f->step++;
+  f->global_first = 0;
+  f->global_n = out.n;
+  if (!clustered) {
+    if (f->params.resample_type == QMCL_RESAMPLE_KLD) {
+      // failed KLD: bins stay reset, nothing to label
+      f->clusters_valid = true;
+    } else {
+      QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, out.n));
+      QMCL_TRY(label_clusters(f));
+    }
+  }
+  return normalise_current(f);
+}
+
+qmcl_status qmcl_filter_copy_resample_indices(const qmcl_filter *fc, int64_t *out, size_t cap,
+                                              size_t *n_out) {
+  if (!fc) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  if (n_out) *n_out = f->n_src_index;
+  const size_t n = f->n_src_index < cap ? f->n_src_index : cap;
+  if (!n || !out) return QMCL_OK;
+  QMCL_TRY(use_device(f->map));
+  QMCL_CUDA(cudaMemcpyAsync(out, f->src_index.ptr, n * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                            f->map->stream));
+  QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  return QMCL_OK;
+}
+
+}  // extern "C"

@@ -65,6 +65,12 @@ struct ParticleSet {
   }
 };
 
+// Dense bin grid: bounding box of the occupied KLD/cluster bins.
+struct BinGrid {
+  int x0, y0, t0;
+  int nx, ny, nt;
+};
+
 // quickmcl::ParticleFilter (particle_filter.h)
 struct qmcl_filter {
   qmcl_map *map = nullptr;
@@ -73,6 +79,8 @@ struct qmcl_filter {
   uint64_t seed = 0;
   uint32_t step = 0;
   int shard_rank = 0, n_shards = 1;
+  size_t global_first = 0;  // global index of local particle 0
+  size_t global_n = 0;      // particles over all shards
 
   ParticleSet sets[2];
   int current = 0;
@@ -92,17 +100,25 @@ struct qmcl_filter {
   qmcl::PinnedBuf<double> h_scalars;
 
   // resampling scratch
-  qmcl::DevBuf<double> cdf;
+  qmcl::DevBuf<double> cdf;          // sequentially rounded inclusive running sum
+  qmcl::DevBuf<int64_t> pos;         // positive-weight particles, original indices
+  qmcl::DevBuf<double> incl;         // running sum after each positive-weight particle
   qmcl::DevBuf<int64_t> src_index;
   size_t n_src_index = 0;
   qmcl::DevBuf<uint8_t> scratch;
 
-  // bins / clusters (sorted unique keys)
-  qmcl::DevBuf<unsigned long long> bin_keys;    // packed key per particle / per bin
-  qmcl::DevBuf<unsigned long long> bin_unique;
-  qmcl::DevBuf<int32_t> bin_count;
-  qmcl::DevBuf<int32_t> bin_label;
+  // bins / clusters: dense table over the bin bounding box + sorted bin list
+  BinGrid grid{0, 0, 0, 0, 0, 0};
+  qmcl::DevBuf<int> bbox;
+  qmcl::DevBuf<int32_t> table;        // cell -> bin id + 1 (0 = empty)
+  qmcl::DevBuf<int32_t> bin_cell;     // bin -> dense cell index (ascending)
+  qmcl::DevBuf<int32_t> bin_count;    // particles per bin
+  qmcl::DevBuf<int32_t> bin_label;    // union-find parent, then component root
+  qmcl::DevBuf<int32_t> bin_cluster;  // root bin -> dense cluster id
+  qmcl::DevBuf<uint32_t> scan_tmp;
+  qmcl::DevBuf<double> cluster_acc;
   size_t n_bins = 0, n_clusters = 0;
+  bool bins_built = false;
   bool clusters_valid = false;
 
   ParticleSet &cur() { return sets[current]; }

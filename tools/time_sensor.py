@@ -1,6 +1,9 @@
 """Quick timing of the sensor update alone (K7 + K8) with device-resident inputs.
 Development aid; bench.py is the contract benchmark."""
 import argparse
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import time
 
