@@ -87,6 +87,9 @@ qmcl_status qmcl_map_destroy(qmcl_map *map);
 /* All work of this map (and of filters created on it) is enqueued on
  * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
 qmcl_status qmcl_map_set_stream(qmcl_map *map, void *cuda_stream);
+/* Test hook: 0 = choose automatically (uint16 d^2 palette when the map was
+ * built by qmcl_map_load), 1 = always gather the float32 field. */
+qmcl_status qmcl_map_set_sensor_path(qmcl_map *map, int path);
 
 /* Map::set_parameters (map_likelihood.cpp:40-49). z_hit/z_rand/num_beams/
  * max_laser_distance act on the next sensor update; sigma_hit and

@@ -112,6 +112,10 @@ class MapLikelihood:
         check(self._L.qmcl_map_set_stream(self._h, C.c_void_p(int(cuda_stream))),
               "qmcl_map_set_stream")
 
+    def set_sensor_path(self, path):
+        """Test hook: 0 = auto (palette when built here), 1 = float field gather."""
+        check(self._L.qmcl_map_set_sensor_path(self._h, path), "qmcl_map_set_sensor_path")
+
     # -- quickmcl::Map -------------------------------------------------------
     def set_parameters(self, parameters: LikelihoodMapParameters):
         self.parameters = parameters

@@ -125,6 +125,7 @@ qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) 
   QMCL_TRY(use_device(map));
   qmcl_filter *f = new qmcl_filter();
   f->map = map;
+  map->refs++;
   f->seed = seed;
   QMCL_TRY(f->scalars.ensure(1));
   QMCL_CUDA(cudaMemsetAsync(f->scalars.ptr, 0, sizeof(FilterScalars), map->stream));
@@ -163,8 +164,9 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->bin_cluster.release();
   f->scan_tmp.release();
   f->cluster_acc.release();
+  qmcl_map *map = f->map;
   delete f;
-  return QMCL_OK;
+  return qmcl_map_destroy(map);
 }
 
 qmcl_status qmcl_filter_set_shard(qmcl_filter *f, int shard_rank, int n_shards) {

@@ -6,7 +6,7 @@
 // transform (separable, integer d^2), K3 Gaussian table through a d^2 LUT,
 // K4 free-cell compaction.  All HBM-bound; see DESIGN.md for the byte counts.
 
-#include "state.cuh"
+#include "sensor.cuh"
 
 #include <string>
 #include <vector>
@@ -102,7 +102,8 @@ constexpr int kRowChunk = 256;
 __global__ void __launch_bounds__(kRowChunk)
 edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_dist,
                 const float *__restrict__ lut_field, float *__restrict__ distance,
-                float *__restrict__ field, int w, int h, int R, int kmax) {
+                float *__restrict__ field, uint16_t *__restrict__ code, int w, int h, int R,
+                int kmax) {
   extern __shared__ int sG[];  // kRowChunk + 2R entries
   const int y = blockIdx.y;
   const int x0 = blockIdx.x * kRowChunk;
@@ -133,6 +134,7 @@ edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_di
   const size_t i = static_cast<size_t>(y) * w + x;
   field[i] = __ldg(lut_field + k);
   distance[i] = __ldg(lut_dist + k);
+  if (code) code[i] = static_cast<uint16_t>(k);
 }
 
 // K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
@@ -319,8 +321,11 @@ qmcl_status qmcl_map_create(int device, qmcl_map **out) {
   return QMCL_OK;
 }
 
+// Filters keep a reference to their map (the node owns both through
+// shared_ptr, main.h:68-70), so the storage goes when the last holder lets go.
 qmcl_status qmcl_map_destroy(qmcl_map *m) {
   if (!m) return QMCL_ERR_INVALID_ARG;
+  if (--m->refs > 0) return QMCL_OK;
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   m->field.release();
@@ -331,6 +336,8 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->edt_g.release();
   m->scan_tmp.release();
   m->lut.release();
+  m->code.release();
+  m->pw3_lut.release();
   m->tmp_x.release();
   m->tmp_y.release();
   m->tmp_t.release();
@@ -339,6 +346,12 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->tmp_cloud.release();
   m->tmp_scalars.release();
   delete m;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_set_sensor_path(qmcl_map *m, int path) {
+  if (!m || path < 0 || path > 1) return QMCL_ERR_INVALID_ARG;
+  m->force_field_path = (path == 1);
   return QMCL_OK;
 }
 
@@ -381,6 +394,9 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   QMCL_TRY(m->distance.ensure(n));
   QMCL_TRY(m->edt_g.ensure((n + 1) / 2));
   QMCL_TRY(m->lut.ensure(2 * static_cast<size_t>(kmax + 2)));
+  // the uint16 d^2 code map (sensor model's palette path) exists when d^2 fits
+  const bool with_code = kmax + 2 <= 65535;
+  if (with_code) QMCL_TRY(m->code.ensure(n));
   QMCL_CUDA(cudaMemcpyAsync(m->occ.ptr, occ, n, cudaMemcpyHostToDevice, m->stream));
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
   float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
@@ -399,14 +415,16 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   if (smem > 48 * 1024)
     QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
-  edt_rows_kernel<<<grid2, kRowChunk, smem, m->stream>>>(g, lut_dist, lut_field, m->distance.ptr,
-                                                         m->field.ptr, static_cast<int>(width),
-                                                         static_cast<int>(height), R, kmax);
+  edt_rows_kernel<<<grid2, kRowChunk, smem, m->stream>>>(
+      g, lut_dist, lut_field, m->distance.ptr, m->field.ptr, with_code ? m->code.ptr : nullptr,
+      static_cast<int>(width), static_cast<int>(height), R, kmax);
   QMCL_LAUNCHED();
   QMCL_TRY(rebuild_free_cells(m));
   m->has_map = true;
   m->has_distance = true;
-  return QMCL_OK;
+  m->has_code = with_code;
+  m->n_codes = kmax + 2;
+  return sensor_prepare_map(m);
 }
 
 qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *state,
@@ -425,7 +443,9 @@ qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *s
   QMCL_TRY(rebuild_free_cells(m));
   m->has_map = true;
   m->has_distance = false;
-  return QMCL_OK;
+  m->has_code = false;
+  m->n_codes = 0;
+  return sensor_prepare_map(m);
 }
 
 qmcl_status qmcl_map_size(const qmcl_map *m, uint32_t *width, uint32_t *height) {

@@ -21,6 +21,8 @@ unsigned sensor_grid(size_t n_particles);
 // a dense float2 array; non-finite points are moved far outside the map.
 qmcl_status launch_subsample(const qmcl_map *m, const float *dev_cloud_xy, size_t n_points,
                              float *dev_beams, int *n_used_out);
-qmcl_status launch_sensor(const qmcl_map *m, const SensorLaunch &a);
+qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a);
+// After the map's field/geometry changed: verify the fast division, drop the LUT.
+qmcl_status sensor_prepare_map(qmcl_map *m);
 
 }  // namespace qmcl

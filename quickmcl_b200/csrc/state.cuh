@@ -43,6 +43,19 @@ struct qmcl_map {
   qmcl::DevBuf<uint32_t> scan_tmp;
   qmcl::DevBuf<float> lut;  // d^2 -> distance | likelihood
 
+  // sensor-model palette path: uint16 d^2 code per cell + pw^3 table
+  qmcl::DevBuf<uint16_t> code;
+  qmcl::DevBuf<double> pw3_lut;
+  bool has_code = false;
+  int n_codes = 0;
+  bool fastdiv_ok = false;        // 3-op division verified against IEEE division
+  bool force_field_path = false;  // test hook
+  bool lut_params_valid = false;
+  float lut_z_hit = 0.f, lut_zr = 0.f;
+  double lut_p_max = 0.0;
+
+  int refs = 1;  // the creator + one per filter
+
   // scratch for the host-vector update_importance overload
   qmcl::DevBuf<float> tmp_x, tmp_y, tmp_t;
   qmcl::DevBuf<double> tmp_w;

@@ -142,3 +142,47 @@ def test_empty_inputs():
     f.set_particles(q.make_particles(np.zeros(3), np.zeros(3), np.zeros(3), np.ones(3)))
     f.update_importance_from_observations(np.zeros((0, 2), np.float32))
     assert np.all(f.get_particles()["weight"] == 1.0 / 3)
+
+
+@pytest.mark.parametrize("width,n,beams,fov,num_beams,cloud", [
+    (400, 2000, 360, 360.0, 30, "tracking"),
+    (400, 5000, 360, 360.0, 0, "global"),
+    (2000, 20000, 1081, 270.0, 0, "tracking"),
+])
+def test_palette_path_matches_oracle_and_field_path(width, n, beams, fov, num_beams, cloud):
+    """Map built on the GPU (exact EDT): the uint16-code + pw^3-table path must give
+    the oracle's weights, and exactly the float-field path's bits."""
+    occ, res, origin = syn.make_map(width)
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=num_beams)
+    om = ob.OracleMap(**lp)
+    om.new_map(occ, res, origin, field_mode=ob.FIELD_EXACT_EDT)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**lp))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, beams, fov)
+    if cloud == "tracking":
+        x, y, t = syn.gaussian_cloud(pose, n)
+    else:
+        x, y, t = syn.uniform_cloud(occ, res, origin, n)
+    ref = ob.make_particles(x, y, t, np.ones(n))
+    total_ref = om.update_importance(scan, ref, ob.TRIG_CR)
+    pal = q.make_particles(x, y, t, np.ones(n))
+    total_pal = gm.update_importance(scan, pal)
+    gm.set_sensor_path(1)
+    fld = q.make_particles(x, y, t, np.ones(n))
+    total_fld = gm.update_importance(scan, fld)
+    assert np.array_equal(pal["weight"], fld["weight"])
+    assert total_pal == total_fld
+    assert rel_err(pal["weight"], ref["weight"]).max() <= TIGHT
+    assert abs(total_pal - total_ref) <= TIGHT * total_ref
+    # parameters that only enter the table: changing them must refresh it
+    gm.set_sensor_path(0)
+    lp2 = dict(lp, z_hit=0.6, z_rand=0.4, max_laser_distance=20.0)
+    gm.set_parameters(q.LikelihoodMapParameters(**lp2))
+    om.set_parameters(**lp2)
+    ref2 = ob.make_particles(x, y, t, np.ones(n))
+    om.update_importance(scan, ref2, ob.TRIG_CR)
+    pal2 = q.make_particles(x, y, t, np.ones(n))
+    gm.update_importance(scan, pal2)
+    assert rel_err(pal2["weight"], ref2["weight"]).max() <= TIGHT

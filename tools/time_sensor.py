@@ -19,6 +19,7 @@ ap.add_argument("--map", type=int, default=2000)
 ap.add_argument("--beams", type=int, default=1081)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--cloud", default="tracking")
+ap.add_argument("--path", type=int, default=0)
 args = ap.parse_args()
 
 occ, res, origin = syn.make_map(args.map)
@@ -34,6 +35,7 @@ t0 = time.time()
 gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
 torch.cuda.synchronize()
 print(f"map load {args.map}^2: {1e3 * (time.time() - t0):.2f} ms (second call)")
+gm.set_sensor_path(args.path)
 pose = syn.pick_truth_pose(occ, res, origin)
 scan = syn.make_scan(occ, res, origin, pose, args.beams, 270.0)
 n = args.particles
@@ -56,6 +58,6 @@ for _ in range(args.iters):
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
 ms = float(np.median(times))
-print(f"{args.cloud}: {n} particles x {len(scan)} beams = {evals:.3e} evals; "
+print(f"path={args.path} {args.cloud}: {n} particles x {len(scan)} beams = {evals:.3e} evals; "
       f"median {ms:.4f} ms -> {evals / ms / 1e9 * 1e3:.1f} G evals/s "
       f"({evals * 4.02 / ms / 1e6:.0f} GB/s algorithmic)")
