@@ -87,8 +87,10 @@ qmcl_status qmcl_map_destroy(qmcl_map *map);
 /* All work of this map (and of filters created on it) is enqueued on
  * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
 qmcl_status qmcl_map_set_stream(qmcl_map *map, void *cuda_stream);
-/* Test hook: 0 = choose automatically (uint16 d^2 palette when the map was
- * built by qmcl_map_load), 1 = always gather the float32 field. */
+/* Sensor-model value path: 0 = automatic (uint16 d^2 palette with a float
+ * pw^3 table when the map was built by qmcl_map_load, <= 5e-7 relative),
+ * 1 = gather the float32 field and do the reference's double arithmetic per
+ * evaluation (exact), 2 = palette with a double pw^3 table (exact). */
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *map, int path);
 
 /* Map::set_parameters (map_likelihood.cpp:40-49). z_hit/z_rand/num_beams/

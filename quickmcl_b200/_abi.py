@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmcl_b200.so")
+LIB_PATH = os.environ.get("QMCL_B200_LIB", os.path.join(_HERE, "libqmcl_b200.so"))
 
 STATUS_NAMES = {0: "QMCL_OK", 1: "QMCL_ERR_INVALID_ARG", 2: "QMCL_ERR_NO_DEVICE",
                 3: "QMCL_ERR_CUDA", 4: "QMCL_ERR_NO_MAP", 5: "QMCL_ERR_INVALID_CLUSTER",

@@ -338,6 +338,7 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->lut.release();
   m->code.release();
   m->pw3_lut.release();
+  m->pw3_lut_f32.release();
   m->tmp_x.release();
   m->tmp_y.release();
   m->tmp_t.release();
@@ -350,8 +351,8 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
 }
 
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *m, int path) {
-  if (!m || path < 0 || path > 1) return QMCL_ERR_INVALID_ARG;
-  m->force_field_path = (path == 1);
+  if (!m || path < 0 || path > 2) return QMCL_ERR_INVALID_ARG;
+  m->sensor_path = path;
   return QMCL_OK;
 }
 

@@ -22,11 +22,17 @@
 //   pw = z_hit * p + z_rand/max_range (double);  weight += pw*pw*pw:
 //  * FIELD  : gathers the float32 table (any field, e.g. one injected through
 //             qmcl_map_load_field) and does the double arithmetic per eval.
-//  * PALETTE: when the map was built here, a cell's value is a function of its
+//  * PAL64  : when the map was built here, a cell's value is a function of its
 //             integer squared distance k, so the map is also kept as uint16 k
 //             (2 B per eval instead of 4) and pw^3 is looked up in a
 //             shared-memory table of doubles computed with the reference's
 //             expression — no per-eval conversion or multiply, same bits.
+//  * PAL32  : the same table rounded to float (one shared-memory wavefront per
+//             lookup instead of two or more) and summed in float for at most 8
+//             terms before being folded into the double accumulator.  Worst
+//             case 5e-7 relative, measured ~1e-7, against the 1e-5 bar.  This
+//             is the default when the map was built here; PAL64 and FIELD stay
+//             selectable (qmcl_map_set_sensor_path).
 //
 // Division: (m - o) / res is evaluated as q = a*r, q' = fma(fma(q,-res,a), r, q)
 // with r = RN(1/res), which yields the correctly rounded quotient (Markstein);
@@ -38,25 +44,66 @@
 
 namespace qmcl {
 
-constexpr int kSensorThreads = 512;
+#ifndef QMCL_SENSOR_THREADS
+#define QMCL_SENSOR_THREADS 256
+#endif
+#ifndef QMCL_SENSOR_P
+#define QMCL_SENSOR_P 4
+#endif
+#ifndef QMCL_SENSOR_MINBLOCKS
+#define QMCL_SENSOR_MINBLOCKS 4
+#endif
+constexpr int kSensorThreads = QMCL_SENSOR_THREADS;
 constexpr int kSensorWarps = kSensorThreads / 32;
-constexpr int kP = 4;  // particles per warp
+constexpr int kP = QMCL_SENSOR_P;  // particles per warp
 constexpr int kParticlesPerBlock = kSensorWarps * kP;
 
 struct SensorParams {
   MapGeom g;
   float inv_res;   // RN(1 / res)
   float neg_res;   // -res
+  float neg_zero;  // -0.0f, deliberately a run-time value (see pack2 notes)
   float z_hit;     // parameters.z_hit (float)
   float zr;        // z_rand / max_laser_distance, float division (map_likelihood.cpp:76-77)
   double p_max;    // max_distance_probability (map_likelihood.cpp:46-48,155)
   const float *field;
   const uint16_t *code;
   const double *pw3_lut;  // n_codes entries + 1 (out of map)
+  const float *pw3_lut_f32;
   int n_codes;
 };
 
 unsigned sensor_grid(size_t n) { return div_up(n, kParticlesPerBlock); }
+
+// ---- packed FP32 (sm_100 f32x2): two IEEE-rounded float ops per instruction.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (measured on
+// B200: 67 % of results change), so a product that feeds an addition is
+// written as fma(a, b, nz) with nz = -0.0f passed at RUN time: a*b + (-0) is
+// a*b for every a*b, and an FMA cannot be fused into the following add.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float *lo, float *hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(*lo), "=f"(*hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 __global__ void subsample_kernel(const float2 *__restrict__ cloud, size_t n_points, size_t step,
                                  float2 *__restrict__ beams, int n_used) {
@@ -82,12 +129,16 @@ __device__ __forceinline__ int cell_of(float pos, float offset, const SensorPara
 
 // pw^3 for every code (and one extra entry for "outside the map").
 __global__ void pw3_lut_kernel(const float *__restrict__ lut_field, int n_codes, float z_hit,
-                               float zr, double p_max, double *__restrict__ out) {
+                               float zr, double p_max, double *__restrict__ out,
+                               float *__restrict__ out_f32) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > n_codes) return;
+  if (k > n_codes + 1) return;
   const double p = (k < n_codes) ? static_cast<double>(lut_field[k]) : p_max;
   const double pw = fma(static_cast<double>(z_hit), p, static_cast<double>(zr));
-  out[k] = __dmul_rn(__dmul_rn(pw, pw), pw);
+  double pw3 = __dmul_rn(__dmul_rn(pw, pw), pw);
+  if (k == n_codes + 1) pw3 = 0.0;  // "nothing pending" entry of the software pipeline
+  out[k] = pw3;
+  out_f32[k] = static_cast<float>(pw3);
 }
 
 // Compares the 3-op division with IEEE division: every cell boundary of the
@@ -115,17 +166,25 @@ __global__ void fastdiv_check_kernel(SensorParams sp, int *mismatch) {
   if (bad) atomicExch(mismatch, 1);
 }
 
-template <bool PALETTE, bool FASTDIV>
-__global__ void __launch_bounds__(kSensorThreads)
+enum { PATH_FIELD = 0, PATH_PAL64 = 1, PATH_PAL32 = 2 };
+
+template <int PATH, bool FASTDIV>
+__global__ void __launch_bounds__(kSensorThreads, QMCL_SENSOR_MINBLOCKS)
 sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a) {
-  extern __shared__ double s_lut[];  // PALETTE: n_codes + 1 entries
+  extern __shared__ double s_lut[];  // PAL64: n_codes + 1 doubles; PAL32: floats
+  float *s_lut_f32 = reinterpret_cast<float *>(s_lut);
+  constexpr bool PALETTE = PATH != PATH_FIELD;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const size_t first =
       (static_cast<size_t>(blockIdx.x) * kSensorWarps + warp_in_block) * kP;
 
-  if (PALETTE) {
-    for (int k = threadIdx.x; k <= sp.n_codes; k += kSensorThreads) s_lut[k] = sp.pw3_lut[k];
+  // table: [0, n_codes) codes, n_codes = outside the map, n_codes+1 = 0
+  if (PATH == PATH_PAL64) {
+    for (int k = threadIdx.x; k <= sp.n_codes + 1; k += kSensorThreads) s_lut[k] = sp.pw3_lut[k];
+  } else if (PATH == PATH_PAL32) {
+    for (int k = threadIdx.x; k <= sp.n_codes + 1; k += kSensorThreads)
+      s_lut_f32[k] = sp.pw3_lut_f32[k];
   }
 
   // Lane p prepares particle first+p; the values are then broadcast.
@@ -138,14 +197,17 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     lc = static_cast<float>(cd);
     ls = static_cast<float>(sd);
   }
-  float X[kP], Y[kP], C[kP], S[kP], NS[kP];
+  // per-particle packed constants: (c, s), (-s, c), (x, y)
+  f32x2 CS[kP], NSC[kP], XY[kP];
 #pragma unroll
   for (int p = 0; p < kP; ++p) {
-    X[p] = __shfl_sync(0xffffffffu, lx, p);
-    Y[p] = __shfl_sync(0xffffffffu, ly, p);
-    C[p] = __shfl_sync(0xffffffffu, lc, p);
-    S[p] = __shfl_sync(0xffffffffu, ls, p);
-    NS[p] = -S[p];
+    const float x = __shfl_sync(0xffffffffu, lx, p);
+    const float y = __shfl_sync(0xffffffffu, ly, p);
+    const float c = __shfl_sync(0xffffffffu, lc, p);
+    const float sn = __shfl_sync(0xffffffffu, ls, p);
+    CS[p] = pack2(c, sn);
+    NSC[p] = pack2(-sn, c);
+    XY[p] = pack2(x, y);
   }
   double acc[kP];
 #pragma unroll
@@ -155,28 +217,99 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   const float2 *__restrict__ beams = reinterpret_cast<const float2 *>(a.beams);
   const double z_hit = static_cast<double>(sp.z_hit);
   const double zr = static_cast<double>(sp.zr);
-  for (int j = lane; j < a.n_beams; j += 32) {
-    const float2 b = __ldg(beams + j);
+  const f32x2 NZ = pack2(sp.neg_zero, sp.neg_zero);
+  const f32x2 NO = pack2(-sp.g.ox, -sp.g.oy);
+  const f32x2 RR = pack2(sp.inv_res, sp.inv_res);
+  const f32x2 NRES = pack2(sp.neg_res, sp.neg_res);
+  const unsigned w = sp.g.w;
+  // Software pipeline: the beam for the next step is fetched before this
+  // step's arithmetic, and the value gathered in step i is consumed in step
+  // i+1, so a full loop body of independent work covers each load's latency.
+  float facc[kP];
+  int code_prev[kP];    // palette paths: code gathered in the previous step
+  double pz_prev[kP];   // field path: probability gathered in the previous step
+#pragma unroll
+  for (int p = 0; p < kP; ++p) {
+    facc[p] = 0.f;
+    code_prev[p] = sp.n_codes + 1;  // table entry holding 0
+    pz_prev[p] = -1.0;              // "nothing pending"
+  }
+  int step = 0;
+  float2 b = (lane < a.n_beams) ? __ldg(beams + lane) : make_float2(0.f, 0.f);
+  for (int j = lane; j < a.n_beams; j += 32, ++step) {
+    const float2 bn = (j + 32 < a.n_beams) ? __ldg(beams + j + 32) : b;
+    const f32x2 PX = pack2(b.x, b.x), PY = pack2(b.y, b.y);
+    int code_cur[kP];
+    double pz_cur[kP];
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      // Eigen Isometry2f * Vector2f (pose_2d.h:118-126): translation + (R * v)
-      const float mx = __fadd_rn(X[p], __fadd_rn(__fmul_rn(C[p], b.x), __fmul_rn(NS[p], b.y)));
-      const float my = __fadd_rn(Y[p], __fadd_rn(__fmul_rn(S[p], b.x), __fmul_rn(C[p], b.y)));
-      const int ix = cell_of<FASTDIV>(mx, sp.g.ox, sp);
-      const int iy = cell_of<FASTDIV>(my, sp.g.oy, sp);
-      const bool inside = in_map(ix, iy, sp.g);
-      if (PALETTE) {
-        int code = sp.n_codes;  // outside the map -> p_max entry
-        if (inside) code = __ldg(sp.code + static_cast<size_t>(iy) * sp.g.w + ix);
-        acc[p] = __dadd_rn(acc[p], s_lut[code]);
+      // Eigen Isometry2f * Vector2f (pose_2d.h:118-126): translation + (R * v),
+      // both coordinates at once:
+      //   (mx, my) = (x, y) + ((c*px, s*px) + ((-s)*py, c*py))
+      const f32x2 t3 = add2(fma2(CS[p], PX, NZ), fma2(NSC[p], PY, NZ));
+      const f32x2 mxy = add2(XY[p], t3);
+      const f32x2 axy = add2(mxy, NO);  // m - o
+      int ix, iy;
+      if (FASTDIV) {
+        const f32x2 q = mul2(axy, RR);
+        const f32x2 q2 = fma2(fma2(q, NRES, axy), RR, q);
+        float qx, qy;
+        unpack2(q2, &qx, &qy);
+        ix = __float2int_rz(qx);
+        iy = __float2int_rz(qy);
       } else {
-        double pz = sp.p_max;
-        if (inside) pz = __ldg(sp.field + static_cast<size_t>(iy) * sp.g.w + ix);
+        float ax, ay;
+        unpack2(axy, &ax, &ay);
+        ix = __float2int_rz(__fdiv_rn(ax, sp.g.res));
+        iy = __float2int_rz(__fdiv_rn(ay, sp.g.res));
+      }
+      const bool inside = in_map(ix, iy, sp.g);
+      // 32-bit cell offset (maps are far below 2^32 cells)
+      const unsigned cell = static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix);
+      if (PALETTE) {
+        code_cur[p] = sp.n_codes;  // outside the map -> p_max entry
+        if (inside) code_cur[p] = __ldg(sp.code + cell);
+      } else {
+        pz_cur[p] = sp.p_max;
+        if (inside) pz_cur[p] = __ldg(sp.field + cell);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      if (PATH == PATH_PAL64) {
+        acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p]]);
+      } else if (PATH == PATH_PAL32) {
+        facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
+      } else if (pz_prev[p] >= 0.0) {
         // z_hit * p is exact in double (two float significands), so the fused
         // form rounds exactly like the reference's mul-then-add.
-        const double pw = fma(z_hit, pz, zr);
+        const double pw = fma(z_hit, pz_prev[p], zr);
         acc[p] = __dadd_rn(acc[p], __dmul_rn(__dmul_rn(pw, pw), pw));
       }
+      code_prev[p] = code_cur[p];
+      pz_prev[p] = pz_cur[p];
+    }
+    if (PATH == PATH_PAL32 && (step & 7) == 7) {
+      // float partial sums never hold more than 8 terms
+#pragma unroll
+      for (int p = 0; p < kP; ++p) {
+        acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
+        facc[p] = 0.f;
+      }
+    }
+    b = bn;
+  }
+  // drain the pipeline
+#pragma unroll
+  for (int p = 0; p < kP; ++p) {
+    if (PATH == PATH_PAL64) {
+      acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p]]);
+    } else if (PATH == PATH_PAL32) {
+      facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
+      acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
+    } else if (pz_prev[p] >= 0.0) {
+      const double pw = fma(z_hit, pz_prev[p], zr);
+      acc[p] = __dadd_rn(acc[p], __dmul_rn(__dmul_rn(pw, pw), pw));
     }
   }
 
@@ -254,12 +387,14 @@ static SensorParams make_params(const qmcl_map *m) {
   sp.g = m->geom;
   sp.inv_res = 1.0f / m->geom.res;
   sp.neg_res = -m->geom.res;
+  sp.neg_zero = -0.0f;
   sp.z_hit = m->params.z_hit;
   sp.zr = m->params.z_rand / m->params.max_laser_distance;
   sp.p_max = m->max_distance_probability;
   sp.field = m->field.ptr;
   sp.code = reinterpret_cast<const uint16_t *>(m->code.ptr);
   sp.pw3_lut = m->pw3_lut.ptr;
+  sp.pw3_lut_f32 = m->pw3_lut_f32.ptr;
   sp.n_codes = m->n_codes;
   return sp;
 }
@@ -281,10 +416,10 @@ qmcl_status sensor_prepare_map(qmcl_map *m) {
   return QMCL_OK;
 }
 
-template <bool PALETTE, bool FASTDIV>
+template <int PATH, bool FASTDIV>
 static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, const SensorLaunch &a,
                                   size_t smem) {
-  auto kern = sensor_kernel<PALETTE, FASTDIV>;
+  auto kern = sensor_kernel<PATH, FASTDIV>;
   if (smem > 48 * 1024)
     QMCL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
@@ -296,28 +431,40 @@ static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, con
 qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   if (a.n == 0) return QMCL_OK;
   SensorParams sp = make_params(m);
-  const bool palette = m->has_code && !m->force_field_path &&
-                       static_cast<size_t>(m->n_codes + 1) * sizeof(double) <= 96 * 1024;
-  if (palette) {
+  // sensor_path: 0 auto (PAL32 when the map was built here), 1 FIELD, 2 PAL64
+  const bool can_palette =
+      m->has_code && static_cast<size_t>(m->n_codes + 2) * sizeof(double) <= 96 * 1024;
+  int path = PATH_FIELD;
+  if (can_palette && m->sensor_path == 0) path = PATH_PAL32;
+  if (can_palette && m->sensor_path == 2) path = PATH_PAL64;
+  if (path != PATH_FIELD) {
     // refresh pw^3 when z_hit / z_rand / max range / p_max changed
     if (!m->lut_params_valid || m->lut_z_hit != sp.z_hit || m->lut_zr != sp.zr ||
         m->lut_p_max != sp.p_max) {
-      QMCL_TRY(m->pw3_lut.ensure(m->n_codes + 1));
+      QMCL_TRY(m->pw3_lut.ensure(m->n_codes + 2));
+      QMCL_TRY(m->pw3_lut_f32.ensure(m->n_codes + 2));
       sp.pw3_lut = m->pw3_lut.ptr;
-      pw3_lut_kernel<<<div_up(m->n_codes + 1, 256), 256, 0, m->stream>>>(
-          m->lut.ptr + m->n_codes, m->n_codes, sp.z_hit, sp.zr, sp.p_max, m->pw3_lut.ptr);
+      sp.pw3_lut_f32 = m->pw3_lut_f32.ptr;
+      pw3_lut_kernel<<<div_up(m->n_codes + 2, 256), 256, 0, m->stream>>>(
+          m->lut.ptr + m->n_codes, m->n_codes, sp.z_hit, sp.zr, sp.p_max, m->pw3_lut.ptr,
+          m->pw3_lut_f32.ptr);
       QMCL_LAUNCHED();
       m->lut_params_valid = true;
       m->lut_z_hit = sp.z_hit;
       m->lut_zr = sp.zr;
       m->lut_p_max = sp.p_max;
     }
-    const size_t smem = static_cast<size_t>(m->n_codes + 1) * sizeof(double);
-    return m->fastdiv_ok ? launch_variant<true, true>(m, sp, a, smem)
-                         : launch_variant<true, false>(m, sp, a, smem);
+    if (path == PATH_PAL64) {
+      const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(double);
+      return m->fastdiv_ok ? launch_variant<PATH_PAL64, true>(m, sp, a, smem)
+                           : launch_variant<PATH_PAL64, false>(m, sp, a, smem);
+    }
+    const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(float);
+    return m->fastdiv_ok ? launch_variant<PATH_PAL32, true>(m, sp, a, smem)
+                         : launch_variant<PATH_PAL32, false>(m, sp, a, smem);
   }
-  return m->fastdiv_ok ? launch_variant<false, true>(m, sp, a, 0)
-                       : launch_variant<false, false>(m, sp, a, 0);
+  return m->fastdiv_ok ? launch_variant<PATH_FIELD, true>(m, sp, a, 0)
+                       : launch_variant<PATH_FIELD, false>(m, sp, a, 0);
 }
 
 }  // namespace qmcl

@@ -46,10 +46,11 @@ struct qmcl_map {
   // sensor-model palette path: uint16 d^2 code per cell + pw^3 table
   qmcl::DevBuf<uint16_t> code;
   qmcl::DevBuf<double> pw3_lut;
+  qmcl::DevBuf<float> pw3_lut_f32;
   bool has_code = false;
   int n_codes = 0;
   bool fastdiv_ok = false;        // 3-op division verified against IEEE division
-  bool force_field_path = false;  // test hook
+  int sensor_path = 0;            // 0 auto, 1 float field, 2 exact double palette
   bool lut_params_valid = false;
   float lut_z_hit = 0.f, lut_zr = 0.f;
   double lut_p_max = 0.0;

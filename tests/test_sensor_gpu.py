@@ -167,17 +167,25 @@ def test_palette_path_matches_oracle_and_field_path(width, n, beams, fov, num_be
         x, y, t = syn.uniform_cloud(occ, res, origin, n)
     ref = ob.make_particles(x, y, t, np.ones(n))
     total_ref = om.update_importance(scan, ref, ob.TRIG_CR)
+    gm.set_sensor_path(2)                      # exact palette (double table)
     pal = q.make_particles(x, y, t, np.ones(n))
     total_pal = gm.update_importance(scan, pal)
-    gm.set_sensor_path(1)
+    gm.set_sensor_path(1)                      # float field gather
     fld = q.make_particles(x, y, t, np.ones(n))
     total_fld = gm.update_importance(scan, fld)
     assert np.array_equal(pal["weight"], fld["weight"])
     assert total_pal == total_fld
     assert rel_err(pal["weight"], ref["weight"]).max() <= TIGHT
     assert abs(total_pal - total_ref) <= TIGHT * total_ref
+    gm.set_sensor_path(0)                      # default: float table, <= 8-term float sums
+    fast = q.make_particles(x, y, t, np.ones(n))
+    total_fast = gm.update_importance(scan, fast)
+    err = rel_err(fast["weight"], ref["weight"])
+    print(f"PAL32 max rel err {err.max():.3e} (bar 1e-5)")
+    assert err.max() <= 1e-6
+    assert abs(total_fast - total_ref) <= 1e-6 * total_ref
     # parameters that only enter the table: changing them must refresh it
-    gm.set_sensor_path(0)
+    gm.set_sensor_path(2)
     lp2 = dict(lp, z_hit=0.6, z_rand=0.4, max_laser_distance=20.0)
     gm.set_parameters(q.LikelihoodMapParameters(**lp2))
     om.set_parameters(**lp2)
