@@ -199,6 +199,34 @@ qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast
 /* Wait for everything enqueued by this filter. */
 qmcl_status qmcl_filter_synchronize(qmcl_filter *f);
 
+/* ---- measurement hooks (replace the reference's CodeTimer scopes,
+ *      timer.cpp:37-55; laser_handler.cpp:244,253,262) ---- */
+enum {
+  QMCL_STAGE_MOTION = 0,      /* K6 motion model */
+  QMCL_STAGE_SENSOR = 1,      /* K7 sensor kernel alone (the roofline kernel) */
+  QMCL_STAGE_NORMALISE = 2,   /* K8 */
+  QMCL_STAGE_CDF = 3,         /* K9 sequentially rounded running sum (+ records) */
+  QMCL_STAGE_SELECT = 4,      /* K10 index search / draws */
+  QMCL_STAGE_GATHER = 5,      /* K12 */
+  QMCL_STAGE_KLD = 6,         /* K11 first occurrence, prefix count, stop rule */
+  QMCL_STAGE_BINS = 7,        /* bin table + occupied-bin list */
+  QMCL_STAGE_LABEL = 8,       /* K13 connected components */
+  QMCL_STAGE_POST_NORMALISE = 9,
+  QMCL_STAGE_MOMENTS = 10,    /* K14 */
+  QMCL_N_STAGES = 11
+};
+const char *qmcl_stage_name(int stage);
+/* level 0 = off, 1 = CUDA events around the sensor kernel only, 2 = around
+ * every stage.  Events are recorded on the filter's stream. */
+qmcl_status qmcl_filter_set_timing(qmcl_filter *f, int level);
+/* Synchronises, then returns accumulated device milliseconds and the number
+ * of timed occurrences per stage since the last reset. */
+qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
+                                   uint64_t count_out[QMCL_N_STAGES], int reset);
+/* Bytes this library has copied host->device (out[0]) and device->host
+ * (out[1]) so far in this process. */
+qmcl_status qmcl_transfer_bytes(uint64_t out[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,6 @@ use and there is no CPU fallback.
 from .api import (LikelihoodMapParameters, MapLikelihood, MapState, OccupancyGrid,  # noqa: F401
                   ParticleFilter, ParticleFilterParameters, ResampleType,
                   create_likelihood_map, create_particle_filter, kernel_launch_count,
-                  make_particles, particles_array)
+                  make_particles, particles_array, transfer_bytes)
 
 __version__ = "0.1.0"

@@ -97,12 +97,17 @@ SIGNATURES = {
     "qmcl_filter_get_lowpass": [vp, pf64],
     "qmcl_filter_set_lowpass": [vp, f64, f64],
     "qmcl_filter_synchronize": [vp],
+    "qmcl_filter_set_timing": [vp, C.c_int],
+    "qmcl_filter_get_timing": [vp, pf64, C.POINTER(u64), C.c_int],
+    "qmcl_transfer_bytes": [C.POINTER(u64)],
 }
 _OTHER = {
     "qmcl_version": (C.c_char_p, []),
     "qmcl_last_error": (C.c_char_p, []),
     "qmcl_kernel_launch_count": (u64, []),
+    "qmcl_stage_name": (C.c_char_p, [C.c_int]),
 }
+N_STAGES = 11
 
 _lib = None
 

@@ -349,6 +349,20 @@ class ParticleFilter:
     def synchronize(self):
         check(self._L.qmcl_filter_synchronize(self._h), "qmcl_filter_synchronize")
 
+    # -- measurement hooks (the reference's CodeTimer scopes, timer.cpp:37-55) --
+    def set_timing(self, level):
+        """0 off, 1 CUDA events around the sensor kernel, 2 around every stage."""
+        check(self._L.qmcl_filter_set_timing(self._h, level), "qmcl_filter_set_timing")
+
+    def get_timing(self, reset=True):
+        """{stage name: (device ms, occurrences)} accumulated since the last reset."""
+        ms = np.zeros(_abi.N_STAGES)
+        cnt = np.zeros(_abi.N_STAGES, np.uint64)
+        check(self._L.qmcl_filter_get_timing(self._h, ptr(ms, C.c_double), ptr(cnt, C.c_uint64),
+                                             int(reset)), "qmcl_filter_get_timing")
+        return {self._L.qmcl_stage_name(i).decode(): (float(ms[i]), int(cnt[i]))
+                for i in range(_abi.N_STAGES)}
+
 
 def create_likelihood_map(device=-1, stream=None) -> MapLikelihood:
     """map_factory.h:29"""
@@ -362,3 +376,10 @@ def create_particle_filter(map_: MapLikelihood, seed=0) -> ParticleFilter:
 
 def kernel_launch_count():
     return _abi.lib().qmcl_kernel_launch_count()
+
+
+def transfer_bytes():
+    """(host->device, device->host) bytes copied by the library so far."""
+    out = np.zeros(2, np.uint64)
+    check(_abi.lib().qmcl_transfer_bytes(ptr(out, C.c_uint64)), "qmcl_transfer_bytes")
+    return int(out[0]), int(out[1])

@@ -385,6 +385,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     return QMCL_OK;
   }
   const BinParams bp = bin_params(f);
+  StageScope sc(f, QMCL_STAGE_BINS);
   QMCL_TRY(f->bbox.ensure(8));
   bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
   QMCL_LAUNCHED();
@@ -392,7 +393,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
   QMCL_LAUNCHED();
   int hb[6];
-  QMCL_CUDA(cudaMemcpyAsync(hb, f->bbox.ptr, sizeof(hb), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   BinGrid g;
   g.x0 = hb[0];
@@ -427,7 +428,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
                        EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
                        cells, f->scan_tmp.ptr, d_total));
   unsigned long long nb = 0;
-  QMCL_CUDA(cudaMemcpyAsync(&nb, d_total, sizeof(nb), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(&nb, d_total, sizeof(nb), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   f->n_bins = nb;
   f->bins_built = true;
@@ -443,6 +444,7 @@ qmcl_status label_clusters(qmcl_filter *f) {
     return QMCL_OK;
   }
   const BinParams bp = bin_params(f);
+  StageScope sc(f, QMCL_STAGE_LABEL);
   cc_hook_kernel<<<div_up(f->n_bins * 3, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, f->n_bins,
                                                             f->grid, bp, f->bin_label.ptr);
   QMCL_LAUNCHED();
@@ -454,7 +456,7 @@ qmcl_status label_clusters(qmcl_filter *f) {
   QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr}, EmitRootId{f->bin_cluster.ptr}, f->n_bins,
                        f->scan_tmp.ptr, d_total));
   unsigned long long nc = 0;
-  QMCL_CUDA(cudaMemcpyAsync(&nc, d_total, sizeof(nc), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(&nc, d_total, sizeof(nc), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   f->n_clusters = nc;
   f->clusters_valid = true;
@@ -488,6 +490,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
     return QMCL_ERR_INVALID_CLUSTER;
   }
   const BinParams bp = bin_params(f);
+  StageScope sc(f, QMCL_STAGE_MOMENTS);
   QMCL_TRY(f->cluster_acc.ensure(f->n_clusters * kAccSlots + 16));
   double *acc = f->cluster_acc.ptr;
   double *d_out = acc + f->n_clusters * kAccSlots;
@@ -502,7 +505,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   estimate_finalise_kernel<<<1, 256, 0, s>>>(acc, f->n_clusters, d_out);
   QMCL_LAUNCHED();
   double h[16];
-  QMCL_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(h, d_out, sizeof(h), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   int flag;
   std::memcpy(&flag, &h[14], sizeof(int));
@@ -549,8 +552,8 @@ qmcl_status qmcl_filter_copy_bins(const qmcl_filter *fc, int32_t *keys4, int32_t
       f->bin_cell.ptr, f->bin_count.ptr, f->clusters_valid ? f->bin_label.ptr : nullptr, n, f->grid,
       d_keys, d_labels);
   QMCL_LAUNCHED();
-  QMCL_CUDA(cudaMemcpyAsync(keys4, d_keys, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  QMCL_CUDA(cudaMemcpyAsync(labels, d_labels, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(keys4, d_keys, n * 4 * sizeof(int32_t), s));
+  QMCL_CUDA(copy_d2h(labels, d_labels, n * sizeof(int32_t), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   return QMCL_OK;
 }

@@ -16,6 +16,18 @@ namespace qmcl {
 // ------------------------------------------------------------ error plumbing
 void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_h2d_bytes, g_d2h_bytes;
+
+// Host<->device copies go through these so that the bytes crossing PCIe are
+// counted (qmcl_transfer_bytes; bench.py reports them per step).
+inline cudaError_t copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+  g_h2d_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+inline cudaError_t copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+  g_d2h_bytes.fetch_add(bytes, std::memory_order_relaxed);
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+}
 
 #define QMCL_CUDA(expr)                                                        \
   do {                                                                         \

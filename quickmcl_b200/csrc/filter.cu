@@ -95,13 +95,18 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
   a.n_beams = n_used;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
-  QMCL_TRY(launch_sensor(m, a));
-  normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
-  QMCL_LAUNCHED();
+  {
+    StageScope sc(f, QMCL_STAGE_SENSOR, 1);
+    QMCL_TRY(launch_sensor(m, a));
+  }
+  {
+    StageScope sc(f, QMCL_STAGE_NORMALISE);
+    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+    QMCL_LAUNCHED();
+  }
   // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
   // total: one 8-byte read back per scan.
-  QMCL_CUDA(cudaMemcpyAsync(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double),
-                            cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   const double total = f->h_scalars.ptr[0];
   f->last_total = total;
@@ -164,6 +169,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->bin_cluster.release();
   f->scan_tmp.release();
   f->cluster_acc.release();
+  f->timer.release();
   qmcl_map *map = f->map;
   delete f;
   return qmcl_map_destroy(map);
@@ -217,7 +223,7 @@ qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, si
   if (!n) return QMCL_OK;
   void *stage = nullptr;
   QMCL_TRY(filter_scratch(f, n * sizeof(qmcl_particle), &stage));
-  QMCL_CUDA(cudaMemcpyAsync(stage, p, n * sizeof(qmcl_particle), cudaMemcpyHostToDevice, s));
+  QMCL_CUDA(copy_h2d(stage, p, n * sizeof(qmcl_particle), s));
   QMCL_TRY(launch_aos_to_soa(s, static_cast<const qmcl_particle *>(stage), n, ps.x.ptr, ps.y.ptr,
                              ps.t.ptr, ps.w.ptr));
   QMCL_CUDA(cudaStreamSynchronize(s));
@@ -236,7 +242,7 @@ qmcl_status qmcl_filter_copy_particles(const qmcl_filter *fc, qmcl_particle *out
   QMCL_TRY(filter_scratch(f, n * sizeof(qmcl_particle), &stage));
   QMCL_TRY(launch_soa_to_aos(s, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, n,
                              static_cast<qmcl_particle *>(stage)));
-  QMCL_CUDA(cudaMemcpyAsync(out, stage, n * sizeof(qmcl_particle), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(out, stage, n * sizeof(qmcl_particle), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   return QMCL_OK;
 }
@@ -251,8 +257,7 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, siz
   QMCL_TRY(f->h_beams.ensure(2 * n_points + 2));
   // stage through pinned memory so the H2D copy is a true async DMA
   std::memcpy(f->h_beams.ptr, cloud_xy, 2 * n_points * sizeof(float));
-  QMCL_CUDA(cudaMemcpyAsync(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float),
-                            cudaMemcpyHostToDevice, s));
+  QMCL_CUDA(copy_h2d(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float), s));
   int n_used = 0;
   QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
   return sensor_update_common(f, n_used);
@@ -288,6 +293,29 @@ qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast
   return QMCL_OK;
 }
 
+qmcl_status qmcl_filter_set_timing(qmcl_filter *f, int level) {
+  if (!f || level < 0 || level > 2) return QMCL_ERR_INVALID_ARG;
+  f->timer.level = level;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
+                                   uint64_t count_out[QMCL_N_STAGES], int reset) {
+  if (!f || !ms_out || !count_out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(use_device(f->map));
+  QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  f->timer.resolve();
+  for (int i = 0; i < QMCL_N_STAGES; ++i) {
+    ms_out[i] = f->timer.ms[i];
+    count_out[i] = f->timer.count[i];
+    if (reset) {
+      f->timer.ms[i] = 0.0;
+      f->timer.count[i] = 0;
+    }
+  }
+  return QMCL_OK;
+}
+
 qmcl_status qmcl_filter_synchronize(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
@@ -314,9 +342,8 @@ qmcl_status qmcl_map_update_importance(qmcl_map *m, const float *cloud_xy, size_
   QMCL_TRY(m->tmp_scalars.ensure(1));
   qmcl_particle *d_aos = reinterpret_cast<qmcl_particle *>(m->tmp_aos.ptr);
   QMCL_CUDA(cudaMemsetAsync(m->tmp_scalars.ptr, 0, sizeof(FilterScalars), s));
-  QMCL_CUDA(cudaMemcpyAsync(d_aos, particles, n * sizeof(qmcl_particle), cudaMemcpyHostToDevice, s));
-  QMCL_CUDA(cudaMemcpyAsync(m->tmp_cloud.ptr, cloud_xy, 2 * n_points * sizeof(float),
-                            cudaMemcpyHostToDevice, s));
+  QMCL_CUDA(copy_h2d(d_aos, particles, n * sizeof(qmcl_particle), s));
+  QMCL_CUDA(copy_h2d(m->tmp_cloud.ptr, cloud_xy, 2 * n_points * sizeof(float), s));
   QMCL_TRY(launch_aos_to_soa(s, d_aos, n, m->tmp_x.ptr, m->tmp_y.ptr, m->tmp_t.ptr, m->tmp_w.ptr));
   float *d_beams = m->tmp_cloud.ptr + 2 * n_points + 2;
   int n_used = 0;
@@ -333,10 +360,9 @@ qmcl_status qmcl_map_update_importance(qmcl_map *m, const float *cloud_xy, size_
   a.scalars = m->tmp_scalars.ptr;
   QMCL_TRY(launch_sensor(m, a));
   QMCL_TRY(launch_soa_to_aos(s, a.x, a.y, a.t, a.w, n, d_aos));
-  QMCL_CUDA(cudaMemcpyAsync(particles, d_aos, n * sizeof(qmcl_particle), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(particles, d_aos, n * sizeof(qmcl_particle), s));
   double total = 0.0;
-  QMCL_CUDA(cudaMemcpyAsync(&total, &m->tmp_scalars.ptr->total_weight, sizeof(double),
-                            cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(&total, &m->tmp_scalars.ptr->total_weight, sizeof(double), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   if (total_out) *total_out = total;
   return QMCL_OK;

@@ -14,6 +14,7 @@
 namespace qmcl {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 static thread_local std::string g_error;
 
 void set_error(const char *fmt, ...) {
@@ -272,7 +273,7 @@ static qmcl_status rebuild_free_cells(qmcl_map *m) {
   scan_counts_kernel<<<1, 1024, 0, m->stream>>>(m->scan_tmp.ptr, blocks, d_total);
   QMCL_LAUNCHED();
   unsigned long long total = 0;
-  QMCL_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, m->stream));
+  QMCL_CUDA(copy_d2h(&total, d_total, sizeof(total), m->stream));
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
   m->n_free = total;
   QMCL_TRY(m->free_cells.ensure(2 * total + 2));
@@ -303,6 +304,18 @@ extern "C" {
 const char *qmcl_version(void) { return "quickmcl_b200 0.1 (sm_100a)"; }
 const char *qmcl_last_error(void) { return qmcl::g_error.c_str(); }
 uint64_t qmcl_kernel_launch_count(void) { return g_launches.load(); }
+qmcl_status qmcl_transfer_bytes(uint64_t out[2]) {
+  if (!out) return QMCL_ERR_INVALID_ARG;
+  out[0] = g_h2d_bytes.load();
+  out[1] = g_d2h_bytes.load();
+  return QMCL_OK;
+}
+const char *qmcl_stage_name(int stage) {
+  static const char *names[QMCL_N_STAGES] = {"motion", "sensor", "normalise", "cdf", "select",
+                                             "gather", "kld", "bins", "label",
+                                             "post_normalise", "moments"};
+  return (stage >= 0 && stage < QMCL_N_STAGES) ? names[stage] : "?";
+}
 
 qmcl_status qmcl_map_create(int device, qmcl_map **out) {
   if (!out) return QMCL_ERR_INVALID_ARG;
@@ -398,7 +411,7 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   // the uint16 d^2 code map (sensor model's palette path) exists when d^2 fits
   const bool with_code = kmax + 2 <= 65535;
   if (with_code) QMCL_TRY(m->code.ensure(n));
-  QMCL_CUDA(cudaMemcpyAsync(m->occ.ptr, occ, n, cudaMemcpyHostToDevice, m->stream));
+  QMCL_CUDA(copy_h2d(m->occ.ptr, occ, n, m->stream));
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
   float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
 
@@ -438,9 +451,8 @@ qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *s
   set_geometry(m, width, height, resolution, origin_x, origin_y);
   QMCL_TRY(m->state.ensure(n));
   QMCL_TRY(m->field.ensure(n));
-  QMCL_CUDA(cudaMemcpyAsync(m->field.ptr, field, n * sizeof(float), cudaMemcpyHostToDevice,
-                            m->stream));
-  QMCL_CUDA(cudaMemcpyAsync(m->state.ptr, state, n, cudaMemcpyHostToDevice, m->stream));
+  QMCL_CUDA(copy_h2d(m->field.ptr, field, n * sizeof(float), m->stream));
+  QMCL_CUDA(copy_h2d(m->state.ptr, state, n, m->stream));
   QMCL_TRY(rebuild_free_cells(m));
   m->has_map = true;
   m->has_distance = false;
@@ -460,7 +472,7 @@ static qmcl_status copy_out(const qmcl_map *m, const void *src, void *dst, size_
   if (!m || !dst) return QMCL_ERR_INVALID_ARG;
   if (!m->has_map) return QMCL_ERR_NO_MAP;
   QMCL_TRY(use_device(m));
-  QMCL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, m->stream));
+  QMCL_CUDA(copy_d2h(dst, src, bytes, m->stream));
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
   return QMCL_OK;
 }

@@ -251,6 +251,7 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double nw[3], cons
   mp.sd_rot2 = std::sqrt(rot2_var);
   ParticleSet &ps = f->cur();
   if (ps.n) {
+    StageScope sc(f, QMCL_STAGE_MOTION);
     motion_kernel<<<div_up(ps.n, 256), 256, 0, f->map->stream>>>(
         ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n, f->global_first, mp, f->seed, f->step);
     QMCL_LAUNCHED();

@@ -254,6 +254,7 @@ static qmcl_status normalise_current(qmcl_filter *f) {
   ParticleSet &ps = f->cur();
   if (!ps.n) return QMCL_OK;
   cudaStream_t s = f->map->stream;
+  StageScope sc(f, QMCL_STAGE_POST_NORMALISE);
   const unsigned blocks = static_cast<unsigned>(std::min<size_t>(div_up(ps.n, 256 * 4), 4 * kSMs));
   QMCL_TRY(f->partials.ensure(blocks));
   weight_sum_kernel<<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
@@ -285,17 +286,26 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
   if (M == 0) return QMCL_OK;
   QMCL_TRY(f->cdf.ensure(M));
   QMCL_TRY(f->src_index.ensure(M));
-  QMCL_TRY(sequential_prefix(f, in.w.ptr, M, f->cdf.ptr));
+  {
+    StageScope sc(f, QMCL_STAGE_CDF);
+    QMCL_TRY(sequential_prefix(f, in.w.ptr, M, f->cdf.ptr));
+  }
   const double minv = static_cast<double>(1.0f / static_cast<float>(M));
   uint32_t r4[4];
   rng_draw(f->seed, f->step, P_LV_OFFSET, 0, r4);
   const double r = uniform53(r4[0], r4[1]) * minv;
-  lv_select_kernel<<<div_up(M, 256), 256, 0, s>>>(f->cdf.ptr, M, r, minv, f->src_index.ptr);
-  QMCL_LAUNCHED();
-  gather_kernel<<<div_up(M, 256), 256, 0, s>>>(in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr,
-                                               f->src_index.ptr, M, out.x.ptr, out.y.ptr, out.t.ptr,
-                                               out.w.ptr);
-  QMCL_LAUNCHED();
+  {
+    StageScope sc(f, QMCL_STAGE_SELECT);
+    lv_select_kernel<<<div_up(M, 256), 256, 0, s>>>(f->cdf.ptr, M, r, minv, f->src_index.ptr);
+    QMCL_LAUNCHED();
+  }
+  {
+    StageScope sc(f, QMCL_STAGE_GATHER);
+    gather_kernel<<<div_up(M, 256), 256, 0, s>>>(in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr,
+                                                 f->src_index.ptr, M, out.x.ptr, out.y.ptr,
+                                                 out.t.ptr, out.w.ptr);
+    QMCL_LAUNCHED();
+  }
   return QMCL_OK;
 }
 
@@ -310,6 +320,7 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
   QMCL_TRY(f->cdf.ensure(in.n));
   QMCL_TRY(f->pos.ensure(in.n));
   QMCL_TRY(f->incl.ensure(in.n));
+  StageScope sc(f, QMCL_STAGE_CDF);
   QMCL_TRY(sequential_prefix(f, in.w.ptr, in.n, f->cdf.ptr));
   QMCL_TRY(f->scan_tmp.ensure(scan_blocks(in.n) + 4));
   unsigned long long *d_total =
@@ -318,8 +329,8 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
                        in.n, f->scan_tmp.ptr, d_total));
   unsigned long long P = 0;
   double total = 0.0;
-  QMCL_CUDA(cudaMemcpyAsync(&P, d_total, sizeof(P), cudaMemcpyDeviceToHost, s));
-  QMCL_CUDA(cudaMemcpyAsync(&total, f->cdf.ptr + (in.n - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(&P, d_total, sizeof(P), s));
+  QMCL_CUDA(copy_d2h(&total, f->cdf.ptr + (in.n - 1), sizeof(double), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   *P_out = P;
   *total_out = total;
@@ -339,6 +350,7 @@ static qmcl_status launch_draws(qmcl_filter *f, const ParticleSet &in, ParticleS
     return QMCL_ERR_NO_MAP;
   }
   QMCL_TRY(f->src_index.ensure(n_draws));
+  StageScope sc(f, QMCL_STAGE_SELECT);
   draw_kernel<<<div_up(n_draws, 256), 256, 0, s>>>(
       in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr, f->pos.ptr, f->incl.ptr, P, w_diff, n_draws,
       f->map->free_cells.ptr, f->map->n_free, f->map->geom, f->seed, f->step, out.x.ptr, out.y.ptr,
@@ -414,19 +426,22 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   kp.z = f->params.kld_z;
   kp.nmin = f->params.particle_count_min;
   kp.nmax = f->params.particle_count_max;
-  QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0x7f, cells * sizeof(int32_t), s));
-  kld_first_kernel<<<div_up(n_max, 256), 256, 0, s>>>(out.x.ptr, out.y.ptr, out.t.ptr, n_max, kp, g,
-                                                      f->table.ptr);
-  QMCL_LAUNCHED();
   QMCL_TRY(f->scan_tmp.ensure(scan_blocks(n_max) + 8));
   unsigned long long *d_total =
       reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(n_max) + 1) & ~1u));
   unsigned long long *d_stop = d_total + 1;
-  QMCL_CUDA(cudaMemsetAsync(d_stop, 0xff, sizeof(unsigned long long), s));
-  QMCL_TRY(device_scan(s, NewBinFlag{out.x.ptr, out.y.ptr, out.t.ptr, kp, g, f->table.ptr},
-                       StopRule{kp, d_stop}, n_max, f->scan_tmp.ptr, d_total));
+  {
+    StageScope sc(f, QMCL_STAGE_KLD);
+    QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0x7f, cells * sizeof(int32_t), s));
+    kld_first_kernel<<<div_up(n_max, 256), 256, 0, s>>>(out.x.ptr, out.y.ptr, out.t.ptr, n_max, kp,
+                                                        g, f->table.ptr);
+    QMCL_LAUNCHED();
+    QMCL_CUDA(cudaMemsetAsync(d_stop, 0xff, sizeof(unsigned long long), s));
+    QMCL_TRY(device_scan(s, NewBinFlag{out.x.ptr, out.y.ptr, out.t.ptr, kp, g, f->table.ptr},
+                         StopRule{kp, d_stop}, n_max, f->scan_tmp.ptr, d_total));
+  }
   unsigned long long stop = 0;
-  QMCL_CUDA(cudaMemcpyAsync(&stop, d_stop, sizeof(stop), cudaMemcpyDeviceToHost, s));
+  QMCL_CUDA(copy_d2h(&stop, d_stop, sizeof(stop), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   const size_t n_out = (stop >= n_max) ? n_max : static_cast<size_t>(stop) + 1;
   out.n = n_out;
@@ -493,8 +508,7 @@ qmcl_status qmcl_filter_copy_resample_indices(const qmcl_filter *fc, int64_t *ou
   const size_t n = f->n_src_index < cap ? f->n_src_index : cap;
   if (!n || !out) return QMCL_OK;
   QMCL_TRY(use_device(f->map));
-  QMCL_CUDA(cudaMemcpyAsync(out, f->src_index.ptr, n * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                            f->map->stream));
+  QMCL_CUDA(copy_d2h(out, f->src_index.ptr, n * sizeof(int64_t), f->map->stream));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
   return QMCL_OK;
 }

@@ -409,7 +409,7 @@ qmcl_status sensor_prepare_map(qmcl_map *m) {
   fastdiv_check_kernel<<<div_up(threads, 256), 256, 0, m->stream>>>(sp, d_flag);
   QMCL_LAUNCHED();
   int flag = 1;
-  QMCL_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  QMCL_CUDA(copy_d2h(&flag, d_flag, sizeof(int), m->stream));
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
   m->fastdiv_ok = (flag == 0);
   m->lut_params_valid = false;

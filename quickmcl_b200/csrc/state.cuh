@@ -3,6 +3,8 @@
 
 #include "common.cuh"
 
+#include <vector>
+
 // Device-resident scalars of one filter.
 struct FilterScalars {
   double total_weight;   // pre-penalty total of the last sensor update
@@ -85,6 +87,44 @@ struct BinGrid {
   int nx, ny, nt;
 };
 
+// CUDA-event stage timers (qmcl_filter_set_timing / get_timing).
+struct StageTimer {
+  int level = 0;
+  struct Pending { int stage; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> pool;
+  std::vector<Pending> pending;
+  double ms[QMCL_N_STAGES] = {};
+  uint64_t count[QMCL_N_STAGES] = {};
+  cudaEvent_t take() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  // Folds finished pairs into ms[]; the stream must be idle.
+  void resolve() {
+    for (const Pending &p : pending) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) {
+        ms[p.stage] += t;
+        count[p.stage]++;
+      }
+      pool.push_back(p.a);
+      pool.push_back(p.b);
+    }
+    pending.clear();
+  }
+  void release() {
+    resolve();
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
+
 // quickmcl::ParticleFilter (particle_filter.h)
 struct qmcl_filter {
   qmcl_map *map = nullptr;
@@ -135,10 +175,31 @@ struct qmcl_filter {
   bool bins_built = false;
   bool clusters_valid = false;
 
+  StageTimer timer;
+
   ParticleSet &cur() { return sets[current]; }
   const ParticleSet &cur() const { return sets[current]; }
 };
 
 namespace qmcl {
 qmcl_status use_device(const qmcl_map *m);
+
+// RAII: times the enclosed launches on the filter's stream when the timing
+// level is at least `min_level`.
+struct StageScope {
+  qmcl_filter *f;
+  int stage;
+  cudaEvent_t a = nullptr;
+  StageScope(qmcl_filter *f_, int stage_, int min_level = 2) : f(f_), stage(stage_) {
+    if (f->timer.level < min_level) return;
+    a = f->timer.take();
+    cudaEventRecord(a, f->map->stream);
+  }
+  ~StageScope() {
+    if (!a) return;
+    cudaEvent_t b = f->timer.take();
+    cudaEventRecord(b, f->map->stream);
+    f->timer.pending.push_back({stage, a, b});
+  }
+};
 }
