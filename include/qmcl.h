@@ -196,6 +196,12 @@ qmcl_status qmcl_filter_copy_bins(const qmcl_filter *f, int32_t *keys4,
 qmcl_status qmcl_filter_num_clusters(const qmcl_filter *f, size_t *out);
 qmcl_status qmcl_filter_get_lowpass(const qmcl_filter *f, double out[2]);
 qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast);
+/* Running-sum kernel selection: 0 = parallel, bit-identical to the sequential
+ * loop (default); 1 = the literal one-warp sequential loop (cross-check). */
+qmcl_status qmcl_filter_set_prefix_mode(qmcl_filter *f, int mode);
+/* out[i] = sequentially rounded running sum of carry_in, w[0..i] (host arrays). */
+qmcl_status qmcl_filter_debug_prefix(qmcl_filter *f, const double *w, size_t n,
+                                     double carry_in, double *out, double *carry_out);
 /* Wait for everything enqueued by this filter. */
 qmcl_status qmcl_filter_synchronize(qmcl_filter *f);
 

@@ -97,6 +97,8 @@ SIGNATURES = {
     "qmcl_filter_get_lowpass": [vp, pf64],
     "qmcl_filter_set_lowpass": [vp, f64, f64],
     "qmcl_filter_synchronize": [vp],
+    "qmcl_filter_set_prefix_mode": [vp, C.c_int],
+    "qmcl_filter_debug_prefix": [vp, pf64, sz, f64, pf64, pf64],
     "qmcl_filter_set_timing": [vp, C.c_int],
     "qmcl_filter_get_timing": [vp, pf64, C.POINTER(u64), C.c_int],
     "qmcl_transfer_bytes": [C.POINTER(u64)],

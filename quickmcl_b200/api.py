@@ -346,6 +346,20 @@ class ParticleFilter:
     def set_lowpass(self, w_slow, w_fast):
         check(self._L.qmcl_filter_set_lowpass(self._h, w_slow, w_fast), "qmcl_filter_set_lowpass")
 
+    def set_prefix_mode(self, mode):
+        """0 = parallel bit-exact running sum (default), 1 = one-warp sequential loop."""
+        check(self._L.qmcl_filter_set_prefix_mode(self._h, mode), "qmcl_filter_set_prefix_mode")
+
+    def debug_prefix(self, w, carry_in=0.0):
+        """Sequentially rounded running sum of a host array; returns (sums, carry_out)."""
+        w = np.ascontiguousarray(w, np.float64)
+        out = np.zeros_like(w)
+        co = C.c_double(0)
+        check(self._L.qmcl_filter_debug_prefix(self._h, ptr(w, C.c_double), len(w), carry_in,
+                                               ptr(out, C.c_double), C.byref(co)),
+              "qmcl_filter_debug_prefix")
+        return out, co.value
+
     def synchronize(self):
         check(self._L.qmcl_filter_synchronize(self._h), "qmcl_filter_synchronize")
 

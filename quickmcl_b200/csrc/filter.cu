@@ -161,6 +161,8 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->incl.release();
   f->src_index.release();
   f->scratch.release();
+  f->prefix_scratch.release();
+  f->prefix_carry.release();
   f->bbox.release();
   f->table.release();
   f->bin_cell.release();

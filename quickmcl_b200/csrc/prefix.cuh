@@ -1,13 +1,13 @@
-// prefix.cuh — the reference-faithful (sequentially rounded) running sum.
+// prefix.cuh — K9: sequentially rounded running sum (see prefix.cu).
 #pragma once
 
 #include "filter.cuh"
 
 namespace qmcl {
 
-// out[i] = fl(fl(...fl(w[0] + w[1]) ...) + w[i]): the exact sequence of
-// rounded double additions of the reference's running sums
-// (particle_filter.cpp:225-236, particle.cpp:66-82).  w[i] >= 0.
-qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double *out);
+// out[i] = fl(...fl(fl(carry_in + w[0]) + w[1])... + w[i]), bit-identical to
+// the sequential loop; the last value is also left in f->prefix_carry.ptr[0].
+qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double *out,
+                              double carry_in = 0.0);
 
 }  // namespace qmcl

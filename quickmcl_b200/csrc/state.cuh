@@ -160,6 +160,9 @@ struct qmcl_filter {
   qmcl::DevBuf<int64_t> src_index;
   size_t n_src_index = 0;
   qmcl::DevBuf<uint8_t> scratch;
+  qmcl::DevBuf<uint8_t> prefix_scratch;  // chunk / tile summaries of prefix.cu
+  qmcl::DevBuf<double> prefix_carry;     // [0] = running sum after the last element
+  int prefix_mode = 0;                   // 0 parallel exact, 1 one-warp sequential loop
 
   // bins / clusters: dense table over the bin bounding box + sorted bin list
   BinGrid grid{0, 0, 0, 0, 0, 0};

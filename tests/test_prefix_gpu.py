@@ -1,0 +1,126 @@
+"""K9: the parallel running sum must be bit-identical to the reference's
+sequential loop `c += w[i]` (particle_filter.cpp:225-236, particle.cpp:66-82).
+
+numpy's cumsum over float64 is that loop (np.add.accumulate is strictly
+sequential), so it is the oracle here; the library's one-warp sequential kernel
+is the second witness.  Comparison is on the raw 64-bit patterns."""
+import numpy as np
+import pytest
+
+import quickmcl_b200 as q
+from quickmcl_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def filt():
+    occ, res, origin = syn.make_map(400)
+    gm = q.create_likelihood_map(device=0)
+    gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    return q.create_particle_filter(gm, seed=1)
+
+
+def seq_cumsum(w, carry=0.0):
+    return np.cumsum(np.concatenate([[carry], w]))[1:]
+
+
+def check(filt, w, carry=0.0, oracle=True):
+    w = np.ascontiguousarray(w, np.float64)
+    filt.set_prefix_mode(0)
+    got, co = filt.debug_prefix(w, carry)
+    filt.set_prefix_mode(1)
+    seq, co_seq = filt.debug_prefix(w, carry)
+    filt.set_prefix_mode(0)
+    assert np.array_equal(got.view(np.uint64), seq.view(np.uint64)), \
+        f"parallel != one-warp sequential at {np.flatnonzero(got.view(np.uint64) != seq.view(np.uint64))[:5]}"
+    assert np.float64(co).view(np.uint64) == np.float64(co_seq).view(np.uint64)
+    if oracle:
+        with np.errstate(all="ignore"):
+            want = seq_cumsum(w, carry)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), \
+            f"first mismatch at {np.flatnonzero(got.view(np.uint64) != want.view(np.uint64))[:5]}"
+        if len(w):
+            assert co == want[-1] or (np.isnan(co) and np.isnan(want[-1]))
+    return got
+
+
+@pytest.mark.parametrize("n", [1, 7, 31, 32, 255, 256, 257, 2047, 2048, 2049, 4096, 100_000,
+                               1_000_003])
+def test_equal_weights(filt, n):
+    check(filt, np.full(n, 1.0 / n))
+
+
+@pytest.mark.parametrize("n,seed", [(1000, 1), (50_000, 2), (300_000, 3), (2_000_000, 4)])
+def test_random_normalised_weights(filt, n, seed):
+    rng = np.random.default_rng(seed)
+    w = rng.lognormal(0.0, 3.0, n)
+    w[rng.random(n) < 0.2] = 0.0           # penalised particles
+    w /= w.sum()
+    check(filt, w)
+    # the parallel sum is NOT what a reassociated sum gives: make sure the test can tell
+    pair = w.reshape(-1, 2).sum(axis=1).cumsum() if n % 2 == 0 else None
+    if pair is not None and n >= 300_000:
+        assert not np.array_equal(pair, seq_cumsum(w)[1::2])
+
+
+def test_ties_round_half_even(filt):
+    # carry in [0.5, 1): ulp = 2^-53; weights that are odd multiples of 2^-54 are exact ties
+    rng = np.random.default_rng(5)
+    n = 200_000
+    odd = (2 * rng.integers(0, 1 << 20, n) + 1).astype(np.float64)
+    w = odd * 2.0 ** -54
+    w[::3] = rng.random(len(w[::3])) * 2.0 ** -34   # non-ties in between
+    w[5::17] = 2.0 ** -54                           # the smallest tie: q = 0
+    got = check(filt, w, carry=0.5)
+    assert got[-1] < 1.0
+    # and in the binade of a sum that starts from nothing
+    check(filt, w)
+
+
+def test_binade_crossings_everywhere(filt):
+    # the sum doubles every ~50 elements for 600 binades
+    i = np.arange(30_000)
+    w = 2.0 ** (i / 50.0 - 620.0)
+    check(filt, w)
+    # one dominant weight in the middle, dust before and after
+    rng = np.random.default_rng(6)
+    w = rng.random(100_000) * 1e-12
+    w[43_210] = 1.0
+    check(filt, w)
+    # descending magnitudes: later weights are absorbed completely
+    w = 2.0 ** -(np.arange(5000) / 10.0)
+    check(filt, w)
+
+
+def test_carry_in_chains_shards(filt):
+    rng = np.random.default_rng(7)
+    w = rng.random(700_001)
+    w /= w.sum()
+    whole = check(filt, w)
+    cut = [0, 1, 255, 100_000, 350_000, 700_001]
+    carry = 0.0
+    for a, b in zip(cut[:-1], cut[1:]):
+        part = check(filt, w[a:b], carry)
+        assert np.array_equal(part, whole[a:b])
+        carry = part[-1]
+
+
+def test_degenerate_inputs_fall_back_to_true_additions(filt):
+    rng = np.random.default_rng(8)
+    w = rng.random(20_000)
+    w[100] = -0.25            # negative
+    w[5000] = 5e-324          # subnormal
+    w[12_000] = 0.0
+    w[12_001] = -0.0
+    check(filt, w)
+    w[15_000] = np.inf
+    check(filt, w)
+    w[15_000] = np.nan
+    check(filt, w, oracle=False)   # NaN payloads: compare the two kernels only
+    check(filt, np.zeros(3000))
+    check(filt, np.zeros(0))
+    z = np.zeros(10_000)
+    z[7777] = 1.0
+    check(filt, z)
