@@ -191,9 +191,165 @@ struct EmitRootId {
   }
 };
 
-// K14 accumulation.  Slots per cluster:
-// 0 W, 1..4 S = w*(x, y, sin, cos), 5..8 C = (w*d_i)*d_j (i,j<2), 9 count.
-constexpr int kAccSlots = 10;
+// ---------------------------------------------------------------- K14
+// Pose estimate = weighted mean of the cluster with the largest total weight,
+// covariance = statistics of all particles (particle_filter.cpp:186-212,
+// statistics.cpp:23-79).  Only two sets of moments are ever read — the best
+// cluster's and the global one — so instead of accumulating ten doubles per
+// cluster with floating-point atomics (contended, and order-dependent), this is
+// done in three deterministic steps:
+//   1. wmax_kernel: largest weight (fixes the fixed-point scale);
+//   2. cluster_weight_kernel: per-cluster total weight as an *integer*
+//      fixed-point sum (order-independent, warp-aggregated), cluster id per
+//      particle kept for step 3;
+//   3. best_cluster_kernel + moments_kernel: argmax, then the moments of the
+//      best cluster and of all particles, reduced in a fixed order.
+constexpr int kMom = 10;  // 0 W, 1..4 S = w*(x, y, sin, cos), 5..8 C, 9 count
+constexpr int kMomentBlocks = 4 * kSMs;
+
+struct EstimateScalars {
+  unsigned long long wmax_bits;   // largest weight, as the bits of a non-negative double
+  unsigned long long best_w;      // fixed-point total of the best cluster
+  int best;                       // its id, -1 if none
+  int invalid;                    // a particle's bin has no cluster
+  unsigned int blocks_done;
+  unsigned int pad;
+};
+
+__global__ void __launch_bounds__(256)
+wmax_kernel(const double *__restrict__ w, size_t n, EstimateScalars *__restrict__ es) {
+  unsigned long long m = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double v = w[i];
+    if (v > 0) m = max(m, static_cast<unsigned long long>(__double_as_longlong(v)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&es->wmax_bits, m);
+}
+
+// Scale 2^k with n * wmax * 2^k < 2^62.
+__device__ __forceinline__ int fixed_point_shift(unsigned long long wmax_bits, size_t n) {
+  if (wmax_bits == 0) return 0;
+  const int e = static_cast<int>(wmax_bits >> 52) - 1023 + 1;  // wmax < 2^e
+  const int ln = 64 - __clzll(static_cast<unsigned long long>(n));  // n < 2^ln
+  return 62 - e - ln;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_weight_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                      const float *__restrict__ t, const double *__restrict__ w, size_t n,
+                      BinParams bp, BinGrid g, const int32_t *__restrict__ table,
+                      const int32_t *__restrict__ label,
+                      const int32_t *__restrict__ cluster_of_root,
+                      int32_t *__restrict__ cid_out, unsigned long long *__restrict__ cluster_w,
+                      EstimateScalars *__restrict__ es) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int shift = fixed_point_shift(es->wmax_bits, n);
+  int cid = -1;
+  unsigned long long fx = 0;
+  if (i < n) {
+    int kx, ky, kt;
+    bin_key(x[i], y[i], t[i], bp, &kx, &ky, &kt);
+    const long long idx = grid_index(g, kx, ky, kt);
+    const int b = idx >= 0 ? table[idx] - 1 : -1;
+    if (b < 0) {
+      atomicExch(&es->invalid, 1);  // particle_filter.cpp:375-379
+    } else {
+      cid = cluster_of_root[label[b]];
+      const double wi = w[i];
+      if (wi > 0) fx = static_cast<unsigned long long>(__double2ll_rn(scalbn(wi, shift)));
+    }
+    cid_out[i] = cid;
+  }
+  // aggregate lanes of the same cluster: three 21-bit limbs through REDUX
+  const unsigned mask = __match_any_sync(0xffffffffu, cid);
+  const unsigned l0 = __reduce_add_sync(mask, static_cast<unsigned>(fx & 0x1fffffu));
+  const unsigned l1 = __reduce_add_sync(mask, static_cast<unsigned>((fx >> 21) & 0x1fffffu));
+  const unsigned l2 = __reduce_add_sync(mask, static_cast<unsigned>(fx >> 42));
+  const unsigned long long sum = static_cast<unsigned long long>(l0) +
+                                 (static_cast<unsigned long long>(l1) << 21) +
+                                 (static_cast<unsigned long long>(l2) << 42);
+  const bool leader = (__ffs(mask) - 1) == static_cast<int>(threadIdx.x & 31);
+  // block-uniform clusters (tracking): one atomic per block
+  __shared__ unsigned long long s_sum[8];
+  __shared__ int s_cid[8];
+  const int wid = threadIdx.x >> 5;
+  const bool warp_uniform = mask == 0xffffffffu;
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[wid] = sum;
+    s_cid[wid] = warp_uniform ? cid : -2;
+  }
+  __syncthreads();
+  bool block_uniform = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) block_uniform &= (s_cid[k] == s_cid[0]) && s_cid[k] != -2;
+  if (block_uniform) {
+    if (threadIdx.x == 0 && s_cid[0] >= 0) {
+      unsigned long long tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += s_sum[k];
+      if (tot) atomicAdd(cluster_w + s_cid[0], tot);
+    }
+    return;
+  }
+  if (leader && cid >= 0 && sum) atomicAdd(cluster_w + cid, sum);
+}
+
+// First maximum of the cluster weights (ties -> smallest canonical id).
+__global__ void __launch_bounds__(1024)
+best_cluster_kernel(const unsigned long long *__restrict__ cluster_w, size_t n_clusters,
+                    EstimateScalars *__restrict__ es) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ long long s_i[32];
+  unsigned long long bw = 0;
+  long long bi = -1;
+  for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x) {
+    const unsigned long long v = cluster_w[c];
+    if (bi < 0 || v > bw) {
+      bw = v;
+      bi = static_cast<long long>(c);
+    }
+  }
+  auto better = [](unsigned long long w1, long long i1, unsigned long long w2, long long i2) {
+    if (i1 < 0) return false;
+    if (i2 < 0) return true;
+    return w1 > w2 || (w1 == w2 && i1 < i2);
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ow, oi, bw, bi)) {
+      bw = ow;
+      bi = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_w[wid] = bw;
+    s_i[wid] = bi;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    bw = s_w[lane];
+    bi = s_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ow, oi, bw, bi)) {
+        bw = ow;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      es->best = static_cast<int>(bi);
+      es->best_w = bw;
+    }
+  }
+}
 
 __device__ __forceinline__ double block_sum_256(double v, double *smem) {
   v = warp_sum_xor(v);
@@ -209,130 +365,11 @@ __device__ __forceinline__ double block_sum_256(double v, double *smem) {
   return t;
 }
 
-// statistics.cpp:23-41 for every particle, into its cluster's slots.  Blocks
-// (then warps) whose particles all share one cluster reduce first and issue a
-// single set of atomics; mixed warps fall back to per-lane atomics.
-__global__ void __launch_bounds__(256)
-moments_kernel(const float *__restrict__ x, const float *__restrict__ y,
-               const float *__restrict__ t, const double *__restrict__ w, size_t n, BinParams bp,
-               BinGrid g, const int32_t *__restrict__ table, const int32_t *__restrict__ label,
-               const int32_t *__restrict__ cluster_of_root, double *__restrict__ acc,
-               int *__restrict__ invalid_flag) {
-  __shared__ double smem[8];
-  __shared__ int s_first;
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  int cid = -1;
-  double v[kAccSlots];
-#pragma unroll
-  for (int k = 0; k < kAccSlots; ++k) v[k] = 0.0;
-  const bool active = i < n;
-  if (active) {
-    const float px = x[i], py = y[i], pt = t[i];
-    int kx, ky, kt;
-    bin_key(px, py, pt, bp, &kx, &ky, &kt);
-    const long long idx = grid_index(g, kx, ky, kt);
-    const int b = idx >= 0 ? table[idx] - 1 : -1;
-    if (b < 0) {
-      atomicExch(invalid_flag, 1);  // particle_filter.cpp:375-379
-    } else {
-      cid = cluster_of_root[label[b]];
-      const double wi = w[i];
-      double sn, cs;
-      sincos(static_cast<double>(pt), &sn, &cs);
-      const double d0 = static_cast<double>(px), d1 = static_cast<double>(py);
-      v[0] = wi;
-      v[1] = wi * d0;
-      v[2] = wi * d1;
-      v[3] = wi * sn;
-      v[4] = wi * cs;
-      v[5] = (wi * d0) * d0;
-      v[6] = (wi * d0) * d1;
-      v[7] = (wi * d1) * d0;
-      v[8] = (wi * d1) * d1;
-      v[9] = 1.0;
-    }
-  }
-  if (threadIdx.x == 0) s_first = cid;
-  __syncthreads();
-  const int first = s_first;
-  const bool same = (cid == first) || !active || cid < 0;
-  if (__syncthreads_and(same) && first >= 0) {
-#pragma unroll
-    for (int k = 0; k < kAccSlots; ++k) {
-      const double s = block_sum_256(v[k], smem);
-      if (threadIdx.x == 0) atomicAdd(acc + static_cast<size_t>(first) * kAccSlots + k, s);
-    }
-    return;
-  }
-  // warp level
-  const int wfirst = __shfl_sync(0xffffffffu, cid, 0);
-  const bool wsame = (cid == wfirst) || cid < 0;
-  if (__all_sync(0xffffffffu, wsame) && wfirst >= 0) {
-#pragma unroll
-    for (int k = 0; k < kAccSlots; ++k) {
-      const double s = warp_sum_xor(v[k]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(acc + static_cast<size_t>(wfirst) * kAccSlots + k, s);
-    }
-    return;
-  }
-  if (cid >= 0) {
-#pragma unroll
-    for (int k = 0; k < kAccSlots; ++k) atomicAdd(acc + static_cast<size_t>(cid) * kAccSlots + k, v[k]);
-  }
-}
-
-// statistics.cpp:50-79 + particle_filter.cpp:186-212: global = sum of the
-// clusters (in canonical cluster order), finalise, pick the first strict
-// maximum of total weight.  out = {valid, pose[3], cov[9]}.
-__global__ void __launch_bounds__(256)
-estimate_finalise_kernel(const double *__restrict__ acc, size_t n_clusters,
-                         double *__restrict__ out) {
-  __shared__ double s_best_w[256];
-  __shared__ long long s_best_i[256];
-  // best cluster: max W, ties -> smallest id (== "first strict maximum")
-  double bw = -1.0;
-  long long bi = -1;
-  for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x) {
-    const double wv = acc[c * kAccSlots];
-    if (wv > bw) {
-      bw = wv;
-      bi = static_cast<long long>(c);
-    }
-  }
-  s_best_w[threadIdx.x] = bw;
-  s_best_i[threadIdx.x] = bi;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      const double ow = s_best_w[threadIdx.x + o];
-      const long long oi = s_best_i[threadIdx.x + o];
-      if (oi >= 0 && (ow > s_best_w[threadIdx.x] ||
-                      (ow == s_best_w[threadIdx.x] && (s_best_i[threadIdx.x] < 0 || oi < s_best_i[threadIdx.x])))) {
-        s_best_w[threadIdx.x] = ow;
-        s_best_i[threadIdx.x] = oi;
-      }
-    }
-    __syncthreads();
-  }
-  // global statistics = sum of the clusters (statistics.cpp:50-57); summed as
-  // a strided tree here, which differs from the sequential order by rounding only
-  __shared__ double s_g[kAccSlots];
-  __shared__ double s_red[8];
-  for (int k = 0; k < kAccSlots; ++k) {
-    double part = 0.0;
-    for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x)
-      part = __dadd_rn(part, acc[c * kAccSlots + k]);
-    const double tot = block_sum_256(part, s_red);
-    if (threadIdx.x == 0) s_g[k] = tot;
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  const double *gsum = s_g;
-  const long long best = s_best_i[0];
-  const double best_w = s_best_w[0];
+// statistics.cpp:50-79 + particle_filter.cpp:201-211 on the reduced moments
+// (b = best cluster, gsum = all particles).  out = {valid, pose[3], cov[9]}.
+__device__ void finalise_estimate(const double *b, const double *gsum, double *out) {
   for (int k = 0; k < 13; ++k) out[k] = 0.0;
-  if (best < 0 || !(best_w > 0)) return;
-  const double *b = acc + static_cast<size_t>(best) * kAccSlots;
+  if (!(b[0] > 0)) return;
   out[0] = 1.0;
   out[1] = b[1] / b[0];
   out[2] = b[2] / b[0];
@@ -346,6 +383,82 @@ estimate_finalise_kernel(const double *__restrict__ acc, size_t n_clusters,
   cov[4] = gsum[8] / W - m1 * m1;
   const double R = sqrt(gsum[3] * gsum[3] + gsum[4] * gsum[4]);  // un-normalised, as the reference
   cov[8] = 1 - R;
+}
+
+// statistics.cpp:23-41 for the best cluster and for all particles.  Every
+// thread sums its grid-stride particles in index order, blocks reduce in a
+// fixed tree, the last block adds the block partials in block order: the
+// result depends on n only, not on scheduling.  partials: [gridDim][2*kMom].
+// When `finalise` is set the last block also writes out[0..13).
+__global__ void __launch_bounds__(256)
+moments_kernel(const float *__restrict__ x, const float *__restrict__ y,
+               const float *__restrict__ t, const double *__restrict__ w,
+               const int32_t *__restrict__ cid, size_t n, double *__restrict__ partials,
+               EstimateScalars *__restrict__ es, double *__restrict__ sums_out,
+               double *__restrict__ out, int finalise) {
+  __shared__ double smem[8];
+  __shared__ bool s_last;
+  const int best = es->best;
+  double vg[kMom], vb[kMom];
+#pragma unroll
+  for (int k = 0; k < kMom; ++k) vg[k] = vb[k] = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = cid[i];
+    if (c < 0) continue;
+    const float px = x[i], py = y[i], pt = t[i];
+    const double wi = w[i];
+    double sn, cs;
+    sincos(static_cast<double>(pt), &sn, &cs);
+    const double d0 = static_cast<double>(px), d1 = static_cast<double>(py);
+    double v[kMom];
+    v[0] = wi;
+    v[1] = wi * d0;
+    v[2] = wi * d1;
+    v[3] = wi * sn;
+    v[4] = wi * cs;
+    v[5] = (wi * d0) * d0;
+    v[6] = (wi * d0) * d1;
+    v[7] = (wi * d1) * d0;
+    v[8] = (wi * d1) * d1;
+    v[9] = 1.0;
+    const bool in_best = c == best;
+#pragma unroll
+    for (int k = 0; k < kMom; ++k) {
+      vg[k] = __dadd_rn(vg[k], v[k]);
+      if (in_best) vb[k] = __dadd_rn(vb[k], v[k]);
+    }
+  }
+  double *mine = partials + static_cast<size_t>(blockIdx.x) * 2 * kMom;
+#pragma unroll
+  for (int k = 0; k < kMom; ++k) {
+    const double sg = block_sum_256(vg[k], smem);
+    const double sb = block_sum_256(vb[k], smem);
+    if (threadIdx.x == 0) {
+      mine[k] = sg;
+      mine[kMom + k] = sb;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&es->blocks_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_tot[2 * kMom];
+  if (threadIdx.x < 2 * kMom) {
+    double a = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b)
+      a = __dadd_rn(a, __ldcg(partials + static_cast<size_t>(b) * 2 * kMom + threadIdx.x));
+    s_tot[threadIdx.x] = a;
+    sums_out[threadIdx.x] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    es->blocks_done = 0;
+    if (finalise) finalise_estimate(s_tot + kMom, s_tot, out);
+  }
 }
 
 __global__ void decode_bins_kernel(const int32_t *__restrict__ bin_cell,
@@ -491,24 +604,42 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   }
   const BinParams bp = bin_params(f);
   StageScope sc(f, QMCL_STAGE_MOMENTS);
-  QMCL_TRY(f->cluster_acc.ensure(f->n_clusters * kAccSlots + 16));
-  double *acc = f->cluster_acc.ptr;
-  double *d_out = acc + f->n_clusters * kAccSlots;
-  QMCL_CUDA(cudaMemsetAsync(acc, 0, (f->n_clusters * kAccSlots + 16) * sizeof(double), s));
-  int *d_flag = reinterpret_cast<int *>(d_out + 14);
+  const unsigned blocks =
+      static_cast<unsigned>(std::min<size_t>(std::max<size_t>(div_up(ps.n, 256), 1), kMomentBlocks));
+  // layout of cluster_acc (doubles): [n_clusters] fixed-point cluster weights |
+  // [blocks * 2 * kMom] block partials | [2 * kMom] sums | [16] out | EstimateScalars
+  const size_t o_part = f->n_clusters;
+  const size_t o_sums = o_part + static_cast<size_t>(blocks) * 2 * kMom;
+  const size_t o_out = o_sums + 2 * kMom;
+  const size_t o_es = o_out + 16;
+  const size_t total = o_es + (sizeof(EstimateScalars) + 7) / 8;
+  QMCL_TRY(f->cluster_acc.ensure(total));
+  QMCL_TRY(f->particle_cid.ensure(ps.n + 1));
+  double *base = f->cluster_acc.ptr;
+  unsigned long long *cluster_w = reinterpret_cast<unsigned long long *>(base);
+  double *d_out = base + o_out;
+  EstimateScalars *es = reinterpret_cast<EstimateScalars *>(base + o_es);
+  QMCL_CUDA(cudaMemsetAsync(base, 0, f->n_clusters * sizeof(double), s));
+  QMCL_CUDA(cudaMemsetAsync(base + o_sums, 0, (2 * kMom + 16) * sizeof(double) + sizeof(EstimateScalars), s));
   if (ps.n) {
-    moments_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n,
-                                                     bp, f->grid, f->table.ptr, f->bin_label.ptr,
-                                                     f->bin_cluster.ptr, acc, d_flag);
+    wmax_kernel<<<std::min<unsigned>(blocks, 2 * kSMs), 256, 0, s>>>(ps.w.ptr, ps.n, es);
+    QMCL_LAUNCHED();
+    cluster_weight_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(
+        ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n, bp, f->grid, f->table.ptr, f->bin_label.ptr,
+        f->bin_cluster.ptr, f->particle_cid.ptr, cluster_w, es);
     QMCL_LAUNCHED();
   }
-  estimate_finalise_kernel<<<1, 256, 0, s>>>(acc, f->n_clusters, d_out);
+  best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, f->n_clusters, es);
   QMCL_LAUNCHED();
+  moments_kernel<<<blocks, 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, f->particle_cid.ptr,
+                                        ps.n, base + o_part, es, base + o_sums, d_out, 1);
+  QMCL_LAUNCHED();
+  // one read back: out[0..13) + the invalid flag
   double h[16];
-  QMCL_CUDA(copy_d2h(h, d_out, sizeof(h), s));
+  QMCL_CUDA(copy_d2h(h, d_out, 13 * sizeof(double), s));
+  int flag = 0;
+  QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
-  int flag;
-  std::memcpy(&flag, &h[14], sizeof(int));
   if (flag) {
     set_error("get_estimate: a particle's bin has no cluster (reference abort()s here)");
     return QMCL_ERR_INVALID_CLUSTER;

@@ -171,6 +171,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->bin_cluster.release();
   f->scan_tmp.release();
   f->cluster_acc.release();
+  f->particle_cid.release();
   f->timer.release();
   qmcl_map *map = f->map;
   delete f;

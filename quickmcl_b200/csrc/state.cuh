@@ -174,6 +174,7 @@ struct qmcl_filter {
   qmcl::DevBuf<int32_t> bin_cluster;  // root bin -> dense cluster id
   qmcl::DevBuf<uint32_t> scan_tmp;
   qmcl::DevBuf<double> cluster_acc;
+  qmcl::DevBuf<int32_t> particle_cid;  // cluster id per particle (K14)
   size_t n_bins = 0, n_clusters = 0;
   bool bins_built = false;
   bool clusters_valid = false;

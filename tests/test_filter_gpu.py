@@ -277,6 +277,32 @@ def test_cluster_and_estimate_match_oracle(cloud, n):
     print(f"{cloud}: {gf.num_clusters()} clusters, {len(gk)} bins")
 
 
+def test_estimate_at_one_million_particles_many_clusters():
+    """K14 at scale: a global cloud has hundreds of thousands of bins and many
+    clusters; the fixed-point cluster weights must pick the oracle's best cluster."""
+    occ, res, origin, om, gm, of, gf = make_pair(width=1000)
+    n = 1_000_000
+    x, y, t = syn.uniform_cloud(occ, res, origin, n, seed=11)
+    rng = np.random.default_rng(12)
+    w = rng.random(n) ** 4
+    w[rng.random(n) < 0.3] = 0.0
+    w /= w.sum()
+    set_both(of, gf, x, y, t, w)
+    of.cluster()
+    gf.cluster()
+    assert gf.num_clusters() == of.num_clusters()
+    assert np.array_equal(gf.bins()[1], of.bins()[1])
+    g_ok, g_pose, g_cov = gf.get_estimated_pose()
+    o_ok, o_pose, o_cov = of.get_estimated_pose()
+    assert g_ok and o_ok == 1
+    assert np.max(np.abs(g_pose - o_pose)) <= 1e-9
+    assert np.max(np.abs(g_cov - o_cov)) <= 1e-9
+    # deterministic: the same bits on a second call
+    g_ok2, g_pose2, g_cov2 = gf.get_estimated_pose()
+    assert np.array_equal(g_pose, g_pose2) and np.array_equal(g_cov, g_cov2)
+    print(f"1M global: {gf.num_clusters()} clusters, {len(gf.bins()[0])} bins")
+
+
 def test_theta_wrap_joins_clusters():
     """Bins at theta ~ +pi and ~ -pi are neighbours (space_partitioning.cpp:110-114)."""
     _, _, _, om, gm, of, gf = make_pair()
