@@ -33,7 +33,9 @@ typedef enum qmcl_status {
   /* get_estimate met a particle whose bin has no cluster: the reference
    * abort()s here (particle_filter.cpp:375-379). */
   QMCL_ERR_INVALID_CLUSTER = 5,
-  QMCL_ERR_CAPACITY = 6
+  QMCL_ERR_CAPACITY = 6,
+  QMCL_ERR_COMM = 7,        /* a qmcl_comm collective failed */
+  QMCL_ERR_UNSUPPORTED = 8  /* not available on a sharded filter yet */
 } qmcl_status;
 
 /* quickmcl::WeightedParticle (particle.h:32-47): Pose2D<float> + double. */
@@ -139,10 +141,51 @@ qmcl_status qmcl_map_generate_random_pose(const qmcl_map *map, uint64_t seed,
 /* create_particle_filter(map) (particle_filter_factory.h:30-31). */
 qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out);
 qmcl_status qmcl_filter_destroy(qmcl_filter *f);
-/* Particle sharding (north_star / SURVEY §8e): this handle owns the
- * contiguous global slice [first, first+count) of a filter of `global_count`
- * particles.  Defaults: one shard holding everything. */
-qmcl_status qmcl_filter_set_shard(qmcl_filter *f, int shard_rank, int n_shards);
+/* ---- particle sharding (north_star / SURVEY 8e) ----------------------------
+ * One filter handle per GPU owns a contiguous block of the global particle
+ * index range; the blocks are ordered by rank, so the global CDF is the
+ * concatenation of the shards' CDFs.  The map, state map and scan are
+ * replicated.  The handful of exchanges per cycle (weight total, running-sum
+ * carry, bin occupancy, cluster weights, estimate moments, particle
+ * rebalancing) go through these host-supplied collectives; the host decides
+ * what carries them (torch.distributed over NCCL in quickmcl_b200/sharded.py;
+ * an MPI or raw NCCL host fills the same table).
+ *
+ * Every buffer is a DEVICE pointer.  A call must be ordered after the work
+ * already enqueued on `stream` (the filter's cudaStream_t) and the filter's
+ * later work on that stream must see its result.  Return 0 on success. */
+enum { QMCL_DT_I32 = 0, QMCL_DT_I64 = 1, QMCL_DT_F64 = 2 };
+enum { QMCL_OP_SUM = 0, QMCL_OP_MIN = 1, QMCL_OP_MAX = 2 };
+typedef struct qmcl_comm {
+  int rank, size;
+  void *ctx;
+  /* in place: buf holds size * bytes_per_rank bytes, this rank's part at
+   * rank * bytes_per_rank */
+  int (*allgather)(void *ctx, void *dev_buf, size_t bytes_per_rank, void *stream);
+  /* in place over `count` elements of dtype (QMCL_DT_*) with op (QMCL_OP_*) */
+  int (*allreduce)(void *ctx, void *dev_buf, size_t count, int dtype, int op, void *stream);
+  /* byte counts and offsets per peer (arrays of `size`) */
+  int (*alltoallv)(void *ctx, const void *dev_send, const uint64_t *send_bytes,
+                   const uint64_t *send_offsets, void *dev_recv, const uint64_t *recv_bytes,
+                   const uint64_t *recv_offsets, void *stream);
+} qmcl_comm;
+/* comm == NULL (or size 1) returns the filter to the single-GPU path. */
+qmcl_status qmcl_filter_set_comm(qmcl_filter *f, const qmcl_comm *comm);
+/* After a sharded resampling, move particles so that every rank again owns an
+ * equal contiguous block (default 1 = on). */
+qmcl_status qmcl_filter_set_rebalance(qmcl_filter *f, int enabled);
+/* This shard's block: first global index and local count. */
+qmcl_status qmcl_filter_shard_range(const qmcl_filter *f, uint64_t *first, uint64_t *count,
+                                    uint64_t *global_count);
+/* Pure host helpers of the sharded path (no device needed; used by the CPU
+ * tests of the multi-rank logic).
+ * qmcl_shard_slice: block [first, first+count) of rank `rank` of `size` over n.
+ * qmcl_lv_owner_range: output slots [m_lo, m_hi) of the low-variance resampler
+ * (particle_filter.cpp:225-238) whose position U_m = r + m * minv selects a
+ * particle of the shard whose running sum spans (c_lo, c_hi]. */
+void qmcl_shard_slice(uint64_t n, int rank, int size, uint64_t *first, uint64_t *count);
+void qmcl_lv_owner_range(uint64_t M, double r, double minv, double c_lo, double c_hi,
+                         int is_first, int is_last, uint64_t *m_lo, uint64_t *m_hi);
 
 /* IParticleFilter::set_parameters (particle_filter.cpp:177-184). */
 qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p);
@@ -182,6 +225,10 @@ qmcl_status qmcl_filter_copy_particles(const qmcl_filter *f, qmcl_particle *out,
 
 /* ---- test hooks (not part of the reference interface) ---- */
 qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n);
+/* Sharded variant: p[0..n) is this rank's block, starting at global index
+ * `global_first` of `global_count` particles. */
+qmcl_status qmcl_filter_set_particles_shard(qmcl_filter *f, const qmcl_particle *p, size_t n,
+                                            uint64_t global_first, uint64_t global_count);
 qmcl_status qmcl_filter_set_rng(qmcl_filter *f, uint64_t seed, uint32_t step);
 /* Pre-penalty total weight of the last sensor update. */
 qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out);

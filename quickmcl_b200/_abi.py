@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("QMCL_B200_LIB", os.path.join(_HERE, "libqmcl_b200.so"
 
 STATUS_NAMES = {0: "QMCL_OK", 1: "QMCL_ERR_INVALID_ARG", 2: "QMCL_ERR_NO_DEVICE",
                 3: "QMCL_ERR_CUDA", 4: "QMCL_ERR_NO_MAP", 5: "QMCL_ERR_INVALID_CLUSTER",
-                6: "QMCL_ERR_CAPACITY"}
+                6: "QMCL_ERR_CAPACITY", 7: "QMCL_ERR_COMM", 8: "QMCL_ERR_UNSUPPORTED"}
 
 
 class QmclError(RuntimeError):
@@ -74,7 +74,10 @@ SIGNATURES = {
     "qmcl_map_generate_random_pose": [vp, u64, u32, u64, pf32],
     "qmcl_filter_create": [vp, u64, C.POINTER(vp)],
     "qmcl_filter_destroy": [vp],
-    "qmcl_filter_set_shard": [vp, C.c_int, C.c_int],
+    "qmcl_filter_set_comm": [vp, vp],
+    "qmcl_filter_set_rebalance": [vp, C.c_int],
+    "qmcl_filter_shard_range": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
+    "qmcl_filter_set_particles_shard": [vp, pP, sz, u64, u64],
     "qmcl_filter_set_params": [vp, C.POINTER(PFParams)],
     "qmcl_filter_initialise": [vp, pf32, pf32],
     "qmcl_filter_initialise_factor": [vp, pf32, pf32],
@@ -108,6 +111,9 @@ _OTHER = {
     "qmcl_last_error": (C.c_char_p, []),
     "qmcl_kernel_launch_count": (u64, []),
     "qmcl_stage_name": (C.c_char_p, [C.c_int]),
+    "qmcl_shard_slice": (None, [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
+    "qmcl_lv_owner_range": (None, [u64, f64, f64, f64, f64, C.c_int, C.c_int, C.POINTER(u64),
+                                   C.POINTER(u64)]),
 }
 N_STAGES = 11
 

@@ -17,6 +17,7 @@
 #include "cluster.cuh"
 
 #include "scan.cuh"
+#include "shard.cuh"
 
 namespace qmcl {
 
@@ -244,9 +245,9 @@ cluster_weight_kernel(const float *__restrict__ x, const float *__restrict__ y,
                       const int32_t *__restrict__ label,
                       const int32_t *__restrict__ cluster_of_root,
                       int32_t *__restrict__ cid_out, unsigned long long *__restrict__ cluster_w,
-                      EstimateScalars *__restrict__ es) {
+                      EstimateScalars *__restrict__ es, size_t n_total) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int shift = fixed_point_shift(es->wmax_bits, n);
+  const int shift = fixed_point_shift(es->wmax_bits, n_total);
   int cid = -1;
   unsigned long long fx = 0;
   if (i < n) {
@@ -367,7 +368,7 @@ __device__ __forceinline__ double block_sum_256(double v, double *smem) {
 
 // statistics.cpp:50-79 + particle_filter.cpp:201-211 on the reduced moments
 // (b = best cluster, gsum = all particles).  out = {valid, pose[3], cov[9]}.
-__device__ void finalise_estimate(const double *b, const double *gsum, double *out) {
+__host__ __device__ void finalise_estimate(const double *b, const double *gsum, double *out) {
   for (int k = 0; k < 13; ++k) out[k] = 0.0;
   if (!(b[0] > 0)) return;
   out[0] = 1.0;
@@ -492,7 +493,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   f->n_clusters = 0;
   f->bins_built = false;
   f->clusters_valid = false;
-  if (n == 0) {
+  if (n == 0 && !sharded(f)) {
     f->grid = BinGrid{0, 0, 0, 0, 0, 0};
     f->bins_built = true;
     return QMCL_OK;
@@ -502,12 +503,31 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(f->bbox.ensure(8));
   bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
   QMCL_LAUNCHED();
-  const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
-  bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
-  QMCL_LAUNCHED();
+  if (n) {
+    const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
+    bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
+    QMCL_LAUNCHED();
+  }
   int hb[6];
-  QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
+  if (sharded(f)) {
+    // Exchange: the bin grid is the bounding box over all shards.
+    std::vector<int> all(6 * f->n_shards);
+    QMCL_TRY(shard_gather(f, f->bbox.ptr, true, 6 * sizeof(int), all.data()));
+    for (int d = 0; d < 6; ++d) hb[d] = all[d];
+    for (int r = 1; r < f->n_shards; ++r)
+      for (int d = 0; d < 3; ++d) {
+        hb[d] = std::min(hb[d], all[6 * r + d]);
+        hb[3 + d] = std::max(hb[3 + d], all[6 * r + 3 + d]);
+      }
+    if (hb[0] > hb[3]) {  // no particle anywhere
+      f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+      f->bins_built = true;
+      return QMCL_OK;
+    }
+  } else {
+    QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+  }
   BinGrid g;
   g.x0 = hb[0];
   g.y0 = hb[1];
@@ -527,9 +547,18 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   f->grid = g;
   QMCL_TRY(f->table.ensure(cells));
   QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0, cells * sizeof(int32_t), s));
-  bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);
-  QMCL_LAUNCHED();
-  const size_t max_bins = std::min(n, cells);
+  if (n) {
+    bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);
+    QMCL_LAUNCHED();
+  }
+  size_t n_all = n;
+  if (sharded(f)) {
+    // Exchange: bin occupancy counts summed over the shards; the occupied-bin
+    // list and the labels are then computed identically on every rank.
+    QMCL_TRY(shard_allreduce(f, f->table.ptr, cells, QMCL_DT_I32, QMCL_OP_SUM));
+    n_all = f->global_n;
+  }
+  const size_t max_bins = std::min(n_all, cells);
   QMCL_TRY(f->bin_cell.ensure(max_bins));
   QMCL_TRY(f->bin_count.ensure(max_bins));
   QMCL_TRY(f->bin_label.ensure(max_bins));
@@ -597,8 +626,10 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   cudaStream_t s = f->map->stream;
   *valid = 0;
   const ParticleSet &ps = f->cur();
-  if (ps.n == 0 && f->n_clusters == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
-  if (ps.n > 0 && (!f->bins_built || f->n_clusters == 0)) {
+  // every rank of a sharded filter must take the same branch here
+  const size_t n_any = sharded(f) ? f->global_n : ps.n;
+  if (n_any == 0 && f->n_clusters == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
+  if (n_any > 0 && (!f->bins_built || f->n_clusters == 0)) {
     set_error("get_estimate: particles have no cluster (call cluster() or resample first)");
     return QMCL_ERR_INVALID_CLUSTER;
   }
@@ -624,22 +655,55 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   if (ps.n) {
     wmax_kernel<<<std::min<unsigned>(blocks, 2 * kSMs), 256, 0, s>>>(ps.w.ptr, ps.n, es);
     QMCL_LAUNCHED();
+  }
+  if (sharded(f)) {
+    // Exchange: the fixed-point scale needs the largest weight of all shards.
+    std::vector<unsigned long long> all(f->n_shards);
+    QMCL_TRY(shard_gather(f, &es->wmax_bits, true, sizeof(unsigned long long), all.data()));
+    unsigned long long gmax = 0;
+    for (unsigned long long v : all) gmax = std::max(gmax, v);
+    QMCL_CUDA(copy_h2d(&es->wmax_bits, &gmax, sizeof(gmax), s));
+  }
+  if (ps.n) {
     cluster_weight_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(
         ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n, bp, f->grid, f->table.ptr, f->bin_label.ptr,
-        f->bin_cluster.ptr, f->particle_cid.ptr, cluster_w, es);
+        f->bin_cluster.ptr, f->particle_cid.ptr, cluster_w, es,
+        sharded(f) ? f->global_n : ps.n);
     QMCL_LAUNCHED();
   }
+  // Exchange: cluster weights are integers, so their sum over shards is exact
+  // and order-independent.
+  if (sharded(f)) QMCL_TRY(shard_allreduce(f, cluster_w, f->n_clusters, QMCL_DT_I64, QMCL_OP_SUM));
   best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, f->n_clusters, es);
   QMCL_LAUNCHED();
   moments_kernel<<<blocks, 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, f->particle_cid.ptr,
-                                        ps.n, base + o_part, es, base + o_sums, d_out, 1);
+                                        ps.n, base + o_part, es, base + o_sums, d_out,
+                                        sharded(f) ? 0 : 1);
   QMCL_LAUNCHED();
-  // one read back: out[0..13) + the invalid flag
   double h[16];
-  QMCL_CUDA(copy_d2h(h, d_out, 13 * sizeof(double), s));
   int flag = 0;
-  QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
+  if (sharded(f)) {
+    // Exchange: moments of the best cluster and of all particles, summed in rank order.
+    struct Part { double sums[2 * kMom]; double invalid; } mine;
+    QMCL_CUDA(copy_d2h(mine.sums, base + o_sums, sizeof(mine.sums), s));
+    QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    mine.invalid = flag;
+    std::vector<Part> parts(f->n_shards);
+    QMCL_TRY(shard_gather(f, &mine, false, sizeof(Part), parts.data()));
+    double tot[2 * kMom] = {0};
+    flag = 0;
+    for (const Part &pt : parts) {
+      for (int k = 0; k < 2 * kMom; ++k) tot[k] += pt.sums[k];
+      if (pt.invalid != 0.0) flag = 1;
+    }
+    finalise_estimate(tot + kMom, tot, h);
+  } else {
+    // one read back: out[0..13) + the invalid flag
+    QMCL_CUDA(copy_d2h(h, d_out, 13 * sizeof(double), s));
+    QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+  }
   if (flag) {
     set_error("get_estimate: a particle's bin has no cluster (reference abort()s here)");
     return QMCL_ERR_INVALID_CLUSTER;

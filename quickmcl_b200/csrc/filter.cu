@@ -6,6 +6,7 @@
 
 #include "filter.cuh"
 #include "sensor.cuh"
+#include "shard.cuh"
 
 namespace qmcl {
 
@@ -69,6 +70,15 @@ qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out) {
   return QMCL_OK;
 }
 
+// Sharded variant: the total is the sum of the shards' totals (known on the
+// host), N is the global particle count.
+__global__ void normalise_by_value_kernel(double *__restrict__ w, size_t n, double total,
+                                          double n_global) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  w[i] = (total > 0) ? __ddiv_rn(w[i], total) : __ddiv_rn(1.0, n_global);
+}
+
 // low_pass_filter.h:39-50
 static void lowpass_update(double *value, double alpha, double x) {
   if (*value == 0) *value = x;
@@ -80,11 +90,11 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   cudaStream_t s = m->stream;
-  if (ps.n == 0) {
+  if (ps.n == 0 && !sharded(f)) {
     f->last_total = 0.0;
     return QMCL_OK;
   }
-  QMCL_TRY(f->partials.ensure(sensor_grid(ps.n)));
+  QMCL_TRY(f->partials.ensure(sensor_grid(ps.n) + 1));
   SensorLaunch a;
   a.x = ps.x.ptr;
   a.y = ps.y.ptr;
@@ -95,23 +105,40 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
   a.n_beams = n_used;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
-  {
+  if (ps.n) {
     StageScope sc(f, QMCL_STAGE_SENSOR, 1);
     QMCL_TRY(launch_sensor(m, a));
+  } else {
+    QMCL_CUDA(cudaMemsetAsync(&f->scalars.ptr->total_weight, 0, sizeof(double), s));
   }
-  {
-    StageScope sc(f, QMCL_STAGE_NORMALISE);
-    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
-    QMCL_LAUNCHED();
+  double total = 0.0;
+  double n_total = static_cast<double>(ps.n);
+  if (sharded(f)) {
+    // Exchange 1: the pre-penalty total is the sum over shards.
+    std::vector<double> totals;
+    QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->total_weight, &totals));
+    total = ordered_sum(totals);
+    n_total = static_cast<double>(f->global_n);
+    if (ps.n) {
+      StageScope sc(f, QMCL_STAGE_NORMALISE);
+      normalise_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total, n_total);
+      QMCL_LAUNCHED();
+    }
+  } else {
+    {
+      StageScope sc(f, QMCL_STAGE_NORMALISE);
+      normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+      QMCL_LAUNCHED();
+    }
+    // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
+    // total: one 8-byte read back per scan.
+    QMCL_CUDA(copy_d2h(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    total = f->h_scalars.ptr[0];
   }
-  // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
-  // total: one 8-byte read back per scan.
-  QMCL_CUDA(copy_d2h(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
-  const double total = f->h_scalars.ptr[0];
   f->last_total = total;
   if (total > 0) {
-    const double avg = total / static_cast<double>(ps.n);
+    const double avg = total / n_total;
     lowpass_update(&f->w_slow, f->params.alpha_slow, avg);
     lowpass_update(&f->w_fast, f->params.alpha_fast, avg);
   }
@@ -163,6 +190,9 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->scratch.release();
   f->prefix_scratch.release();
   f->prefix_carry.release();
+  f->xchg.release();
+  f->xchg_send.release();
+  f->xchg_recv.release();
   f->bbox.release();
   f->table.release();
   f->bin_cell.release();
@@ -176,13 +206,6 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   qmcl_map *map = f->map;
   delete f;
   return qmcl_map_destroy(map);
-}
-
-qmcl_status qmcl_filter_set_shard(qmcl_filter *f, int shard_rank, int n_shards) {
-  if (!f || n_shards < 1 || shard_rank < 0 || shard_rank >= n_shards) return QMCL_ERR_INVALID_ARG;
-  f->shard_rank = shard_rank;
-  f->n_shards = n_shards;
-  return QMCL_OK;
 }
 
 // particle_filter.cpp:177-184 + space_partitioning.cpp:23-37
@@ -209,7 +232,16 @@ qmcl_status qmcl_filter_set_rng(qmcl_filter *f, uint64_t seed, uint32_t step) {
 
 qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
-  *out = f->cur().n;
+  *out = sharded(f) ? f->global_n : f->cur().n;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_set_particles_shard(qmcl_filter *f, const qmcl_particle *p, size_t n,
+                                            uint64_t global_first, uint64_t global_count) {
+  if (!f || global_first + n > global_count) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(qmcl_filter_set_particles(f, p, n));
+  f->global_first = global_first;
+  f->global_n = global_count;
   return QMCL_OK;
 }
 

@@ -172,7 +172,7 @@ prefix_chunk_sums_kernel(const double *__restrict__ w, size_t n, double *__restr
 // Exclusive scan of the chunk sums by one block, offset by the carry-in.
 __global__ void __launch_bounds__(1024)
 prefix_scan_chunk_sums_kernel(const double *__restrict__ chunk_sum, size_t nc, double carry_in,
-                              double *__restrict__ approx_in) {
+                              double *__restrict__ approx_in, double *__restrict__ total_out) {
   __shared__ double warp_tot[32];
   __shared__ double chunk_total;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -204,6 +204,7 @@ prefix_scan_chunk_sums_kernel(const double *__restrict__ chunk_sum, size_t nc, d
     carry += chunk_total;
     __syncthreads();
   }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
 struct PrefixBuffers {
@@ -460,23 +461,17 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double *out,
-                              double carry_in) {
-  cudaStream_t s = f->map->stream;
+namespace {
+
+struct PrefixPlan {
+  size_t nc, nt;
+  PrefixBuffers pb;
+};
+
+qmcl_status plan_prefix(qmcl_filter *f, size_t n, PrefixPlan *pl) {
   QMCL_TRY(f->prefix_carry.ensure(2));
-  if (!n) {
-    set_double_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr, carry_in);
-    QMCL_LAUNCHED();
-    return QMCL_OK;
-  }
-  if (f->prefix_mode == 1) {
-    sequential_prefix_kernel<<<1, 32, 0, s>>>(w, n, carry_in, out, f->prefix_carry.ptr);
-    QMCL_LAUNCHED();
-    return QMCL_OK;
-  }
   const size_t nc = (n + kChunk - 1) / kChunk;
   const size_t nt = (n + kTile - 1) / kTile;
-  // carve the scratch
   size_t off = 0;
   auto carve = [&](size_t bytes) {
     const size_t at = off;
@@ -487,9 +482,9 @@ qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double 
                o_ca1 = carve(nc * 8), o_ccin = carve(nc * 8), o_ta0 = carve(nt * 8),
                o_ta1 = carve(nt * 8), o_tcin = carve(nt * 8), o_cE = carve(nc * 2),
                o_tE = carve(nt * 2), o_cm = carve(nc), o_tm = carve(nt);
-  QMCL_TRY(f->prefix_scratch.ensure(off));
+  QMCL_TRY(f->prefix_scratch.ensure(off + 16));
   uint8_t *b = f->prefix_scratch.ptr;
-  PrefixBuffers pb;
+  PrefixBuffers &pb = pl->pb;
   pb.chunk_sum = reinterpret_cast<double *>(b + o_sum);
   pb.approx_in = reinterpret_cast<double *>(b + o_apx);
   pb.chunk_a0 = reinterpret_cast<unsigned long long *>(b + o_ca0);
@@ -503,18 +498,90 @@ qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double 
   pb.chunk_mode = b + o_cm;
   pb.tile_mode = b + o_tm;
   pb.carry_out = f->prefix_carry.ptr;
-  const unsigned tiles = static_cast<unsigned>(nt);
-  prefix_chunk_sums_kernel<<<tiles, 256, 0, s>>>(w, n, pb.chunk_sum);
+  pl->nc = nc;
+  pl->nt = nt;
+  return QMCL_OK;
+}
+
+}  // namespace
+
+// Phase 0: chunk sums; the shard's approximate total is left in prefix_carry[1].
+qmcl_status prefix_local_total(qmcl_filter *f, const double *w, size_t n) {
+  cudaStream_t s = f->map->stream;
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  if (!n) {
+    set_double_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr + 1, 0.0);
+    QMCL_LAUNCHED();
+    return QMCL_OK;
+  }
+  prefix_chunk_sums_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.pb.chunk_sum);
   QMCL_LAUNCHED();
-  prefix_scan_chunk_sums_kernel<<<1, 1024, 0, s>>>(pb.chunk_sum, nc, carry_in, pb.approx_in);
-  QMCL_LAUNCHED();
-  prefix_summaries_kernel<<<tiles, 256, 0, s>>>(w, n, nc, pb);
-  QMCL_LAUNCHED();
-  prefix_resolve_kernel<<<1, 32, 0, s>>>(w, n, nc, nt, carry_in, pb, out);
-  QMCL_LAUNCHED();
-  prefix_apply_kernel<<<tiles, 256, 0, s>>>(w, n, nc, pb, out);
+  prefix_scan_chunk_sums_kernel<<<1, 1024, 0, s>>>(pl.pb.chunk_sum, pl.nc, 0.0, pl.pb.approx_in,
+                                                  f->prefix_carry.ptr + 1);
   QMCL_LAUNCHED();
   return QMCL_OK;
+}
+
+// Phase 1: binade guesses from the approximate carry-in, chunk/tile summaries.
+qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double approx_carry_in) {
+  if (!n) return QMCL_OK;
+  cudaStream_t s = f->map->stream;
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  prefix_scan_chunk_sums_kernel<<<1, 1024, 0, s>>>(pl.pb.chunk_sum, pl.nc, approx_carry_in,
+                                                  pl.pb.approx_in, nullptr);
+  QMCL_LAUNCHED();
+  prefix_summaries_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.nc, pl.pb);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// Phase 2: exact carry through the shard; carry_out -> prefix_carry[0].
+qmcl_status prefix_resolve(qmcl_filter *f, const double *w, size_t n, double *out,
+                           double carry_in) {
+  cudaStream_t s = f->map->stream;
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  if (!n) {
+    set_double_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr, carry_in);
+    QMCL_LAUNCHED();
+    return QMCL_OK;
+  }
+  prefix_resolve_kernel<<<1, 32, 0, s>>>(w, n, pl.nc, pl.nt, carry_in, pl.pb, out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// Phase 3: expand.
+qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out) {
+  if (!n) return QMCL_OK;
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  prefix_apply_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, f->map->stream>>>(w, n, pl.nc, pl.pb,
+                                                                               out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double *out,
+                              double carry_in) {
+  cudaStream_t s = f->map->stream;
+  QMCL_TRY(f->prefix_carry.ensure(2));
+  if (f->prefix_mode == 1 && n) {
+    sequential_prefix_kernel<<<1, 32, 0, s>>>(w, n, carry_in, out, f->prefix_carry.ptr);
+    QMCL_LAUNCHED();
+    return QMCL_OK;
+  }
+  if (n) {
+    PrefixPlan pl;
+    QMCL_TRY(plan_prefix(f, n, &pl));
+    prefix_chunk_sums_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.pb.chunk_sum);
+    QMCL_LAUNCHED();
+  }
+  QMCL_TRY(prefix_summaries(f, w, n, carry_in));
+  QMCL_TRY(prefix_resolve(f, w, n, out, carry_in));
+  return prefix_apply(f, w, n, out);
 }
 
 }  // namespace qmcl

@@ -10,4 +10,15 @@ namespace qmcl {
 qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double *out,
                               double carry_in = 0.0);
 
+// The same in four steps, for shards that chain their carries:
+//   prefix_local_total : chunk sums; approximate shard total -> prefix_carry[1]
+//   prefix_summaries   : binade guesses from the approximate carry-in + summaries
+//   prefix_resolve     : exact carry through the shard; carry-out -> prefix_carry[0]
+//   prefix_apply       : expand into out[]
+qmcl_status prefix_local_total(qmcl_filter *f, const double *w, size_t n);
+qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double approx_carry_in);
+qmcl_status prefix_resolve(qmcl_filter *f, const double *w, size_t n, double *out,
+                           double carry_in);
+qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out);
+
 }  // namespace qmcl

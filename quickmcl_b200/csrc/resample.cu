@@ -16,6 +16,7 @@
 #include "cluster.cuh"
 #include "prefix.cuh"
 #include "scan.cuh"
+#include "shard.cuh"
 
 #include <cmath>
 
@@ -25,21 +26,23 @@ namespace qmcl {
 // particle_filter.cpp:225-238: U = r + m * minv (two rounded double ops), walk
 // to the first i with c_i >= U.  Deviation: i is clamped to
 // M-1 where the reference's .at(i) would throw.
+// Sharded use: this shard holds the running sums cdf[0..n_cdf) of its own block
+// and produces the output slots m_first + [0, count) that fall into it.
 __global__ void __launch_bounds__(256)
-lv_select_kernel(const double *__restrict__ cdf, size_t M, double r, double minv,
-                 int64_t *__restrict__ src) {
-  const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const double U = __dadd_rn(r, __dmul_rn(static_cast<double>(m), minv));
+lv_select_kernel(const double *__restrict__ cdf, size_t n_cdf, size_t m_first, size_t count,
+                 double r, double minv, int64_t *__restrict__ src) {
+  const size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double U = __dadd_rn(r, __dmul_rn(static_cast<double>(m_first + k), minv));
   // first i with !(U > c_i)
-  size_t lo = 0, hi = M;
+  size_t lo = 0, hi = n_cdf;
   while (lo < hi) {
     const size_t mid = (lo + hi) >> 1;
     if (U > cdf[mid]) lo = mid + 1;
     else hi = mid;
   }
-  if (lo > M - 1) lo = M - 1;
-  src[m] = static_cast<int64_t>(lo);
+  if (lo > n_cdf - 1) lo = n_cdf - 1;
+  src[k] = static_cast<int64_t>(lo);
 }
 
 // K12: copy pose and weight of the selected source (particle_filter.cpp:237).
@@ -250,15 +253,33 @@ divide_by_post_total_kernel(double *__restrict__ w, size_t n, const FilterScalar
   if (i < n) w[i] = __ddiv_rn(w[i], sc->post_total);
 }
 
+__global__ void __launch_bounds__(256)
+divide_by_value_kernel(double *__restrict__ w, size_t n, double total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = __ddiv_rn(w[i], total);
+}
+
 static qmcl_status normalise_current(qmcl_filter *f) {
   ParticleSet &ps = f->cur();
-  if (!ps.n) return QMCL_OK;
+  if (!ps.n && !sharded(f)) return QMCL_OK;
   cudaStream_t s = f->map->stream;
   StageScope sc(f, QMCL_STAGE_POST_NORMALISE);
-  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(div_up(ps.n, 256 * 4), 4 * kSMs));
+  const unsigned blocks = static_cast<unsigned>(
+      std::min<size_t>(std::max<size_t>(div_up(ps.n, 256 * 4), 1), 4 * kSMs));
   QMCL_TRY(f->partials.ensure(blocks));
   weight_sum_kernel<<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
   QMCL_LAUNCHED();
+  if (sharded(f)) {
+    // Exchange: the normalising total is the sum of the shards' totals.
+    std::vector<double> totals;
+    QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->post_total, &totals));
+    const double total = ordered_sum(totals);
+    if (ps.n) {
+      divide_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total);
+      QMCL_LAUNCHED();
+    }
+    return QMCL_OK;
+  }
   divide_by_post_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
   QMCL_LAUNCHED();
   return QMCL_OK;
@@ -296,7 +317,8 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
   const double r = uniform53(r4[0], r4[1]) * minv;
   {
     StageScope sc(f, QMCL_STAGE_SELECT);
-    lv_select_kernel<<<div_up(M, 256), 256, 0, s>>>(f->cdf.ptr, M, r, minv, f->src_index.ptr);
+    lv_select_kernel<<<div_up(M, 256), 256, 0, s>>>(f->cdf.ptr, M, 0, M, r, minv,
+                                                    f->src_index.ptr);
     QMCL_LAUNCHED();
   }
   {
@@ -306,6 +328,137 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
                                                  out.t.ptr, out.w.ptr);
     QMCL_LAUNCHED();
   }
+  return QMCL_OK;
+}
+
+// particle_filter.cpp:214-239 over a sharded particle set.  The
+// global CDF is the concatenation of the shards' running sums, chained through
+// one exact carry per shard; the output slots are global, and every shard
+// produces the slots whose position falls into its own CDF segment
+// (owner-computes: no particle leaves its GPU during selection).  The optional
+// rebalancing afterwards restores equal contiguous blocks with one all-to-all.
+static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleSet &in,
+                                                 ParticleSet &out) {
+  cudaStream_t s = f->map->stream;
+  const int G = f->n_shards, me = f->shard_rank;
+  const size_t M = f->global_n;
+  f->n_src_index = 0;
+  if (M == 0) {
+    out.n = 0;
+    return QMCL_OK;
+  }
+  QMCL_TRY(f->cdf.ensure(in.n + 1));
+  // 1. approximate shard totals -> approximate carry-ins (binade guesses only)
+  struct Info { double approx_total; double count; };
+  std::vector<Info> info(G);
+  {
+    StageScope sc(f, QMCL_STAGE_CDF);
+    QMCL_TRY(prefix_local_total(f, in.w.ptr, in.n));
+    Info mine;
+    QMCL_CUDA(copy_d2h(&mine.approx_total, f->prefix_carry.ptr + 1, sizeof(double), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    mine.count = static_cast<double>(in.n);
+    QMCL_TRY(shard_gather(f, &mine, false, sizeof(Info), info.data()));
+    double approx_in = 0.0;
+    for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
+    QMCL_TRY(prefix_summaries(f, in.w.ptr, in.n, approx_in));
+  }
+  // 2. the exact carry, shard after shard: carry[r] = running sum before shard r
+  std::vector<double> carry(G + 1, 0.0);
+  {
+    StageScope sc(f, QMCL_STAGE_CDF);
+    std::vector<double> round(G);
+    for (int r = 0; r < G; ++r) {
+      if (r == me) QMCL_TRY(prefix_resolve(f, in.w.ptr, in.n, f->cdf.ptr, carry[r]));
+      QMCL_TRY(shard_gather(f, f->prefix_carry.ptr, true, sizeof(double), round.data()));
+      carry[r + 1] = round[r];
+    }
+    QMCL_TRY(prefix_apply(f, in.w.ptr, in.n, f->cdf.ptr));
+  }
+  // 3. owner ranges of all shards (every rank computes the same table)
+  const double minv = static_cast<double>(1.0f / static_cast<float>(M));
+  uint32_t r4[4];
+  rng_draw(f->seed, f->step, P_LV_OFFSET, 0, r4);
+  const double r0 = uniform53(r4[0], r4[1]) * minv;
+  int first_rank = -1, last_rank = -1;
+  for (int r = 0; r < G; ++r)
+    if (info[r].count > 0) {
+      if (first_rank < 0) first_rank = r;
+      last_rank = r;
+    }
+  std::vector<uint64_t> m_lo(G, 0), m_hi(G, 0);
+  for (int r = 0; r < G; ++r) {
+    if (r < first_rank) {
+      m_lo[r] = m_hi[r] = 0;
+    } else if (r > last_rank) {
+      m_lo[r] = m_hi[r] = M;
+    } else {
+      // empty shards in between have carry[r] == carry[r + 1]: an empty range
+      qmcl_lv_owner_range(M, r0, minv, carry[r], carry[r + 1], r == first_rank, r == last_rank,
+                          &m_lo[r], &m_hi[r]);
+    }
+  }
+  const size_t n_out = static_cast<size_t>(m_hi[me] - m_lo[me]);
+  QMCL_TRY(out.ensure(n_out));
+  out.n = n_out;
+  QMCL_TRY(f->src_index.ensure(n_out + 1));
+  if (n_out) {
+    {
+      StageScope sc(f, QMCL_STAGE_SELECT);
+      lv_select_kernel<<<div_up(n_out, 256), 256, 0, s>>>(f->cdf.ptr, in.n, m_lo[me], n_out, r0, minv,
+                                                        f->src_index.ptr);
+      QMCL_LAUNCHED();
+    }
+    StageScope sc(f, QMCL_STAGE_GATHER);
+    gather_kernel<<<div_up(n_out, 256), 256, 0, s>>>(in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr,
+                                                     f->src_index.ptr, n_out, out.x.ptr, out.y.ptr,
+                                                     out.t.ptr, out.w.ptr);
+    QMCL_LAUNCHED();
+  }
+  f->n_src_index = n_out;
+  f->global_first = m_lo[me];
+  f->global_n = M;
+  // 4. rebalance to equal blocks
+  bool balanced = true;
+  for (int r = 0; r < G; ++r) {
+    size_t a, c;
+    shard_slice_of(M, r, G, &a, &c);
+    balanced &= (m_lo[r] == a && m_hi[r] == a + c);
+  }
+  if (!f->rebalance || balanced) return QMCL_OK;
+  StageScope sc(f, QMCL_STAGE_GATHER);
+  size_t my_a, my_c;
+  shard_slice_of(M, me, G, &my_a, &my_c);
+  std::vector<uint64_t> sb(G), so(G), rb(G), ro(G);
+  constexpr uint64_t kRec = sizeof(qmcl_particle);
+  for (int d = 0; d < G; ++d) {
+    size_t a, c;
+    shard_slice_of(M, d, G, &a, &c);
+    // what I send to d: [m_lo[me], m_hi[me]) ∩ [a, a+c)
+    const uint64_t lo = std::max<uint64_t>(m_lo[me], a), hi = std::min<uint64_t>(m_hi[me], a + c);
+    sb[d] = hi > lo ? (hi - lo) * kRec : 0;
+    so[d] = hi > lo ? (lo - m_lo[me]) * kRec : 0;
+    // what I receive from d: [m_lo[d], m_hi[d]) ∩ [my_a, my_a+my_c)
+    const uint64_t rlo = std::max<uint64_t>(m_lo[d], my_a),
+                   rhi = std::min<uint64_t>(m_hi[d], my_a + my_c);
+    rb[d] = rhi > rlo ? (rhi - rlo) * kRec : 0;
+    ro[d] = rhi > rlo ? (rlo - my_a) * kRec : 0;
+  }
+  QMCL_TRY(f->xchg_send.ensure(std::max<size_t>(n_out, 1) * kRec));
+  QMCL_TRY(f->xchg_recv.ensure(std::max<size_t>(my_c, 1) * kRec));
+  QMCL_TRY(launch_soa_to_aos(s, out.x.ptr, out.y.ptr, out.t.ptr, out.w.ptr, n_out,
+                             reinterpret_cast<qmcl_particle *>(f->xchg_send.ptr)));
+  if (f->comm.alltoallv(f->comm.ctx, f->xchg_send.ptr, sb.data(), so.data(), f->xchg_recv.ptr,
+                        rb.data(), ro.data(), s) != 0) {
+    set_error("qmcl_comm.alltoallv failed");
+    return QMCL_ERR_COMM;
+  }
+  f->n_collectives++;
+  QMCL_TRY(out.ensure(my_c));
+  out.n = my_c;
+  QMCL_TRY(launch_aos_to_soa(s, reinterpret_cast<const qmcl_particle *>(f->xchg_recv.ptr), my_c,
+                             out.x.ptr, out.y.ptr, out.t.ptr, out.w.ptr));
+  f->global_first = my_a;
   return QMCL_OK;
 }
 
@@ -467,6 +620,10 @@ extern "C" {
 qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  if (sharded(f) && f->params.resample_type != QMCL_RESAMPLE_LOW_VARIANCE) {
+    set_error("sharded filters resample with low_variance only (adaptive/KLD: single GPU)");
+    return QMCL_ERR_UNSUPPORTED;
+  }
   const ParticleSet &in = f->sets[f->current];
   ParticleSet &out = f->sets[(f->current + 1) % 2];
   f->current = (f->current + 1) % 2;
@@ -474,7 +631,8 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   bool clustered = false;
   switch (f->params.resample_type) {
   case QMCL_RESAMPLE_LOW_VARIANCE:
-    QMCL_TRY(resample_low_variance(f, in, out));
+    if (sharded(f)) QMCL_TRY(resample_low_variance_sharded(f, in, out));
+    else QMCL_TRY(resample_low_variance(f, in, out));
     break;
   case QMCL_RESAMPLE_ADAPTIVE:
     QMCL_TRY(resample_adaptive(f, in, out));
@@ -486,8 +644,10 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
     return QMCL_ERR_INVALID_ARG;
   }
   f->step++;
-  f->global_first = 0;
-  f->global_n = out.n;
+  if (!sharded(f)) {
+    f->global_first = 0;
+    f->global_n = out.n;
+  }
   if (!clustered) {
     if (f->params.resample_type == QMCL_RESAMPLE_KLD) {
       // failed KLD: bins stay reset, nothing to label

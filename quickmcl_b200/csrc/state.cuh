@@ -133,6 +133,11 @@ struct qmcl_filter {
   uint64_t seed = 0;
   uint32_t step = 0;
   int shard_rank = 0, n_shards = 1;
+  qmcl_comm comm{0, 1, nullptr, nullptr, nullptr, nullptr};
+  bool rebalance = true;
+  qmcl::DevBuf<uint8_t> xchg;        // collective payloads
+  qmcl::DevBuf<uint8_t> xchg_send, xchg_recv;  // particle rebalancing (AoS)
+  uint64_t n_collectives = 0;
   size_t global_first = 0;  // global index of local particle 0
   size_t global_n = 0;      // particles over all shards
 
