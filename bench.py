@@ -258,7 +258,9 @@ def run_b200(args, wl):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=120))
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
 
@@ -354,7 +356,7 @@ def run_b200(args, wl):
     clocks = sampler.stop() if rank == 0 else None
 
     # optional per-stage breakdown (untimed extra pass, stderr only)
-    if args.breakdown and rank == 0:
+    if args.breakdown:   # every rank takes part (the steps contain collectives)
         f.set_timing(2)
         f.get_timing(reset=True)
         for i in range(args.steps):
@@ -362,10 +364,11 @@ def run_b200(args, wl):
             step_device()
         tb = f.get_timing(reset=True)
         f.set_timing(0)
-        log("stage breakdown (device ms per step, CUDA events inside the library):")
-        for k, (ms, cnt) in tb.items():
-            if cnt:
-                log(f"  {k:15s} {ms / args.steps:9.4f} ms  ({cnt / args.steps:.1f} scopes/step)")
+        if rank == 0:
+            log("stage breakdown (device ms per step, CUDA events inside the library):")
+            for k, (ms, cnt) in tb.items():
+                if cnt:
+                    log(f"  {k:15s} {ms / args.steps:9.4f} ms  ({cnt / args.steps:.1f} scopes/step)")
 
     global_n = n
     evals_job = global_n * len(scan)
