@@ -68,12 +68,24 @@ bin_bbox_kernel(const float *__restrict__ x, const float *__restrict__ y,
       mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
   }
+  __shared__ int s_mn[8][3], s_mx[8][3];
+  const int wid = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      atomicMin(bbox + d, mn[d]);
-      atomicMax(bbox + 3 + d, mx[d]);
+      s_mn[wid][d] = mn[d];
+      s_mx[wid][d] = mx[d];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int a = INT_MAX, b = INT_MIN;
+    for (int k = 0; k < 8; ++k) {
+      a = min(a, s_mn[k][threadIdx.x]);
+      b = max(b, s_mx[k][threadIdx.x]);
+    }
+    atomicMin(bbox + threadIdx.x, a);
+    atomicMax(bbox + 3 + threadIdx.x, b);
   }
 }
 
@@ -92,7 +104,11 @@ bin_mark_kernel(const float *__restrict__ x, const float *__restrict__ y,
   int kx, ky, kt;
   bin_key(x[i], y[i], t[i], bp, &kx, &ky, &kt);
   const long long idx = grid_index(g, kx, ky, kt);
-  if (idx >= 0) atomicAdd(table + idx, 1);
+  // one atomic per distinct bin per warp (a tracking cloud has ~100 bins for
+  // 10^5 particles, so per-particle atomics would serialise on a few addresses)
+  const unsigned peers = __match_any_sync(__activemask(), idx);
+  if (idx >= 0 && (__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31))
+    atomicAdd(table + idx, __popc(peers));
 }
 
 struct OccupiedFlag {
@@ -487,8 +503,11 @@ static BinParams bin_params(const qmcl_filter *f) {
 
 // SpacePartitioning::reset + add_point for x/y/t[0..n): bbox, dense table,
 // sorted occupied-bin list.  Leaves parent[b] = b.
-qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n) {
+qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n,
+                       bool reuse_grid) {
   cudaStream_t s = f->map->stream;
+  const BinGrid prev_grid = f->grid;
+  const bool have_prev = reuse_grid && f->bins_built && prev_grid.nx > 0;
   f->n_bins = 0;
   f->n_clusters = 0;
   f->bins_built = false;
@@ -500,33 +519,42 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   }
   const BinParams bp = bin_params(f);
   StageScope sc(f, QMCL_STAGE_BINS);
-  QMCL_TRY(f->bbox.ensure(8));
-  bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
-  QMCL_LAUNCHED();
-  if (n) {
-    const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
-    bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
-    QMCL_LAUNCHED();
-  }
   int hb[6];
-  if (sharded(f)) {
-    // Exchange: the bin grid is the bounding box over all shards.
-    std::vector<int> all(6 * f->n_shards);
-    QMCL_TRY(shard_gather(f, f->bbox.ptr, true, 6 * sizeof(int), all.data()));
-    for (int d = 0; d < 6; ++d) hb[d] = all[d];
-    for (int r = 1; r < f->n_shards; ++r)
-      for (int d = 0; d < 3; ++d) {
-        hb[d] = std::min(hb[d], all[6 * r + d]);
-        hb[3 + d] = std::max(hb[3 + d], all[6 * r + 3 + d]);
-      }
-    if (hb[0] > hb[3]) {  // no particle anywhere
-      f->grid = BinGrid{0, 0, 0, 0, 0, 0};
-      f->bins_built = true;
-      return QMCL_OK;
-    }
+  if (have_prev) {
+    hb[0] = prev_grid.x0;
+    hb[1] = prev_grid.y0;
+    hb[2] = prev_grid.t0;
+    hb[3] = prev_grid.x0 + prev_grid.nx - 1;
+    hb[4] = prev_grid.y0 + prev_grid.ny - 1;
+    hb[5] = prev_grid.t0 + prev_grid.nt - 1;
   } else {
-    QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
-    QMCL_CUDA(cudaStreamSynchronize(s));
+    QMCL_TRY(f->bbox.ensure(8));
+    bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
+    QMCL_LAUNCHED();
+    if (n) {
+      const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
+      bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
+      QMCL_LAUNCHED();
+    }
+    if (sharded(f)) {
+      // Exchange: the bin grid is the bounding box over all shards.
+      std::vector<int> all(6 * f->n_shards);
+      QMCL_TRY(shard_gather(f, f->bbox.ptr, true, 6 * sizeof(int), all.data()));
+      for (int d = 0; d < 6; ++d) hb[d] = all[d];
+      for (int r = 1; r < f->n_shards; ++r)
+        for (int d = 0; d < 3; ++d) {
+          hb[d] = std::min(hb[d], all[6 * r + d]);
+          hb[3 + d] = std::max(hb[3 + d], all[6 * r + 3 + d]);
+        }
+      if (hb[0] > hb[3]) {  // no particle anywhere
+        f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+        f->bins_built = true;
+        return QMCL_OK;
+      }
+    } else {
+      QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
+      QMCL_CUDA(cudaStreamSynchronize(s));
+    }
   }
   BinGrid g;
   g.x0 = hb[0];

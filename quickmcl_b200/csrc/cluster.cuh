@@ -8,7 +8,11 @@
 namespace qmcl {
 
 // SpacePartitioning::reset + add_point for every pose in x/y/t[0..n).
-qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n);
+// reuse_grid: keep the dense grid (bounding box) of the previous call — valid
+// when the new poses are a subset of the previous ones; the sorted bin list
+// does not depend on the grid's extent.
+qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n,
+                       bool reuse_grid = false);
 // SpacePartitioning::assign_clusters on the bins built last.
 qmcl_status label_clusters(qmcl_filter *f);
 

@@ -272,12 +272,56 @@ prefix_summaries_kernel(const double *__restrict__ w, size_t n, size_t nc, Prefi
   }
 }
 
+// Exact running sums of one chunk from the exact carry `c` (warp-uniform), for
+// chunks whose summary cannot be used: the literal sequence of double
+// additions.  The warp stages the chunk in shared memory, lane 0 runs the
+// dependent chain (bound by the DADD latency, the loads are issued ahead in
+// groups of 16), the warp writes the result back coalesced.  (A closed-form
+// variant that re-summarised the lanes around the crossing was tried; on one
+// latency-bound warp its ~800 instructions per round were slower than these
+// 256 additions.)
+__device__ double exact_chunk(const double *__restrict__ w, size_t e0, int cnt, double c,
+                              double *__restrict__ out, int lane, double *s_w, double *s_o) {
+#pragma unroll
+  for (int i = 0; i < kChunk / 32; ++i) {
+    const int k = lane + 32 * i;
+    s_w[k] = (k < cnt) ? w[e0 + k] : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double cc = c;
+    for (int base = 0; base < kChunk; base += 16) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = s_w[base + i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        cc = __dadd_rn(cc, v[i]);
+        v[i] = cc;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s_o[base + i] = v[i];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kChunk / 32; ++i) {
+    const int k = lane + 32 * i;
+    if (k < cnt) out[e0 + k] = s_o[k];
+  }
+  const double r = s_o[cnt - 1];
+  __syncwarp();
+  return r;
+}
+
 // ---- phase 2: the exact carry through all tiles (one warp)
 __global__ void __launch_bounds__(32)
 prefix_resolve_kernel(const double *__restrict__ w, size_t n, size_t nc, size_t nt, double carry_in,
                       PrefixBuffers pb, double *__restrict__ out) {
-  __shared__ double s_w[kChunk];
-  __shared__ double s_o[kChunk];
+  // chunk summaries of the current batch of 32 tiles, staged on demand
+  __shared__ unsigned long long s_a0[32 * kTileChunks], s_a1[32 * kTileChunks];
+  __shared__ int16_t s_E[32 * kTileChunks];
+  __shared__ double s_w[kChunk], s_o[kChunk];
   const int lane = threadIdx.x;
   double c = carry_in;  // uniform across the warp
   for (size_t base = 0; base < nt; base += 32) {
@@ -307,8 +351,20 @@ prefix_resolve_kernel(const double *__restrict__ w, size_t n, size_t nc, size_t 
         continue;
       }
     }
-    // Walk these (up to) 32 tiles one by one.
+    // Walk these (up to) 32 tiles one by one; stage their chunk summaries first.
     const size_t t_end = (base + 32 < nt) ? base + 32 : nt;
+    {
+      const size_t cb = base * kTileChunks;
+      for (int i = lane; i < 32 * kTileChunks; i += 32) {
+        const size_t ch = cb + i;
+        if (ch < nc) {
+          s_a0[i] = pb.chunk_a0[ch];
+          s_a1[i] = pb.chunk_a1[ch];
+          s_E[i] = pb.chunk_E[ch];
+        }
+      }
+      __syncwarp();
+    }
     for (size_t tt = base; tt < t_end; ++tt) {
       const Fn tf = fn_shfl(f, static_cast<int>(tt - base));
       const int tE = __shfl_sync(0xffffffffu, E, static_cast<int>(tt - base));
@@ -330,20 +386,12 @@ prefix_resolve_kernel(const double *__restrict__ w, size_t n, size_t nc, size_t 
       }
       const size_t ch0 = tt * kTileChunks;
       const size_t ch1 = (ch0 + kTileChunks < nc) ? ch0 + kTileChunks : nc;
-      // lanes 0..7 fetch the tile's chunk summaries once
-      Fn lane_cf = fn_identity();
-      int lane_cE = kInvalidE;
-      if (ch0 + lane < ch1) {
-        lane_cf.a0 = pb.chunk_a0[ch0 + lane];
-        lane_cf.a1 = pb.chunk_a1[ch0 + lane];
-        lane_cE = pb.chunk_E[ch0 + lane];
-      }
       for (size_t ch = ch0; ch < ch1; ++ch) {
+        const int si = static_cast<int>(ch - base * kTileChunks);
         cE = biased_exponent_if_normal(c);
-        const int chE = __shfl_sync(0xffffffffu, lane_cE, static_cast<int>(ch - ch0));
-        const Fn cf = fn_shfl(lane_cf, static_cast<int>(ch - ch0));
+        const int chE = s_E[si];
         if (chE != kInvalidE && chE == cE) {
-          const unsigned long long Kend = fn_apply(cf, mantissa_int(c));
+          const unsigned long long Kend = fn_apply(Fn{s_a0[si], s_a1[si]}, mantissa_int(c));
           if (Kend < kKLimit) {
             if (lane == 0) {
               pb.chunk_cin[ch] = c;
@@ -353,26 +401,15 @@ prefix_resolve_kernel(const double *__restrict__ w, size_t n, size_t nc, size_t 
             continue;
           }
         }
-        // True sequential additions for this chunk.
         const size_t e0 = ch * kChunk;
         const int cnt = static_cast<int>((e0 + kChunk <= n) ? kChunk : n - e0);
-        for (int i = lane; i < kChunk; i += 32) s_w[i] = (i < cnt) ? w[e0 + i] : 0.0;
-        __syncwarp();
         if (lane == 0) {
-          double cc = c;
-#pragma unroll 8
-          for (int i = 0; i < kChunk; ++i) {
-            cc = __dadd_rn(cc, s_w[i]);
-            s_o[i] = cc;
-          }
-          pb.chunk_mode[ch] = MODE_SLOW;
+          pb.chunk_mode[ch] = MODE_SLOW;  // written here, phase 3 skips it
           pb.chunk_cin[ch] = c;
         }
-        __syncwarp();
-        for (int i = lane; i < cnt; i += 32) out[e0 + i] = s_o[i];
-        c = s_o[cnt - 1];
-        __syncwarp();
+        c = exact_chunk(w, e0, cnt, c, out, lane, s_w, s_o);
       }
+      __syncwarp();
     }
   }
   if (lane == 0) *pb.carry_out = c;

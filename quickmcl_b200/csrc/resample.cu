@@ -180,7 +180,12 @@ kld_first_kernel(const float *__restrict__ x, const float *__restrict__ y,
                  int32_t *__restrict__ table) {
   const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (m >= n) return;
-  atomicMin(table + kld_cell(x[m], y[m], t[m], kp, g), static_cast<int32_t>(m));
+  // lanes of a warp that fall into the same bin: the lowest lane has the
+  // smallest draw index, one atomic per distinct bin per warp
+  const long long cell = kld_cell(x[m], y[m], t[m], kp, g);
+  const unsigned peers = __match_any_sync(__activemask(), cell);
+  if ((__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31))
+    atomicMin(table + cell, static_cast<int32_t>(m));
 }
 
 // flag(m) = draw m opened a new bin.
@@ -200,7 +205,15 @@ struct StopRule {
   unsigned long long *first_stop;
   __device__ void operator()(size_t m, uint32_t before, uint32_t flag) const {
     const unsigned long long k = static_cast<unsigned long long>(before) + flag;
-    if (m >= kld_limit(k, kp)) atomicMin(first_stop, static_cast<unsigned long long>(m));
+    // Every draw past the stop point qualifies, so without aggregation most
+    // threads would hit one address: take the warp minimum first (m < 2^31)
+    // and skip warps that cannot lower the current value.
+    const unsigned cand = (m >= kld_limit(k, kp)) ? static_cast<unsigned>(m) : 0xffffffffu;
+    const unsigned mask = __activemask();
+    const unsigned wmin = __reduce_min_sync(mask, cand);
+    if (wmin != 0xffffffffu && cand == wmin &&
+        static_cast<unsigned long long>(wmin) < *reinterpret_cast<volatile unsigned long long *>(first_stop))
+      atomicMin(first_stop, static_cast<unsigned long long>(wmin));
   }
 };
 
@@ -603,8 +616,9 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
     f->w_fast = 0;
     f->w_slow = 0;
   }
-  // the bins the reference holds at this point are those of the kept draws
-  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_out));
+  // the bins the reference holds at this point are those of the kept draws; they
+  // lie inside the candidates' bounding box, so the grid is reused
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_out, true));
   QMCL_TRY(label_clusters(f));
   *clustered = true;
   return QMCL_OK;
