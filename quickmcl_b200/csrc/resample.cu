@@ -344,6 +344,93 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
   return QMCL_OK;
 }
 
+// The exact (sequentially rounded) running sum of a sharded weight array:
+// f->cdf[i] = global running sum after local particle i.  carry[r] = running
+// sum before shard r's first particle (carry[G] = grand total), the same bits
+// on every rank; count[r] = particles of shard r.
+qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
+                                 std::vector<double> *carry_out, std::vector<double> *count_out) {
+  cudaStream_t s = f->map->stream;
+  const int G = f->n_shards, me = f->shard_rank;
+  QMCL_TRY(f->cdf.ensure(n + 1));
+  StageScope sc(f, QMCL_STAGE_CDF);
+  // approximate shard totals -> approximate carry-ins (binade guesses only)
+  struct Info { double approx_total; double count; };
+  std::vector<Info> info(G);
+  QMCL_TRY(prefix_local_total(f, w, n));
+  Info mine;
+  QMCL_CUDA(copy_d2h(&mine.approx_total, f->prefix_carry.ptr + 1, sizeof(double), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  mine.count = static_cast<double>(n);
+  QMCL_TRY(shard_gather(f, &mine, false, sizeof(Info), info.data()));
+  double approx_in = 0.0;
+  for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
+  QMCL_TRY(prefix_summaries(f, w, n, approx_in));
+  // the exact carry, shard after shard
+  std::vector<double> &carry = *carry_out;
+  carry.assign(G + 1, 0.0);
+  std::vector<double> round(G);
+  for (int r = 0; r < G; ++r) {
+    if (r == me) QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[r]));
+    QMCL_TRY(shard_gather(f, f->prefix_carry.ptr, true, sizeof(double), round.data()));
+    carry[r + 1] = round[r];
+  }
+  QMCL_TRY(prefix_apply(f, w, n, f->cdf.ptr));
+  count_out->resize(G);
+  for (int r = 0; r < G; ++r) (*count_out)[r] = info[r].count;
+  return QMCL_OK;
+}
+
+// Moves particles so that every rank owns its equal contiguous block of the M
+// global slots again.  lo/hi: the slot range [lo[r], hi[r]) rank r holds now
+// (consecutive, tiling [0, M)); `set` holds this rank's slots in order.
+qmcl_status rebalance_blocks(qmcl_filter *f, ParticleSet &set, const std::vector<uint64_t> &lo,
+                             const std::vector<uint64_t> &hi, size_t M) {
+  cudaStream_t s = f->map->stream;
+  const int G = f->n_shards, me = f->shard_rank;
+  bool balanced = true;
+  for (int r = 0; r < G; ++r) {
+    size_t a, c;
+    shard_slice_of(M, r, G, &a, &c);
+    balanced &= (lo[r] == a && hi[r] == a + c);
+  }
+  if (!f->rebalance || balanced) return QMCL_OK;
+  StageScope sc(f, QMCL_STAGE_GATHER);
+  const size_t n_have = static_cast<size_t>(hi[me] - lo[me]);
+  size_t my_a, my_c;
+  shard_slice_of(M, me, G, &my_a, &my_c);
+  std::vector<uint64_t> sb(G), so(G), rb(G), ro(G);
+  constexpr uint64_t kRec = sizeof(qmcl_particle);
+  for (int d = 0; d < G; ++d) {
+    size_t a, c;
+    shard_slice_of(M, d, G, &a, &c);
+    // what I send to d: [lo[me], hi[me]) ∩ [a, a+c)
+    const uint64_t l = std::max<uint64_t>(lo[me], a), h = std::min<uint64_t>(hi[me], a + c);
+    sb[d] = h > l ? (h - l) * kRec : 0;
+    so[d] = h > l ? (l - lo[me]) * kRec : 0;
+    // what I receive from d: [lo[d], hi[d]) ∩ [my_a, my_a+my_c)
+    const uint64_t rl = std::max<uint64_t>(lo[d], my_a), rh = std::min<uint64_t>(hi[d], my_a + my_c);
+    rb[d] = rh > rl ? (rh - rl) * kRec : 0;
+    ro[d] = rh > rl ? (rl - my_a) * kRec : 0;
+  }
+  QMCL_TRY(f->xchg_send.ensure(std::max<size_t>(n_have, 1) * kRec));
+  QMCL_TRY(f->xchg_recv.ensure(std::max<size_t>(my_c, 1) * kRec));
+  QMCL_TRY(launch_soa_to_aos(s, set.x.ptr, set.y.ptr, set.t.ptr, set.w.ptr, n_have,
+                             reinterpret_cast<qmcl_particle *>(f->xchg_send.ptr)));
+  if (f->comm.alltoallv(f->comm.ctx, f->xchg_send.ptr, sb.data(), so.data(), f->xchg_recv.ptr,
+                        rb.data(), ro.data(), s) != 0) {
+    set_error("qmcl_comm.alltoallv failed");
+    return QMCL_ERR_COMM;
+  }
+  f->n_collectives++;
+  QMCL_TRY(set.ensure(my_c));
+  set.n = my_c;
+  QMCL_TRY(launch_aos_to_soa(s, reinterpret_cast<const qmcl_particle *>(f->xchg_recv.ptr), my_c,
+                             set.x.ptr, set.y.ptr, set.t.ptr, set.w.ptr));
+  f->global_first = my_a;
+  return QMCL_OK;
+}
+
 // particle_filter.cpp:214-239 over a sharded particle set.  The
 // global CDF is the concatenation of the shards' running sums, chained through
 // one exact carry per shard; the output slots are global, and every shard
@@ -360,34 +447,11 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
     out.n = 0;
     return QMCL_OK;
   }
-  QMCL_TRY(f->cdf.ensure(in.n + 1));
-  // 1. approximate shard totals -> approximate carry-ins (binade guesses only)
-  struct Info { double approx_total; double count; };
+  std::vector<double> carry, count;
+  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count));
+  struct Info { double count; };
   std::vector<Info> info(G);
-  {
-    StageScope sc(f, QMCL_STAGE_CDF);
-    QMCL_TRY(prefix_local_total(f, in.w.ptr, in.n));
-    Info mine;
-    QMCL_CUDA(copy_d2h(&mine.approx_total, f->prefix_carry.ptr + 1, sizeof(double), s));
-    QMCL_CUDA(cudaStreamSynchronize(s));
-    mine.count = static_cast<double>(in.n);
-    QMCL_TRY(shard_gather(f, &mine, false, sizeof(Info), info.data()));
-    double approx_in = 0.0;
-    for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
-    QMCL_TRY(prefix_summaries(f, in.w.ptr, in.n, approx_in));
-  }
-  // 2. the exact carry, shard after shard: carry[r] = running sum before shard r
-  std::vector<double> carry(G + 1, 0.0);
-  {
-    StageScope sc(f, QMCL_STAGE_CDF);
-    std::vector<double> round(G);
-    for (int r = 0; r < G; ++r) {
-      if (r == me) QMCL_TRY(prefix_resolve(f, in.w.ptr, in.n, f->cdf.ptr, carry[r]));
-      QMCL_TRY(shard_gather(f, f->prefix_carry.ptr, true, sizeof(double), round.data()));
-      carry[r + 1] = round[r];
-    }
-    QMCL_TRY(prefix_apply(f, in.w.ptr, in.n, f->cdf.ptr));
-  }
+  for (int r = 0; r < G; ++r) info[r].count = count[r];
   // 3. owner ranges of all shards (every rank computes the same table)
   const double minv = static_cast<double>(1.0f / static_cast<float>(M));
   uint32_t r4[4];
@@ -432,47 +496,7 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
   f->global_first = m_lo[me];
   f->global_n = M;
   // 4. rebalance to equal blocks
-  bool balanced = true;
-  for (int r = 0; r < G; ++r) {
-    size_t a, c;
-    shard_slice_of(M, r, G, &a, &c);
-    balanced &= (m_lo[r] == a && m_hi[r] == a + c);
-  }
-  if (!f->rebalance || balanced) return QMCL_OK;
-  StageScope sc(f, QMCL_STAGE_GATHER);
-  size_t my_a, my_c;
-  shard_slice_of(M, me, G, &my_a, &my_c);
-  std::vector<uint64_t> sb(G), so(G), rb(G), ro(G);
-  constexpr uint64_t kRec = sizeof(qmcl_particle);
-  for (int d = 0; d < G; ++d) {
-    size_t a, c;
-    shard_slice_of(M, d, G, &a, &c);
-    // what I send to d: [m_lo[me], m_hi[me]) ∩ [a, a+c)
-    const uint64_t lo = std::max<uint64_t>(m_lo[me], a), hi = std::min<uint64_t>(m_hi[me], a + c);
-    sb[d] = hi > lo ? (hi - lo) * kRec : 0;
-    so[d] = hi > lo ? (lo - m_lo[me]) * kRec : 0;
-    // what I receive from d: [m_lo[d], m_hi[d]) ∩ [my_a, my_a+my_c)
-    const uint64_t rlo = std::max<uint64_t>(m_lo[d], my_a),
-                   rhi = std::min<uint64_t>(m_hi[d], my_a + my_c);
-    rb[d] = rhi > rlo ? (rhi - rlo) * kRec : 0;
-    ro[d] = rhi > rlo ? (rlo - my_a) * kRec : 0;
-  }
-  QMCL_TRY(f->xchg_send.ensure(std::max<size_t>(n_out, 1) * kRec));
-  QMCL_TRY(f->xchg_recv.ensure(std::max<size_t>(my_c, 1) * kRec));
-  QMCL_TRY(launch_soa_to_aos(s, out.x.ptr, out.y.ptr, out.t.ptr, out.w.ptr, n_out,
-                             reinterpret_cast<qmcl_particle *>(f->xchg_send.ptr)));
-  if (f->comm.alltoallv(f->comm.ctx, f->xchg_send.ptr, sb.data(), so.data(), f->xchg_recv.ptr,
-                        rb.data(), ro.data(), s) != 0) {
-    set_error("qmcl_comm.alltoallv failed");
-    return QMCL_ERR_COMM;
-  }
-  f->n_collectives++;
-  QMCL_TRY(out.ensure(my_c));
-  out.n = my_c;
-  QMCL_TRY(launch_aos_to_soa(s, reinterpret_cast<const qmcl_particle *>(f->xchg_recv.ptr), my_c,
-                             out.x.ptr, out.y.ptr, out.t.ptr, out.w.ptr));
-  f->global_first = my_a;
-  return QMCL_OK;
+  return rebalance_blocks(f, out, m_lo, m_hi, M);
 }
 
 // Builds the running-sum records of `in`; *P_out = number of records,
@@ -624,6 +648,455 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   return QMCL_OK;
 }
 
+// ===================================================================== sharded
+// Adaptive and KLD resampling over a sharded particle set.  Draws
+// come from the counter-based stream, so every rank can enumerate all of them;
+// a rank keeps the draws whose running-sum record lies in its own block
+// (owner computes), one all-to-all then delivers every output slot m to the
+// rank that owns slot m's block, and the KLD stop rule runs on the
+// slot-ordered shards with a min-allreduce of the per-bin first draw index.
+
+constexpr int kMaxShards = 32;
+
+// Keys (running sum before a positive-weight particle) at the edges of each
+// shard's record list, the same on every rank.
+struct ShardKeys {
+  int G, me;
+  unsigned long long per;  // slots per block (ceil)
+  int has[kMaxShards];
+  double first[kMaxShards];   // key of the shard's first record
+  double second[kMaxShards];  // smallest key > first (inf if none)
+  double last[kMaxShards];    // key of its last record
+};
+
+// The shard holding the record ParticlesRunningSum::lookup_index(r) returns:
+// the record with the largest key <= r, the first one among equal keys
+// (particle.h:99-107, particle.cpp:77).  Equal keys across a shard boundary
+// happen when the weights in between are too small to move the sum.
+__device__ __forceinline__ int draw_owner(const ShardKeys &T, double rr) {
+  int p = 0;
+  for (int s = 0; s < T.G; ++s)
+    if (T.has[s] && T.first[s] <= rr) p = s;
+  if (rr < T.second[p]) {  // the record found has key == first[p]: look for earlier equals
+    const double K = T.first[p];
+    for (int s = p - 1; s >= 0; --s) {
+      if (!T.has[s]) continue;
+      if (T.last[s] != K) break;
+      p = s;
+      if (T.first[s] != K) break;
+    }
+  }
+  return p;
+}
+__device__ __forceinline__ int slot_owner(const ShardKeys &T, size_t m) {
+  const unsigned long long o = m / T.per;
+  return static_cast<int>(o < static_cast<unsigned long long>(T.G) ? o : T.G - 1);
+}
+
+struct SlotRec {  // one output slot in flight (32 bytes)
+  long long m;
+  float x, y, t;
+  uint32_t src;  // global source index, 0xffffffff = injected
+  double w;
+};
+
+struct DrawCtx {
+  ShardKeys T;
+  uint64_t seed;
+  uint32_t step;
+  double w_diff;
+};
+
+struct OwnedFlag {
+  DrawCtx c;
+  __device__ uint32_t operator()(size_t m) const {
+    uint32_t r[4];
+    rng_draw(c.seed, c.step, P_DRAW, m, r);
+    if (uniform53(r[0], r[1]) < c.w_diff) return slot_owner(c.T, m) == c.T.me ? 1u : 0u;
+    return draw_owner(c.T, uniform53(r[2], r[3])) == c.T.me ? 1u : 0u;
+  }
+};
+
+struct EmitOwned {
+  DrawCtx c;
+  const float *ix, *iy, *it;
+  const double *iw;
+  const int64_t *pos;
+  const double *incl;
+  size_t P;
+  size_t global_first;
+  const int32_t *free_xy;
+  unsigned long long n_free;
+  MapGeom g;
+  SlotRec *rec;
+  __device__ void operator()(size_t m, uint32_t at, uint32_t flag) const {
+    if (!flag) return;
+    uint32_t r[4];
+    rng_draw(c.seed, c.step, P_DRAW, m, r);
+    SlotRec o;
+    o.m = static_cast<long long>(m);
+    if (uniform53(r[0], r[1]) < c.w_diff) {
+      uint32_t q[4];
+      rng_draw(c.seed, c.step, P_INJECT, m, q);
+      random_free_pose(free_xy, n_free, g, q, &o.x, &o.y, &o.t);
+      o.w = 0.0;
+      o.src = 0xffffffffu;
+    } else {
+      const int64_t sidx = pos[running_sum_lookup(incl, P, uniform53(r[2], r[3]))];
+      o.x = ix[sidx];
+      o.y = iy[sidx];
+      o.t = it[sidx];
+      o.w = iw[sidx];
+      o.src = static_cast<uint32_t>(global_first + static_cast<size_t>(sidx));
+    }
+    rec[at] = o;
+  }
+};
+
+// {has, first, second, last} of this shard's record list.
+__global__ void shard_keys_kernel(const double *__restrict__ incl, size_t P, double carry_in,
+                                  double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out[0] = P ? 1.0 : 0.0;
+  out[1] = carry_in;
+  // keys: carry_in, incl[0], ..., incl[P-2]; second = first key > carry_in
+  size_t lo = 0, hi = P ? P - 1 : 0;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (incl[mid] > carry_in) hi = mid;
+    else lo = mid + 1;
+  }
+  out[2] = (P >= 2 && lo < P - 1) ? incl[lo] : __longlong_as_double(0x7ff0000000000000ll);
+  out[3] = (P >= 2) ? incl[P - 2] : carry_in;
+}
+
+// bounds[d] = first record whose slot is >= d * per (records are sorted by slot).
+__global__ void dest_bounds_kernel(const SlotRec *__restrict__ rec, size_t n_rec,
+                                   unsigned long long per, int G,
+                                   unsigned long long *__restrict__ bounds) {
+  const int d = threadIdx.x;
+  if (d > G) return;
+  const long long key = static_cast<long long>(per) * d;
+  size_t lo = 0, hi = n_rec;
+  if (d == G) lo = n_rec;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (rec[mid].m < key) lo = mid + 1;
+    else hi = mid;
+  }
+  bounds[d] = lo;
+}
+
+__global__ void __launch_bounds__(256)
+scatter_slots_kernel(const SlotRec *__restrict__ rec, size_t n_rec, size_t slot_first,
+                     float *__restrict__ x, float *__restrict__ y, float *__restrict__ t,
+                     double *__restrict__ w, int64_t *__restrict__ src) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rec) return;
+  const SlotRec r = rec[i];
+  const size_t k = static_cast<size_t>(r.m) - slot_first;
+  x[k] = r.x;
+  y[k] = r.y;
+  t[k] = r.t;
+  w[k] = r.w;
+  src[k] = r.src == 0xffffffffu ? -1 : static_cast<int64_t>(r.src);
+}
+
+// Fills `out` with this rank's block of the n_draws output slots.  *ok = false
+// (on every rank alike) when no particle has weight.
+static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in, ParticleSet &out,
+                                          size_t n_draws, double w_diff, bool *ok) {
+  cudaStream_t s = f->map->stream;
+  const int G = f->n_shards, me = f->shard_rank;
+  *ok = false;
+  if (G > kMaxShards) {
+    set_error("sharded adaptive/KLD resampling supports at most %d shards", kMaxShards);
+    return QMCL_ERR_CAPACITY;
+  }
+  size_t my_first, my_count;
+  shard_slice_of(n_draws, me, G, &my_first, &my_count);
+  // 1. exact global running sum + local records
+  std::vector<double> carry, count;
+  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count));
+  if (!(carry[G] > 0)) return QMCL_OK;  // "No particles have any weights!"
+  if (w_diff > 0 && f->map->n_free == 0) {
+    set_error("adaptive injection needs a map with free cells");
+    return QMCL_ERR_NO_MAP;
+  }
+  QMCL_TRY(f->pos.ensure(in.n + 1));
+  QMCL_TRY(f->incl.ensure(in.n + 1));
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(std::max(in.n, n_draws)) + 16 + 2 * (kMaxShards + 2)));
+  unsigned long long P = 0;
+  {
+    StageScope sc(f, QMCL_STAGE_CDF);
+    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
+        f->scan_tmp.ptr + ((scan_blocks(std::max(in.n, n_draws)) + 1) & ~1u));
+    QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
+                         in.n, f->scan_tmp.ptr, d_total));
+    QMCL_CUDA(copy_d2h(&P, d_total, sizeof(P), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+  }
+  // 2. the shards' edge keys
+  struct Keys { double has, first, second, last; };
+  std::vector<Keys> keys(G);
+  {
+    QMCL_TRY(f->partials.ensure(8));
+    shard_keys_kernel<<<1, 32, 0, s>>>(f->incl.ptr, P, carry[me], f->partials.ptr);
+    QMCL_LAUNCHED();
+    QMCL_TRY(shard_gather(f, f->partials.ptr, true, sizeof(Keys), keys.data()));
+  }
+  DrawCtx ctx;
+  ctx.T.G = G;
+  ctx.T.me = me;
+  ctx.T.per = std::max<size_t>((n_draws + G - 1) / G, 1);
+  for (int r = 0; r < G; ++r) {
+    ctx.T.has[r] = keys[r].has != 0.0;
+    ctx.T.first[r] = keys[r].first;
+    ctx.T.second[r] = keys[r].second;
+    ctx.T.last[r] = keys[r].last;
+  }
+  ctx.seed = f->seed;
+  ctx.step = f->step;
+  ctx.w_diff = w_diff;
+  // 3. the draws this rank owns, compacted in slot order
+  StageScope sc(f, QMCL_STAGE_SELECT);
+  const unsigned blocks = scan_blocks(n_draws);
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((blocks + 1) & ~1u));
+  const OwnedFlag flag{ctx};
+  scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(flag, n_draws, f->scan_tmp.ptr);
+  QMCL_LAUNCHED();
+  scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_tmp.ptr, blocks, d_total);
+  QMCL_LAUNCHED();
+  unsigned long long n_owned = 0;
+  QMCL_CUDA(copy_d2h(&n_owned, d_total, sizeof(n_owned), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  QMCL_TRY(f->xchg_send.ensure((n_owned + 1) * sizeof(SlotRec)));
+  SlotRec *send = reinterpret_cast<SlotRec *>(f->xchg_send.ptr);
+  const EmitOwned emit{ctx,        in.x.ptr,          in.y.ptr,
+                       in.t.ptr,   in.w.ptr,          f->pos.ptr,
+                       f->incl.ptr, static_cast<size_t>(P), f->global_first,
+                       f->map->free_cells.ptr, f->map->n_free, f->map->geom, send};
+  scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(flag, emit, n_draws, f->scan_tmp.ptr);
+  QMCL_LAUNCHED();
+  // 4. deliver every slot to the rank that owns its block
+  std::vector<unsigned long long> bounds(G + 1);
+  {
+    unsigned long long *d_bounds = d_total + 2;  // inside the allocation made above
+    dest_bounds_kernel<<<1, 64, 0, s>>>(send, n_owned, ctx.T.per, G, d_bounds);
+    QMCL_LAUNCHED();
+    QMCL_CUDA(copy_d2h(bounds.data(), d_bounds, (G + 1) * sizeof(unsigned long long), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<uint64_t> sb(G), so(G), rb(G), ro(G), matrix(static_cast<size_t>(G) * G);
+  for (int d = 0; d < G; ++d) {
+    sb[d] = (bounds[d + 1] - bounds[d]) * sizeof(SlotRec);
+    so[d] = bounds[d] * sizeof(SlotRec);
+  }
+  QMCL_TRY(shard_gather(f, sb.data(), false, G * sizeof(uint64_t), matrix.data()));
+  uint64_t at = 0;
+  for (int r = 0; r < G; ++r) {
+    rb[r] = matrix[static_cast<size_t>(r) * G + me];
+    ro[r] = at;
+    at += rb[r];
+  }
+  if (at != my_count * sizeof(SlotRec)) {
+    set_error("sharded resampling: rank %d received %llu slots, expected %llu", me,
+              static_cast<unsigned long long>(at / sizeof(SlotRec)),
+              static_cast<unsigned long long>(my_count));
+    return QMCL_ERR_COMM;
+  }
+  QMCL_TRY(f->xchg_recv.ensure((my_count + 1) * sizeof(SlotRec)));
+  if (f->comm.alltoallv(f->comm.ctx, f->xchg_send.ptr, sb.data(), so.data(), f->xchg_recv.ptr,
+                        rb.data(), ro.data(), s) != 0) {
+    set_error("qmcl_comm.alltoallv failed");
+    return QMCL_ERR_COMM;
+  }
+  f->n_collectives++;
+  QMCL_TRY(out.ensure(my_count));
+  QMCL_TRY(f->src_index.ensure(my_count + 1));
+  out.n = my_count;
+  if (my_count) {
+    scatter_slots_kernel<<<div_up(my_count, 256), 256, 0, s>>>(
+        reinterpret_cast<const SlotRec *>(f->xchg_recv.ptr), my_count, my_first, out.x.ptr,
+        out.y.ptr, out.t.ptr, out.w.ptr, f->src_index.ptr);
+    QMCL_LAUNCHED();
+  }
+  f->n_src_index = my_count;
+  f->global_first = my_first;
+  f->global_n = n_draws;
+  *ok = true;
+  return QMCL_OK;
+}
+
+// particle_filter.cpp:241-291, sharded.
+static qmcl_status resample_adaptive_sharded(qmcl_filter *f, const ParticleSet &in,
+                                             ParticleSet &out) {
+  const double w_diff = adaptiveness(f);
+  const size_t n_out = static_cast<size_t>(f->params.particle_count_min);
+  bool ok = false;
+  f->n_src_index = 0;
+  QMCL_TRY(resample_draws_sharded(f, in, out, n_out, w_diff, &ok));
+  if (!ok) {
+    // failure path of the reference: the output buffer is resized, not filled;
+    // here every slot of the block is a default particle
+    size_t a, c;
+    shard_slice_of(n_out, f->shard_rank, f->n_shards, &a, &c);
+    QMCL_TRY(out.ensure(c));
+    if (c) {
+      fill_default_kernel<<<div_up(c, 256), 256, 0, f->map->stream>>>(out.x.ptr, out.y.ptr,
+                                                                     out.t.ptr, out.w.ptr, 0, c);
+      QMCL_LAUNCHED();
+    }
+    out.n = c;
+    f->global_first = a;
+    f->global_n = n_out;
+    return QMCL_OK;
+  }
+  if (w_diff > 0.0) {
+    f->w_fast = 0;
+    f->w_slow = 0;
+  }
+  return QMCL_OK;
+}
+
+// Sharded variants of the KLD scan functors: slot index and bin count are global.
+struct NewBinFlagAt {
+  const float *x, *y, *t;
+  KldParams kp;
+  BinGrid g;
+  const int32_t *table;
+  size_t slot_first;
+  __device__ uint32_t operator()(size_t i) const {
+    return table[kld_cell(x[i], y[i], t[i], kp, g)] == static_cast<int32_t>(slot_first + i) ? 1u : 0u;
+  }
+};
+struct StopRuleAt {
+  KldParams kp;
+  unsigned long long *first_stop;
+  size_t slot_first;
+  unsigned long long bins_before;  // new bins opened by the earlier shards
+  __device__ void operator()(size_t i, uint32_t before, uint32_t flag) const {
+    const unsigned long long k = bins_before + before + flag;
+    const size_t m = slot_first + i;
+    const unsigned cand = (m >= kld_limit(k, kp)) ? static_cast<unsigned>(m) : 0xffffffffu;
+    const unsigned mask = __activemask();
+    const unsigned wmin = __reduce_min_sync(mask, cand);
+    if (wmin != 0xffffffffu && cand == wmin &&
+        static_cast<unsigned long long>(wmin) < *reinterpret_cast<volatile unsigned long long *>(first_stop))
+      atomicMin(first_stop, static_cast<unsigned long long>(wmin));
+  }
+};
+__global__ void __launch_bounds__(256)
+kld_first_at_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                    const float *__restrict__ t, size_t n, size_t slot_first, KldParams kp,
+                    BinGrid g, int32_t *__restrict__ table) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long cell = kld_cell(x[i], y[i], t[i], kp, g);
+  const unsigned peers = __match_any_sync(__activemask(), cell);
+  if ((__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31))
+    atomicMin(table + cell, static_cast<int32_t>(slot_first + i));
+}
+
+// particle_filter.cpp:293-348, sharded.
+static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, ParticleSet &out,
+                                        bool *clustered) {
+  cudaStream_t s = f->map->stream;
+  const int G = f->n_shards, me = f->shard_rank;
+  *clustered = false;
+  const double w_diff = adaptiveness(f);
+  const size_t n_max = static_cast<size_t>(f->params.particle_count_max);
+  f->n_src_index = 0;
+  f->n_bins = 0;
+  f->n_clusters = 0;
+  f->bins_built = true;
+  f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+  if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
+  bool ok = false;
+  if (n_max) QMCL_TRY(resample_draws_sharded(f, in, out, n_max, w_diff, &ok));
+  if (!ok) {  // output_set->particles.clear()
+    out.n = 0;
+    f->global_first = 0;
+    f->global_n = 0;
+    return QMCL_OK;
+  }
+  const size_t slot_first = f->global_first, n_loc = out.n;
+  // bins of all candidates (global grid, occupancy summed over shards)
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_loc));
+  const BinGrid g = f->grid;
+  const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
+  KldParams kp;
+  kp.res_xy = f->params.res_xy;
+  kp.res_t = f->params.res_theta;
+  kp.eps2 = 2 * f->params.kld_epsilon;
+  kp.z = f->params.kld_z;
+  kp.nmin = f->params.particle_count_min;
+  kp.nmax = f->params.particle_count_max;
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(std::max<size_t>(n_loc, 1)) + 8));
+  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
+      f->scan_tmp.ptr + ((scan_blocks(std::max<size_t>(n_loc, 1)) + 1) & ~1u));
+  unsigned long long *d_stop = d_total + 1;
+  unsigned long long stop = ~0ull;
+  {
+    StageScope sc(f, QMCL_STAGE_KLD);
+    // smallest global draw index per bin: local atomicMin, then min over shards
+    QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0x7f, cells * sizeof(int32_t), s));
+    if (n_loc) {
+      kld_first_at_kernel<<<div_up(n_loc, 256), 256, 0, s>>>(out.x.ptr, out.y.ptr, out.t.ptr, n_loc,
+                                                             slot_first, kp, g, f->table.ptr);
+      QMCL_LAUNCHED();
+    }
+    QMCL_TRY(shard_allreduce(f, f->table.ptr, cells, QMCL_DT_I32, QMCL_OP_MIN));
+    // new bins opened by the earlier shards
+    const NewBinFlagAt nb{out.x.ptr, out.y.ptr, out.t.ptr, kp, g, f->table.ptr, slot_first};
+    const unsigned blocks = scan_blocks(std::max<size_t>(n_loc, 1));
+    QMCL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+    if (n_loc) {
+      scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(nb, n_loc, f->scan_tmp.ptr);
+      QMCL_LAUNCHED();
+      scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_tmp.ptr, blocks, d_total);
+      QMCL_LAUNCHED();
+    }
+    std::vector<unsigned long long> opened(G);
+    QMCL_TRY(shard_gather(f, d_total, true, sizeof(unsigned long long), opened.data()));
+    unsigned long long before = 0;
+    for (int r = 0; r < me; ++r) before += opened[r];
+    QMCL_CUDA(cudaMemsetAsync(d_stop, 0xff, sizeof(unsigned long long), s));
+    if (n_loc) {
+      scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(nb, StopRuleAt{kp, d_stop, slot_first, before},
+                                                     n_loc, f->scan_tmp.ptr);
+      QMCL_LAUNCHED();
+    }
+    std::vector<unsigned long long> stops(G);
+    QMCL_TRY(shard_gather(f, d_stop, true, sizeof(unsigned long long), stops.data()));
+    for (unsigned long long v : stops) stop = std::min(stop, v);
+  }
+  const size_t n_out = (stop >= n_max) ? n_max : static_cast<size_t>(stop) + 1;
+  if (w_diff > 0.0) {
+    f->w_fast = 0;
+    f->w_slow = 0;
+  }
+  // keep the first n_out slots, then give every rank an equal block again
+  std::vector<uint64_t> lo(G), hi(G);
+  for (int r = 0; r < G; ++r) {
+    size_t a, c;
+    shard_slice_of(n_max, r, G, &a, &c);
+    lo[r] = std::min<uint64_t>(a, n_out);
+    hi[r] = std::min<uint64_t>(a + c, n_out);
+  }
+  out.n = static_cast<size_t>(hi[me] - lo[me]);
+  f->n_src_index = out.n;
+  f->global_first = lo[me];
+  f->global_n = n_out;
+  QMCL_TRY(rebalance_blocks(f, out, lo, hi, n_out));
+  // the bins the reference holds at this point are those of the kept draws
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, out.n, true));
+  QMCL_TRY(label_clusters(f));
+  *clustered = true;
+  return QMCL_OK;
+}
+
 }  // namespace qmcl
 
 using namespace qmcl;
@@ -634,10 +1107,7 @@ extern "C" {
 qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
-  if (sharded(f) && f->params.resample_type != QMCL_RESAMPLE_LOW_VARIANCE) {
-    set_error("sharded filters resample with low_variance only (adaptive/KLD: single GPU)");
-    return QMCL_ERR_UNSUPPORTED;
-  }
+
   const ParticleSet &in = f->sets[f->current];
   ParticleSet &out = f->sets[(f->current + 1) % 2];
   f->current = (f->current + 1) % 2;
@@ -649,10 +1119,12 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
     else QMCL_TRY(resample_low_variance(f, in, out));
     break;
   case QMCL_RESAMPLE_ADAPTIVE:
-    QMCL_TRY(resample_adaptive(f, in, out));
+    if (sharded(f)) QMCL_TRY(resample_adaptive_sharded(f, in, out));
+    else QMCL_TRY(resample_adaptive(f, in, out));
     break;
   case QMCL_RESAMPLE_KLD:
-    QMCL_TRY(resample_kld(f, in, out, &clustered));
+    if (sharded(f)) QMCL_TRY(resample_kld_sharded(f, in, out, &clustered));
+    else QMCL_TRY(resample_kld(f, in, out, &clustered));
     break;
   default:
     return QMCL_ERR_INVALID_ARG;

@@ -231,15 +231,98 @@ def test_multi_cycle_sharded_tracking_matches_oracle():
         assert len(got) == of.num_particles()
 
 
-def test_sharded_kld_is_refused_loudly():
-    s = Setup(resample_type=2)
+def _draw_resample_case(G, n_in, cloud, rtype, nmin, nmax, lowpass, tiny_boundary=False,
+                        rebalance=True):
+    s = Setup(resample_type=rtype, particle_count_min=nmin, particle_count_max=nmax)
+    if cloud == "tracking":
+        x, y, t = syn.gaussian_cloud(s.pose, n_in)
+    else:
+        x, y, t = syn.uniform_cloud(s.occ, s.res, s.origin, n_in)
+    of = s.of
+    of.set_particles(ob.make_particles(x, y, t, np.full(n_in, 1.0 / n_in)))
+    of.set_trig_mode(ob.TRIG_CR)
+    of.update_importance_from_observations(s.scan)
+    start = of.get_particles()
+    if tiny_boundary:
+        # weights too small to move the running sum on both sides of every shard
+        # boundary: equal keys across shards (first record wins, particle.cpp:77)
+        for r in range(1, G):
+            b = sharded.shard_slice(n_in, r, G)[0]
+            start["weight"][b - 40:b + 40] = 1e-30
+        start["weight"][:5] = 0.0
+    of.set_particles(start)
+    of.set_lowpass(*lowpass)
 
     def body(f, rank):
         f.set_parameters(s.gpu_params())
-        f.set_rng(3, 0)
-        f.global_localization()
-        with pytest.raises(q._abi.QmclError) as e:
-            f.resample_and_cluster()
-        return e.value.status
+        check(f._L.qmcl_filter_set_rebalance(f._h, int(rebalance)), "rebalance")
+        set_block(f, rank, G, start)
+        f.set_lowpass(*lowpass)
+        f.set_rng(3, 9)
+        f.resample_and_cluster()
+        parts = local_particles(f)
+        est = f.get_estimated_pose()
+        keys, labels = f.bins()
+        return parts, est, keys, labels, f.num_clusters(), f.num_particles(), tuple(f.lowpass())
 
-    assert sharded.run_local_shards(2, s.make_map, body, seed=3) == [8, 8]
+    res = sharded.run_local_shards(G, s.make_map, body, seed=3)
+    of.set_rng(3, 9)
+    of.resample_and_cluster()
+    want = of.get_particles()
+    got = assemble([r[0] for r in res])
+    assert len(got) == len(want) == res[0][5]
+    for k in ("x", "y", "theta"):
+        assert np.array_equal(got[k], want[k]), k
+    assert rel_err(got["weight"], want["weight"]) <= 1e-11
+    okeys, olabels = of.bins()
+    ok, o_pose, o_cov = of.get_estimated_pose()
+    for r in res:
+        assert np.array_equal(r[2], okeys) and np.array_equal(r[3], olabels)   # bin counts bit-exact
+        assert r[4] == of.num_clusters()
+        g_ok, g_pose, g_cov = r[1]
+        assert bool(g_ok) == (ok == 1)
+        if ok == 1:
+            assert np.max(np.abs(g_pose[:2] - o_pose[:2])) <= 1e-4
+            assert abs(math.remainder(g_pose[2] - o_pose[2], 2 * math.pi)) <= 1e-4
+        assert np.allclose(r[6], of.lowpass())
+    return len(want)
+
+
+@pytest.mark.parametrize("G,n_in,cloud,nmin,lowpass,tiny", [
+    (2, 5000, "tracking", 3000, (0.0, 0.0), False),
+    (3, 40_001, "global", 50_000, (1.0, 0.7), False),     # 30 % injected slots
+    (8, 40_001, "global", 9_999, (0.0, 0.0), True),
+    (4, 30_000, "tracking", 30_000, (1.0, 2.0), True),
+])
+def test_adaptive_resample_sharded_matches_oracle(G, n_in, cloud, nmin, lowpass, tiny):
+    n = _draw_resample_case(G, n_in, cloud, 1, nmin, nmin, lowpass, tiny)
+    assert n == nmin
+
+
+@pytest.mark.parametrize("G,n_in,cloud,nmax,lowpass,tiny,rebalance", [
+    (2, 5000, "tracking", 5000, (0.0, 0.0), False, True),
+    (3, 40_001, "global", 30_000, (0.0, 0.0), False, True),
+    (8, 40_001, "global", 50_000, (1.0, 0.8), True, True),
+    (4, 100_000, "tracking", 100_000, (0.0, 0.0), True, False),
+])
+def test_kld_resample_sharded_matches_oracle(G, n_in, cloud, nmax, lowpass, tiny, rebalance):
+    n = _draw_resample_case(G, n_in, cloud, 2, 100, nmax, lowpass, tiny, rebalance)
+    assert 100 < n <= nmax
+    print(f"KLD sharded x{G}: {n} of {nmax} kept")
+
+
+def test_sharded_draws_without_any_weight_fail_like_the_reference():
+    """particle_filter.cpp:255-259, :307-311: error, return; KLD leaves an empty set."""
+    s = Setup(resample_type=2)
+    n = 1000
+    x, y, t = syn.gaussian_cloud(s.pose, n)
+    start = q.make_particles(x, y, t, np.zeros(n))
+
+    def body(f, rank):
+        f.set_parameters(s.gpu_params())
+        set_block(f, rank, 2, start)
+        f.set_rng(3, 0)
+        f.resample_and_cluster()
+        return f.num_particles(), f.get_estimated_pose()[0]
+
+    assert sharded.run_local_shards(2, s.make_map, body, seed=3) == [(0, False), (0, False)]
