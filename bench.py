@@ -229,7 +229,7 @@ def run_reference(args, wl):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -240,7 +240,8 @@ def workload_config(args, wl, n_used_beams):
             "resample": RESAMPLE_NAMES[wl["pf"]["resample_type"]],
             "step": "handle_odometry+update_sensor+resample_and_cluster+get_estimate",
             "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed",
-            "sharding": "particles, contiguous global-index blocks" if args.gpus > 1 else "none"}
+            "sharding": (f"particles, contiguous global-index blocks; exchanges via {args.transport}"
+                         if args.gpus > 1 else "none")}
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -276,7 +277,7 @@ def run_b200(args, wl):
     pfp.resample_type = q.ResampleType(wl["pf"]["resample_type"])
     if world > 1:
         from quickmcl_b200.sharded import ShardedParticleFilter
-        f = ShardedParticleFilter(gm, seed=3, group=dist.group.WORLD)
+        f = ShardedParticleFilter(gm, seed=3, group=dist.group.WORLD, transport=args.transport)
     else:
         f = q.create_particle_filter(gm, seed=3)
     f.set_parameters(pfp)
@@ -439,13 +440,31 @@ def run_b200(args, wl):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "estimate": [float(v) for v in dev["estimate"][1]] if dev["estimate"] else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL's version
+    banner, library chatter) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -455,6 +474,8 @@ def main():
     ap.add_argument("--breakdown", action="store_true",
                     help="extra untimed pass with per-stage CUDA events, printed to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "torch"],
+                    help="sharded exchanges: the library's built-in NCCL table or torch.distributed")
     args = ap.parse_args()
     if args.workload is None:
         # N=1: the configuration the metric is quoted on (configs[1]); N>1: the sharded config

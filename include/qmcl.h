@@ -169,6 +169,13 @@ typedef struct qmcl_comm {
                    const uint64_t *send_offsets, void *dev_recv, const uint64_t *recv_bytes,
                    const uint64_t *recv_offsets, void *stream);
 } qmcl_comm;
+/* Built-in table on NCCL (resolved with dlopen at first use).  Rank 0 obtains
+ * a 128-byte ncclUniqueId, the host hands it to every rank, each rank creates
+ * its communicator on `device` (< 0: current device). */
+qmcl_status qmcl_nccl_unique_id(uint8_t out[128]);
+qmcl_status qmcl_nccl_comm_create(const uint8_t id[128], int rank, int size, int device,
+                                  qmcl_comm *out);
+qmcl_status qmcl_nccl_comm_destroy(qmcl_comm *comm);
 /* comm == NULL (or size 1) returns the filter to the single-GPU path. */
 qmcl_status qmcl_filter_set_comm(qmcl_filter *f, const qmcl_comm *comm);
 /* After a sharded resampling, move particles so that every rank again owns an

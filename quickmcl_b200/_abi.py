@@ -75,6 +75,9 @@ SIGNATURES = {
     "qmcl_filter_create": [vp, u64, C.POINTER(vp)],
     "qmcl_filter_destroy": [vp],
     "qmcl_filter_set_comm": [vp, vp],
+    "qmcl_nccl_unique_id": [C.POINTER(C.c_uint8)],
+    "qmcl_nccl_comm_create": [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, vp],
+    "qmcl_nccl_comm_destroy": [vp],
     "qmcl_filter_set_rebalance": [vp, C.c_int],
     "qmcl_filter_shard_range": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
     "qmcl_filter_set_particles_shard": [vp, pP, sz, u64, u64],

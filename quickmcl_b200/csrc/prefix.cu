@@ -470,6 +470,50 @@ prefix_apply_kernel(const double *__restrict__ w, size_t n, size_t nc, PrefixBuf
   }
 }
 
+// Summary of a whole shard: the composition of its tile summaries, usable only
+// if every tile was summarised under one and the same binade.  out[0] = binade
+// (biased exponent, -1 = no closed form), out[1], out[2] = a0, a1.
+__global__ void __launch_bounds__(256)
+prefix_shard_summary_kernel(PrefixBuffers pb, size_t nt, unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long s_a0[8], s_a1[8];
+  __shared__ int s_E[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // thread t composes a contiguous run of tiles, in order
+  const size_t per = (nt + blockDim.x - 1) / blockDim.x;
+  const size_t t0 = static_cast<size_t>(threadIdx.x) * per;
+  const size_t t1 = (t0 + per < nt) ? t0 + per : nt;
+  Fn f = fn_identity();
+  int E = -2;  // -2: nothing yet
+  for (size_t t = t0; t < t1; ++t) {
+    const int tE = pb.tile_E[t];
+    if (E == -2) E = tE;
+    else if (tE != E) E = kInvalidE;
+    f = fn_compose(f, Fn{pb.tile_a0[t], pb.tile_a1[t]});
+  }
+  // combine E across the warp / block: all non-empty must agree
+  auto merge_E = [](int a, int b) { return a == -2 ? b : (b == -2 ? a : (a == b ? a : kInvalidE)); };
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) E = merge_E(E, __shfl_xor_sync(0xffffffffu, E, o));
+  f = fn_warp_scan(f, lane);
+  if (lane == 31) {
+    s_a0[wid] = f.a0;
+    s_a1[wid] = f.a1;
+  }
+  if (lane == 0) s_E[wid] = E;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Fn tot = fn_identity();
+    int Eb = -2;
+    for (int k = 0; k < 8; ++k) {
+      tot = fn_compose(tot, Fn{s_a0[k], s_a1[k]});
+      Eb = merge_E(Eb, s_E[k]);
+    }
+    out[0] = static_cast<unsigned long long>(static_cast<long long>(Eb < 0 ? -1 : Eb));
+    out[1] = tot.a0;
+    out[2] = tot.a1;
+  }
+}
+
 // The literal loop on one warp: coalesced loads of 32 weights, lane-uniform
 // dependent additions.  Kept as the in-library cross-check of the parallel
 // path (qmcl_filter_set_prefix_mode(f, 1)).
@@ -572,6 +616,46 @@ qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double a
   prefix_summaries_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.nc, pl.pb);
   QMCL_LAUNCHED();
   return QMCL_OK;
+}
+
+// After prefix_summaries: the shard's summary {binade, a0, a1} as three 64-bit
+// words in dev_out (device memory).
+qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *dev_out) {
+  cudaStream_t s = f->map->stream;
+  if (!n) {
+    // an empty shard adds nothing under any binade: mark as "identity"
+    const unsigned long long ident[3] = {~0ull - 1, 0ull, 0ull};  // binade word -2
+    QMCL_CUDA(cudaMemcpyAsync(dev_out, ident, sizeof(ident), cudaMemcpyHostToDevice, s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    return QMCL_OK;
+  }
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  prefix_shard_summary_kernel<<<1, 256, 0, s>>>(pl.pb, pl.nt, dev_out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// Host replay of one summary on an exact carry: true and *carry_out set when
+// the carry is in the summary's binade and stays there.
+bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], double *carry_out) {
+  const long long Eb = static_cast<long long>(summary[0]);
+  if (Eb == -2) {  // empty shard
+    *carry_out = carry_in;
+    return true;
+  }
+  if (Eb < 0) return false;
+  unsigned long long bits;
+  std::memcpy(&bits, &carry_in, sizeof(bits));
+  if (carry_in <= 0.0 || (bits >> 63)) return false;
+  const long long ce = static_cast<long long>(bits >> 52);
+  if (ce == 0 || ce == 0x7ff || ce != Eb) return false;
+  const unsigned long long K = (bits & kMantMask) | kImplicit;
+  const unsigned long long Kend = K + ((K & 1ull) ? summary[2] : summary[1]);
+  if (Kend >= kKLimit || Kend < K) return false;
+  const unsigned long long ob = (static_cast<unsigned long long>(Eb) << 52) | (Kend & kMantMask);
+  std::memcpy(carry_out, &ob, sizeof(ob));
+  return true;
 }
 
 // Phase 2: exact carry through the shard; carry_out -> prefix_carry[0].

@@ -20,5 +20,10 @@ qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double a
 qmcl_status prefix_resolve(qmcl_filter *f, const double *w, size_t n, double *out,
                            double carry_in);
 qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out);
+// Shard-level shortcut for the carry chain: {binade, a0, a1} of the whole
+// shard (three 64-bit words, device memory; binade -1 = no closed form, -2 =
+// empty shard), and its replay on an exact carry on the host.
+qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *dev_out);
+bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], double *carry_out);
 
 }  // namespace qmcl

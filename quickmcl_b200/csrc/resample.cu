@@ -366,15 +366,31 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   double approx_in = 0.0;
   for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
   QMCL_TRY(prefix_summaries(f, w, n, approx_in));
-  // the exact carry, shard after shard
+  // The exact carry, shard after shard.  A shard whose particles all fall into
+  // one binade of the running sum publishes a closed-form summary, which every
+  // rank replays locally; only shards without one (the first, and those in
+  // which the sum crosses a power of two) cost a round of the chain.
+  struct Summary { unsigned long long w[3]; };
+  std::vector<Summary> summaries(G);
+  QMCL_TRY(f->partials.ensure(8));
+  unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(f->partials.ptr);
+  QMCL_TRY(prefix_shard_summary(f, n, d_sum));
+  QMCL_TRY(shard_gather(f, d_sum, true, sizeof(Summary), summaries.data()));
   std::vector<double> &carry = *carry_out;
   carry.assign(G + 1, 0.0);
   std::vector<double> round(G);
+  bool resolved = false;
   for (int r = 0; r < G; ++r) {
-    if (r == me) QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[r]));
+    if (prefix_apply_summary(carry[r], summaries[r].w, &carry[r + 1])) continue;
+    if (r == me) {
+      QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[r]));
+      resolved = true;
+    }
     QMCL_TRY(shard_gather(f, f->prefix_carry.ptr, true, sizeof(double), round.data()));
     carry[r + 1] = round[r];
+    f->n_chain_rounds++;
   }
+  if (!resolved) QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[me]));
   QMCL_TRY(prefix_apply(f, w, n, f->cdf.ptr));
   count_out->resize(G);
   for (int r = 0; r < G; ++r) (*count_out)[r] = info[r].count;

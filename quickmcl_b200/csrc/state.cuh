@@ -138,6 +138,7 @@ struct qmcl_filter {
   qmcl::DevBuf<uint8_t> xchg;        // collective payloads
   qmcl::DevBuf<uint8_t> xchg_send, xchg_recv;  // particle rebalancing (AoS)
   uint64_t n_collectives = 0;
+  uint64_t n_chain_rounds = 0;  // carry-chain rounds that needed an exchange
   size_t global_first = 0;  // global index of local particle 0
   size_t global_n = 0;      // particles over all shards
 

@@ -168,19 +168,51 @@ class ShardedParticleFilter(ParticleFilter):
     the whole set in global order.
     """
 
-    def __init__(self, map_, seed=0, group=None):
+    def __init__(self, map_, seed=0, group=None, transport="nccl"):
+        """transport="nccl": the library's built-in NCCL table (qmcl_nccl_comm_create; the
+        process group only carries the 128-byte unique id once).  transport="torch": every
+        collective goes through torch.distributed (TorchComm)."""
         super().__init__(map_, seed)
-        self.comm = TorchComm(group, "cuda")
-        check(self._L.qmcl_filter_set_comm(self._h, C.byref(self.comm.struct)),
-              "qmcl_filter_set_comm")
+        self.group = group if group is not None else dist.group.WORLD
+        self._rank = dist.get_rank(self.group)
+        self._size = dist.get_world_size(self.group)
+        self.comm = None
+        self._nccl = None
+        if transport == "torch":
+            self.comm = TorchComm(self.group, "cuda")
+            check(self._L.qmcl_filter_set_comm(self._h, C.byref(self.comm.struct)),
+                  "qmcl_filter_set_comm")
+        elif transport == "nccl":
+            uid = (C.c_uint8 * 128)()
+            if self._rank == 0:
+                check(self._L.qmcl_nccl_unique_id(uid), "qmcl_nccl_unique_id")
+            box = [bytes(uid)]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0),
+                                       group=self.group)
+            uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+            self._nccl = QmclComm()
+            check(self._L.qmcl_nccl_comm_create(uid, self._rank, self._size,
+                                                torch.cuda.current_device(),
+                                                C.byref(self._nccl)), "qmcl_nccl_comm_create")
+            check(self._L.qmcl_filter_set_comm(self._h, C.byref(self._nccl)),
+                  "qmcl_filter_set_comm")
+        else:
+            raise ValueError(transport)
+
+    def close(self):
+        if getattr(self, "_nccl", None) is not None and getattr(self, "_h", None):
+            self._L.qmcl_filter_set_comm(self._h, None)
+            self._L.qmcl_nccl_comm_destroy(C.byref(self._nccl))
+            self._nccl = None
+        super().close()
 
     @property
     def rank(self):
-        return self.comm.rank
+        return self._rank
 
     @property
     def world_size(self):
-        return self.comm.size
+        return self._size
 
     def set_rebalance(self, enabled):
         check(self._L.qmcl_filter_set_rebalance(self._h, int(enabled)),
@@ -216,14 +248,14 @@ class ShardedParticleFilter(ParticleFilter):
         mine = self.get_particles()
         first, count, total = self.shard_range()
         meta = [None] * self.world_size
-        dist.all_gather_object(meta, (first, mine), group=self.comm.group)
+        dist.all_gather_object(meta, (first, mine), group=self.group)
         meta.sort(key=lambda m: m[0])
         out = np.concatenate([m[1] for m in meta]) if meta else mine
         assert len(out) == total, (len(out), total)
         return out
 
     def _raise_comm(self):
-        if self.comm.error is not None:
+        if self.comm is not None and self.comm.error is not None:
             e, self.comm.error = self.comm.error, None
             raise e
 
