@@ -130,6 +130,11 @@ struct EmitBin {
   }
 };
 
+// Lock-free union-find.  Invariant: parent[v] < v for every non-root, roots
+// point to themselves, a node stops being a root exactly once (the CAS in
+// uf_union).  Path halving replaces parent[v] by an ancestor, which keeps the
+// invariant under any interleaving; a stale (L1) read only shows an older,
+// less merged forest and at worst costs a CAS retry.
 __device__ __forceinline__ int uf_find(int32_t *parent, int v) {
   int p = parent[v];
   while (p != v) {
@@ -137,6 +142,17 @@ __device__ __forceinline__ int uf_find(int32_t *parent, int v) {
     if (gp != p) parent[v] = gp;  // path halving (benign race)
     v = p;
     p = gp;
+  }
+  return v;
+}
+// Read-only find for the flatten pass: there every thread publishes the final
+// root of its own bin, and a halving store from another thread arriving later
+// would overwrite that root with an intermediate ancestor.
+__device__ __forceinline__ int uf_find_readonly(const int32_t *parent, int v) {
+  int p = __ldcg(parent + v);
+  while (p != v) {
+    v = p;
+    p = __ldcg(parent + v);
   }
   return v;
 }
@@ -171,6 +187,7 @@ cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bi
   const int it = cell % g.nt;
   const int iy = (cell / g.nt) % g.ny;
   const int ix = cell / (g.nt * g.ny);
+  const bool regular = it + g.t0 >= bp.theta_lo && it + g.t0 <= bp.theta_hi;
   int kt = it + g.t0 + dt;
   if (kt < bp.theta_lo) kt = bp.theta_hi;
   else if (kt > bp.theta_hi) kt = bp.theta_lo;
@@ -183,7 +200,12 @@ cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bi
       const int jy = iy + dy;
       if (jy < 0 || jy >= g.ny) continue;
       const int v = table[(static_cast<size_t>(jx) * g.ny + jy) * g.nt + jt];
-      if (v > 0 && v - 1 != b) uf_union(parent, b, v - 1);
+      // Every reciprocal edge once: the bin with the larger index does the
+      // union.  Bins outside [theta_lo, theta_hi] (theta == -pi rounds to bin
+      // -18 at 10 degrees) see neighbours that do not see them back
+      // (space_partitioning.cpp:110-114 wraps them onto the other end), so
+      // they union everything they see.
+      if (v > 0 && v - 1 != b && (!regular || v - 1 < b)) uf_union(parent, b, v - 1);
     }
   }
 }
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(256)
 cc_flatten_kernel(int32_t *__restrict__ parent, size_t n_bins) {
   const size_t b = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (b >= n_bins) return;
-  parent[b] = uf_find(parent, static_cast<int>(b));
+  parent[b] = uf_find_readonly(parent, static_cast<int>(b));
 }
 
 struct RootFlag {
