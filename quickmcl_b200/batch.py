@@ -1,0 +1,85 @@
+"""Multi-robot batch (BASELINE.json configs[4]): many independent filters on one GPU.
+
+Every robot has its own particle set, scan and odometry; the filters never
+exchange data ("replicas / round-robin, no communication").  One
+filter's update at QuickMCL's default size (2000 particles) is far too small to
+fill a B200 — it is a chain of ~40 short kernels and a few 8-byte read-backs —
+so the batch runs `lanes` of them concurrently: each lane is a host thread with
+its own CUDA stream and its own map handle (the field is replicated per lane;
+0.8 MB for a 400 x 400 map), and filters are dealt round-robin to the lanes.
+ctypes releases the GIL during library calls, so the lanes overlap both on the
+host and on the device.
+
+The reference has no counterpart (one filter per process); the per-robot call
+sequence is laser_handler.cpp:243-276.
+"""
+import concurrent.futures as cf
+
+import numpy as np
+import torch
+
+from .api import (LikelihoodMapParameters, OccupancyGrid, ParticleFilterParameters,
+                  create_likelihood_map, create_particle_filter)
+
+
+class FilterBatch:
+    def __init__(self, n_filters, grid: OccupancyGrid, map_parameters: LikelihoodMapParameters,
+                 filter_parameters: ParticleFilterParameters, lanes=16, seed=0, device=None):
+        self.n = int(n_filters)
+        self.lanes = max(1, min(int(lanes), self.n))
+        self.device = torch.cuda.current_device() if device is None else device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)]
+        self.maps = []
+        for s in self.streams:
+            m = create_likelihood_map(device=self.device)
+            m.set_stream(s.cuda_stream)
+            m.set_parameters(map_parameters)
+            m.new_map(grid)
+            self.maps.append(m)
+        self.filters = []
+        for i in range(self.n):
+            f = create_particle_filter(self.maps[i % self.lanes], seed=seed + i)
+            f.set_parameters(filter_parameters)
+            self.filters.append(f)
+        self.pool = cf.ThreadPoolExecutor(max_workers=self.lanes)
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for f in self.filters:
+            f.close()
+        for m in self.maps:
+            m.close()
+        self.filters, self.maps = [], []
+
+    def _lane(self, lane, fn):
+        out = {}
+        with torch.cuda.device(self.device):
+            for i in range(lane, self.n, self.lanes):
+                out[i] = fn(i, self.filters[i])
+        return out
+
+    def for_each(self, fn):
+        """Run fn(index, filter) for every filter, lanes in parallel; returns results by index."""
+        futs = [self.pool.submit(self._lane, lane, fn) for lane in range(self.lanes)]
+        merged = {}
+        for fu in futs:
+            merged.update(fu.result())
+        return [merged[i] for i in range(self.n)]
+
+    def initialise(self, poses, covariance):
+        poses = np.asarray(poses, np.float32)
+        return self.for_each(lambda i, f: f.initialise(poses[i], covariance))
+
+    def update(self, odom_new, odom_old, alpha, scans, resample=True):
+        """One scan cycle per robot (laser_handler.cpp:243-276): motion, sensor, resample (or
+        cluster), estimate.  odom_*: [n, 3]; scans: list of float32 [B_i, 2].
+        Returns [(ok, pose, covariance)] per robot."""
+        def one(i, f):
+            f.handle_odometry(odom_new[i], odom_old[i], alpha)
+            f.update_importance_from_observations(scans[i])
+            if resample:
+                f.resample_and_cluster()
+            else:
+                f.cluster()
+            return f.get_estimated_pose()
+        return self.for_each(one)
