@@ -202,14 +202,15 @@ __host__ __device__ __forceinline__ double angle_delta(double a, double b) {
 
 // map_base.cpp:58-64 under the RNG contract: free cell from words 0-1, heading
 // from word 2; the pose is the cell *corner* (scaled_map.h:101-105).
-__device__ __forceinline__ void random_free_pose(const int32_t *__restrict__ free_xy,
+__device__ __forceinline__ void random_free_pose(const uint32_t *__restrict__ free_idx,
                                                  unsigned long long n_free, const MapGeom &g,
                                                  const uint32_t r[4], float *x, float *y,
                                                  float *t) {
   const unsigned long long idx =
       __umul64hi((static_cast<unsigned long long>(r[1]) << 32) | r[0], n_free);
-  const float cx = static_cast<float>(free_xy[2 * idx]);
-  const float cy = static_cast<float>(free_xy[2 * idx + 1]);
+  const unsigned cell = free_idx[idx];
+  const float cx = static_cast<float>(cell % g.w);
+  const float cy = static_cast<float>(cell / g.w);
   *x = __fadd_rn(__fmul_rn(cx, g.res), g.ox);
   *y = __fadd_rn(__fmul_rn(cy, g.res), g.oy);
   const double u = static_cast<double>(r[2]) * 0x1.0p-32;

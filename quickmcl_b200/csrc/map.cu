@@ -76,6 +76,62 @@ edt_columns_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
   }
 }
 
+// Vectorised pass 1 for widths that are a multiple of 4 and R <= 253: a thread
+// owns four adjacent columns (char4 loads = 128 B per warp instruction,
+// ushort4 / char4 stores), the down-sweep distances of the segment stay in
+// shared memory as bytes (anything above R is "out of reach" for pass 2), so g
+// is written exactly once.  Traffic per cell: ~2.6 B of occupancy (the two
+// sweeps re-read the R-row halo), 1 B state, 2 B g.
+constexpr int kColSeg = 64;     // rows per segment
+constexpr int kColThreads = 128;  // x 4 columns = 512 columns per block
+__device__ __forceinline__ int8_t tri_state(int v) {
+  // distance_calculator.cpp:194-206
+  return (v == -1) ? 2 : (v < 35) ? 0 : (v > 65) ? 1 : 2;
+}
+__global__ void __launch_bounds__(kColThreads)
+edt_columns4_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
+                    uint16_t *__restrict__ g, int w, int h, int R) {
+  __shared__ uchar4 s_down[kColSeg][kColThreads];
+  const int x = (blockIdx.x * kColThreads + threadIdx.x) * 4;
+  if (x >= w) return;
+  const int y0 = blockIdx.y * kColSeg;
+  const int y1 = min(h, y0 + kColSeg);
+  int d0 = 255, d1 = 255, d2 = 255, d3 = 255;
+#pragma unroll 4
+  for (int y = max(0, y0 - R); y < y1; ++y) {
+    const size_t i = static_cast<size_t>(y) * w + x;
+    const char4 v = __ldg(reinterpret_cast<const char4 *>(occ + i));
+    d0 = (v.x > 65) ? 0 : min(d0 + 1, 255);
+    d1 = (v.y > 65) ? 0 : min(d1 + 1, 255);
+    d2 = (v.z > 65) ? 0 : min(d2 + 1, 255);
+    d3 = (v.w > 65) ? 0 : min(d3 + 1, 255);
+    if (y >= y0) {
+      s_down[y - y0][threadIdx.x] = make_uchar4(d0, d1, d2, d3);
+      *reinterpret_cast<char4 *>(state + i) =
+          make_char4(tri_state(v.x), tri_state(v.y), tri_state(v.z), tri_state(v.w));
+    }
+  }
+  d0 = d1 = d2 = d3 = 255;
+#pragma unroll 4
+  for (int y = min(h, y1 + R) - 1; y >= y0; --y) {
+    const size_t i = static_cast<size_t>(y) * w + x;
+    const char4 v = __ldg(reinterpret_cast<const char4 *>(occ + i));
+    d0 = (v.x > 65) ? 0 : min(d0 + 1, 255);
+    d1 = (v.y > 65) ? 0 : min(d1 + 1, 255);
+    d2 = (v.z > 65) ? 0 : min(d2 + 1, 255);
+    d3 = (v.w > 65) ? 0 : min(d3 + 1, 255);
+    if (y < y1) {
+      const uchar4 dn = s_down[y - y0][threadIdx.x];
+      ushort4 o;
+      o.x = static_cast<uint16_t>(min(d0, static_cast<int>(dn.x)));
+      o.y = static_cast<uint16_t>(min(d1, static_cast<int>(dn.y)));
+      o.z = static_cast<uint16_t>(min(d2, static_cast<int>(dn.z)));
+      o.w = static_cast<uint16_t>(min(d3, static_cast<int>(dn.w)));
+      *reinterpret_cast<ushort4 *>(g + i) = o;
+    }
+  }
+}
+
 // Tri-state map only (used by load_field's callers that bring their own).
 // d^2 -> (distance, likelihood) table.  distance_calculator.cpp:150-157 for
 // the clipping, map_likelihood.cpp:60 for the Gaussian.  The last entry is the
@@ -110,32 +166,48 @@ edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_di
   const int x0 = blockIdx.x * kRowChunk;
   const int span = kRowChunk + 2 * R;
   const int big = 1 << 28;
-  int any = 0;
   for (int i = threadIdx.x; i < span; i += kRowChunk) {
     const int xx = x0 - R + i;
     int v = big;
     if (xx >= 0 && xx < w) {
       const int gy = g[static_cast<size_t>(y) * w + xx];
-      if (gy <= R) {
-        v = gy * gy;
-        any = 1;
-      }
+      if (gy <= R) v = gy * gy;
     }
     sG[i] = v;
   }
-  any = __syncthreads_or(any);
+  __syncthreads();
+  // Does anything within reach of this warp's 32 cells have an obstacle above
+  // or below?  Window of the warp: span entries [32*warp, 32*warp + 32 + 2R).
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  int any = 0;
+  for (int i = lane; i < 32 + 2 * R; i += 32) any |= sG[wbase + i] != big;
+  any = __any_sync(0xffffffffu, any);
   const int x = x0 + threadIdx.x;
   if (x >= w) return;
   int best = big;
   if (any) {
     const int *c = sG + threadIdx.x + R;  // centre of this thread's window
-    for (int dx = -R; dx <= R; ++dx) best = min(best, c[dx] + dx * dx);
+    best = c[0];
+    // outward: a term dx^2 + G cannot improve on `best` once dx^2 >= best
+    for (int dx = 1; dx <= R; ++dx) {
+      const int dd = dx * dx;
+      if (dd >= best) break;
+      best = min(best, min(c[-dx], c[dx]) + dd);
+    }
   }
   const int k = (best > kmax) ? (kmax + 1) : best;
   const size_t i = static_cast<size_t>(y) * w + x;
   field[i] = __ldg(lut_field + k);
-  distance[i] = __ldg(lut_dist + k);
+  if (distance) distance[i] = __ldg(lut_dist + k);
   if (code) code[i] = static_cast<uint16_t>(k);
+}
+
+// Distance field on demand (qmcl_map_copy_distance): code -> metres.
+__global__ void __launch_bounds__(256)
+distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__restrict__ lut_dist,
+                          size_t n, float *__restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ldg(lut_dist + code[i]);
 }
 
 // K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
@@ -167,14 +239,32 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int *total) {
   return offset + incl - v;
 }
 
+// 16 consecutive state bytes as a 16-bit "is free" mask (one 16-byte load when
+// the run is inside the map and aligned).
+__device__ __forceinline__ unsigned free_mask16(const int8_t *__restrict__ state, size_t base,
+                                                size_t n) {
+  unsigned mask = 0;
+  if (base + 16 <= n && (reinterpret_cast<uintptr_t>(state + base) & 15u) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(state + base));
+    const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (((wds[k] >> (8 * j)) & 0xffu) == 0) mask |= 1u << (4 * k + j);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (base + i < n && state[base + i] == 0) mask |= 1u << i;
+  }
+  return mask;
+}
+
 __global__ void __launch_bounds__(kCompactBlock)
 free_count_kernel(const int8_t *__restrict__ state, size_t n, uint32_t *__restrict__ counts) {
   const size_t base =
       (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
-  int c = 0;
-#pragma unroll
-  for (int i = 0; i < kCompactItems; ++i)
-    if (base + i < n && state[base + i] == 0) ++c;
+  const int c = __popc(free_mask16(state, base, n));
   int total;
   block_exclusive_scan_256(c, &total);
   if (threadIdx.x == 0) counts[blockIdx.x] = static_cast<uint32_t>(total);
@@ -217,25 +307,30 @@ scan_counts_kernel(uint32_t *__restrict__ counts, size_t n, unsigned long long *
   if (threadIdx.x == 0 && out_total) *out_total = carry;
 }
 
+// The free-cell list holds linear cell indices (y * w + x, 4 bytes) in
+// row-major order, which is the order of map_base.cpp:46-55.
 __global__ void __launch_bounds__(kCompactBlock)
-free_scatter_kernel(const int8_t *__restrict__ state, size_t n, int w,
-                    const uint32_t *__restrict__ block_offsets, int32_t *__restrict__ out_xy) {
+free_scatter_kernel(const int8_t *__restrict__ state, size_t n,
+                    const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ out_idx) {
   const size_t base =
       (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
-  unsigned mask = 0;
-#pragma unroll
-  for (int i = 0; i < kCompactItems; ++i)
-    if (base + i < n && state[base + i] == 0) mask |= 1u << i;
+  const unsigned mask = free_mask16(state, base, n);
   int total;
   size_t pos = block_offsets[blockIdx.x] + block_exclusive_scan_256(__popc(mask), &total);
 #pragma unroll
   for (int i = 0; i < kCompactItems; ++i)
-    if (mask & (1u << i)) {
-      const size_t cell = base + i;
-      out_xy[2 * pos] = static_cast<int32_t>(cell % w);
-      out_xy[2 * pos + 1] = static_cast<int32_t>(cell / w);
-      ++pos;
-    }
+    if (mask & (1u << i)) out_idx[pos++] = static_cast<uint32_t>(base + i);
+}
+
+// qmcl_map_copy_free_cells: (x, y) pairs as the reference's Vector2i list.
+__global__ void __launch_bounds__(256)
+free_cells_xy_kernel(const uint32_t *__restrict__ idx, size_t n_free, unsigned w,
+                     int32_t *__restrict__ out_xy) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_free) return;
+  const unsigned c = idx[i];
+  out_xy[2 * i] = static_cast<int32_t>(c % w);
+  out_xy[2 * i + 1] = static_cast<int32_t>(c / w);
 }
 
 // map_likelihood.cpp:132-146: int8(100 * p + 0.5f)
@@ -252,7 +347,7 @@ __global__ void state_at_kernel(const int8_t *__restrict__ state, MapGeom g, flo
   *out = in_map(ix, iy, g) ? state[static_cast<size_t>(iy) * g.w + ix] : int8_t(2);
 }
 
-__global__ void random_pose_kernel(const int32_t *__restrict__ free_xy, unsigned long long n_free,
+__global__ void random_pose_kernel(const uint32_t *__restrict__ free_xy, unsigned long long n_free,
                                    MapGeom g, uint64_t seed, uint32_t step, uint64_t index,
                                    float *out) {
   uint32_t r[4];
@@ -276,10 +371,10 @@ static qmcl_status rebuild_free_cells(qmcl_map *m) {
   QMCL_CUDA(copy_d2h(&total, d_total, sizeof(total), m->stream));
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
   m->n_free = total;
-  QMCL_TRY(m->free_cells.ensure(2 * total + 2));
+  QMCL_TRY(m->free_cells.ensure(total + 2));
   if (total) {
-    free_scatter_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(
-        m->state.ptr, n, static_cast<int>(m->geom.w), m->scan_tmp.ptr, m->free_cells.ptr);
+    free_scatter_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(m->state.ptr, n, m->scan_tmp.ptr,
+                                                                 m->free_cells.ptr);
     QMCL_LAUNCHED();
   }
   return QMCL_OK;
@@ -405,12 +500,12 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   QMCL_TRY(m->occ.ensure(n));
   QMCL_TRY(m->state.ensure(n));
   QMCL_TRY(m->field.ensure(n));
-  QMCL_TRY(m->distance.ensure(n));
   QMCL_TRY(m->edt_g.ensure((n + 1) / 2));
   QMCL_TRY(m->lut.ensure(2 * static_cast<size_t>(kmax + 2)));
   // the uint16 d^2 code map (sensor model's palette path) exists when d^2 fits
   const bool with_code = kmax + 2 <= 65535;
   if (with_code) QMCL_TRY(m->code.ensure(n));
+  else QMCL_TRY(m->distance.ensure(n));  // with codes the distance field is derived on demand
   QMCL_CUDA(copy_h2d(m->occ.ptr, occ, n, m->stream));
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
   float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
@@ -418,10 +513,16 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   edt_lut_kernel<<<div_up(kmax + 2, 256), 256, 0, m->stream>>>(lut_dist, lut_field, kmax + 2,
                                                                resolution, max_dist, m->z_hit_pre);
   QMCL_LAUNCHED();
-  dim3 grid1(div_up(width, 128), div_up(height, kSegLen));
-  edt_columns_kernel<<<grid1, 128, 0, m->stream>>>(m->occ.ptr, m->state.ptr, g,
-                                                   static_cast<int>(width),
-                                                   static_cast<int>(height), R);
+  if (width % 4 == 0 && R <= 253) {
+    dim3 grid1(div_up(width, 4 * kColThreads), div_up(height, kColSeg));
+    edt_columns4_kernel<<<grid1, kColThreads, 0, m->stream>>>(
+        m->occ.ptr, m->state.ptr, g, static_cast<int>(width), static_cast<int>(height), R);
+  } else {
+    dim3 grid1(div_up(width, 128), div_up(height, kSegLen));
+    edt_columns_kernel<<<grid1, 128, 0, m->stream>>>(m->occ.ptr, m->state.ptr, g,
+                                                     static_cast<int>(width),
+                                                     static_cast<int>(height), R);
+  }
   QMCL_LAUNCHED();
   dim3 grid2(div_up(width, kRowChunk), height);
   const size_t smem = (kRowChunk + 2 * static_cast<size_t>(R)) * sizeof(int);
@@ -430,7 +531,8 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
     QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
   edt_rows_kernel<<<grid2, kRowChunk, smem, m->stream>>>(
-      g, lut_dist, lut_field, m->distance.ptr, m->field.ptr, with_code ? m->code.ptr : nullptr,
+      g, lut_dist, lut_field, with_code ? nullptr : m->distance.ptr, m->field.ptr,
+      with_code ? m->code.ptr : nullptr,
       static_cast<int>(width), static_cast<int>(height), R, kmax);
   QMCL_LAUNCHED();
   QMCL_TRY(rebuild_free_cells(m));
@@ -484,7 +586,16 @@ qmcl_status qmcl_map_copy_field(const qmcl_map *m, float *out) {
 qmcl_status qmcl_map_copy_distance(const qmcl_map *m, float *out) {
   if (!m) return QMCL_ERR_INVALID_ARG;
   if (!m->has_distance) return QMCL_ERR_NO_MAP;
-  return copy_out(m, m->distance.ptr, out, sizeof(float) * m->geom.w * m->geom.h);
+  const size_t n = static_cast<size_t>(m->geom.w) * m->geom.h;
+  if (m->has_code) {
+    qmcl_map *mm = const_cast<qmcl_map *>(m);
+    QMCL_TRY(use_device(m));
+    QMCL_TRY(mm->distance.ensure(n));
+    distance_from_code_kernel<<<div_up(n, 256), 256, 0, m->stream>>>(
+        reinterpret_cast<const uint16_t *>(m->code.ptr), m->lut.ptr, n, mm->distance.ptr);
+    QMCL_LAUNCHED();
+  }
+  return copy_out(m, m->distance.ptr, out, sizeof(float) * n);
 }
 qmcl_status qmcl_map_copy_state(const qmcl_map *m, int8_t *out) {
   if (!m) return QMCL_ERR_INVALID_ARG;
@@ -499,7 +610,14 @@ qmcl_status qmcl_map_num_free_cells(const qmcl_map *m, uint64_t *out) {
 qmcl_status qmcl_map_copy_free_cells(const qmcl_map *m, int32_t *xy_out) {
   if (!m) return QMCL_ERR_INVALID_ARG;
   if (m->n_free == 0) return m->has_map ? QMCL_OK : QMCL_ERR_NO_MAP;
-  return copy_out(m, m->free_cells.ptr, xy_out, sizeof(int32_t) * 2 * m->n_free);
+  qmcl_map *mm = const_cast<qmcl_map *>(m);
+  QMCL_TRY(use_device(m));
+  QMCL_TRY(mm->tmp_cloud.ensure(2 * m->n_free + 2));  // staging (int32 pairs)
+  int32_t *d_xy = reinterpret_cast<int32_t *>(mm->tmp_cloud.ptr);
+  free_cells_xy_kernel<<<div_up(m->n_free, 256), 256, 0, m->stream>>>(m->free_cells.ptr, m->n_free,
+                                                                      m->geom.w, d_xy);
+  QMCL_LAUNCHED();
+  return copy_out(m, d_xy, xy_out, sizeof(int32_t) * 2 * m->n_free);
 }
 
 qmcl_status qmcl_map_state_at(const qmcl_map *m, float x, float y, int8_t *out) {

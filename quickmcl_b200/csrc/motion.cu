@@ -82,7 +82,7 @@ init_gaussian_kernel(float *__restrict__ x, float *__restrict__ y, float *__rest
 __global__ void __launch_bounds__(256)
 init_global_kernel(float *__restrict__ x, float *__restrict__ y, float *__restrict__ t,
                    double *__restrict__ w, size_t n, size_t global_first, size_t global_n,
-                   const int32_t *__restrict__ free_xy, unsigned long long n_free, MapGeom g,
+                   const uint32_t *__restrict__ free_xy, unsigned long long n_free, MapGeom g,
                    uint64_t seed, uint32_t step) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256)
 draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
             const float *__restrict__ it, const double *__restrict__ iw,
             const int64_t *__restrict__ pos, const double *__restrict__ incl, size_t P,
-            double w_diff, size_t n_draws, const int32_t *__restrict__ free_xy,
+            double w_diff, size_t n_draws, const uint32_t *__restrict__ free_xy,
             unsigned long long n_free, MapGeom g, uint64_t seed, uint32_t step,
             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ ot,
             double *__restrict__ ow, int64_t *__restrict__ src) {
@@ -741,7 +741,7 @@ struct EmitOwned {
   const double *incl;
   size_t P;
   size_t global_first;
-  const int32_t *free_xy;
+  const uint32_t *free_xy;
   unsigned long long n_free;
   MapGeom g;
   SlotRec *rec;

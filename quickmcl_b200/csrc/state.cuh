@@ -32,11 +32,11 @@ struct qmcl_map {
   //   field    float32  W*H   likelihood table exp(-d^2 / 2 sigma^2)
   //   distance float32  W*H   clipped distance in metres (only after load())
   //   state    int8     W*H   0 free / 1 occupied / 2 unknown (map_state.h)
-  //   free     int32x2  nfree cells with state free, row-major order
+  //   free     uint32   nfree linear indices (y*w + x) of the free cells, row-major order
   qmcl::DevBuf<float> field;
   qmcl::DevBuf<float> distance;
   qmcl::DevBuf<int8_t> state;
-  qmcl::DevBuf<int32_t> free_cells;
+  qmcl::DevBuf<uint32_t> free_cells;
   uint64_t n_free = 0;
 
   // scratch for load()

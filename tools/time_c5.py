@@ -18,6 +18,7 @@ out = {}
 # ---- field rebuild
 W = 8192
 occ, res, origin = syn.make_map(W)
+occ = torch.from_numpy(occ).pin_memory().numpy()   # pinned: the 67 MB host->device copy is a plain DMA
 lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
 gm = q.create_likelihood_map()
 stream = torch.cuda.current_stream()
