@@ -86,7 +86,7 @@ static void lowpass_update(double *value, double alpha, double x) {
 }
 
 // Runs K7 + K8 on the current set with the beams already in f->beams.
-static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
+static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_points) {
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   cudaStream_t s = m->stream;
@@ -103,6 +103,7 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used) {
   a.n = ps.n;
   a.beams = f->beams.ptr;
   a.n_beams = n_used;
+  a.rmax = f->beams.ptr + 2 * n_points;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
   if (ps.n) {
@@ -295,7 +296,7 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, siz
   QMCL_CUDA(copy_h2d(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float), s));
   int n_used = 0;
   QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
-  return sensor_update_common(f, n_used);
+  return sensor_update_common(f, n_used, n_points);
 }
 
 qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
@@ -306,7 +307,7 @@ qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud
   QMCL_TRY(f->beams.ensure(2 * n_points + 2));
   int n_used = 0;
   QMCL_TRY(launch_subsample(f->map, dev_cloud_xy, n_points, f->beams.ptr, &n_used));
-  return sensor_update_common(f, n_used);
+  return sensor_update_common(f, n_used, n_points);
 }
 
 qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out) {
@@ -391,6 +392,7 @@ qmcl_status qmcl_map_update_importance(qmcl_map *m, const float *cloud_xy, size_
   a.n = n;
   a.beams = d_beams;
   a.n_beams = n_used;
+  a.rmax = d_beams + 2 * n_points;
   a.partials = m->tmp_w.ptr + n;
   a.scalars = m->tmp_scalars.ptr;
   QMCL_TRY(launch_sensor(m, a));

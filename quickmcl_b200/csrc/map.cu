@@ -199,7 +199,8 @@ edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_di
   const size_t i = static_cast<size_t>(y) * w + x;
   field[i] = __ldg(lut_field + k);
   if (distance) distance[i] = __ldg(lut_dist + k);
-  if (code) code[i] = static_cast<uint16_t>(k);
+  // stored pre-multiplied by 4: a byte offset into the float pw^3 table (sensor.cu)
+  if (code) code[i] = static_cast<uint16_t>(4 * k);
 }
 
 // Distance field on demand (qmcl_map_copy_distance): code -> metres.
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256)
 distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__restrict__ lut_dist,
                           size_t n, float *__restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __ldg(lut_dist + code[i]);
+  if (i < n) out[i] = __ldg(lut_dist + (code[i] >> 2));
 }
 
 // K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
@@ -503,7 +504,7 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   QMCL_TRY(m->edt_g.ensure((n + 1) / 2));
   QMCL_TRY(m->lut.ensure(2 * static_cast<size_t>(kmax + 2)));
   // the uint16 d^2 code map (sensor model's palette path) exists when d^2 fits
-  const bool with_code = kmax + 2 <= 65535;
+  const bool with_code = 4 * (kmax + 4) <= 65535;
   if (with_code) QMCL_TRY(m->code.ensure(n));
   else QMCL_TRY(m->distance.ensure(n));  // with codes the distance field is derived on demand
   QMCL_CUDA(copy_h2d(m->occ.ptr, occ, n, m->stream));

@@ -42,6 +42,8 @@
 
 #include "sensor.cuh"
 
+#include <type_traits>
+
 namespace qmcl {
 
 #ifndef QMCL_SENSOR_THREADS
@@ -105,15 +107,25 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 
+// Also leaves an upper bound of the longest used beam in *rmax (float bits,
+// zeroed by the launcher): particles farther than that from every map edge can
+// skip the in-map test of each evaluation.
 __global__ void subsample_kernel(const float2 *__restrict__ cloud, size_t n_points, size_t step,
-                                 float2 *__restrict__ beams, int n_used) {
+                                 float2 *__restrict__ beams, int n_used,
+                                 unsigned *__restrict__ rmax) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_used) return;
-  float2 p = cloud[static_cast<size_t>(j) * step];
-  // x86 float->int of a NaN/huge value yields INT_MIN, i.e. "outside the map";
-  // make that explicit instead of relying on conversion corner cases.
-  if (!(fabsf(p.x) < 1e30f) || !(fabsf(p.y) < 1e30f)) p = make_float2(1e30f, 1e30f);
-  beams[j] = p;
+  float len = 0.f;
+  if (j < n_used) {
+    float2 p = cloud[static_cast<size_t>(j) * step];
+    // x86 float->int of a NaN/huge value yields INT_MIN, i.e. "outside the map";
+    // make that explicit instead of relying on conversion corner cases.
+    if (!(fabsf(p.x) < 1e30f) || !(fabsf(p.y) < 1e30f)) p = make_float2(1e30f, 1e30f);
+    beams[j] = p;
+    len = __fadd_ru(fabsf(p.x), fabsf(p.y));  // |p|_1 >= |p|_2, rounded up
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax(rmax, __float_as_uint(len));
 }
 
 template <bool FASTDIV>
@@ -168,6 +180,12 @@ __global__ void fastdiv_check_kernel(SensorParams sp, int *mismatch) {
 
 enum { PATH_FIELD = 0, PATH_PAL64 = 1, PATH_PAL32 = 2 };
 
+// Shared-memory float table read by byte offset: the code map stores 4 * code,
+// so the lookup needs no address arithmetic.
+__device__ __forceinline__ float lds_f32_at(const float *table, unsigned byte_off) {
+  return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(table) + byte_off);
+}
+
 template <int PATH, bool FASTDIV>
 __global__ void __launch_bounds__(kSensorThreads, QMCL_SENSOR_MINBLOCKS)
 sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a) {
@@ -189,6 +207,9 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 
   // Lane p prepares particle first+p; the values are then broadcast.
   float lx = 0.f, ly = 0.f, lc = 1.f, ls = 0.f;
+  // every beam end of this particle lies inside the map for sure; padding
+  // particles past the end of the set sit at (0, 0) and are never "safe"
+  bool safe = lane >= kP;
   if (lane < kP && first + lane < a.n) {
     lx = a.x[first + lane];
     ly = a.y[first + lane];
@@ -196,7 +217,14 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     sincos(static_cast<double>(a.t[first + lane]), &sd, &cd);
     lc = static_cast<float>(cd);
     ls = static_cast<float>(sd);
+    // |R v| <= |v|_1 <= rmax; two cells of slack cover every rounding on the way
+    const float reach = __ldg(a.rmax) + 2.f * sp.g.res;
+    const float dx = lx - sp.g.ox, dy = ly - sp.g.oy;
+    safe = dx - reach > 0.f && dy - reach > 0.f &&
+           dx + reach < static_cast<float>(sp.g.w) * sp.g.res &&
+           dy + reach < static_cast<float>(sp.g.h) * sp.g.res;
   }
+  const bool group_safe = __all_sync(0xffffffffu, safe);
   // per-particle packed constants: (c, s), (-s, c), (x, y)
   f32x2 CS[kP], NSC[kP], XY[kP];
 #pragma unroll
@@ -231,9 +259,12 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 #pragma unroll
   for (int p = 0; p < kP; ++p) {
     facc[p] = 0.f;
-    code_prev[p] = sp.n_codes + 1;  // table entry holding 0
+    code_prev[p] = 4 * (sp.n_codes + 1);  // table entry holding 0 (codes are byte offsets)
     pz_prev[p] = -1.0;              // "nothing pending"
   }
+  // The walk over the scan, instantiated with and without the in-map test.
+  auto walk = [&](auto checked_tag) {
+  constexpr bool CHECKED = decltype(checked_tag)::value;
   int step = 0;
   float2 b = (lane < a.n_beams) ? __ldg(beams + lane) : make_float2(0.f, 0.f);
   for (int j = lane; j < a.n_beams; j += 32, ++step) {
@@ -263,11 +294,11 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
         ix = __float2int_rz(__fdiv_rn(ax, sp.g.res));
         iy = __float2int_rz(__fdiv_rn(ay, sp.g.res));
       }
-      const bool inside = in_map(ix, iy, sp.g);
+      const bool inside = !CHECKED || in_map(ix, iy, sp.g);
       // 32-bit cell offset (maps are far below 2^32 cells)
       const unsigned cell = static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix);
       if (PALETTE) {
-        code_cur[p] = sp.n_codes;  // outside the map -> p_max entry
+        code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry
         if (inside) code_cur[p] = __ldg(sp.code + cell);
       } else {
         pz_cur[p] = sp.p_max;
@@ -277,9 +308,9 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       if (PATH == PATH_PAL64) {
-        acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p]]);
+        acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p] >> 2]);
       } else if (PATH == PATH_PAL32) {
-        facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
+        facc[p] = __fadd_rn(facc[p], lds_f32_at(s_lut_f32, code_prev[p]));
       } else if (pz_prev[p] >= 0.0) {
         // z_hit * p is exact in double (two float significands), so the fused
         // form rounds exactly like the reference's mul-then-add.
@@ -299,13 +330,16 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     }
     b = bn;
   }
+  };
+  if (group_safe) walk(std::false_type{});
+  else walk(std::true_type{});
   // drain the pipeline
 #pragma unroll
   for (int p = 0; p < kP; ++p) {
     if (PATH == PATH_PAL64) {
-      acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p]]);
+      acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p] >> 2]);
     } else if (PATH == PATH_PAL32) {
-      facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
+      facc[p] = __fadd_rn(facc[p], lds_f32_at(s_lut_f32, code_prev[p]));
       acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
     } else if (pz_prev[p] >= 0.0) {
       const double pw = fma(z_hit, pz_prev[p], zr);
@@ -375,9 +409,12 @@ qmcl_status launch_subsample(const qmcl_map *m, const float *dev_cloud_xy, size_
   const size_t n_used = n_points ? (n_points + step - 1) / step : 0;
   *n_used_out = static_cast<int>(n_used);
   if (n_used == 0) return QMCL_OK;
+  // the bound lives behind the beams (callers allocate 2 * n_points + 2 floats)
+  unsigned *rmax = reinterpret_cast<unsigned *>(dev_beams + 2 * n_points);
+  QMCL_CUDA(cudaMemsetAsync(rmax, 0, sizeof(unsigned), m->stream));
   subsample_kernel<<<div_up(n_used, 256), 256, 0, m->stream>>>(
       reinterpret_cast<const float2 *>(dev_cloud_xy), n_points, step,
-      reinterpret_cast<float2 *>(dev_beams), static_cast<int>(n_used));
+      reinterpret_cast<float2 *>(dev_beams), static_cast<int>(n_used), rmax);
   QMCL_LAUNCHED();
   return QMCL_OK;
 }

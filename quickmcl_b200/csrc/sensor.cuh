@@ -11,6 +11,7 @@ struct SensorLaunch {
   size_t n;                // particles
   const float *beams;      // used beams, float2, base frame
   int n_beams;
+  const float *rmax;       // device: upper bound of the longest used beam (launch_subsample)
   double *partials;        // >= sensor_grid(n) doubles
   FilterScalars *scalars;  // total_weight written by the last block
 };

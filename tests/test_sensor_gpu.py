@@ -115,6 +115,26 @@ def test_libm_trig_mode_reports_flip_fraction():
     assert abs(host["weight"].sum() - ref["weight"].sum()) <= 1e-6 * ref["weight"].sum()
 
 
+def test_ragged_particle_counts_and_small_map_edges():
+    """Particle counts that do not fill the last warp group, on a map small enough
+    that beams leave it: the interior fast path (no in-map test) must not be taken
+    for padding particles or for particles within reach of an edge."""
+    occ, res, origin, om, gm = build_pair(400)
+    # the palette path (codes) is the default one when the map is built here
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, 360, 360.0)
+    for n in (1, 3, 5, 33, 3001, 2999):
+        x, y, t = syn.uniform_cloud(occ, res, origin, n, seed=n)
+        ref = ob.make_particles(x, y, t, np.ones(n))
+        total_ref = om.update_importance(scan, ref, ob.TRIG_CR)
+        got = q.make_particles(x, y, t, np.ones(n))
+        total = gm.update_importance(scan, got)
+        assert abs(total - total_ref) <= 1e-6 * total_ref
+        nz = ref["weight"] > 0
+        assert rel_err(got["weight"][nz], ref["weight"][nz]).max() <= 1e-5
+
+
 def test_zero_total_equalises():
     """particle_filter.cpp:113-120: zero total weight -> every weight 1/N."""
     occ, res, origin = syn.make_map(400)
