@@ -217,6 +217,17 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy,
  * already in HBM (dev_cloud_xy), nothing is copied to the host. */
 qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
                                           size_t n_points);
+/* The same update fed with a raw planar LaserScan: the projection
+ * of laser_handler.cpp:108-121 (laser_geometry: a point per range with
+ * range_min <= r < range_max at angle_min + i * angle_increment) and the rigid
+ * laser->base mount transform (x, y, yaw) run on the device, so only the 4 B
+ * ranges cross PCIe.  n_points_out (optional) receives the number of valid points. */
+qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, size_t n_ranges,
+                                           float angle_min, float angle_increment,
+                                           float range_min, float range_max,
+                                           const double mount[3], size_t *n_points_out);
+/* Test hook: the projected cloud of the last qmcl_filter_update_sensor_scan. */
+qmcl_status qmcl_filter_copy_cloud(const qmcl_filter *f, float *xy_out, size_t cap, size_t *n_out);
 /* IParticleFilter::resample_and_cluster (particle_filter.cpp:138-161). */
 qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f);
 /* IParticleFilter::cluster (particle_filter.cpp:163-175). */

@@ -126,6 +126,7 @@ def lib():
         "orc_filter_set_lowpass": (None, [vp, f64, f64]),
         "orc_filter_last_total_weight": (f64, [vp]),
         "orc_last_seconds": (f64, []),
+        "orc_project_scan": (sz, [pf32, sz, f32, f32, f32, f32, pf64, pf32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -328,6 +329,16 @@ class OracleFilter:
 
     def last_total_weight(self):
         return self.L.orc_filter_last_total_weight(self.h)
+
+
+def project_scan(ranges, angle_min, angle_increment, range_min, range_max, mount=(0.0, 0.0, 0.0)):
+    """LaserScan -> base-frame points (laser_handler.cpp:108-121); float32 [k, 2]."""
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    mount = np.asarray(mount, np.float64)
+    out = np.zeros((len(ranges), 2), np.float32)
+    k = lib().orc_project_scan(_ptr(ranges, C.c_float), len(ranges), angle_min, angle_increment,
+                               range_min, range_max, _ptr(mount, C.c_double), _ptr(out, C.c_float))
+    return out[:k]
 
 
 def last_seconds():

@@ -802,6 +802,32 @@ extern "C" {
 
 double orc_last_seconds(void) { return g_last_seconds; }
 
+// laser_handler.cpp:108-121 (laser_geometry projection + mount transform).
+size_t orc_project_scan(const float *ranges, size_t n, float angle_min,
+                        float angle_increment, float range_min,
+                        float range_max, const double mount[3],
+                        float *out_xy) {
+  const double cy = std::cos(mount[2]), sy = std::sin(mount[2]);
+  size_t k = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double r = ranges[i];
+    if (!(r < static_cast<double>(range_max) &&
+          r >= static_cast<double>(range_min)))
+      continue;
+    const double a = static_cast<double>(angle_min) +
+                     static_cast<double>(i) * static_cast<double>(angle_increment);
+    const float px = static_cast<float>(r * std::cos(a));
+    const float py = static_cast<float>(r * std::sin(a));
+    // tf2::Transform: basis row . v + origin, in double
+    const double x = (cy * px + (-sy) * py) + mount[0];
+    const double y = (sy * px + cy * py) + mount[1];
+    out_xy[2 * k] = static_cast<float>(x);
+    out_xy[2 * k + 1] = static_cast<float>(y);
+    ++k;
+  }
+  return k;
+}
+
 void orc_distance_cache(float resolution, float max_dist, int *size_out,
                         float *out, size_t cap) {
   int n = 0;

@@ -166,6 +166,21 @@ void orc_filter_get_lowpass(const orc_filter *f, double out[2]);
 void orc_filter_set_lowpass(orc_filter *f, double w_slow, double w_fast);
 double orc_filter_last_total_weight(const orc_filter *f);
 
+/* LaserScan -> base-frame point cloud: what
+ * laser_handler.cpp:108-121 obtains from laser_geometry's
+ * transformLaserScanToPointCloud(localised_frame, scan, cloud, tf, -1.0, 0)
+ * followed by pcl::fromROSMsg (laser.cpp:25-34), for a laser mounted rigidly on
+ * the base.  laser_geometry (1.6, ROS Melodic) is a third-party dependency that
+ * is not in the reference tree; this restates its published algorithm: a point
+ * per range with range_min <= r < range_max at angle_min + i * increment,
+ * cos/sin in double, stored as float, then the rigid mount transform in double
+ * (tf2), stored as float.  Parity unpinned (no reference test covers it).
+ * out_xy holds up to n points (x, y); returns the number written. */
+size_t orc_project_scan(const float *ranges, size_t n, float angle_min,
+                        float angle_increment, float range_min,
+                        float range_max, const double mount[3],
+                        float *out_xy);
+
 /* Stage timings of the last call, seconds (steady_clock). */
 double orc_last_seconds(void);
 

@@ -88,6 +88,8 @@ SIGNATURES = {
     "qmcl_filter_handle_odometry": [vp, pf64, pf64, pf32],
     "qmcl_filter_update_sensor": [vp, pf32, sz],
     "qmcl_filter_update_sensor_dev": [vp, vp, sz],
+    "qmcl_filter_update_sensor_scan": [vp, pf32, sz, f32, f32, f32, f32, pf64, C.POINTER(sz)],
+    "qmcl_filter_copy_cloud": [vp, pf32, sz, C.POINTER(sz)],
     "qmcl_filter_resample_and_cluster": [vp],
     "qmcl_filter_cluster": [vp],
     "qmcl_filter_get_estimate": [vp, pf64, pf64, C.POINTER(C.c_int)],

@@ -244,6 +244,29 @@ class ParticleFilter:
         check(self._L.qmcl_filter_update_sensor(self._h, ptr(cloud, C.c_float), cloud.shape[0]),
               "qmcl_filter_update_sensor")
 
+    def update_importance_from_scan(self, ranges, angle_min, angle_increment, range_min,
+                                    range_max, mount=(0.0, 0.0, 0.0)):
+        """The sensor update fed with a raw LaserScan: projection (laser_handler.cpp:108-121)
+        and the laser->base mount transform run on the device.  Returns the number of
+        valid points."""
+        ranges = np.ascontiguousarray(ranges, np.float32)
+        mount = np.asarray(mount, np.float64)
+        n = C.c_size_t(0)
+        check(self._L.qmcl_filter_update_sensor_scan(
+            self._h, ptr(ranges, C.c_float), len(ranges), angle_min, angle_increment, range_min,
+            range_max, ptr(mount, C.c_double), C.byref(n)), "qmcl_filter_update_sensor_scan")
+        return n.value
+
+    def last_cloud(self):
+        """Test hook: the projected cloud of the last update_importance_from_scan."""
+        n = C.c_size_t(0)
+        check(self._L.qmcl_filter_copy_cloud(self._h, None, 0, C.byref(n)), "qmcl_filter_copy_cloud")
+        out = np.zeros((n.value, 2), np.float32)
+        if n.value:
+            check(self._L.qmcl_filter_copy_cloud(self._h, ptr(out, C.c_float), n.value,
+                                                 C.byref(n)), "qmcl_filter_copy_cloud")
+        return out
+
     def resample_and_cluster(self):
         check(self._L.qmcl_filter_resample_and_cluster(self._h),
               "qmcl_filter_resample_and_cluster")

@@ -526,7 +526,7 @@ static BinParams bin_params(const qmcl_filter *f) {
 // SpacePartitioning::reset + add_point for x/y/t[0..n): bbox, dense table,
 // sorted occupied-bin list.  Leaves parent[b] = b.
 qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n,
-                       bool reuse_grid) {
+                       bool reuse_grid, bool grid_only) {
   cudaStream_t s = f->map->stream;
   const BinGrid prev_grid = f->grid;
   const bool have_prev = reuse_grid && f->bins_built && prev_grid.nx > 0;
@@ -596,6 +596,10 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   const size_t cells = static_cast<size_t>(nx) * ny * nt;
   f->grid = g;
   QMCL_TRY(f->table.ensure(cells));
+  if (grid_only) {  // the caller only needs the dense grid (KLD's first-draw table)
+    f->bins_built = true;
+    return QMCL_OK;
+  }
   QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0, cells * sizeof(int32_t), s));
   if (n) {
     bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);

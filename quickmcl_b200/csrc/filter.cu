@@ -7,6 +7,7 @@
 #include "filter.cuh"
 #include "sensor.cuh"
 #include "shard.cuh"
+#include "scan.cuh"
 
 namespace qmcl {
 
@@ -78,6 +79,40 @@ __global__ void normalise_by_value_kernel(double *__restrict__ w, size_t n, doub
   if (i >= n) return;
   w[i] = (total > 0) ? __ddiv_rn(w[i], total) : __ddiv_rn(1.0, n_global);
 }
+
+// LaserScan -> base-frame points (laser_handler.cpp:108-121 via laser_geometry,
+// then the rigid mount transform of tf2 in double).  Valid ranges are compacted
+// in order with the device-wide scan.
+struct ScanGeom {
+  float angle_min, angle_increment, range_min, range_max;
+  double mx, my, cy, sy;
+};
+struct ValidRange {
+  const float *ranges;
+  ScanGeom g;
+  __device__ uint32_t operator()(size_t i) const {
+    const double r = ranges[i];
+    return (r < static_cast<double>(g.range_max) && r >= static_cast<double>(g.range_min)) ? 1u : 0u;
+  }
+};
+struct EmitPoint {
+  const float *ranges;
+  ScanGeom g;
+  float2 *out;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+    if (!flag) return;
+    const double r = ranges[i];
+    const double a = static_cast<double>(g.angle_min) +
+                     static_cast<double>(i) * static_cast<double>(g.angle_increment);
+    double sa, ca;
+    sincos(a, &sa, &ca);
+    const float px = static_cast<float>(r * ca);
+    const float py = static_cast<float>(r * sa);
+    const double x = __dadd_rn(__dadd_rn(__dmul_rn(g.cy, px), __dmul_rn(-g.sy, py)), g.mx);
+    const double y = __dadd_rn(__dadd_rn(__dmul_rn(g.sy, px), __dmul_rn(g.cy, py)), g.my);
+    out[pos] = make_float2(static_cast<float>(x), static_cast<float>(y));
+  }
+};
 
 // low_pass_filter.h:39-50
 static void lowpass_update(double *value, double alpha, double x) {
@@ -180,6 +215,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   }
   f->beams.release();
   f->cloud.release();
+  f->ranges.release();
   f->partials.release();
   f->scalars.release();
   f->h_beams.release();
@@ -308,6 +344,50 @@ qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud
   int n_used = 0;
   QMCL_TRY(launch_subsample(f->map, dev_cloud_xy, n_points, f->beams.ptr, &n_used));
   return sensor_update_common(f, n_used, n_points);
+}
+
+qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, size_t n_ranges,
+                                           float angle_min, float angle_increment,
+                                           float range_min, float range_max,
+                                           const double mount[3], size_t *n_points_out) {
+  if (!f || (!ranges && n_ranges) || !mount) return QMCL_ERR_INVALID_ARG;
+  if (!f->map->has_map) return QMCL_ERR_NO_MAP;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  QMCL_TRY(f->ranges.ensure(n_ranges + 2));
+  QMCL_TRY(f->cloud.ensure(2 * n_ranges + 2));
+  QMCL_TRY(f->beams.ensure(2 * n_ranges + 2));
+  QMCL_TRY(f->h_beams.ensure(2 * n_ranges + 2));
+  std::memcpy(f->h_beams.ptr, ranges, n_ranges * sizeof(float));
+  QMCL_CUDA(copy_h2d(f->ranges.ptr, f->h_beams.ptr, n_ranges * sizeof(float), s));
+  ScanGeom g{angle_min, angle_increment, range_min, range_max, mount[0], mount[1],
+             std::cos(mount[2]), std::sin(mount[2])};
+  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(n_ranges) + 4));
+  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
+      f->scan_tmp.ptr + ((scan_blocks(n_ranges) + 1) & ~1u));
+  QMCL_TRY(device_scan(s, ValidRange{f->ranges.ptr, g},
+                       EmitPoint{f->ranges.ptr, g, reinterpret_cast<float2 *>(f->cloud.ptr)},
+                       n_ranges, f->scan_tmp.ptr, d_total));
+  unsigned long long n_points = 0;  // the subsampling step depends on it (map_likelihood.cpp:67-74)
+  QMCL_CUDA(copy_d2h(&n_points, d_total, sizeof(n_points), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  f->n_cloud = n_points;
+  if (n_points_out) *n_points_out = n_points;
+  int n_used = 0;
+  QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
+  return sensor_update_common(f, n_used, n_points);
+}
+
+qmcl_status qmcl_filter_copy_cloud(const qmcl_filter *fc, float *xy_out, size_t cap, size_t *n_out) {
+  if (!fc) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  if (n_out) *n_out = f->n_cloud;
+  const size_t n = f->n_cloud < cap ? f->n_cloud : cap;
+  if (!n || !xy_out) return QMCL_OK;
+  QMCL_TRY(use_device(f->map));
+  QMCL_CUDA(copy_d2h(xy_out, f->cloud.ptr, 2 * n * sizeof(float), f->map->stream));
+  QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  return QMCL_OK;
 }
 
 qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out) {

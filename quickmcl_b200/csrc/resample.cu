@@ -621,8 +621,8 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
   QMCL_TRY(out.ensure(n_max));
   QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_max));
-  // bins of all candidates
-  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max));
+  // the dense bin grid spanned by all candidates
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max, false, true));
   const BinGrid g = f->grid;
   const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
   KldParams kp;
@@ -1038,8 +1038,8 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
     return QMCL_OK;
   }
   const size_t slot_first = f->global_first, n_loc = out.n;
-  // bins of all candidates (global grid, occupancy summed over shards)
-  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_loc));
+  // the dense bin grid spanned by all candidates of all shards
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_loc, false, true));
   const BinGrid g = f->grid;
   const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
   KldParams kp;

@@ -153,6 +153,8 @@ struct qmcl_filter {
   int theta_lo = -17, theta_hi = 17;
 
   qmcl::DevBuf<float> cloud;        // the scan as received, float2
+  qmcl::DevBuf<float> ranges;       // raw LaserScan ranges (update_sensor_scan)
+  size_t n_cloud = 0;               // points of the last projected scan
   qmcl::DevBuf<float> beams;        // compacted used beams, float2
   qmcl::DevBuf<double> partials;    // per-block partial sums
   qmcl::DevBuf<FilterScalars> scalars;
