@@ -241,6 +241,18 @@ qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out);
 qmcl_status qmcl_filter_copy_particles(const qmcl_filter *f, qmcl_particle *out,
                                        size_t cap);
 
+/* ---- multi-robot batch (BASELINE configs[4]) ------------------------------
+ * One scan cycle (laser_handler.cpp:243-276: odometry, sensor, resample or
+ * cluster, estimate) for n_filters independent filters, dealt round-robin to
+ * `lanes` native host threads.  Filters handled by different lanes must sit on
+ * different map handles (streams).  odom_*: n x 3 doubles; clouds_xy[i] holds
+ * n_points[i] x {x, y}; poses_out n x 3, covs_out n x 9, valid_out n. */
+qmcl_status qmcl_batch_update(qmcl_filter *const *filters, size_t n_filters, int lanes,
+                              const double *odom_new, const double *odom_old,
+                              const float alpha[4], const float *const *clouds_xy,
+                              const size_t *n_points, int resample, double *poses_out,
+                              double *covs_out, int *valid_out);
+
 /* ---- test hooks (not part of the reference interface) ---- */
 qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n);
 /* Sharded variant: p[0..n) is this rank's block, starting at global index

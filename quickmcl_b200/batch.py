@@ -14,10 +14,13 @@ The reference has no counterpart (one filter per process); the per-robot call
 sequence is laser_handler.cpp:243-276.
 """
 import concurrent.futures as cf
+import ctypes as C
 
 import numpy as np
 import torch
 
+from . import _abi
+from ._abi import check, ptr
 from .api import (LikelihoodMapParameters, OccupancyGrid, ParticleFilterParameters,
                   create_likelihood_map, create_particle_filter)
 
@@ -69,6 +72,28 @@ class FilterBatch:
     def initialise(self, poses, covariance):
         poses = np.asarray(poses, np.float32)
         return self.for_each(lambda i, f: f.initialise(poses[i], covariance))
+
+    def update_native(self, odom_new, odom_old, alpha, scans, resample=True):
+        """The same cycle through qmcl_batch_update: the lanes are native threads inside the
+        library (no interpreter on the per-robot path).  Filter i runs on lane i % lanes,
+        which is the lane whose map handle it was created on."""
+        n = self.n
+        a = np.ascontiguousarray(odom_new, np.float64).reshape(n, 3)
+        b = np.ascontiguousarray(odom_old, np.float64).reshape(n, 3)
+        al = np.asarray(alpha, np.float32)
+        clouds = [np.ascontiguousarray(s, np.float32) for s in scans]
+        cptr = (C.POINTER(C.c_float) * n)(*[ptr(c, C.c_float) for c in clouds])
+        npts = (C.c_size_t * n)(*[c.shape[0] for c in clouds])
+        handles = (C.c_void_p * n)(*[f._h for f in self.filters])
+        poses = np.zeros((n, 3))
+        covs = np.zeros((n, 9))
+        valid = np.zeros(n, np.int32)
+        check(_abi.lib().qmcl_batch_update(handles, n, self.lanes, ptr(a, C.c_double),
+                                           ptr(b, C.c_double), ptr(al, C.c_float), cptr, npts,
+                                           int(resample), ptr(poses, C.c_double),
+                                           ptr(covs, C.c_double), ptr(valid, C.c_int32)),
+              "qmcl_batch_update")
+        return [(bool(valid[i]), poses[i], covs[i].reshape(3, 3)) for i in range(n)]
 
     def update(self, odom_new, odom_old, alpha, scans, resample=True):
         """One scan cycle per robot (laser_handler.cpp:243-276): motion, sensor, resample (or

@@ -68,7 +68,7 @@ def test_filter_batch_matches_independent_oracles():
                              f.initialise_factor(poses[i].astype(np.float32), factor)))
     odom_new = np.tile([0.02, 0.01, 0.01], (n_filters, 1))
     odom_old = np.zeros((n_filters, 3))
-    got = b.update(odom_new, odom_old, syn.NODE_ALPHA, scans)
+    got = b.update_native(odom_new, odom_old, syn.NODE_ALPHA, scans)
     om = ob.OracleMap(**lp)
     om.new_map(occ, res, origin, field_mode=ob.FIELD_EXACT_EDT)
     for i in range(n_filters):

@@ -73,6 +73,16 @@ for lanes in (1, 8, 16, 32):
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.median(ts))
+    tn = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        b.update_native(odo_new, odo_old, syn.NODE_ALPHA, scans)
+        torch.cuda.synchronize()
+        tn.append(time.perf_counter() - t0)
+    msn = 1e3 * float(np.median(tn))
+    out[f"batch256_native_lanes{lanes}"] = {"ms_per_batch_update": msn,
+                                            "filter_updates_per_s": n_filters / (msn * 1e-3),
+                                            "evals_per_s": n_filters * n_particles * len(scan) / (msn * 1e-3)}
     out[f"batch256_lanes{lanes}"] = {"ms_per_batch_update": ms,
                                      "filter_updates_per_s": n_filters / (ms * 1e-3),
                                      "evals_per_s": n_filters * n_particles * len(scan) / (ms * 1e-3)}
