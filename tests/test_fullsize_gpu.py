@@ -1,0 +1,180 @@
+"""BASELINE.json's full sizes (C2: 100 k particles / 2000^2 map / 1081 beams /
+KLD; C3: 1 M particles / 4000^2 map / adaptive) through size-independent
+properties, because the oracle cannot run them whole in test time:
+
+* per-particle weights are independent of the rest of the set, so a random
+  subset re-evaluated by the oracle must match the GPU's weights;
+* normalised weights sum to the post-penalty share of the total;
+* the running sum is the sequential one (checked against numpy on the full array);
+* low-variance indices are non-decreasing and consistent with that running sum;
+* the KLD output size satisfies the reference's stop rule for the bins it reports;
+* a sharded run (4 shards as threads) equals the single-GPU run slot by slot."""
+import math
+
+import numpy as np
+import pytest
+
+import quickmcl_b200 as q
+from quickmcl_b200 import sharded, synthetic as syn
+from quickmcl_b200._abi import PARTICLE_DTYPE, Particle, check, ptr
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+RES_THETA = float(np.float32(math.pi / 18))
+
+
+def setup(width, n, cloud, beams=1081, fov=270.0):
+    occ, res, origin = syn.make_map(width)
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**lp))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, beams, fov)
+    if cloud == "tracking":
+        x, y, t = syn.gaussian_cloud(pose, n)
+    else:
+        x, y, t = syn.uniform_cloud(occ, res, origin, n)
+    return occ, res, origin, lp, gm, scan, q.make_particles(x, y, t, np.full(n, 1.0 / n))
+
+
+def oracle_subset_weights(gm, lp, res, origin, scan, parts):
+    """Oracle weights (pre-normalisation, after the penalty) of `parts` on the GPU's own field."""
+    om = ob.OracleMap(**lp)
+    om.load_field(gm.field(), gm.state(), res, origin)
+    sub = ob.make_particles(parts["x"], parts["y"], parts["theta"], np.ones(len(parts)))
+    om.update_importance(scan, sub, ob.TRIG_CR)
+    return sub["weight"]
+
+
+@pytest.mark.parametrize("width,n,cloud", [(2000, 100_000, "tracking"), (4000, 1_000_000, "global")])
+def test_sensor_update_full_size_subset_parity_and_normalisation(width, n, cloud):
+    occ, res, origin, lp, gm, scan, start = setup(width, n, cloud)
+    f = q.create_particle_filter(gm, seed=3)
+    f.set_particles(start)
+    f.update_importance_from_observations(scan)
+    got = f.get_particles()
+    total = f.last_total_weight()
+    rng = np.random.default_rng(1)
+    pick = rng.choice(n, 1500, replace=False)
+    want = oracle_subset_weights(gm, lp, res, origin, scan, start[pick])
+    g = got["weight"][pick] * total                     # undo the normalisation
+    nz = want > 0
+    assert np.array_equal(nz, g > 0)
+    assert np.max(np.abs(g[nz] - want[nz]) / want[nz]) <= 1e-5
+    # normalised by the PRE-penalty total (map_likelihood.cpp:112): the sum is the
+    # surviving share, never above 1
+    s = float(np.sum(got["weight"]))
+    assert 0.0 < s <= 1.0 + 1e-9
+    if cloud == "tracking":
+        assert abs(s - 1.0) < 1e-9                       # nobody is penalised near the truth
+
+
+def test_running_sum_and_low_variance_full_size():
+    n = 1_000_000
+    occ, res, origin, lp, gm, scan, start = setup(4000, n, "global")
+    f = q.create_particle_filter(gm, seed=3)
+    f.set_parameters(q.ParticleFilterParameters(resample_type=q.ResampleType.low_variance,
+                                                particle_count_min=n, particle_count_max=n))
+    f.set_particles(start)
+    f.update_importance_from_observations(scan)
+    w = f.get_particles()["weight"].copy()
+    cdf, carry = f.debug_prefix(w)
+    want = np.cumsum(w)                                  # the sequential loop
+    assert np.array_equal(cdf.view(np.uint64), want.view(np.uint64))
+    f.set_rng(3, 7)
+    f.resample_and_cluster()
+    idx = f.resample_indices()
+    assert len(idx) == n and np.all(np.diff(idx) >= 0)
+    # consistency with the running sum: U_m = r + m * minv lands in (c[i-1], c[i]]
+    minv = float(np.float32(1.0) / np.float32(n))
+    m = np.arange(0, n, 997)
+    i = idx[m]
+    lo = np.where(i > 0, want[np.maximum(i - 1, 0)], -1.0)
+    r_lo = lo - m * minv                                 # bounds on r from every sampled slot
+    r_hi = want[i] - m * minv
+    clamped = i == n - 1                                 # the overrun clamp has no upper bound
+    assert np.max(r_lo) <= np.min(r_hi[~clamped]) + 1e-12
+    ok, pose, cov = f.get_estimated_pose()
+    assert ok and np.all(np.isfinite(pose)) and np.all(np.isfinite(cov))
+
+
+def test_kld_full_size_stop_rule_property():
+    n = 100_000
+    occ, res, origin, lp, gm, scan, start = setup(2000, n, "tracking")
+    f = q.create_particle_filter(gm, seed=3)
+    pf = q.ParticleFilterParameters(resample_type=q.ResampleType.kld, particle_count_min=100,
+                                    particle_count_max=n, kld_epsilon=0.05, kld_z=0.95,
+                                    space_partitioning_resolution_theta=RES_THETA)
+    f.set_parameters(pf)
+    f.set_particles(start)
+    f.update_importance_from_observations(scan)
+    f.set_rng(3, 11)
+    f.resample_and_cluster()
+    n_out = f.num_particles()
+    keys, labels = f.bins()
+    k = len(keys)
+    assert int(keys[:, 3].sum()) == n_out               # bin counts add up to the set
+    lim = ob.lib().orc_kld_limit(k, 0.05, 0.95, 100, n)
+    # the loop stops at the first m with m >= limit(k_m): m = n_out - 1, and k_m = k
+    assert n_out - 1 >= lim or n_out == n
+    if n_out < n:
+        # one draw earlier the rule did not fire: with k or k - 1 bins
+        lim_prev = min(ob.lib().orc_kld_limit(k, 0.05, 0.95, 100, n),
+                       ob.lib().orc_kld_limit(max(k - 1, 0), 0.05, 0.95, 100, n))
+        assert n_out - 2 < max(lim, lim_prev) or n_out - 2 < lim
+    src = f.resample_indices()
+    assert len(src) == n_out and src.min() >= 0 and src.max() < n
+    got = f.get_particles()
+    assert np.array_equal(got["x"], start["x"][src])    # copies of their sources (motion-free)
+    assert abs(float(got["weight"].sum()) - 1.0) < 1e-9
+
+
+def test_sharded_equals_single_gpu_at_one_million():
+    n, G = 1_000_000, 4
+    occ, res, origin, lp, gm, scan, start = setup(4000, n, "global")
+    pf = q.ParticleFilterParameters(resample_type=q.ResampleType.low_variance,
+                                    particle_count_min=n, particle_count_max=n,
+                                    space_partitioning_resolution_theta=RES_THETA)
+    f = q.create_particle_filter(gm, seed=3)
+    f.set_parameters(pf)
+    f.set_particles(start)
+    f.set_rng(3, 2)
+    f.handle_odometry((0.25, 0.05, 0.1), (0, 0, 0), syn.NODE_ALPHA)
+    f.update_importance_from_observations(scan)
+    f.resample_and_cluster()
+    single = f.get_particles()
+    ok1, pose1, cov1 = f.get_estimated_pose()
+
+    def make_map():
+        m = q.create_likelihood_map()
+        m.set_parameters(q.LikelihoodMapParameters(**lp))
+        m.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+        return m
+
+    def body(fs, rank):
+        import ctypes as C
+        fs.set_parameters(pf)
+        first, count = sharded.shard_slice(n, rank, G)
+        mine = np.ascontiguousarray(start[first:first + count])
+        check(fs._L.qmcl_filter_set_particles_shard(fs._h, ptr(mine, Particle), count, first, n), "set")
+        fs.set_rng(3, 2)
+        fs.handle_odometry((0.25, 0.05, 0.1), (0, 0, 0), syn.NODE_ALPHA)
+        fs.update_importance_from_observations(scan)
+        fs.resample_and_cluster()
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(fs._L.qmcl_filter_shard_range(fs._h, C.byref(a), C.byref(b), C.byref(c)), "range")
+        out = np.zeros(b.value, dtype=PARTICLE_DTYPE)
+        check(fs._L.qmcl_filter_copy_particles(fs._h, ptr(out, Particle), b.value), "copy")
+        return a.value, out, fs.get_estimated_pose()
+
+    res_ = sharded.run_local_shards(G, make_map, body, seed=3)
+    parts = sorted(res_, key=lambda r: r[0])
+    got = np.concatenate([p[1] for p in parts])
+    assert len(got) == len(single)
+    # weights before resampling differ only in the rounding of the total, so an index can
+    # flip where a slot position falls within that rounding of a CDF step: count them
+    same = (got["x"] == single["x"]) & (got["y"] == single["y"]) & (got["theta"] == single["theta"])
+    assert same.mean() > 0.9999, same.mean()
+    ok2, pose2, cov2 = parts[0][2]
+    assert ok1 and ok2 and np.max(np.abs(pose1 - pose2)) <= 1e-6
