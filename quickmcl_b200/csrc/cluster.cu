@@ -617,9 +617,9 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(f->bin_count.ensure(max_bins));
   QMCL_TRY(f->bin_label.ensure(max_bins));
   QMCL_TRY(f->bin_cluster.ensure(max_bins));
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(cells) + 4));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(cells) + 4));
   unsigned long long *d_total =
-      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(cells) + 1) & ~1u));
+      scan_total_ptr(f->scan_tmp.ptr, cells);
   QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
                        EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
                        cells, f->scan_tmp.ptr, d_total));
@@ -646,9 +646,8 @@ qmcl_status label_clusters(qmcl_filter *f) {
   QMCL_LAUNCHED();
   cc_flatten_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->bin_label.ptr, f->n_bins);
   QMCL_LAUNCHED();
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(f->n_bins) + 4));
-  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
-      f->scan_tmp.ptr + ((scan_blocks(f->n_bins) + 1) & ~1u));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(f->n_bins) + 4));
+  unsigned long long *d_total = scan_total_ptr(f->scan_tmp.ptr, f->n_bins);
   QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr}, EmitRootId{f->bin_cluster.ptr}, f->n_bins,
                        f->scan_tmp.ptr, d_total));
   unsigned long long nc = 0;

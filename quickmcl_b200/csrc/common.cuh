@@ -70,6 +70,18 @@ template <typename T> struct DevBuf {
     cap = want;
     return QMCL_OK;
   }
+  // Grow; new storage starts out zeroed (the scan's status words need that).
+  qmcl_status ensure_zero(size_t n) {
+    if (n <= cap) return QMCL_OK;
+    const size_t want = n + n / 8 + 16;
+    T *np = nullptr;
+    QMCL_CUDA(cudaMalloc(&np, want * sizeof(T)));
+    QMCL_CUDA(cudaMemset(np, 0, want * sizeof(T)));
+    if (ptr) cudaFree(ptr);
+    ptr = np;
+    cap = want;
+    return QMCL_OK;
+  }
   // Grow and keep the first `keep` elements.
   qmcl_status ensure_keep(size_t n, size_t keep, cudaStream_t s) {
     if (n <= cap) return QMCL_OK;

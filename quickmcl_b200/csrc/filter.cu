@@ -237,6 +237,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->bin_label.release();
   f->bin_cluster.release();
   f->scan_tmp.release();
+  f->scan_legacy.release();
   f->cluster_acc.release();
   f->particle_cid.release();
   f->timer.release();
@@ -362,9 +363,8 @@ qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, 
   QMCL_CUDA(copy_h2d(f->ranges.ptr, f->h_beams.ptr, n_ranges * sizeof(float), s));
   ScanGeom g{angle_min, angle_increment, range_min, range_max, mount[0], mount[1],
              std::cos(mount[2]), std::sin(mount[2])};
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(n_ranges) + 4));
-  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
-      f->scan_tmp.ptr + ((scan_blocks(n_ranges) + 1) & ~1u));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(n_ranges) + 4));
+  unsigned long long *d_total = scan_total_ptr(f->scan_tmp.ptr, n_ranges);
   QMCL_TRY(device_scan(s, ValidRange{f->ranges.ptr, g},
                        EmitPoint{f->ranges.ptr, g, reinterpret_cast<float2 *>(f->cloud.ptr)},
                        n_ranges, f->scan_tmp.ptr, d_total));

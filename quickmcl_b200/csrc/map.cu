@@ -15,6 +15,7 @@ namespace qmcl {
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
+std::atomic<uint32_t> g_scan_epoch{1};
 static thread_local std::string g_error;
 
 void set_error(const char *fmt, ...) {

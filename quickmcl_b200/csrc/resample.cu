@@ -528,9 +528,9 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
   QMCL_TRY(f->incl.ensure(in.n));
   StageScope sc(f, QMCL_STAGE_CDF);
   QMCL_TRY(sequential_prefix(f, in.w.ptr, in.n, f->cdf.ptr));
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(in.n) + 4));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(in.n) + 4));
   unsigned long long *d_total =
-      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(in.n) + 1) & ~1u));
+      scan_total_ptr(f->scan_tmp.ptr, in.n);
   QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
                        in.n, f->scan_tmp.ptr, d_total));
   unsigned long long P = 0;
@@ -632,9 +632,9 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   kp.z = f->params.kld_z;
   kp.nmin = f->params.particle_count_min;
   kp.nmax = f->params.particle_count_max;
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(n_max) + 8));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(n_max) + 8));
   unsigned long long *d_total =
-      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((scan_blocks(n_max) + 1) & ~1u));
+      scan_total_ptr(f->scan_tmp.ptr, n_max);
   unsigned long long *d_stop = d_total + 1;
   {
     StageScope sc(f, QMCL_STAGE_KLD);
@@ -841,12 +841,11 @@ static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in,
   }
   QMCL_TRY(f->pos.ensure(in.n + 1));
   QMCL_TRY(f->incl.ensure(in.n + 1));
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(std::max(in.n, n_draws)) + 16 + 2 * (kMaxShards + 2)));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(std::max(in.n, n_draws)) + 16 + 2 * (kMaxShards + 2)));
   unsigned long long P = 0;
   {
     StageScope sc(f, QMCL_STAGE_CDF);
-    unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
-        f->scan_tmp.ptr + ((scan_blocks(std::max(in.n, n_draws)) + 1) & ~1u));
+    unsigned long long *d_total = scan_total_ptr(f->scan_tmp.ptr, std::max(in.n, n_draws));
     QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
                          in.n, f->scan_tmp.ptr, d_total));
     QMCL_CUDA(copy_d2h(&P, d_total, sizeof(P), s));
@@ -876,13 +875,16 @@ static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in,
   ctx.w_diff = w_diff;
   // 3. the draws this rank owns, compacted in slot order
   StageScope sc(f, QMCL_STAGE_SELECT);
+  // (three-kernel scan: the host needs the count between the two passes; its
+  // block sums live in their own buffer, never in the status words of scan_tmp)
   const unsigned blocks = scan_blocks(n_draws);
+  QMCL_TRY(f->scan_legacy.ensure(blocks + 16 + 2 * (kMaxShards + 2)));
   unsigned long long *d_total =
-      reinterpret_cast<unsigned long long *>(f->scan_tmp.ptr + ((blocks + 1) & ~1u));
+      reinterpret_cast<unsigned long long *>(f->scan_legacy.ptr + ((blocks + 1) & ~1u));
   const OwnedFlag flag{ctx};
-  scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(flag, n_draws, f->scan_tmp.ptr);
+  scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(flag, n_draws, f->scan_legacy.ptr);
   QMCL_LAUNCHED();
-  scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_tmp.ptr, blocks, d_total);
+  scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_legacy.ptr, blocks, d_total);
   QMCL_LAUNCHED();
   unsigned long long n_owned = 0;
   QMCL_CUDA(copy_d2h(&n_owned, d_total, sizeof(n_owned), s));
@@ -893,7 +895,7 @@ static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in,
                        in.t.ptr,   in.w.ptr,          f->pos.ptr,
                        f->incl.ptr, static_cast<size_t>(P), f->global_first,
                        f->map->free_cells.ptr, f->map->n_free, f->map->geom, send};
-  scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(flag, emit, n_draws, f->scan_tmp.ptr);
+  scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(flag, emit, n_draws, f->scan_legacy.ptr);
   QMCL_LAUNCHED();
   // 4. deliver every slot to the rank that owns its block
   std::vector<unsigned long long> bounds(G + 1);
@@ -1049,9 +1051,10 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
   kp.z = f->params.kld_z;
   kp.nmin = f->params.particle_count_min;
   kp.nmax = f->params.particle_count_max;
-  QMCL_TRY(f->scan_tmp.ensure(scan_blocks(std::max<size_t>(n_loc, 1)) + 8));
-  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
-      f->scan_tmp.ptr + ((scan_blocks(std::max<size_t>(n_loc, 1)) + 1) & ~1u));
+  const unsigned kld_blocks = scan_blocks(std::max<size_t>(n_loc, 1));
+  QMCL_TRY(f->scan_legacy.ensure(kld_blocks + 16));
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(f->scan_legacy.ptr + ((kld_blocks + 1) & ~1u));
   unsigned long long *d_stop = d_total + 1;
   unsigned long long stop = ~0ull;
   {
@@ -1069,9 +1072,9 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
     const unsigned blocks = scan_blocks(std::max<size_t>(n_loc, 1));
     QMCL_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
     if (n_loc) {
-      scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(nb, n_loc, f->scan_tmp.ptr);
+      scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(nb, n_loc, f->scan_legacy.ptr);
       QMCL_LAUNCHED();
-      scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_tmp.ptr, blocks, d_total);
+      scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_legacy.ptr, blocks, d_total);
       QMCL_LAUNCHED();
     }
     std::vector<unsigned long long> opened(G);
@@ -1081,7 +1084,7 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
     QMCL_CUDA(cudaMemsetAsync(d_stop, 0xff, sizeof(unsigned long long), s));
     if (n_loc) {
       scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(nb, StopRuleAt{kp, d_stop, slot_first, before},
-                                                     n_loc, f->scan_tmp.ptr);
+                                                     n_loc, f->scan_legacy.ptr);
       QMCL_LAUNCHED();
     }
     std::vector<unsigned long long> stops(G);

@@ -112,8 +112,97 @@ scan_apply_kernel(F f, G g, size_t n, const uint32_t *__restrict__ block_offsets
     }
 }
 
-// Host driver.  tmp must hold scan_blocks(n) + 2 uint32 (8-byte aligned tail
-// for the total).  Leaves the grand total in *dev_total (device).
+// ---- single-pass variant (decoupled look-back) ------------------------------
+// One launch instead of three.  Every tile publishes its aggregate in a 64-bit
+// status word {epoch:30, state:2, value:32}; a tile's exclusive prefix is the sum
+// of the aggregates of its predecessors up to the first one that already knows
+// its inclusive prefix.  The epoch (unique per call) makes words left by earlier
+// scans read as "not ready", so the status array is never cleared; it only has
+// to start out zeroed (DevBuf::ensure_zero).  Tiles are taken in blockIdx order,
+// which is the order the hardware dispatches them in, so a predecessor is
+// always running or finished.
+constexpr unsigned long long kScanAggregate = 1ull << 32, kScanInclusive = 2ull << 32;
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, unsigned long long state,
+                                                        uint32_t value) {
+  return (static_cast<unsigned long long>(epoch) << 34) | state | value;
+}
+
+template <typename F, typename G>
+__global__ void __launch_bounds__(kScanBlock)
+scan_onepass_kernel(F f, G g, size_t n, unsigned long long *__restrict__ status, uint32_t epoch,
+                    unsigned long long *__restrict__ out_total) {
+  __shared__ uint32_t s_prefix;
+  const unsigned tile = blockIdx.x;
+  const size_t base = (static_cast<size_t>(tile) * kScanBlock + threadIdx.x) * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? f(base + i) : 0u;
+    c += v[i];
+  }
+  uint32_t total;
+  const uint32_t local = block_excl_scan_u32(c, &total);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long *st = status;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st[0] = scan_pack(epoch, kScanInclusive, total);
+    } else {
+      if (lane == 0) st[tile] = scan_pack(epoch, kScanAggregate, total);
+      __threadfence();
+      // look back over windows of 32 predecessors
+      int hi = static_cast<int>(tile) - 1;
+      while (true) {
+        const int t = hi - lane;
+        unsigned long long wd = 0;
+        bool ready;
+        do {
+          wd = (t >= 0) ? st[t] : scan_pack(epoch, kScanInclusive, 0u);
+          ready = (wd >> 34) == epoch && (wd & (3ull << 32)) != 0;
+        } while (!__all_sync(0xffffffffu, ready));
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, (wd & kScanInclusive) != 0);
+        // lanes up to and including the first "inclusive" one contribute
+        const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+        uint32_t part = (lane <= stop) ? static_cast<uint32_t>(wd) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (incl_mask) break;
+        hi -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        st[tile] = scan_pack(epoch, kScanInclusive, excl + total);
+      }
+    }
+    if (lane == 0) {
+      s_prefix = excl;
+      if (tile == gridDim.x - 1 && out_total) *out_total = static_cast<unsigned long long>(excl) + total;
+    }
+  }
+  __syncthreads();
+  uint32_t pos = s_prefix + local;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) {
+      g(base + i, pos, v[i]);
+      pos += v[i];
+    }
+}
+
+extern std::atomic<uint32_t> g_scan_epoch;
+
+// uint32 words a scan over n items needs in `tmp` (status words + room for the
+// 64-bit results the callers keep behind them), and where those results start.
+inline size_t scan_tmp_words(size_t n) { return 2 * static_cast<size_t>(scan_blocks(n)) + 16; }
+inline unsigned long long *scan_total_ptr(uint32_t *tmp, size_t n) {
+  return reinterpret_cast<unsigned long long *>(tmp) + scan_blocks(n);
+}
+
+// Host driver.  tmp: scan_tmp_words(n) uint32, zero-initialised when allocated
+// (DevBuf::ensure_zero).  Leaves the grand total in *dev_total (device).
 template <typename F, typename G>
 qmcl_status device_scan(cudaStream_t s, F f, G g, size_t n, uint32_t *tmp,
                         unsigned long long *dev_total) {
@@ -121,12 +210,10 @@ qmcl_status device_scan(cudaStream_t s, F f, G g, size_t n, uint32_t *tmp,
     QMCL_CUDA(cudaMemsetAsync(dev_total, 0, sizeof(unsigned long long), s));
     return QMCL_OK;
   }
-  const unsigned blocks = scan_blocks(n);
-  scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(f, n, tmp);
-  QMCL_LAUNCHED();
-  scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(tmp, blocks, dev_total);
-  QMCL_LAUNCHED();
-  scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(f, g, n, tmp);
+  uint32_t epoch = g_scan_epoch.fetch_add(1, std::memory_order_relaxed) & 0x3fffffffu;
+  if (epoch == 0) epoch = g_scan_epoch.fetch_add(1, std::memory_order_relaxed) & 0x3fffffffu;
+  scan_onepass_kernel<<<scan_blocks(n), kScanBlock, 0, s>>>(
+      f, g, n, reinterpret_cast<unsigned long long *>(tmp), epoch, dev_total);
   QMCL_LAUNCHED();
   return QMCL_OK;
 }

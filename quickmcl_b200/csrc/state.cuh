@@ -180,7 +180,8 @@ struct qmcl_filter {
   qmcl::DevBuf<int32_t> bin_count;    // particles per bin
   qmcl::DevBuf<int32_t> bin_label;    // union-find parent, then component root
   qmcl::DevBuf<int32_t> bin_cluster;  // root bin -> dense cluster id
-  qmcl::DevBuf<uint32_t> scan_tmp;
+  qmcl::DevBuf<uint32_t> scan_tmp;     // status words of the single-pass scans (+ results)
+  qmcl::DevBuf<uint32_t> scan_legacy;  // block sums of the three-kernel scans (sharded paths)
   qmcl::DevBuf<double> cluster_acc;
   qmcl::DevBuf<int32_t> particle_cid;  // cluster id per particle (K14)
   size_t n_bins = 0, n_clusters = 0;
