@@ -94,6 +94,15 @@ qmcl_status qmcl_map_set_stream(qmcl_map *map, void *cuda_stream);
  * 1 = gather the float32 field and do the reference's double arithmetic per
  * evaluation (exact), 2 = palette with a double pw^3 table (exact). */
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *map, int path);
+/* Cell-index division (m - o) / res of map_base.cpp:66-77.  At load the
+ * library checks two multiply-based forms against IEEE division around every
+ * cell boundary of the map and uses the cheapest one whose truncated quotient
+ * never differs: 2 = a*r_hi + a*r_lo (two ops), 1 = Markstein's three-op
+ * correctly rounded quotient, 0 = IEEE division.  `mode` caps that choice
+ * (-1 = no cap; a form the check rejected is never used); get_ returns the
+ * verified form of the loaded map. */
+qmcl_status qmcl_map_set_division_mode(qmcl_map *map, int mode);
+qmcl_status qmcl_map_get_division_mode(const qmcl_map *map, int *verified);
 
 /* Map::set_parameters (map_likelihood.cpp:40-49). z_hit/z_rand/num_beams/
  * max_laser_distance act on the next sensor update; sigma_hit and

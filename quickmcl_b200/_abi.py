@@ -59,6 +59,8 @@ SIGNATURES = {
     "qmcl_map_destroy": [vp],
     "qmcl_map_set_stream": [vp, vp],
     "qmcl_map_set_sensor_path": [vp, C.c_int],
+    "qmcl_map_set_division_mode": [vp, C.c_int],
+    "qmcl_map_get_division_mode": [vp, C.POINTER(C.c_int)],
     "qmcl_map_set_params": [vp, C.POINTER(LikelihoodParams)],
     "qmcl_map_load": [vp, pi8, u32, u32, f32, f64, f64],
     "qmcl_map_load_field": [vp, pf32, pi8, u32, u32, f32, f64, f64],

@@ -116,6 +116,16 @@ class MapLikelihood:
         """Test hook: 0 = auto (palette when built here), 1 = float field gather."""
         check(self._L.qmcl_map_set_sensor_path(self._h, path), "qmcl_map_set_sensor_path")
 
+    def set_division_mode(self, mode):
+        """Test hook: cap the cell-index division form (-1 auto, 0 IEEE, 1 three-op, 2 two-op)."""
+        check(self._L.qmcl_map_set_division_mode(self._h, mode), "qmcl_map_set_division_mode")
+
+    def division_mode(self):
+        """The cheapest division form the load-time self-check verified for this map."""
+        v = C.c_int(-1)
+        check(self._L.qmcl_map_get_division_mode(self._h, C.byref(v)), "qmcl_map_get_division_mode")
+        return v.value
+
     # -- quickmcl::Map -------------------------------------------------------
     def set_parameters(self, parameters: LikelihoodMapParameters):
         self.parameters = parameters

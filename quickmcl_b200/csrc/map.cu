@@ -201,15 +201,17 @@ edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_di
   field[i] = __ldg(lut_field + k);
   if (distance) distance[i] = __ldg(lut_dist + k);
   // stored pre-multiplied by 4: a byte offset into the float pw^3 table (sensor.cu)
-  if (code) code[i] = static_cast<uint16_t>(4 * k);
+  if (code) code[code_offset(x, y, code_strip_stride(h))] = static_cast<uint16_t>(4 * k);
 }
 
 // Distance field on demand (qmcl_map_copy_distance): code -> metres.
 __global__ void __launch_bounds__(256)
 distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__restrict__ lut_dist,
-                          size_t n, float *__restrict__ out) {
+                          uint32_t w, uint32_t h, float *__restrict__ out) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __ldg(lut_dist + (code[i] >> 2));
+  if (i >= static_cast<size_t>(w) * h) return;
+  const uint32_t y = static_cast<uint32_t>(i / w), x = static_cast<uint32_t>(i - size_t(y) * w);
+  out[i] = __ldg(lut_dist + (code[code_offset(x, y, code_strip_stride(h))] >> 2));
 }
 
 // K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
@@ -466,6 +468,18 @@ qmcl_status qmcl_map_set_sensor_path(qmcl_map *m, int path) {
   return QMCL_OK;
 }
 
+qmcl_status qmcl_map_set_division_mode(qmcl_map *m, int mode) {
+  if (!m || mode < -1 || mode > 2) return QMCL_ERR_INVALID_ARG;
+  m->div_forced = mode;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_map_get_division_mode(const qmcl_map *m, int *verified) {
+  if (!m || !verified) return QMCL_ERR_INVALID_ARG;
+  *verified = m->div_verified;
+  return QMCL_OK;
+}
+
 qmcl_status qmcl_map_set_stream(qmcl_map *m, void *cuda_stream) {
   if (!m) return QMCL_ERR_INVALID_ARG;
   m->stream = static_cast<cudaStream_t>(cuda_stream);
@@ -506,7 +520,7 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   QMCL_TRY(m->lut.ensure(2 * static_cast<size_t>(kmax + 2)));
   // the uint16 d^2 code map (sensor model's palette path) exists when d^2 fits
   const bool with_code = 4 * (kmax + 4) <= 65535;
-  if (with_code) QMCL_TRY(m->code.ensure(n));
+  if (with_code) QMCL_TRY(m->code.ensure(code_map_elems(width, height)));
   else QMCL_TRY(m->distance.ensure(n));  // with codes the distance field is derived on demand
   QMCL_CUDA(copy_h2d(m->occ.ptr, occ, n, m->stream));
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
@@ -594,7 +608,8 @@ qmcl_status qmcl_map_copy_distance(const qmcl_map *m, float *out) {
     QMCL_TRY(use_device(m));
     QMCL_TRY(mm->distance.ensure(n));
     distance_from_code_kernel<<<div_up(n, 256), 256, 0, m->stream>>>(
-        reinterpret_cast<const uint16_t *>(m->code.ptr), m->lut.ptr, n, mm->distance.ptr);
+        reinterpret_cast<const uint16_t *>(m->code.ptr), m->lut.ptr, m->geom.w, m->geom.h,
+        mm->distance.ptr);
     QMCL_LAUNCHED();
   }
   return copy_out(m, m->distance.ptr, out, sizeof(float) * n);

@@ -46,6 +46,12 @@
 
 namespace qmcl {
 
+#ifndef QMCL_DIAG
+#define QMCL_DIAG 0
+#endif
+#ifndef QMCL_SENSOR_FLOOR_FMA
+#define QMCL_SENSOR_FLOOR_FMA 0
+#endif
 #ifndef QMCL_SENSOR_THREADS
 #define QMCL_SENSOR_THREADS 256
 #endif
@@ -53,7 +59,7 @@ namespace qmcl {
 #define QMCL_SENSOR_P 4
 #endif
 #ifndef QMCL_SENSOR_MINBLOCKS
-#define QMCL_SENSOR_MINBLOCKS 4
+#define QMCL_SENSOR_MINBLOCKS 5  // float-table path: 48 registers, no spills; others 4
 #endif
 constexpr int kSensorThreads = QMCL_SENSOR_THREADS;
 constexpr int kSensorWarps = kSensorThreads / 32;
@@ -63,6 +69,8 @@ constexpr int kParticlesPerBlock = kSensorWarps * kP;
 struct SensorParams {
   MapGeom g;
   float inv_res;   // RN(1 / res)
+  float inv_res_lo;  // RN(1/res - inv_res): the second word of the reciprocal
+  float tiny;      // 2^-149 (see floor2_nonneg)
   float neg_res;   // -res
   float neg_zero;  // -0.0f, deliberately a run-time value (see pack2 notes)
   float z_hit;     // parameters.z_hit (float)
@@ -107,6 +115,15 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 
+// trunc() of two non-negative floats below 2^23 without the conversion unit:
+// q * 2^-149 rounded toward zero is the subnormal whose bit pattern is the
+// integer trunc(q) (subnormals are multiples of 2^-149; no flush-to-zero here).
+__device__ __forceinline__ void floor2_nonneg(f32x2 q, f32x2 tiny2, int *lo, int *hi) {
+  f32x2 r;
+  asm("mul.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(q), "l"(tiny2));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(*lo), "=r"(*hi) : "l"(r));
+}
+
 // Also leaves an upper bound of the longest used beam in *rmax (float bits,
 // zeroed by the launcher): particles farther than that from every map edge can
 // skip the in-map test of each evaluation.
@@ -128,10 +145,16 @@ __global__ void subsample_kernel(const float2 *__restrict__ cloud, size_t n_poin
   if ((threadIdx.x & 31) == 0 && len > 0.f) atomicMax(rmax, __float_as_uint(len));
 }
 
-template <bool FASTDIV>
+enum { DIV_IEEE = 0, DIV_MARKSTEIN = 1, DIV_SPLIT = 2 };
+
+template <int DIV>
 __device__ __forceinline__ int cell_of(float pos, float offset, const SensorParams &sp) {
   const float a = __fsub_rn(pos, offset);
-  if (FASTDIV) {
+  if (DIV == DIV_SPLIT) {
+    // a * (r_hi + r_lo) with one rounding too many only 2^-24 below the result
+    return __float2int_rz(__fmaf_rn(a, sp.inv_res, __fmul_rn(a, sp.inv_res_lo)));
+  }
+  if (DIV == DIV_MARKSTEIN) {
     const float q = __fmul_rn(a, sp.inv_res);
     const float rem = __fmaf_rn(q, sp.neg_res, a);
     return __float2int_rz(__fmaf_rn(rem, sp.inv_res, q));
@@ -153,19 +176,24 @@ __global__ void pw3_lut_kernel(const float *__restrict__ lut_field, int n_codes,
   out_f32[k] = static_cast<float>(pw3);
 }
 
-// Compares the 3-op division with IEEE division: every cell boundary of the
-// map +-4 ulps on both axes, plus a pseudo-random sweep of the coordinate range.
+// Compares the multiply-based divisions with IEEE division: every cell boundary
+// of the map +-4 ulps on both axes (truncated quotients can only differ where
+// the true quotient is within a few ulps of an integer, and both forms are
+// monotone), plus a pseudo-random sweep of the coordinate range.
+// mismatch[0]: 3-op Markstein form, mismatch[1]: 2-op split-reciprocal form.
 __global__ void fastdiv_check_kernel(SensorParams sp, int *mismatch) {
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned cells = max(sp.g.w, sp.g.h) + 8;
-  bool bad = false;
+  bool bad = false, bad2 = false;
   if (tid < cells * 9) {
     const int cell = static_cast<int>(tid / 9) - 4;
     const int ulps = static_cast<int>(tid % 9) - 4;
     const float edge = __fmul_rn(static_cast<float>(cell), sp.g.res);
     const float a = __int_as_float(__float_as_int(edge) + (edge >= 0 ? ulps : -ulps));
     // pos - offset == a for offset 0; the subtraction is common to both paths
-    bad |= cell_of<true>(a, 0.f, sp) != cell_of<false>(a, 0.f, sp);
+    const int want = cell_of<DIV_IEEE>(a, 0.f, sp);
+    bad |= cell_of<DIV_MARKSTEIN>(a, 0.f, sp) != want;
+    bad2 |= cell_of<DIV_SPLIT>(a, 0.f, sp) != want;
   }
   uint32_t s = tid * 2654435761u + 12345u;
 #pragma unroll 4
@@ -173,9 +201,12 @@ __global__ void fastdiv_check_kernel(SensorParams sp, int *mismatch) {
     s ^= s << 13; s ^= s >> 17; s ^= s << 5;
     const float a = (static_cast<float>(s >> 8) * (1.0f / 16777216.0f)) *
                         (static_cast<float>(cells) * sp.g.res + 4.f) - 2.f;
-    bad |= cell_of<true>(a, 0.f, sp) != cell_of<false>(a, 0.f, sp);
+    const int want = cell_of<DIV_IEEE>(a, 0.f, sp);
+    bad |= cell_of<DIV_MARKSTEIN>(a, 0.f, sp) != want;
+    bad2 |= cell_of<DIV_SPLIT>(a, 0.f, sp) != want;
   }
   if (bad) atomicExch(mismatch, 1);
+  if (bad2) atomicExch(mismatch + 1, 1);
 }
 
 enum { PATH_FIELD = 0, PATH_PAL64 = 1, PATH_PAL32 = 2 };
@@ -186,8 +217,8 @@ __device__ __forceinline__ float lds_f32_at(const float *table, unsigned byte_of
   return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(table) + byte_off);
 }
 
-template <int PATH, bool FASTDIV>
-__global__ void __launch_bounds__(kSensorThreads, QMCL_SENSOR_MINBLOCKS)
+template <int PATH, int DIV>
+__global__ void __launch_bounds__(kSensorThreads, PATH == PATH_PAL32 ? QMCL_SENSOR_MINBLOCKS : 4)
 sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a) {
   extern __shared__ double s_lut[];  // PAL64: n_codes + 1 doubles; PAL32: floats
   float *s_lut_f32 = reinterpret_cast<float *>(s_lut);
@@ -243,13 +274,17 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   if (PALETTE) __syncthreads();
 
   const float2 *__restrict__ beams = reinterpret_cast<const float2 *>(a.beams);
+
   const double z_hit = static_cast<double>(sp.z_hit);
   const double zr = static_cast<double>(sp.zr);
   const f32x2 NZ = pack2(sp.neg_zero, sp.neg_zero);
   const f32x2 NO = pack2(-sp.g.ox, -sp.g.oy);
   const f32x2 RR = pack2(sp.inv_res, sp.inv_res);
+  const f32x2 RLO = pack2(sp.inv_res_lo, sp.inv_res_lo);
   const f32x2 NRES = pack2(sp.neg_res, sp.neg_res);
+  const f32x2 TINY = pack2(sp.tiny, sp.tiny);
   const unsigned w = sp.g.w;
+  const unsigned strip = code_strip_stride(sp.g.h);
   // Software pipeline: the beam for the next step is fetched before this
   // step's arithmetic, and the value gathered in step i is consumed in step
   // i+1, so a full loop body of independent work covers each load's latency.
@@ -262,13 +297,10 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     code_prev[p] = 4 * (sp.n_codes + 1);  // table entry holding 0 (codes are byte offsets)
     pz_prev[p] = -1.0;              // "nothing pending"
   }
-  // The walk over the scan, instantiated with and without the in-map test.
-  auto walk = [&](auto checked_tag) {
-  constexpr bool CHECKED = decltype(checked_tag)::value;
-  int step = 0;
-  float2 b = (lane < a.n_beams) ? __ldg(beams + lane) : make_float2(0.f, 0.f);
-  for (int j = lane; j < a.n_beams; j += 32, ++step) {
-    const float2 bn = (j + 32 < a.n_beams) ? __ldg(beams + j + 32) : b;
+  // One step of the walk: this lane's beam b against the kP particles.  The
+  // gathers of this step are consumed in the next one (see above).
+  auto body = [&](auto checked_tag, const float2 b) {
+    constexpr bool CHECKED = decltype(checked_tag)::value;
     const f32x2 PX = pack2(b.x, b.x), PY = pack2(b.y, b.y);
     int code_cur[kP];
     double pz_cur[kP];
@@ -281,25 +313,47 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       const f32x2 mxy = add2(XY[p], t3);
       const f32x2 axy = add2(mxy, NO);  // m - o
       int ix, iy;
-      if (FASTDIV) {
-        const f32x2 q = mul2(axy, RR);
-        const f32x2 q2 = fma2(fma2(q, NRES, axy), RR, q);
-        float qx, qy;
-        unpack2(q2, &qx, &qy);
-        ix = __float2int_rz(qx);
-        iy = __float2int_rz(qy);
-      } else {
+      if (DIV == DIV_IEEE) {
         float ax, ay;
         unpack2(axy, &ax, &ay);
         ix = __float2int_rz(__fdiv_rn(ax, sp.g.res));
         iy = __float2int_rz(__fdiv_rn(ay, sp.g.res));
+      } else {
+        f32x2 q2;
+        if (DIV == DIV_SPLIT) {
+          q2 = fma2(axy, RR, mul2(axy, RLO));
+        } else {
+          const f32x2 q = mul2(axy, RR);
+          q2 = fma2(fma2(q, NRES, axy), RR, q);
+        }
+#if QMCL_SENSOR_FLOOR_FMA
+        if (!CHECKED) {
+          floor2_nonneg(q2, TINY, &ix, &iy);  // interior: both quotients are >= 0
+        } else
+#endif
+        {
+          // conversion unit (XU): the FP32 pipe is the busier one here
+          float qx, qy;
+          unpack2(q2, &qx, &qy);
+          ix = __float2int_rz(qx);
+          iy = __float2int_rz(qy);
+        }
       }
       const bool inside = !CHECKED || in_map(ix, iy, sp.g);
-      // 32-bit cell offset (maps are far below 2^32 cells)
-      const unsigned cell = static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix);
+      // 32-bit cell offset (maps are far below 2^32 cells); the code map is
+      // stored in 8-cell strips (common.cuh)
+      const unsigned cell =
+          PALETTE ? code_offset(static_cast<unsigned>(ix), static_cast<unsigned>(iy), strip)
+                  : static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix);
       if (PALETTE) {
         code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry
+#if QMCL_DIAG == 2 || QMCL_DIAG == 3
+        if (inside) code_cur[p] = __ldg(sp.code + ((cell & 1u) + 2u * lane + 64u * p + 4096u * (blockIdx.x & 255)));
+#elif QMCL_DIAG == 4
+        if (inside) code_cur[p] = (cell & 0x3ffu) << 2;
+#else
         if (inside) code_cur[p] = __ldg(sp.code + cell);
+#endif
       } else {
         pz_cur[p] = sp.p_max;
         if (inside) pz_cur[p] = __ldg(sp.field + cell);
@@ -310,7 +364,11 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       if (PATH == PATH_PAL64) {
         acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p] >> 2]);
       } else if (PATH == PATH_PAL32) {
+#if QMCL_DIAG == 1 || QMCL_DIAG == 3
+        facc[p] = __fadd_rn(facc[p], __int_as_float(code_prev[p]));
+#else
         facc[p] = __fadd_rn(facc[p], lds_f32_at(s_lut_f32, code_prev[p]));
+#endif
       } else if (pz_prev[p] >= 0.0) {
         // z_hit * p is exact in double (two float significands), so the fused
         // form rounds exactly like the reference's mul-then-add.
@@ -320,16 +378,41 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       code_prev[p] = code_cur[p];
       pz_prev[p] = pz_cur[p];
     }
-    if (PATH == PATH_PAL32 && (step & 7) == 7) {
-      // float partial sums never hold more than 8 terms
+  };
+  // float partial sums never hold more than 8 terms
+  auto fold = [&]() {
+    if (PATH == PATH_PAL32) {
 #pragma unroll
       for (int p = 0; p < kP; ++p) {
         acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
         facc[p] = 0.f;
       }
     }
-    b = bn;
-  }
+  };
+  // The walk over the scan, instantiated with and without the in-map test:
+  // groups of 8 full steps (all 32 lanes busy, straight-line code, one fold per
+  // group), then the ragged rest.
+  auto walk = [&](auto checked_tag) {
+    const int n_beams = a.n_beams;
+    const int n_grouped = n_beams & ~255;
+    float2 b = (lane < n_beams) ? __ldg(beams + lane) : make_float2(0.f, 0.f);
+    for (int base = lane; base < n_grouped; base += 256) {
+#pragma unroll
+      for (int s8 = 0; s8 < 8; ++s8) {
+        const int jn = base + 32 * s8 + 32;
+        const float2 bn = (jn < n_beams) ? __ldg(beams + jn) : b;
+        body(checked_tag, b);
+        b = bn;
+      }
+      fold();
+    }
+    int step = 0;
+    for (int j = n_grouped + lane; j < n_beams; j += 32, ++step) {
+      const float2 bn = (j + 32 < n_beams) ? __ldg(beams + j + 32) : b;
+      body(checked_tag, b);
+      if (step == 7) fold();
+      b = bn;
+    }
   };
   if (group_safe) walk(std::false_type{});
   else walk(std::true_type{});
@@ -358,8 +441,8 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   // total_weight += weight happens before the penalty (map_likelihood.cpp:112)
   const double warp_pre = warp_sum_xor(mine);
   if (valid) {
-    const int ix = cell_of<false>(lx, sp.g.ox, sp);
-    const int iy = cell_of<false>(ly, sp.g.oy, sp);
+    const int ix = cell_of<DIV_IEEE>(lx, sp.g.ox, sp);
+    const int iy = cell_of<DIV_IEEE>(ly, sp.g.oy, sp);
     const int st = in_map(ix, iy, sp.g) ? state[static_cast<size_t>(iy) * sp.g.w + ix] : 2;
     double wgt = mine;
     if (st == 2) wgt = 0.0;
@@ -423,6 +506,9 @@ static SensorParams make_params(const qmcl_map *m) {
   SensorParams sp;
   sp.g = m->geom;
   sp.inv_res = 1.0f / m->geom.res;
+  sp.inv_res_lo = static_cast<float>(1.0 / static_cast<double>(m->geom.res) -
+                                     static_cast<double>(sp.inv_res));
+  sp.tiny = 1.4012984643248171e-45f;  // 0x00000001
   sp.neg_res = -m->geom.res;
   sp.neg_zero = -0.0f;
   sp.z_hit = m->params.z_hit;
@@ -441,22 +527,22 @@ qmcl_status sensor_prepare_map(qmcl_map *m) {
   SensorParams sp = make_params(m);
   QMCL_TRY(m->scan_tmp.ensure(8));
   int *d_flag = reinterpret_cast<int *>(m->scan_tmp.ptr);
-  QMCL_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), m->stream));
+  QMCL_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), m->stream));
   const unsigned threads = (std::max(m->geom.w, m->geom.h) + 8) * 9;
   fastdiv_check_kernel<<<div_up(threads, 256), 256, 0, m->stream>>>(sp, d_flag);
   QMCL_LAUNCHED();
-  int flag = 1;
-  QMCL_CUDA(copy_d2h(&flag, d_flag, sizeof(int), m->stream));
+  int flag[2] = {1, 1};
+  QMCL_CUDA(copy_d2h(flag, d_flag, sizeof(flag), m->stream));
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
-  m->fastdiv_ok = (flag == 0);
+  m->div_verified = flag[0] ? DIV_IEEE : (flag[1] ? DIV_MARKSTEIN : DIV_SPLIT);
   m->lut_params_valid = false;
   return QMCL_OK;
 }
 
-template <int PATH, bool FASTDIV>
+template <int PATH, int DIV>
 static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, const SensorLaunch &a,
                                   size_t smem) {
-  auto kern = sensor_kernel<PATH, FASTDIV>;
+  auto kern = sensor_kernel<PATH, DIV>;
   if (smem > 48 * 1024)
     QMCL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
@@ -471,6 +557,10 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   // sensor_path: 0 auto (PAL32 when the map was built here), 1 FIELD, 2 PAL64
   const bool can_palette =
       m->has_code && static_cast<size_t>(m->n_codes + 2) * sizeof(double) <= 96 * 1024;
+  // division: the cheapest form the self-check allowed, or the one forced
+  // through qmcl_map_set_division_mode (never a form the check rejected)
+  int div = m->div_verified;
+  if (m->div_forced >= 0) div = std::min(div, m->div_forced);
   int path = PATH_FIELD;
   if (can_palette && m->sensor_path == 0) path = PATH_PAL32;
   if (can_palette && m->sensor_path == 2) path = PATH_PAL64;
@@ -493,15 +583,16 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
     }
     if (path == PATH_PAL64) {
       const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(double);
-      return m->fastdiv_ok ? launch_variant<PATH_PAL64, true>(m, sp, a, smem)
-                           : launch_variant<PATH_PAL64, false>(m, sp, a, smem);
+      return div >= DIV_MARKSTEIN ? launch_variant<PATH_PAL64, DIV_MARKSTEIN>(m, sp, a, smem)
+                                  : launch_variant<PATH_PAL64, DIV_IEEE>(m, sp, a, smem);
     }
     const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(float);
-    return m->fastdiv_ok ? launch_variant<PATH_PAL32, true>(m, sp, a, smem)
-                         : launch_variant<PATH_PAL32, false>(m, sp, a, smem);
+    if (div == DIV_SPLIT) return launch_variant<PATH_PAL32, DIV_SPLIT>(m, sp, a, smem);
+    return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL32, DIV_MARKSTEIN>(m, sp, a, smem)
+                                : launch_variant<PATH_PAL32, DIV_IEEE>(m, sp, a, smem);
   }
-  return m->fastdiv_ok ? launch_variant<PATH_FIELD, true>(m, sp, a, 0)
-                       : launch_variant<PATH_FIELD, false>(m, sp, a, 0);
+  return div >= DIV_MARKSTEIN ? launch_variant<PATH_FIELD, DIV_MARKSTEIN>(m, sp, a, 0)
+                              : launch_variant<PATH_FIELD, DIV_IEEE>(m, sp, a, 0);
 }
 
 }  // namespace qmcl

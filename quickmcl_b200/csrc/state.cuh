@@ -51,7 +51,8 @@ struct qmcl_map {
   qmcl::DevBuf<float> pw3_lut_f32;
   bool has_code = false;
   int n_codes = 0;
-  bool fastdiv_ok = false;        // 3-op division verified against IEEE division
+  int div_verified = 0;           // cheapest division form verified against IEEE division at load
+  int div_forced = -1;            // qmcl_map_set_division_mode: -1 auto, else an upper bound
   int sensor_path = 0;            // 0 auto, 1 float field, 2 exact double palette
   bool lut_params_valid = false;
   float lut_z_hit = 0.f, lut_zr = 0.f;

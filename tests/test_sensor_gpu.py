@@ -214,3 +214,44 @@ def test_palette_path_matches_oracle_and_field_path(width, n, beams, fov, num_be
     pal2 = q.make_particles(x, y, t, np.ones(n))
     gm.update_importance(scan, pal2)
     assert rel_err(pal2["weight"], ref2["weight"]).max() <= TIGHT
+
+
+@pytest.mark.parametrize("res,origin_shift", [(0.05, 0.0), (0.1, 0.013), (0.025, -3.7), (0.03, 1e-3),
+                                              (0.0625, 0.0)])
+def test_division_forms_pick_identical_cells(res, origin_shift):
+    """The cell index (m - o) / res (map_base.cpp:66-77) may be computed with IEEE
+    division, the three-op Markstein form or the two-op split reciprocal; whatever
+    the load-time self-check verified must give the very same weights as IEEE
+    division, on the interior fast path (tracking cloud) and on the bounds-checked
+    path (global cloud reaching over the map edge)."""
+    occ, _, origin = syn.make_map(600)
+    origin = (origin[0] * res / 0.05 + origin_shift, origin[1] * res / 0.05 - origin_shift)
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**lp))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    verified = gm.division_mode()
+    print(f"res {res}: verified division form {verified}")
+    assert verified in (0, 1, 2)
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, 725, 270.0)
+    n = 6000
+    for cloud in (syn.gaussian_cloud(pose, n), syn.uniform_cloud(occ, res, origin, n)):
+        x, y, t = cloud
+        got = {}
+        for mode in (0, 1, 2, -1):
+            gm.set_division_mode(mode)
+            for path in (0, 2):
+                gm.set_sensor_path(path)
+                ps = q.make_particles(x, y, t, np.ones(n))
+                total = gm.update_importance(scan, ps)
+                got[(mode, path)] = (ps["weight"].copy(), total)
+        for path in (0, 2):
+            w0, t0 = got[(0, path)]
+            assert w0.max() > 0
+            for mode in (1, 2, -1):
+                w, tt = got[(mode, path)]
+                assert np.array_equal(w.view(np.uint64), w0.view(np.uint64)), (mode, path)
+                assert tt == t0
+    gm.set_division_mode(-1)
+    gm.set_sensor_path(0)
