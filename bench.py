@@ -370,6 +370,10 @@ def run_b200(args, wl):
             for k, (ms, cnt) in tb.items():
                 if cnt:
                     log(f"  {k:15s} {ms / args.steps:9.4f} ms  ({cnt / args.steps:.1f} scopes/step)")
+            try:
+                log(f"  after the last step: {f.num_clusters()} clusters")
+            except Exception as e:  # noqa: BLE001 (diagnostic only)
+                log(f"  cluster count unavailable: {e}")
 
     global_n = n
     evals_job = global_n * len(scan)

@@ -175,37 +175,113 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
 
 // SpacePartitioning::do_cluster's neighbour relation (space_partitioning.cpp:
 // 102-128): theta' = theta + {-1,0,1} wrapped with "< lo -> hi, > hi -> lo",
-// then (x+dx, y+dy) for dx,dy in {-1,0,1}.  One thread per (bin, theta step).
+// then (x+dx, y+dy) for dx,dy in {-1,0,1}.  One thread per bin.
+//
+// Every reciprocal edge has to be accounted for once, by the bin with the
+// larger index.  Most edges need no union of their own: two occupied cells
+// that are both earlier neighbours of this bin and neighbours of each other are
+// already joined through edges between earlier bins (induction over the bin
+// index), so the bin only unions with a set of "hubs" such that every other
+// occupied earlier neighbour is adjacent to a hub.  The hubs are picked
+// greedily in a fixed order that starts with A = (x-1, y, t), which is adjacent
+// to all 13 other candidates, then B = (x, y-1, t).  On a dense cloud (global
+// localisation) that is one table read and one union per bin instead of 27 and
+// up to 13; components, roots and cluster ids are the same.
+// Bins outside [theta_lo, theta_hi] (theta == -pi rounds to bin -18 at 10
+// degrees) see neighbours that do not see them back (space_partitioning.cpp:
+// 110-114 wraps them onto the other end), so they union everything they see.
+namespace hook {
+// candidates of a regular bin: offsets whose cell precedes it in (x, y, t) order
+// (the two in-column ones are checked by index at run time because of the wrap)
+constexpr int kCand = 14;
+constexpr int kDx[kCand] = {-1, 0, -1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0};
+constexpr int kDy[kCand] = {0, -1, 0, 0, -1, -1, -1, 1, 1, 1, -1, -1, 0, 0};
+constexpr int kDt[kCand] = {0, 0, -1, 1, -1, 0, 1, -1, 0, 1, -1, 1, -1, 1};
+constexpr bool adjacent(int i, int j) {
+  const int ax = kDx[i] - kDx[j], ay = kDy[i] - kDy[j], at = kDt[i] - kDt[j];
+  // theta steps -1 and +1 are two apart (adjacent only on rings of three bins
+  // or fewer; treating them as apart is the safe side)
+  return ax >= -1 && ax <= 1 && ay >= -1 && ay <= 1 && at >= -1 && at <= 1;
+}
+constexpr unsigned adjacency_mask(int i) {
+  unsigned m = 0;
+  for (int j = 0; j < kCand; ++j)
+    if (adjacent(i, j)) m |= 1u << j;
+  return m;
+}
+// offsets as arithmetic on the (unrolled) candidate number, checked below
+#define QMCL_HOOK_DX(k) ((k) == 1 || (k) >= 10 ? 0 : -1)
+#define QMCL_HOOK_DY(k) ((k) == 1 || (k) == 10 || (k) == 11 ? -1 : (k) >= 12 || (k) == 0 || (k) == 2 || (k) == 3 ? 0 : (k) <= 6 ? -1 : 1)
+#define QMCL_HOOK_DT(k) ((k) <= 1 ? 0 : (k) == 2 ? -1 : (k) == 3 ? 1 : (k) <= 9 ? ((k) - 4) % 3 - 1 : ((k) % 2 ? 1 : -1))
+constexpr bool offsets_ok() {
+  for (int k = 0; k < kCand; ++k)
+    if (QMCL_HOOK_DX(k) != kDx[k] || QMCL_HOOK_DY(k) != kDy[k] || QMCL_HOOK_DT(k) != kDt[k]) return false;
+  return true;
+}
+static_assert(offsets_ok(), "QMCL_HOOK_D* out of date");
+// adjacency_mask(k), spelled out so that device code sees plain literals
+#define QMCL_HOOK_ADJ(k) \
+  ((k) == 0 ? 0x3fffu : (k) == 1 ? 0x3c7fu : (k) == 2 ? 0x15b7u : (k) == 3 ? 0x2b6bu : (k) == 4 ? 0x1437u : \
+   (k) == 5 ? 0x3c7fu : (k) == 6 ? 0x286bu : (k) == 7 ? 0x1185u : (k) == 8 ? 0x338du : (k) == 9 ? 0x2309u : \
+   (k) == 10 ? 0x1437u : (k) == 11 ? 0x286bu : (k) == 12 ? 0x15b7u : 0x2b6bu)
+constexpr bool masks_ok() {
+  for (int k = 0; k < kCand; ++k)
+    if (QMCL_HOOK_ADJ(k) != adjacency_mask(k)) return false;
+  return true;
+}
+static_assert(masks_ok(), "QMCL_HOOK_ADJ out of date");
+static_assert(adjacency_mask(0) == (1u << kCand) - 1, "A must be adjacent to every candidate");
+}  // namespace hook
+
 __global__ void __launch_bounds__(256)
 cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bin_cell,
                size_t n_bins, BinGrid g, BinParams bp, int32_t *__restrict__ parent) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (tid >= n_bins * 3) return;
-  const int b = static_cast<int>(tid / 3);
-  const int dt = static_cast<int>(tid % 3) - 1;
+  if (tid >= n_bins) return;
+  const int b = static_cast<int>(tid);
   const int cell = bin_cell[b];
   const int it = cell % g.nt;
   const int iy = (cell / g.nt) % g.ny;
   const int ix = cell / (g.nt * g.ny);
-  const bool regular = it + g.t0 >= bp.theta_lo && it + g.t0 <= bp.theta_hi;
-  int kt = it + g.t0 + dt;
-  if (kt < bp.theta_lo) kt = bp.theta_hi;
-  else if (kt > bp.theta_hi) kt = bp.theta_lo;
-  const int jt = kt - g.t0;
-  if (jt < 0 || jt >= g.nt) return;
-  for (int dx = -1; dx <= 1; ++dx) {
-    const int jx = ix + dx;
-    if (jx < 0 || jx >= g.nx) continue;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int jy = iy + dy;
-      if (jy < 0 || jy >= g.ny) continue;
-      const int v = table[(static_cast<size_t>(jx) * g.ny + jy) * g.nt + jt];
-      // Every reciprocal edge once: the bin with the larger index does the
-      // union.  Bins outside [theta_lo, theta_hi] (theta == -pi rounds to bin
-      // -18 at 10 degrees) see neighbours that do not see them back
-      // (space_partitioning.cpp:110-114 wraps them onto the other end), so
-      // they union everything they see.
-      if (v > 0 && v - 1 != b && (!regular || v - 1 < b)) uf_union(parent, b, v - 1);
+  const int kt0 = it + g.t0;
+  const bool regular = kt0 >= bp.theta_lo && kt0 <= bp.theta_hi;
+  auto wrap = [&](int kt) { return kt < bp.theta_lo ? bp.theta_hi : (kt > bp.theta_hi ? bp.theta_lo : kt); };
+  // bin id + 1 of the cell, 0 when empty or outside the grid
+  auto occupant = [&](int jx, int jy, int kt) -> int {
+    const int jt = kt - g.t0;
+    if (jx < 0 || jx >= g.nx || jy < 0 || jy >= g.ny || jt < 0 || jt >= g.nt) return 0;
+    return table[(static_cast<size_t>(jx) * g.ny + jy) * g.nt + jt];
+  };
+  const int kts[3] = {wrap(kt0 - 1), wrap(kt0), wrap(kt0 + 1)};
+  if (!regular) {
+    int v[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) v[k] = occupant(ix + (k / 3) % 3 - 1, iy + k % 3 - 1, kts[k / 9]);
+#pragma unroll
+    for (int k = 0; k < 27; ++k)
+      if (v[k] > 0 && v[k] - 1 != b) uf_union(parent, b, v[k] - 1);
+    return;
+  }
+  // Loads first, unions after: the unions' atomics would otherwise serialise
+  // the (independent) table reads.
+  int v[hook::kCand];
+  v[0] = occupant(ix - 1, iy, kt0);
+  v[1] = occupant(ix, iy - 1, kt0);
+  if (v[0] > 0) {  // adjacent to every other candidate
+    uf_union(parent, b, v[0] - 1);
+    return;
+  }
+#pragma unroll
+  for (int k = 2; k < hook::kCand; ++k) {
+    v[k] = occupant(ix + QMCL_HOOK_DX(k), iy + QMCL_HOOK_DY(k), kts[QMCL_HOOK_DT(k) + 1]);
+    if (v[k] - 1 >= b) v[k] = 0;  // in-column neighbours across the wrap: not an earlier bin
+  }
+  unsigned hubs = 0;
+#pragma unroll
+  for (int k = 1; k < hook::kCand; ++k) {
+    if (v[k] > 0 && !(QMCL_HOOK_ADJ(k) & hubs)) {
+      uf_union(parent, b, v[k] - 1);
+      hubs |= 1u << k;
     }
   }
 }
@@ -641,7 +717,7 @@ qmcl_status label_clusters(qmcl_filter *f) {
   }
   const BinParams bp = bin_params(f);
   StageScope sc(f, QMCL_STAGE_LABEL);
-  cc_hook_kernel<<<div_up(f->n_bins * 3, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, f->n_bins,
+  cc_hook_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, f->n_bins,
                                                             f->grid, bp, f->bin_label.ptr);
   QMCL_LAUNCHED();
   cc_flatten_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->bin_label.ptr, f->n_bins);
