@@ -256,6 +256,13 @@ qmcl_status qmcl_filter_copy_particles(const qmcl_filter *f, qmcl_particle *out,
  * `lanes` native host threads.  Filters handled by different lanes must sit on
  * different map handles (streams).  odom_*: n x 3 doubles; clouds_xy[i] holds
  * n_points[i] x {x, y}; poses_out n x 3, covs_out n x 9, valid_out n. */
+/* The particle cloud as the node publishes it (publishing.cpp:45-67,114-154):
+ * out5[5*i..] = x, y, sin(theta/2), cos(theta/2), float(weight / max_weight),
+ * the maximum taken over the whole set.  Copies min(n, capacity) particles;
+ * n_out / max_weight may be NULL. */
+qmcl_status qmcl_filter_export_markers(const qmcl_filter *filter, float *out5, size_t capacity,
+                                       size_t *n_out, double *max_weight);
+
 qmcl_status qmcl_batch_update(qmcl_filter *const *filters, size_t n_filters, int lanes,
                               const double *odom_new, const double *odom_old,
                               const float alpha[4], const float *const *clouds_xy,

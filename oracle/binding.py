@@ -343,3 +343,23 @@ def project_scan(ranges, angle_min, angle_increment, range_min, range_max, mount
 
 def last_seconds():
     return lib().orc_last_seconds()
+
+
+def export_markers(particles):
+    """Restates Publishing::publish_cloud / to_marker
+    (src/quickmcl_node/publishing.cpp:45-67, 114-154) on a particle array:
+    max_weight is the largest weight of the set (:125-131, starts at 0), and per
+    particle the marker carries x, y, sin(theta / 2.0f), cos(theta / 2.0f) — float
+    arithmetic, std::sin/cos(float) — and float(weight / max_weight) (:61-62).
+    Returns ((n, 5) float32, max_weight)."""
+    w = particles["weight"].astype(np.float64)
+    max_weight = float(max(0.0, w.max())) if len(w) else 0.0
+    half = particles["theta"].astype(np.float32) / np.float32(2.0)
+    out = np.zeros((len(w), 5), np.float32)
+    out[:, 0] = particles["x"]
+    out[:, 1] = particles["y"]
+    out[:, 2] = np.sin(half, dtype=np.float32)
+    out[:, 3] = np.cos(half, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        out[:, 4] = (w / max_weight).astype(np.float32)
+    return out, max_weight

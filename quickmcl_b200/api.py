@@ -311,6 +311,17 @@ class ParticleFilter:
                   "qmcl_filter_copy_particles")
         return out
 
+    def export_markers(self, capacity=None):
+        """The cloud as the node publishes it (publishing.cpp:45-67, 114-154): an (n, 5)
+        float32 array of x, y, sin(theta/2), cos(theta/2), weight/max_weight, and max_weight."""
+        n = self.num_particles() if capacity is None else min(int(capacity), self.num_particles())
+        out = np.zeros((n, 5), np.float32)
+        got = C.c_size_t(0)
+        mw = C.c_double(0.0)
+        check(self._L.qmcl_filter_export_markers(self._h, ptr(out, C.c_float), n, C.byref(got),
+                                                 C.byref(mw)), "qmcl_filter_export_markers")
+        return out[:got.value], mw.value
+
     def num_particles(self):
         n = C.c_size_t(0)
         check(self._L.qmcl_filter_num_particles(self._h, C.byref(n)), "qmcl_filter_num_particles")

@@ -65,6 +65,50 @@ qmcl_status launch_soa_to_aos(cudaStream_t s, const float *x, const float *y, co
   return QMCL_OK;
 }
 
+// max over non-negative doubles = max over their bit patterns
+__global__ void __launch_bounds__(256)
+max_weight_kernel(const double *__restrict__ w, size_t n, unsigned long long *__restrict__ out) {
+  unsigned long long m = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double v = w[i];
+    if (v > 0) m = max(m, static_cast<unsigned long long>(__double_as_longlong(v)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// publishing.cpp:45-67: orientation from theta / 2.0f in float, shade =
+// float(weight / max_weight) with the division in double.
+__global__ void __launch_bounds__(256)
+export_markers_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                      const float *__restrict__ t, const double *__restrict__ w, size_t n,
+                      const unsigned long long *__restrict__ max_bits, float *__restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mw = __longlong_as_double(static_cast<long long>(*max_bits));
+  const float half = __fdiv_rn(t[i], 2.0f);
+  float *o = out + 5 * i;
+  o[0] = x[i];
+  o[1] = y[i];
+  o[2] = sinf(half);
+  o[3] = cosf(half);
+  o[4] = static_cast<float>(__ddiv_rn(w[i], mw));  // 0/0 -> NaN, as on the host
+}
+
+qmcl_status launch_export_markers(cudaStream_t s, const float *x, const float *y, const float *t,
+                                  const double *w, size_t n_all, size_t n_out,
+                                  unsigned long long *d_max, float *d_out) {
+  QMCL_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s));
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(div_up(n_all, 256), 4 * kSMs));
+  max_weight_kernel<<<blocks, 256, 0, s>>>(w, n_all, d_max);
+  QMCL_LAUNCHED();
+  export_markers_kernel<<<div_up(n_out, 256), 256, 0, s>>>(x, y, t, w, n_out, d_max, d_out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
 qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out) {
   QMCL_TRY(f->scratch.ensure(bytes));
   *out = f->scratch.ptr;
@@ -317,6 +361,37 @@ qmcl_status qmcl_filter_copy_particles(const qmcl_filter *fc, qmcl_particle *out
                              static_cast<qmcl_particle *>(stage)));
   QMCL_CUDA(copy_d2h(out, stage, n * sizeof(qmcl_particle), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
+  return QMCL_OK;
+}
+
+// Particle cloud in the form the node publishes it (publishing.cpp:45-67,
+// 114-154): per particle x, y, sin(theta/2), cos(theta/2) — the yaw quaternion,
+// float arithmetic as in to_marker — and weight / max_weight as a float shade.
+// 20 bytes per particle leave the device instead of the 24-byte mirror plus a
+// host pass for the maximum.
+qmcl_status qmcl_filter_export_markers(const qmcl_filter *fc, float *out5, size_t cap,
+                                       size_t *n_out, double *max_weight) {
+  if (!fc || (!out5 && cap)) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  const ParticleSet &ps = f->cur();
+  const size_t n = ps.n < cap ? ps.n : cap;
+  if (n_out) *n_out = n;
+  if (max_weight) *max_weight = 0.0;
+  if (!n) return QMCL_OK;
+  void *stage = nullptr;
+  QMCL_TRY(filter_scratch(f, n * 5 * sizeof(float) + 16, &stage));
+  // the maximum runs over the whole set (publishing.cpp:125-131), also when
+  // fewer particles are copied out
+  unsigned long long *d_max = reinterpret_cast<unsigned long long *>(stage);
+  float *d_out = reinterpret_cast<float *>(static_cast<char *>(stage) + 16);
+  QMCL_TRY(launch_export_markers(s, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n, n, d_max, d_out));
+  QMCL_CUDA(copy_d2h(out5, d_out, n * 5 * sizeof(float), s));
+  double mw = 0.0;
+  QMCL_CUDA(copy_d2h(&mw, d_max, sizeof(double), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  if (max_weight) *max_weight = mw;
   return QMCL_OK;
 }
 

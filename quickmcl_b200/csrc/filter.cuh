@@ -9,6 +9,9 @@ qmcl_status launch_aos_to_soa(cudaStream_t s, const qmcl_particle *dev_in, size_
                               float *y, float *t, double *w);
 qmcl_status launch_soa_to_aos(cudaStream_t s, const float *x, const float *y, const float *t,
                               const double *w, size_t n, qmcl_particle *dev_out);
+qmcl_status launch_export_markers(cudaStream_t s, const float *x, const float *y, const float *t,
+                                  const double *w, size_t n_all, size_t n_out,
+                                  unsigned long long *d_max, float *d_out);
 // Grow-only byte scratch of the filter (contents are not preserved).
 qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out);
 

@@ -1,4 +1,5 @@
-"""The scan cycle of QuickMCL's node without ROS.
+"""The scan cycle of QuickMCL's node without ROS and the pose
+checkpoint (8f-4).
 
 `ScanCycle.on_scan(odom, cloud)` restates `LaserHandler::Impl::cloud_callback`
 (src/quickmcl_node/laser_handler.cpp:179-288): the moved-enough gate, the
@@ -98,3 +99,49 @@ class ScanCycle:
             self._call("cluster")
         ok, pose, cov = self._call("get_estimated_pose")
         return CycleResult(True, resampled, did_global, recompute, bool(ok), pose, cov)
+
+
+class PoseCheckpoint:
+    """PoseRestorer without the parameter server (src/quickmcl/pose_restore.cpp:37-100).
+
+    `store()` is store_pose: the six numbers the node writes to `~initial_pose`
+    (x, y, theta and the diagonal of the covariance), or None when the filter has
+    no estimate ("Couldn't get pose to store").  `restore(v)` is restore_pose: no
+    stored vector means pose 0 with the identity covariance (:59-60); a stored one
+    is read entry by entry, and a missing or NaN entry falls back to 0 for the
+    pose, 0.5^2 / 0.5^2 / 0.1^2 for the variances (:66-71, :80-97).  The filter is
+    then re-initialised with the covariance cast to float (:75-77).
+    """
+    DEFAULTS = (0.0, 0.0, 0.0, 0.5 * 0.5, 0.5 * 0.5, 0.1 * 0.1)
+
+    def __init__(self, particle_filter):
+        self.filter = particle_filter
+        self.warnings = []          # what ROS_WARN would have said
+
+    def store(self):
+        ok, pose, cov = self.filter.get_estimated_pose()
+        if not ok:
+            self.warnings.append("Couldn't get pose to store")
+            return None
+        cov = np.asarray(cov, np.float64).reshape(3, 3)
+        return [float(pose[0]), float(pose[1]), float(pose[2]),
+                float(cov[0, 0]), float(cov[1, 1]), float(cov[2, 2])]
+
+    def _nan_safe(self, v, index):
+        if index >= len(v):
+            self.warnings.append(f"Ignoring initial_pose[{index}] because it is missing")
+            return self.DEFAULTS[index]
+        if math.isnan(v[index]):
+            self.warnings.append(f"Ignoring initial_pose[{index}] because of NaN")
+            return self.DEFAULTS[index]
+        return float(v[index])
+
+    def restore(self, v=None):
+        pose = np.zeros(3)
+        cov = np.eye(3)
+        if v is not None:
+            vals = [self._nan_safe(list(v), i) for i in range(6)]
+            pose[:] = vals[:3]
+            cov[0, 0], cov[1, 1], cov[2, 2] = vals[3:]
+        self.filter.initialise(pose.astype(np.float32), cov.astype(np.float32))
+        return pose, cov

@@ -4,6 +4,7 @@
 
 #include "../../include/qmcl.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -168,6 +169,42 @@ const ParticleCollection &CudaParticleFilter::get_particles() const {
     mirror_valid_ = true;
   }
   return mirror_;
+}
+
+std::vector<CudaParticleFilter::Marker> CudaParticleFilter::export_markers(double *max_weight) const {
+  static_assert(sizeof(Marker) == 5 * sizeof(float), "Marker must be five packed floats");
+  size_t n = 0;
+  check(qmcl_filter_num_particles(filter_, &n), "qmcl_filter_num_particles");
+  std::vector<Marker> out(n);
+  size_t got = 0;
+  check(qmcl_filter_export_markers(filter_, reinterpret_cast<float *>(out.data()), n, &got,
+                                   max_weight),
+        "qmcl_filter_export_markers");
+  out.resize(got);
+  return out;
+}
+
+std::vector<double> PoseCheckpoint::store() const {
+  Pose2D<double> pose;
+  Matrix3d cov;
+  if (!filter_->get_estimated_pose(&pose, &cov)) return {};
+  return {pose.x, pose.y, pose.theta, cov(0, 0), cov(1, 1), cov(2, 2)};
+}
+
+void PoseCheckpoint::restore(const std::vector<double> *v) const {
+  const double defaults[6] = {0.0, 0.0, 0.0, 0.5 * 0.5, 0.5 * 0.5, 0.1 * 0.1};
+  double val[6] = {0.0, 0.0, 0.0, 1.0, 1.0, 1.0};  // no parameter: identity covariance
+  if (v)
+    for (size_t i = 0; i < 6; ++i)
+      val[i] = (i < v->size() && !std::isnan((*v)[i])) ? (*v)[i] : defaults[i];
+  WeightedParticle::ParticleT start;
+  start.x = static_cast<float>(val[0]);
+  start.y = static_cast<float>(val[1]);
+  start.theta = static_cast<float>(val[2]);
+  Matrix3f cov{};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) cov(r, c) = (r == c) ? static_cast<float>(val[3 + r]) : 0.f;
+  filter_->initialise(start, cov);
 }
 
 size_t CudaParticleFilter::num_particles() const {

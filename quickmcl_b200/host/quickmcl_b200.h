@@ -175,12 +175,34 @@ public:
   const ParticleCollection &get_particles() const override;
   size_t num_particles() const override;
   qmcl_filter *handle() const { return filter_; }
+  // The cloud in the form Publishing::publish_cloud sends it (publishing.cpp:
+  // 45-67, 114-154): 5 floats per particle — x, y, sin(theta/2), cos(theta/2),
+  // weight / max_weight — without the 24-byte mirror and the host pass.
+  struct Marker {
+    float x, y, qz, qw, shade;
+  };
+  std::vector<Marker> export_markers(double *max_weight = nullptr) const;
 
 private:
   std::shared_ptr<Map> map_;  // keeps the map alive (particle_filter.h:96)
   qmcl_filter *filter_ = nullptr;
   mutable ParticleCollection mirror_;  // lazy host copy for get_particles()
   mutable bool mirror_valid_ = false;
+};
+
+// quickmcl::PoseRestorer without the parameter server (pose_restore.cpp:37-100):
+// store() yields the six numbers written to ~initial_pose (empty when there is
+// no estimate), restore() re-initialises the filter from them with the
+// reference's defaults for missing / NaN entries; restore(nullptr) is the "no
+// parameter" case (pose 0, identity covariance).
+class PoseCheckpoint {
+public:
+  explicit PoseCheckpoint(const std::shared_ptr<IParticleFilter> &filter) : filter_(filter) {}
+  std::vector<double> store() const;
+  void restore(const std::vector<double> *v) const;
+
+private:
+  std::shared_ptr<IParticleFilter> filter_;
 };
 
 }  // namespace quickmcl_b200

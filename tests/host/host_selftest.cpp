@@ -193,6 +193,38 @@ int main(int argc, char **argv) {
     for (int i = 0; i < 500; ++i)
       EXPECT(std::fabs(host[i].weight - oh[i].weight) <= 1e-5 * std::fabs(oh[i].weight) + 1e-300);
   }
+  // publishing.cpp:45-67,114-154 and pose_restore.cpp:37-100 through the mirror
+  {
+    double max_w = 0.0;
+    auto *cuda_pf = dynamic_cast<CudaParticleFilter *>(pf.get());
+    EXPECT(cuda_pf != nullptr);
+    const auto markers = cuda_pf->export_markers(&max_w);
+    const auto &gp = pf->get_particles();
+    EXPECT(markers.size() == gp.size());
+    double mw = 0.0;
+    for (const auto &p : gp) mw = std::max(mw, p.weight);
+    EXPECT(max_w == mw);
+    for (size_t i = 0; i < gp.size(); i += 97) {
+      EXPECT(markers[i].x == gp[i].data.x && markers[i].y == gp[i].data.y);
+      EXPECT(std::fabs(markers[i].qz - std::sin(gp[i].data.theta / 2.0f)) <= 2.5e-7f);
+      EXPECT(std::fabs(markers[i].qw - std::cos(gp[i].data.theta / 2.0f)) <= 2.5e-7f);
+      EXPECT(markers[i].shade == static_cast<float>(gp[i].weight / mw));
+    }
+    PoseCheckpoint checkpoint(pf);
+    const std::vector<double> stored = checkpoint.store();
+    EXPECT(stored.size() == 6);
+    std::vector<double> damaged = stored;
+    damaged[1] = std::nan("");
+    damaged.resize(4);
+    checkpoint.restore(&damaged);   // y -> 0, var(y) -> 0.25, var(theta) -> 0.01
+    pf->cluster();
+    Pose2D<double> est;
+    Matrix3d cov;
+    EXPECT(pf->get_estimated_pose(&est, &cov));
+    EXPECT(std::fabs(est.x - stored[0]) <= 0.1 && std::fabs(est.y) <= 0.1);
+    EXPECT(std::fabs(cov(1, 1) - 0.25) <= 0.05 && std::fabs(cov(0, 0) - stored[3]) <= 0.2 * stored[3] + 1e-3);
+    std::printf("checkpoint: restored around (%.3f, %.3f, %.3f)\n", est.x, est.y, est.theta);
+  }
   EXPECT(qmcl_kernel_launch_count() > 20);
   orc_filter_destroy(of);
   orc_map_destroy(om);
