@@ -36,7 +36,12 @@ for i, name in enumerate(h):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 k = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-h, R = rows[k], rows[k + 1:]
+h = rows[k]
+R = []
+for r in rows[k + 1:]:            # the first captured launch only
+    if len(r) < len(h):
+        break
+    R.append(r)
 isamp, iex = h.index("# Samples"), h.index("Instructions Executed")
 stall = [i for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
 num = lambda s: int(s or 0)
