@@ -63,6 +63,10 @@ WORKLOADS = {
     "C4": dict(particles=16_000_000, map=4000, beams=1081, fov=270.0, cloud="global",
                pf=dict(resample_type=0, particle_count_min=16_000_000,
                        particle_count_max=16_000_000)),
+    # "C4 low_variance and kld at 16 M" — the KLD variant, not a default of any N
+    "C4K": dict(particles=16_000_000, map=4000, beams=1081, fov=270.0, cloud="global",
+                pf=dict(resample_type=2, particle_count_min=100, particle_count_max=16_000_000,
+                        kld_epsilon=0.05, kld_z=0.95)),
 }
 RESAMPLE_NAMES = {0: "low_variance", 1: "adaptive", 2: "kld"}
 

@@ -95,7 +95,10 @@ __device__ __forceinline__ size_t running_sum_lookup(const double *__restrict__ 
   const size_t tstar = lo;
   if (tstar == 0) return 0;
   const double K = incl[tstar - 1];
-  // first t with key_t == K, i.e. 1 + first j with incl[j] >= K
+  // first t with key_t == K, i.e. 1 + first j with incl[j] >= K.  Keys repeat
+  // only where a weight was too small to move the sum: one look at the
+  // neighbour (same cache line) settles every other case without a second search.
+  if (tstar == 1 || incl[tstar - 2] < K) return tstar;
   lo = 0;
   hi = tstar - 1;
   while (lo < hi) {
