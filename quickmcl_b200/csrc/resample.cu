@@ -790,11 +790,13 @@ __global__ void shard_keys_kernel(const double *__restrict__ incl, size_t P, dou
 }
 
 // bounds[d] = first record whose slot is >= d * per (records are sorted by slot).
-__global__ void dest_bounds_kernel(const SlotRec *__restrict__ rec, size_t n_rec,
+__global__ void dest_bounds_kernel(const SlotRec *__restrict__ rec,
+                                   const unsigned long long *__restrict__ n_rec_dev,
                                    unsigned long long per, int G,
                                    unsigned long long *__restrict__ bounds) {
   const int d = threadIdx.x;
   if (d > G) return;
+  const size_t n_rec = static_cast<size_t>(*n_rec_dev);
   const long long key = static_cast<long long>(per) * d;
   size_t lo = 0, hi = n_rec;
   if (d == G) lo = n_rec;
@@ -878,33 +880,50 @@ static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in,
   ctx.w_diff = w_diff;
   // 3. the draws this rank owns, compacted in slot order
   StageScope sc(f, QMCL_STAGE_SELECT);
-  // (three-kernel scan: the host needs the count between the two passes; its
-  // block sums live in their own buffer, never in the status words of scan_tmp)
-  const unsigned blocks = scan_blocks(n_draws);
-  QMCL_TRY(f->scan_legacy.ensure(blocks + 16 + 2 * (kMaxShards + 2)));
-  unsigned long long *d_total =
-      reinterpret_cast<unsigned long long *>(f->scan_legacy.ptr + ((blocks + 1) & ~1u));
   const OwnedFlag flag{ctx};
-  scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(flag, n_draws, f->scan_legacy.ptr);
-  QMCL_LAUNCHED();
-  scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_legacy.ptr, blocks, d_total);
-  QMCL_LAUNCHED();
-  unsigned long long n_owned = 0;
-  QMCL_CUDA(copy_d2h(&n_owned, d_total, sizeof(n_owned), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
-  QMCL_TRY(f->xchg_send.ensure((n_owned + 1) * sizeof(SlotRec)));
-  SlotRec *send = reinterpret_cast<SlotRec *>(f->xchg_send.ptr);
-  const EmitOwned emit{ctx,        in.x.ptr,          in.y.ptr,
-                       in.t.ptr,   in.w.ptr,          f->pos.ptr,
-                       f->incl.ptr, static_cast<size_t>(P), f->global_first,
-                       f->map->free_cells.ptr, f->map->n_free, f->map->geom, send};
-  scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(flag, emit, n_draws, f->scan_legacy.ptr);
-  QMCL_LAUNCHED();
-  // 4. deliver every slot to the rank that owns its block
+  const size_t worst = n_draws * sizeof(SlotRec);
+  unsigned long long *d_total = nullptr;
   std::vector<unsigned long long> bounds(G + 1);
+  if (worst <= (size_t(1) << 30)) {
+    // One pass: the send buffer is sized for the case that this rank owns every
+    // draw (<= 1 GiB), so the owner test and the Philox draw run once per slot
+    // and the count comes back together with the destination bounds.
+    QMCL_TRY(f->xchg_send.ensure(worst + sizeof(SlotRec)));
+    QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(n_draws) + 2 * (kMaxShards + 4)));
+    d_total = scan_total_ptr(f->scan_tmp.ptr, n_draws);
+    SlotRec *send = reinterpret_cast<SlotRec *>(f->xchg_send.ptr);
+    const EmitOwned emit{ctx,        in.x.ptr,          in.y.ptr,
+                         in.t.ptr,   in.w.ptr,          f->pos.ptr,
+                         f->incl.ptr, static_cast<size_t>(P), f->global_first,
+                         f->map->free_cells.ptr, f->map->n_free, f->map->geom, send};
+    QMCL_TRY(device_scan(s, flag, emit, n_draws, f->scan_tmp.ptr, d_total));
+  } else {
+    // (three-kernel scan: the host needs the count between the two passes; its
+    // block sums live in their own buffer, never in the status words of scan_tmp)
+    const unsigned blocks = scan_blocks(n_draws);
+    QMCL_TRY(f->scan_legacy.ensure(blocks + 16 + 2 * (kMaxShards + 2)));
+    d_total = reinterpret_cast<unsigned long long *>(f->scan_legacy.ptr + ((blocks + 1) & ~1u));
+    scan_reduce_kernel<<<blocks, kScanBlock, 0, s>>>(flag, n_draws, f->scan_legacy.ptr);
+    QMCL_LAUNCHED();
+    scan_block_sums_kernel<0><<<1, 1024, 0, s>>>(f->scan_legacy.ptr, blocks, d_total);
+    QMCL_LAUNCHED();
+    unsigned long long n_owned = 0;
+    QMCL_CUDA(copy_d2h(&n_owned, d_total, sizeof(n_owned), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    QMCL_TRY(f->xchg_send.ensure((n_owned + 1) * sizeof(SlotRec)));
+    SlotRec *send = reinterpret_cast<SlotRec *>(f->xchg_send.ptr);
+    const EmitOwned emit{ctx,        in.x.ptr,          in.y.ptr,
+                         in.t.ptr,   in.w.ptr,          f->pos.ptr,
+                         f->incl.ptr, static_cast<size_t>(P), f->global_first,
+                         f->map->free_cells.ptr, f->map->n_free, f->map->geom, send};
+    scan_apply_kernel<<<blocks, kScanBlock, 0, s>>>(flag, emit, n_draws, f->scan_legacy.ptr);
+    QMCL_LAUNCHED();
+  }
+  // 4. deliver every slot to the rank that owns its block
   {
-    unsigned long long *d_bounds = d_total + 2;  // inside the allocation made above
-    dest_bounds_kernel<<<1, 64, 0, s>>>(send, n_owned, ctx.T.per, G, d_bounds);
+    unsigned long long *d_bounds = d_total + 2;  // inside the allocations made above
+    dest_bounds_kernel<<<1, 64, 0, s>>>(reinterpret_cast<const SlotRec *>(f->xchg_send.ptr), d_total,
+                                        ctx.T.per, G, d_bounds);
     QMCL_LAUNCHED();
     QMCL_CUDA(copy_d2h(bounds.data(), d_bounds, (G + 1) * sizeof(unsigned long long), s));
     QMCL_CUDA(cudaStreamSynchronize(s));
