@@ -297,6 +297,14 @@ qmcl_status qmcl_filter_debug_prefix(qmcl_filter *f, const double *w, size_t n,
                                      double carry_in, double *out, double *carry_out);
 /* Wait for everything enqueued by this filter. */
 qmcl_status qmcl_filter_synchronize(qmcl_filter *f);
+/* Host/device synchronisation policy of a single-GPU filter.  1 (default):
+ * values the host needs only later (the sensor total feeding w_slow / w_fast,
+ * the cluster count) stay in flight and are folded in at the next call that
+ * synchronises anyway, so update_sensor returns before its kernels finish and
+ * a KLD update waits on the device three times instead of seven.  0: one
+ * synchronisation per value.  Results are identical in both modes; the
+ * environment variable QMCL_EAGER_SYNC=1 selects 0 for new filters. */
+qmcl_status qmcl_filter_set_sync_mode(qmcl_filter *f, int lazy);
 
 /* ---- measurement hooks (replace the reference's CodeTimer scopes,
  *      timer.cpp:37-55; laser_handler.cpp:244,253,262) ---- */

@@ -107,6 +107,7 @@ SIGNATURES = {
     "qmcl_filter_get_lowpass": [vp, pf64],
     "qmcl_filter_set_lowpass": [vp, f64, f64],
     "qmcl_filter_synchronize": [vp],
+    "qmcl_filter_set_sync_mode": [vp, C.c_int],
     "qmcl_filter_export_markers": [vp, C.POINTER(C.c_float), C.c_size_t,
                                    C.POINTER(C.c_size_t), C.POINTER(C.c_double)],
     "qmcl_batch_update": [C.POINTER(vp), sz, C.c_int, pf64, pf64, pf32, C.POINTER(pf32),

@@ -376,6 +376,11 @@ class ParticleFilter:
                   "qmcl_filter_copy_bins")
         return keys, labels
 
+    def num_bins(self):
+        n = C.c_size_t(0)
+        check(self._L.qmcl_filter_num_bins(self._h, C.byref(n)), "qmcl_filter_num_bins")
+        return n.value
+
     def num_clusters(self):
         n = C.c_size_t(0)
         check(self._L.qmcl_filter_num_clusters(self._h, C.byref(n)), "qmcl_filter_num_clusters")
@@ -408,6 +413,10 @@ class ParticleFilter:
         check(self._L.qmcl_filter_synchronize(self._h), "qmcl_filter_synchronize")
 
     # -- measurement hooks (the reference's CodeTimer scopes, timer.cpp:37-55) --
+    def set_sync_mode(self, lazy):
+        """True (default): deferred 8-byte read-backs; False: one synchronisation per value."""
+        check(self._L.qmcl_filter_set_sync_mode(self._h, 1 if lazy else 0), "qmcl_filter_set_sync_mode")
+
     def set_timing(self, level):
         """0 off, 1 CUDA events around the sensor kernel, 2 around every stage."""
         check(self._L.qmcl_filter_set_timing(self._h, level), "qmcl_filter_set_timing")

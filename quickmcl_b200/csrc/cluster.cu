@@ -21,7 +21,6 @@
 
 namespace qmcl {
 
-constexpr size_t kMaxTableCells = size_t(1) << 28;  // 1 GiB of int32
 
 struct BinParams {
   float res_xy, res_t;
@@ -415,9 +414,12 @@ cluster_weight_kernel(const float *__restrict__ x, const float *__restrict__ y,
 // First maximum of the cluster weights (ties -> smallest canonical id).
 __global__ void __launch_bounds__(1024)
 best_cluster_kernel(const unsigned long long *__restrict__ cluster_w, size_t n_clusters,
+                    const unsigned long long *__restrict__ n_clusters_dev,
                     EstimateScalars *__restrict__ es) {
   __shared__ unsigned long long s_w[32];
   __shared__ long long s_i[32];
+  // the count may still be on its way to the host (label_clusters, deferred)
+  if (n_clusters_dev) n_clusters = static_cast<size_t>(*n_clusters_dev);
   unsigned long long bw = 0;
   long long bi = -1;
   for (size_t c = threadIdx.x; c < n_clusters; c += blockDim.x) {
@@ -599,15 +601,30 @@ static BinParams bin_params(const qmcl_filter *f) {
   return bp;
 }
 
+qmcl_status launch_bin_bbox(qmcl_filter *f, const float *x, const float *y, const float *t,
+                            size_t n) {
+  cudaStream_t s = f->map->stream;
+  QMCL_TRY(f->bbox.ensure(8));
+  bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
+  QMCL_LAUNCHED();
+  if (n) {
+    const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
+    bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bin_params(f), f->bbox.ptr);
+    QMCL_LAUNCHED();
+  }
+  return QMCL_OK;
+}
+
 // SpacePartitioning::reset + add_point for x/y/t[0..n): bbox, dense table,
 // sorted occupied-bin list.  Leaves parent[b] = b.
 qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const float *t, size_t n,
-                       bool reuse_grid, bool grid_only) {
+                       bool reuse_grid, bool grid_only, const int *known_bbox, long long known_bins) {
   cudaStream_t s = f->map->stream;
   const BinGrid prev_grid = f->grid;
   const bool have_prev = reuse_grid && f->bins_built && prev_grid.nx > 0;
   f->n_bins = 0;
   f->n_clusters = 0;
+  f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = false;
   f->clusters_valid = false;
   if (n == 0 && !sharded(f)) {
@@ -625,15 +642,10 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     hb[3] = prev_grid.x0 + prev_grid.nx - 1;
     hb[4] = prev_grid.y0 + prev_grid.ny - 1;
     hb[5] = prev_grid.t0 + prev_grid.nt - 1;
+  } else if (known_bbox && !sharded(f)) {
+    for (int d = 0; d < 6; ++d) hb[d] = known_bbox[d];
   } else {
-    QMCL_TRY(f->bbox.ensure(8));
-    bbox_init_kernel<<<1, 32, 0, s>>>(f->bbox.ptr);
-    QMCL_LAUNCHED();
-    if (n) {
-      const unsigned bb_blocks = static_cast<unsigned>(std::min<size_t>(div_up(n, 256), 4 * kSMs));
-      bin_bbox_kernel<<<bb_blocks, 256, 0, s>>>(x, y, t, n, bp, f->bbox.ptr);
-      QMCL_LAUNCHED();
-    }
+    QMCL_TRY(launch_bin_bbox(f, x, y, t, n));
     if (sharded(f)) {
       // Exchange: the bin grid is the bounding box over all shards.
       std::vector<int> all(6 * f->n_shards);
@@ -650,8 +662,11 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
         return QMCL_OK;
       }
     } else {
-      QMCL_CUDA(copy_d2h(hb, f->bbox.ptr, sizeof(hb), s));
+      int *h = reinterpret_cast<int *>(f->h_scalars.ptr + HS_BBOX);
+      QMCL_CUDA(copy_d2h(h, f->bbox.ptr, sizeof(hb), s));
       QMCL_CUDA(cudaStreamSynchronize(s));
+      settle_after_sync(f);
+      for (int d = 0; d < 6; ++d) hb[d] = h[d];
     }
   }
   BinGrid g;
@@ -699,10 +714,16 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
                        EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
                        cells, f->scan_tmp.ptr, d_total));
-  unsigned long long nb = 0;
-  QMCL_CUDA(copy_d2h(&nb, d_total, sizeof(nb), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
-  f->n_bins = nb;
+  if (known_bins >= 0 && !sharded(f)) {
+    // the caller counted the bins already (KLD: new-bin flags up to the stop)
+    f->n_bins = static_cast<size_t>(known_bins);
+  } else {
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(f->h_scalars.ptr + HS_NBINS);
+    QMCL_CUDA(copy_d2h(h, d_total, sizeof(*h), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+    settle_after_sync(f);
+    f->n_bins = *h;
+  }
   f->bins_built = true;
   return QMCL_OK;
 }
@@ -711,6 +732,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
 qmcl_status label_clusters(qmcl_filter *f) {
   cudaStream_t s = f->map->stream;
   f->n_clusters = 0;
+  f->clusters_pending = false;  // an older count still in flight is void
   if (f->n_bins == 0) {
     f->clusters_valid = true;
     return QMCL_OK;
@@ -723,13 +745,15 @@ qmcl_status label_clusters(qmcl_filter *f) {
   cc_flatten_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->bin_label.ptr, f->n_bins);
   QMCL_LAUNCHED();
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(f->n_bins) + 4));
-  unsigned long long *d_total = scan_total_ptr(f->scan_tmp.ptr, f->n_bins);
+  // the count goes to a stable device word (K14 reads it there) and to its own
+  // pinned slot; the host needs it only to size K14's buffers, for which the
+  // bin count is a bound, so the copy is left in flight
+  unsigned long long *d_total = &f->scalars.ptr->n_clusters;
   QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr}, EmitRootId{f->bin_cluster.ptr}, f->n_bins,
                        f->scan_tmp.ptr, d_total));
-  unsigned long long nc = 0;
-  QMCL_CUDA(copy_d2h(&nc, d_total, sizeof(nc), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
-  f->n_clusters = nc;
+  QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_NCLUSTERS, d_total, sizeof(unsigned long long), s));
+  f->clusters_pending = true;
+  if (!lazy(f)) QMCL_TRY(settle(f));
   f->clusters_valid = true;
   return QMCL_OK;
 }
@@ -757,8 +781,13 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   const ParticleSet &ps = f->cur();
   // every rank of a sharded filter must take the same branch here
   const size_t n_any = sharded(f) ? f->global_n : ps.n;
-  if (n_any == 0 && f->n_clusters == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
-  if (n_any > 0 && (!f->bins_built || f->n_clusters == 0)) {
+  // A cluster count still on its way to the host (label_clusters) is at least 1
+  // and at most the bin count, which is all the host needs here; K14 reads the
+  // exact value on the device.
+  const bool nc_on_device = f->clusters_pending;
+  const size_t nc_cap = nc_on_device ? f->n_bins : f->n_clusters;
+  if (n_any == 0 && nc_cap == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
+  if (n_any > 0 && (!f->bins_built || nc_cap == 0)) {
     set_error("get_estimate: particles have no cluster (call cluster() or resample first)");
     return QMCL_ERR_INVALID_CLUSTER;
   }
@@ -768,7 +797,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
       static_cast<unsigned>(std::min<size_t>(std::max<size_t>(div_up(ps.n, 256), 1), kMomentBlocks));
   // layout of cluster_acc (doubles): [n_clusters] fixed-point cluster weights |
   // [blocks * 2 * kMom] block partials | [2 * kMom] sums | [16] out | EstimateScalars
-  const size_t o_part = f->n_clusters;
+  const size_t o_part = nc_cap;
   const size_t o_sums = o_part + static_cast<size_t>(blocks) * 2 * kMom;
   const size_t o_out = o_sums + 2 * kMom;
   const size_t o_es = o_out + 16;
@@ -779,7 +808,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   unsigned long long *cluster_w = reinterpret_cast<unsigned long long *>(base);
   double *d_out = base + o_out;
   EstimateScalars *es = reinterpret_cast<EstimateScalars *>(base + o_es);
-  QMCL_CUDA(cudaMemsetAsync(base, 0, f->n_clusters * sizeof(double), s));
+  QMCL_CUDA(cudaMemsetAsync(base, 0, nc_cap * sizeof(double), s));
   QMCL_CUDA(cudaMemsetAsync(base + o_sums, 0, (2 * kMom + 16) * sizeof(double) + sizeof(EstimateScalars), s));
   if (ps.n) {
     wmax_kernel<<<std::min<unsigned>(blocks, 2 * kSMs), 256, 0, s>>>(ps.w.ptr, ps.n, es);
@@ -803,7 +832,8 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   // Exchange: cluster weights are integers, so their sum over shards is exact
   // and order-independent.
   if (sharded(f)) QMCL_TRY(shard_allreduce(f, cluster_w, f->n_clusters, QMCL_DT_I64, QMCL_OP_SUM));
-  best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, f->n_clusters, es);
+  best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, nc_cap,
+                                         nc_on_device ? &f->scalars.ptr->n_clusters : nullptr, es);
   QMCL_LAUNCHED();
   moments_kernel<<<blocks, 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, f->particle_cid.ptr,
                                         ps.n, base + o_part, es, base + o_sums, d_out,
@@ -829,9 +859,13 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
     finalise_estimate(tot + kMom, tot, h);
   } else {
     // one read back: out[0..13) + the invalid flag
-    QMCL_CUDA(copy_d2h(h, d_out, 13 * sizeof(double), s));
-    QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
+    double *hp = f->h_scalars.ptr + HS_EST;
+    QMCL_CUDA(copy_d2h(hp, d_out, 13 * sizeof(double), s));
+    QMCL_CUDA(copy_d2h(hp + 13, &es->invalid, sizeof(int), s));
     QMCL_CUDA(cudaStreamSynchronize(s));
+    settle_after_sync(f);
+    std::memcpy(h, hp, 13 * sizeof(double));
+    std::memcpy(&flag, hp + 13, sizeof(int));
   }
   if (flag) {
     set_error("get_estimate: a particle's bin has no cluster (reference abort()s here)");
@@ -855,6 +889,7 @@ qmcl_status qmcl_filter_num_bins(const qmcl_filter *f, size_t *out) {
 
 qmcl_status qmcl_filter_num_clusters(const qmcl_filter *f, size_t *out) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(const_cast<qmcl_filter *>(f)));
   *out = f->n_clusters;
   return QMCL_OK;
 }

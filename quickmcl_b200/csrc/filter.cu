@@ -9,6 +9,8 @@
 #include "shard.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace qmcl {
 
 // ------------------------------------------------------------------ kernels
@@ -164,11 +166,53 @@ static void lowpass_update(double *value, double alpha, double x) {
   else *value = *value + alpha * (x - *value);
 }
 
+static void apply_total(qmcl_filter *f, double total, double n_total) {
+  f->last_total = total;
+  if (total > 0) {
+    const double avg = total / n_total;
+    lowpass_update(&f->w_slow, f->params.alpha_slow, avg);
+    lowpass_update(&f->w_fast, f->params.alpha_fast, avg);
+  }
+}
+
+void settle_after_sync(qmcl_filter *f) {
+  if (f->total_pending) {
+    f->total_pending = false;
+    apply_total(f, f->h_scalars.ptr[HS_TOTAL], f->pending_n_total);
+  }
+  if (f->clusters_pending) {
+    f->clusters_pending = false;
+    unsigned long long nc;
+    std::memcpy(&nc, &f->h_scalars.ptr[HS_NCLUSTERS], sizeof(nc));
+    f->n_clusters = nc;
+  }
+}
+
+qmcl_status settle(qmcl_filter *f) {
+  if (!f->total_pending && !f->clusters_pending) return QMCL_OK;
+  QMCL_TRY(use_device(f->map));
+  QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  settle_after_sync(f);
+  return QMCL_OK;
+}
+
+// The pinned scan staging buffer may be rewritten once the previous H2D copy
+// out of it has run (update_sensor no longer ends with a synchronisation).
+static qmcl_status staging_free(qmcl_filter *f) {
+  if (!f->staging_read) {
+    QMCL_CUDA(cudaEventCreateWithFlags(&f->staging_read, cudaEventDisableTiming));
+    return QMCL_OK;
+  }
+  QMCL_CUDA(cudaEventSynchronize(f->staging_read));
+  return QMCL_OK;
+}
+
 // Runs K7 + K8 on the current set with the beams already in f->beams.
 static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_points) {
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   cudaStream_t s = m->stream;
+  if (f->total_pending) QMCL_TRY(settle(f));  // the slot is about to be reused
   if (ps.n == 0 && !sharded(f)) {
     f->last_total = 0.0;
     return QMCL_OK;
@@ -191,38 +235,34 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   } else {
     QMCL_CUDA(cudaMemsetAsync(&f->scalars.ptr->total_weight, 0, sizeof(double), s));
   }
-  double total = 0.0;
-  double n_total = static_cast<double>(ps.n);
+  f->clusters_valid = false;
   if (sharded(f)) {
     // Exchange 1: the pre-penalty total is the sum over shards.
     std::vector<double> totals;
     QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->total_weight, &totals));
-    total = ordered_sum(totals);
-    n_total = static_cast<double>(f->global_n);
+    const double total = ordered_sum(totals);
+    const double n_total = static_cast<double>(f->global_n);
     if (ps.n) {
       StageScope sc(f, QMCL_STAGE_NORMALISE);
       normalise_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total, n_total);
       QMCL_LAUNCHED();
     }
-  } else {
-    {
-      StageScope sc(f, QMCL_STAGE_NORMALISE);
-      normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
-      QMCL_LAUNCHED();
-    }
-    // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
-    // total: one 8-byte read back per scan.
-    QMCL_CUDA(copy_d2h(f->h_scalars.ptr, &f->scalars.ptr->total_weight, sizeof(double), s));
-    QMCL_CUDA(cudaStreamSynchronize(s));
-    total = f->h_scalars.ptr[0];
+    apply_total(f, total, n_total);
+    return QMCL_OK;
   }
-  f->last_total = total;
-  if (total > 0) {
-    const double avg = total / n_total;
-    lowpass_update(&f->w_slow, f->params.alpha_slow, avg);
-    lowpass_update(&f->w_fast, f->params.alpha_fast, avg);
+  {
+    StageScope sc(f, QMCL_STAGE_NORMALISE);
+    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+    QMCL_LAUNCHED();
   }
-  f->clusters_valid = false;
+  // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
+  // total: one 8-byte read back per scan.  Nothing on the host depends on it
+  // before the next resampling, so the copy is left in flight (HS_TOTAL) and
+  // folded in at the next synchronisation.
+  QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_TOTAL, &f->scalars.ptr->total_weight, sizeof(double), s));
+  f->total_pending = true;
+  f->pending_n_total = static_cast<double>(ps.n);
+  if (!lazy(f)) QMCL_TRY(settle(f));
   return QMCL_OK;
 }
 
@@ -241,7 +281,8 @@ qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) 
   f->seed = seed;
   QMCL_TRY(f->scalars.ensure(1));
   QMCL_CUDA(cudaMemsetAsync(f->scalars.ptr, 0, sizeof(FilterScalars), map->stream));
-  QMCL_TRY(f->h_scalars.ensure(16));
+  QMCL_TRY(f->h_scalars.ensure(HS_COUNT));
+  if (const char *e = std::getenv("QMCL_EAGER_SYNC")) f->lazy_sync = !(e[0] && e[0] != '0');
   qmcl_filter_set_params(f, &f->params);
   *out = f;
   return QMCL_OK;
@@ -285,6 +326,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->cluster_acc.release();
   f->particle_cid.release();
   f->timer.release();
+  if (f->staging_read) cudaEventDestroy(f->staging_read);
   qmcl_map *map = f->map;
   delete f;
   return qmcl_map_destroy(map);
@@ -294,6 +336,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
 qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p) {
   if (!f || !p) return QMCL_ERR_INVALID_ARG;
   if (!(p->res_xy > 0) || !(p->res_theta > 0)) return QMCL_ERR_INVALID_ARG;
+  if (f->map) QMCL_TRY(settle(f));  // a pending total uses the alphas it was measured under
   f->params = *p;
   // theta_range: world_to_map of (float)(-pi+0.001) and (float)(pi-0.001):
   // float division then truncation (scaled_map.h:43-48).
@@ -301,6 +344,7 @@ qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p) {
   f->theta_hi = static_cast<int>(static_cast<float>(kPi - 0.001) / p->res_theta);
   f->n_bins = 0;
   f->n_clusters = 0;
+  f->clusters_pending = false;  // an older count still in flight is void
   f->clusters_valid = false;
   return QMCL_OK;
 }
@@ -404,8 +448,10 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, siz
   QMCL_TRY(f->beams.ensure(2 * n_points + 2));
   QMCL_TRY(f->h_beams.ensure(2 * n_points + 2));
   // stage through pinned memory so the H2D copy is a true async DMA
+  QMCL_TRY(staging_free(f));
   std::memcpy(f->h_beams.ptr, cloud_xy, 2 * n_points * sizeof(float));
   QMCL_CUDA(copy_h2d(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float), s));
+  QMCL_CUDA(cudaEventRecord(f->staging_read, s));
   int n_used = 0;
   QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
   return sensor_update_common(f, n_used, n_points);
@@ -434,8 +480,10 @@ qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, 
   QMCL_TRY(f->cloud.ensure(2 * n_ranges + 2));
   QMCL_TRY(f->beams.ensure(2 * n_ranges + 2));
   QMCL_TRY(f->h_beams.ensure(2 * n_ranges + 2));
+  QMCL_TRY(staging_free(f));
   std::memcpy(f->h_beams.ptr, ranges, n_ranges * sizeof(float));
   QMCL_CUDA(copy_h2d(f->ranges.ptr, f->h_beams.ptr, n_ranges * sizeof(float), s));
+  QMCL_CUDA(cudaEventRecord(f->staging_read, s));
   ScanGeom g{angle_min, angle_increment, range_min, range_max, mount[0], mount[1],
              std::cos(mount[2]), std::sin(mount[2])};
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(n_ranges) + 4));
@@ -467,20 +515,30 @@ qmcl_status qmcl_filter_copy_cloud(const qmcl_filter *fc, float *xy_out, size_t 
 
 qmcl_status qmcl_filter_last_total_weight(const qmcl_filter *f, double *out) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(const_cast<qmcl_filter *>(f)));
   *out = f->last_total;
   return QMCL_OK;
 }
 
 qmcl_status qmcl_filter_get_lowpass(const qmcl_filter *f, double out[2]) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(const_cast<qmcl_filter *>(f)));
   out[0] = f->w_slow;
   out[1] = f->w_fast;
   return QMCL_OK;
 }
 qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast) {
   if (!f) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(f));
   f->w_slow = w_slow;
   f->w_fast = w_fast;
+  return QMCL_OK;
+}
+
+qmcl_status qmcl_filter_set_sync_mode(qmcl_filter *f, int lazy_mode) {
+  if (!f || lazy_mode < 0 || lazy_mode > 1) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(f));
+  f->lazy_sync = lazy_mode != 0;
   return QMCL_OK;
 }
 
@@ -495,6 +553,7 @@ qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
   if (!f || !ms_out || !count_out) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  settle_after_sync(f);
   f->timer.resolve();
   for (int i = 0; i < QMCL_N_STAGES; ++i) {
     ms_out[i] = f->timer.ms[i];
@@ -511,6 +570,7 @@ qmcl_status qmcl_filter_synchronize(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
+  settle_after_sync(f);
   return QMCL_OK;
 }
 

@@ -12,6 +12,12 @@ qmcl_status launch_soa_to_aos(cudaStream_t s, const float *x, const float *y, co
 qmcl_status launch_export_markers(cudaStream_t s, const float *x, const float *y, const float *t,
                                   const double *w, size_t n_all, size_t n_out,
                                   unsigned long long *d_max, float *d_out);
+// Deferred read-backs (state.cuh): settle_after_sync folds in whatever is
+// pending when the caller has just synchronised the filter's stream; settle
+// synchronises first if anything is pending.  lazy(f): deferral is in effect.
+void settle_after_sync(qmcl_filter *f);
+qmcl_status settle(qmcl_filter *f);
+inline bool lazy(const qmcl_filter *f) { return f->lazy_sync && f->n_shards <= 1; }
 // Grow-only byte scratch of the filter (contents are not preserved).
 qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out);
 

@@ -203,6 +203,8 @@ struct NewBinFlag {
 };
 // After draw m there are k = prefix + flag bins; the loop stops at the first m
 // with m >= limit(k) (particle_filter.cpp:329-334).
+// The stop word is {m:32, k:32}: ordered by m, and it carries the number of
+// bins the reference holds when it stops, so that the host reads both at once.
 struct StopRule {
   KldParams kp;
   unsigned long long *first_stop;
@@ -214,9 +216,10 @@ struct StopRule {
     const unsigned cand = (m >= kld_limit(k, kp)) ? static_cast<unsigned>(m) : 0xffffffffu;
     const unsigned mask = __activemask();
     const unsigned wmin = __reduce_min_sync(mask, cand);
-    if (wmin != 0xffffffffu && cand == wmin &&
-        static_cast<unsigned long long>(wmin) < *reinterpret_cast<volatile unsigned long long *>(first_stop))
-      atomicMin(first_stop, static_cast<unsigned long long>(wmin));
+    if (wmin != 0xffffffffu && cand == wmin) {
+      const unsigned long long word = (static_cast<unsigned long long>(wmin) << 32) | (k & 0xffffffffull);
+      if (word < *reinterpret_cast<volatile unsigned long long *>(first_stop)) atomicMin(first_stop, word);
+    }
   }
 };
 
@@ -520,12 +523,16 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
 
 // Builds the running-sum records of `in`; *P_out = number of records,
 // *total_out = ParticlesRunningSum::get_total_weight().
+// bbox_out (optional, single GPU): the bin bounding box of the input set is
+// computed in the same pass and read back with the same synchronisation; it
+// bounds the bins of every draw that copies an input particle.
 static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size_t *P_out,
-                                     double *total_out) {
+                                     double *total_out, int *bbox_out = nullptr) {
   cudaStream_t s = f->map->stream;
   *P_out = 0;
   *total_out = 0.0;
-  if (in.n == 0) return QMCL_OK;
+  if (bbox_out) bbox_out[0] = 1, bbox_out[3] = 0;  // empty
+  if (in.n == 0) return settle(f);
   QMCL_TRY(f->cdf.ensure(in.n));
   QMCL_TRY(f->pos.ensure(in.n));
   QMCL_TRY(f->incl.ensure(in.n));
@@ -536,13 +543,20 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
       scan_total_ptr(f->scan_tmp.ptr, in.n);
   QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
                        in.n, f->scan_tmp.ptr, d_total));
-  unsigned long long P = 0;
-  double total = 0.0;
-  QMCL_CUDA(copy_d2h(&P, d_total, sizeof(P), s));
-  QMCL_CUDA(copy_d2h(&total, f->cdf.ptr + (in.n - 1), sizeof(double), s));
+  double *h = f->h_scalars.ptr + HS_RS;
+  QMCL_CUDA(copy_d2h(h, d_total, sizeof(unsigned long long), s));
+  QMCL_CUDA(copy_d2h(h + 1, f->cdf.ptr + (in.n - 1), sizeof(double), s));
+  if (bbox_out) {
+    QMCL_TRY(launch_bin_bbox(f, in.x.ptr, in.y.ptr, in.t.ptr, in.n));
+    QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_BBOX, f->bbox.ptr, 6 * sizeof(int), s));
+  }
   QMCL_CUDA(cudaStreamSynchronize(s));
+  settle_after_sync(f);  // the sensor total (w_slow, w_fast) rides on this synchronisation
+  unsigned long long P;
+  std::memcpy(&P, h, sizeof(P));
   *P_out = P;
-  *total_out = total;
+  *total_out = h[1];
+  if (bbox_out) std::memcpy(bbox_out, f->h_scalars.ptr + HS_BBOX, 6 * sizeof(int));
   return QMCL_OK;
 }
 
@@ -571,7 +585,6 @@ static qmcl_status launch_draws(qmcl_filter *f, const ParticleSet &in, ParticleS
 // particle_filter.cpp:241-291
 static qmcl_status resample_adaptive(qmcl_filter *f, const ParticleSet &in, ParticleSet &out) {
   cudaStream_t s = f->map->stream;
-  const double w_diff = adaptiveness(f);
   const size_t n_out = static_cast<size_t>(f->params.particle_count_min);
   // output_particles->resize(output_size): keeps what the buffer held, new
   // slots are default particles
@@ -589,9 +602,17 @@ static qmcl_status resample_adaptive(qmcl_filter *f, const ParticleSet &in, Part
   f->n_src_index = 0;
   size_t P;
   double total;
-  QMCL_TRY(build_running_sum(f, in, &P, &total));
+  int in_bbox[6];
+  QMCL_TRY(build_running_sum(f, in, &P, &total, lazy(f) ? in_bbox : nullptr));
   if (!(total > 0)) return QMCL_OK;  // "No particles have any weights! Failing to resample"
+  const double w_diff = adaptiveness(f);  // after the read-back: it settles w_slow / w_fast
   if (n_out) QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_out));
+  // Without injection the new set copies input particles only: the input set's
+  // bounding box (already on the host) serves the clustering that follows.
+  if (lazy(f) && n_out && !(w_diff > 0.0) && in_bbox[0] <= in_bbox[3]) {
+    std::memcpy(f->bbox_hint, in_bbox, sizeof(in_bbox));
+    f->bbox_hint_valid = true;
+  }
   f->n_src_index = n_out;
   if (w_diff > 0.0) {
     f->w_fast = 0;
@@ -608,24 +629,35 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
                                 bool *clustered) {
   cudaStream_t s = f->map->stream;
   *clustered = false;
-  const double w_diff = adaptiveness(f);
   const size_t n_max = static_cast<size_t>(f->params.particle_count_max);
   out.n = 0;  // output_set->particles.clear()
   f->n_src_index = 0;
   f->n_bins = 0;  // space_partitioning.reset()
   f->n_clusters = 0;
+  f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = true;
   f->grid = BinGrid{0, 0, 0, 0, 0, 0};
   size_t P;
   double total;
-  QMCL_TRY(build_running_sum(f, in, &P, &total));
+  int in_bbox[6];
+  QMCL_TRY(build_running_sum(f, in, &P, &total, lazy(f) ? in_bbox : nullptr));
   if (!(total > 0)) return QMCL_OK;
   if (n_max == 0) return QMCL_OK;
   if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
+  const double w_diff = adaptiveness(f);  // after the read-back: it settles w_slow / w_fast
   QMCL_TRY(out.ensure(n_max));
   QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_max));
-  // the dense bin grid spanned by all candidates
-  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max, false, true));
+  // The dense bin grid spanned by all candidates.  Without injection every
+  // candidate is a copy of an input particle, so the input set's bounding box
+  // (read back together with the running-sum total) contains it.
+  const int *known_bbox = nullptr;
+  if (lazy(f) && !(w_diff > 0.0) && in_bbox[0] <= in_bbox[3]) {
+    const double cells_in = (static_cast<double>(in_bbox[3]) - in_bbox[0] + 1) *
+                            (static_cast<double>(in_bbox[4]) - in_bbox[1] + 1) *
+                            (static_cast<double>(in_bbox[5]) - in_bbox[2] + 1);
+    if (cells_in <= static_cast<double>(kMaxTableCells)) known_bbox = in_bbox;
+  }
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max, false, true, known_bbox));
   const BinGrid g = f->grid;
   const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
   KldParams kp;
@@ -649,10 +681,15 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
     QMCL_TRY(device_scan(s, NewBinFlag{out.x.ptr, out.y.ptr, out.t.ptr, kp, g, f->table.ptr},
                          StopRule{kp, d_stop}, n_max, f->scan_tmp.ptr, d_total));
   }
-  unsigned long long stop = 0;
-  QMCL_CUDA(copy_d2h(&stop, d_stop, sizeof(stop), s));
+  unsigned long long *h = reinterpret_cast<unsigned long long *>(f->h_scalars.ptr + HS_STOP);
+  QMCL_CUDA(copy_d2h(h, d_stop, sizeof(unsigned long long), s));
+  QMCL_CUDA(copy_d2h(h + 1, d_total, sizeof(unsigned long long), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
-  const size_t n_out = (stop >= n_max) ? n_max : static_cast<size_t>(stop) + 1;
+  settle_after_sync(f);
+  // no stop (all ones): every candidate is kept and every new-bin flag counts
+  const bool stopped = h[0] != ~0ull;
+  const size_t n_out = stopped ? static_cast<size_t>(h[0] >> 32) + 1 : n_max;
+  const long long n_bins_kept = static_cast<long long>(stopped ? (h[0] & 0xffffffffull) : h[1]);
   out.n = n_out;
   f->n_src_index = n_out;
   if (w_diff > 0.0) {
@@ -661,7 +698,8 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   }
   // the bins the reference holds at this point are those of the kept draws; they
   // lie inside the candidates' bounding box, so the grid is reused
-  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_out, true));
+  QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_out, true, false, nullptr,
+                      lazy(f) ? n_bins_kept : -1));
   QMCL_TRY(label_clusters(f));
   *clustered = true;
   return QMCL_OK;
@@ -1050,6 +1088,7 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
   f->n_src_index = 0;
   f->n_bins = 0;
   f->n_clusters = 0;
+  f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = true;
   f->grid = BinGrid{0, 0, 0, 0, 0, 0};
   if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
@@ -1153,6 +1192,7 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   ParticleSet &out = f->sets[(f->current + 1) % 2];
   f->current = (f->current + 1) % 2;
   f->clusters_valid = false;
+  f->bbox_hint_valid = false;
   bool clustered = false;
   switch (f->params.resample_type) {
   case QMCL_RESAMPLE_LOW_VARIANCE:
@@ -1180,7 +1220,15 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
       // failed KLD: bins stay reset, nothing to label
       f->clusters_valid = true;
     } else {
-      QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, out.n));
+      const int *known_bbox = nullptr;
+      if (f->bbox_hint_valid) {
+        const double cells = (static_cast<double>(f->bbox_hint[3]) - f->bbox_hint[0] + 1) *
+                             (static_cast<double>(f->bbox_hint[4]) - f->bbox_hint[1] + 1) *
+                             (static_cast<double>(f->bbox_hint[5]) - f->bbox_hint[2] + 1);
+        if (cells <= static_cast<double>(kMaxTableCells)) known_bbox = f->bbox_hint;
+      }
+      f->bbox_hint_valid = false;
+      QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, out.n, false, false, known_bbox));
       QMCL_TRY(label_clusters(f));
     }
   }

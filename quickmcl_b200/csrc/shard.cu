@@ -2,6 +2,7 @@
 // path (block slices, low-variance owner ranges).
 
 #include "shard.cuh"
+#include "filter.cuh"
 
 namespace qmcl {
 
@@ -65,6 +66,7 @@ extern "C" {
 
 qmcl_status qmcl_filter_set_comm(qmcl_filter *f, const qmcl_comm *comm) {
   if (!f) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(f));  // deferred read-backs exist only on single-GPU filters
   if (!comm || comm->size <= 1) {
     f->comm = qmcl_comm{0, 1, nullptr, nullptr, nullptr, nullptr};
     f->shard_rank = 0;

@@ -12,6 +12,7 @@ struct FilterScalars {
   unsigned int blocks_done;
   unsigned int pad0;
   unsigned long long n_out;  // KLD output size
+  unsigned long long n_clusters;  // label_clusters' count (read on the device by K14)
 };
 
 // quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)
@@ -126,6 +127,20 @@ struct StageTimer {
   }
 };
 
+// Slots of qmcl_filter::h_scalars (pinned host memory, 8-byte words).  The
+// deferred values own their slots; the others are consumed right after the
+// synchronisation that follows the copy.
+enum : int {
+  HS_TOTAL = 0,      // pre-penalty sensor total (deferred)
+  HS_NCLUSTERS = 1,  // cluster count (deferred)
+  HS_RS = 2,         // running sum: record count, total weight
+  HS_BBOX = 4,       // 6 ints
+  HS_STOP = 8,       // KLD: packed stop word, number of new-bin flags
+  HS_NBINS = 10,
+  HS_EST = 16,       // estimate: 13 doubles + invalid flag
+  HS_COUNT = 32
+};
+
 // quickmcl::ParticleFilter (particle_filter.h)
 struct qmcl_filter {
   qmcl_map *map = nullptr;
@@ -149,6 +164,20 @@ struct qmcl_filter {
   // low_pass_filter.h: two host scalars
   double w_slow = 0.0, w_fast = 0.0;
   double last_total = 0.0;
+
+  // Deferred 8-byte read-backs (single-GPU filters only).  A value the host
+  // needs only later — the sensor total for the two low-pass scalars, the
+  // cluster count — is copied to its own pinned slot without a stream
+  // synchronisation and folded in by settle()/settle_after_sync() at the next
+  // point that synchronises anyway (filter.cu).  lazy_sync = false restores a
+  // synchronisation per value (qmcl_filter_set_sync_mode).
+  bool lazy_sync = true;
+  bool total_pending = false;
+  double pending_n_total = 0.0;
+  bool clusters_pending = false;
+  cudaEvent_t staging_read = nullptr;  // the last H2D copy out of h_beams
+  int bbox_hint[6] = {0, 0, 0, 0, 0, 0};  // bin bounds of the set just resampled from
+  bool bbox_hint_valid = false;
 
   // space_partitioning.cpp:34-35
   int theta_lo = -17, theta_hi = 17;

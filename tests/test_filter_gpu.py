@@ -366,3 +366,81 @@ def test_multi_cycle_tracking_matches_oracle(rtype, n):
         assert abs(math.remainder(g_pose[2] - o_pose[2], 2 * math.pi)) <= 1e-4, cycle
         assert np.max(np.abs(g_cov - o_cov)) <= 1e-6
     assert np.allclose(gf.lowpass(), of.lowpass(), rtol=1e-9)
+
+
+# ------------------------------------------------- deferred read-backs (sync mode)
+def _run_cycles(gm, occ, res, origin, rtype, n, lazy, cycles=5, inject_at=None):
+    """Whole cycles through the public mirror; returns everything observable."""
+    gf = q.create_particle_filter(gm, seed=7)
+    gf.set_sync_mode(lazy)
+    gf.set_parameters(q.ParticleFilterParameters(
+        resample_type=q.ResampleType(rtype), particle_count_min=n if rtype != 2 else 100,
+        particle_count_max=n, resample_count=2, alpha_fast=0.1, alpha_slow=0.001,
+        kld_epsilon=0.05, kld_z=0.95, space_partitioning_resolution_xy=0.5,
+        space_partitioning_resolution_theta=RES_THETA))
+    pose = syn.pick_truth_pose(occ, res, origin)
+    x, y, t = syn.gaussian_cloud(pose, n)
+    gf.set_particles(q.make_particles(x, y, t, np.full(n, 1.0 / n)))
+    cur = pose.copy()
+    odom_old = np.zeros(3)
+    seen = []
+    for cycle in range(cycles):
+        cur = cur + np.array([0.22 * math.cos(cur[2]), 0.22 * math.sin(cur[2]), 0.05])
+        odom_new = odom_old + np.array([0.22, 0.0, 0.05])
+        scan = syn.make_scan(occ, res, origin, cur, 360, 360.0, seed=40 + cycle)
+        gf.handle_odometry(odom_new, odom_old, syn.NODE_ALPHA)
+        gf.update_importance_from_observations(scan)
+        if cycle == 2:
+            # a second sensor update before anything consumed the first total
+            gf.update_importance_from_observations(scan)
+        if inject_at == cycle:
+            gf.set_lowpass(1.0, 0.7)   # must order after the pending total
+        if cycle % 3 == 2:
+            gf.cluster()
+        else:
+            gf.resample_and_cluster()
+        odom_old = odom_new
+        ok, p, c = gf.get_estimated_pose()
+        keys, labels = gf.bins()
+        seen.append((ok, p.copy(), c.copy(), gf.num_particles(), gf.num_bins(), gf.num_clusters(),
+                     keys.copy(), labels.copy(), np.array(gf.lowpass()), gf.last_total_weight(),
+                     gf.get_particles().copy()))
+    return seen
+
+
+@pytest.mark.parametrize("rtype,n,inject_at", [(0, 3000, None), (1, 4000, None), (1, 4000, 1),
+                                               (2, 20000, None), (2, 20000, 3)])
+def test_sync_modes_agree(rtype, n, inject_at):
+    """qmcl_filter_set_sync_mode: deferring the 8-byte read-backs changes when the host
+    waits, never a result — every observable is identical, bit for bit."""
+    occ, res, origin = syn.make_map(400, seed=1)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=30)))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    a = _run_cycles(gm, occ, res, origin, rtype, n, True, inject_at=inject_at)
+    b = _run_cycles(gm, occ, res, origin, rtype, n, False, inject_at=inject_at)
+    for cycle, (sa, sb) in enumerate(zip(a, b)):
+        assert sa[0] == sb[0], cycle
+        assert np.array_equal(sa[1], sb[1]) and np.array_equal(sa[2], sb[2]), cycle
+        assert sa[3:6] == sb[3:6], (cycle, sa[3:6], sb[3:6])
+        assert np.array_equal(sa[6], sb[6]) and np.array_equal(sa[7], sb[7]), cycle
+        assert np.array_equal(sa[8], sb[8]) and sa[9] == sb[9], cycle
+        assert sa[10].tobytes() == sb[10].tobytes(), cycle
+
+
+def test_deferred_values_settle_on_read():
+    """A getter right after the call that left its value in flight returns the value
+    (the getter synchronises), also when no other call intervenes."""
+    occ, res, origin, om, gm, of, gf = make_pair(resample_type=0, particle_count_min=2000,
+                                                 particle_count_max=2000)
+    pose = syn.pick_truth_pose(occ, res, origin)
+    x, y, t = syn.gaussian_cloud(pose, 2000)
+    set_both(of, gf, x, y, t, np.ones(2000))
+    scan = syn.make_scan(occ, res, origin, pose, 360, 360.0)
+    for f in (of, gf):
+        f.update_importance_from_observations(scan)
+    assert gf.last_total_weight() == pytest.approx(of.last_total_weight(), rel=1e-5)
+    assert np.allclose(gf.lowpass(), of.lowpass(), rtol=1e-5)
+    for f in (of, gf):
+        f.cluster()
+    assert gf.num_clusters() == of.num_clusters() >= 1
