@@ -234,8 +234,11 @@ static_assert(adjacency_mask(0) == (1u << kCand) - 1, "A must be adjacent to eve
 
 __global__ void __launch_bounds__(256)
 cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bin_cell,
-               size_t n_bins, BinGrid g, BinParams bp, int32_t *__restrict__ parent) {
+               size_t n_bins, const unsigned long long *__restrict__ n_bins_dev, BinGrid g,
+               BinParams bp, int32_t *__restrict__ parent) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // n_bins is a launch bound while the count is still on its way to the host
+  if (n_bins_dev) n_bins = static_cast<size_t>(*n_bins_dev);
   if (tid >= n_bins) return;
   const int b = static_cast<int>(tid);
   const int cell = bin_cell[b];
@@ -286,15 +289,19 @@ cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bi
 }
 
 __global__ void __launch_bounds__(256)
-cc_flatten_kernel(int32_t *__restrict__ parent, size_t n_bins) {
+cc_flatten_kernel(int32_t *__restrict__ parent, size_t n_bins,
+                  const unsigned long long *__restrict__ n_bins_dev) {
   const size_t b = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n_bins_dev) n_bins = static_cast<size_t>(*n_bins_dev);
   if (b >= n_bins) return;
   parent[b] = uf_find_readonly(parent, static_cast<int>(b));
 }
 
 struct RootFlag {
   const int32_t *label;
+  const unsigned long long *n_bins_dev;  // non-null: the scan runs over a bound
   __device__ uint32_t operator()(size_t b) const {
+    if (n_bins_dev && b >= *n_bins_dev) return 0u;
     return label[b] == static_cast<int32_t>(b) ? 1u : 0u;
   }
 };
@@ -623,6 +630,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   const BinGrid prev_grid = f->grid;
   const bool have_prev = reuse_grid && f->bins_built && prev_grid.nx > 0;
   f->n_bins = 0;
+  f->bins_pending = false;
   f->n_clusters = 0;
   f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = false;
@@ -709,8 +717,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(f->bin_label.ensure(max_bins));
   QMCL_TRY(f->bin_cluster.ensure(max_bins));
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(cells) + 4));
-  unsigned long long *d_total =
-      scan_total_ptr(f->scan_tmp.ptr, cells);
+  unsigned long long *d_total = &f->scalars.ptr->n_bins;  // stable: the labelling reads it
   QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
                        EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
                        cells, f->scan_tmp.ptr, d_total));
@@ -718,11 +725,12 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     // the caller counted the bins already (KLD: new-bin flags up to the stop)
     f->n_bins = static_cast<size_t>(known_bins);
   } else {
-    unsigned long long *h = reinterpret_cast<unsigned long long *>(f->h_scalars.ptr + HS_NBINS);
-    QMCL_CUDA(copy_d2h(h, d_total, sizeof(*h), s));
-    QMCL_CUDA(cudaStreamSynchronize(s));
-    settle_after_sync(f);
-    f->n_bins = *h;
+    // The host needs the count only to size the labelling launches, for which
+    // max_bins is a bound: in lazy mode the copy is left in flight.
+    QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_NBINS, d_total, sizeof(unsigned long long), s));
+    f->bins_pending = true;
+    f->n_bins_bound = max_bins;
+    if (!lazy(f)) QMCL_TRY(settle(f));
   }
   f->bins_built = true;
   return QMCL_OK;
@@ -733,23 +741,27 @@ qmcl_status label_clusters(qmcl_filter *f) {
   cudaStream_t s = f->map->stream;
   f->n_clusters = 0;
   f->clusters_pending = false;  // an older count still in flight is void
-  if (f->n_bins == 0) {
+  // With the bin count still in flight the launches are sized by its bound and
+  // the kernels read the count on the device.
+  const size_t nb = f->bins_pending ? f->n_bins_bound : f->n_bins;
+  const unsigned long long *nb_dev = f->bins_pending ? &f->scalars.ptr->n_bins : nullptr;
+  if (nb == 0) {
     f->clusters_valid = true;
     return QMCL_OK;
   }
   const BinParams bp = bin_params(f);
   StageScope sc(f, QMCL_STAGE_LABEL);
-  cc_hook_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, f->n_bins,
-                                                            f->grid, bp, f->bin_label.ptr);
+  cc_hook_kernel<<<div_up(nb, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, nb, nb_dev, f->grid,
+                                                 bp, f->bin_label.ptr);
   QMCL_LAUNCHED();
-  cc_flatten_kernel<<<div_up(f->n_bins, 256), 256, 0, s>>>(f->bin_label.ptr, f->n_bins);
+  cc_flatten_kernel<<<div_up(nb, 256), 256, 0, s>>>(f->bin_label.ptr, nb, nb_dev);
   QMCL_LAUNCHED();
-  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(f->n_bins) + 4));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(nb) + 4));
   // the count goes to a stable device word (K14 reads it there) and to its own
   // pinned slot; the host needs it only to size K14's buffers, for which the
   // bin count is a bound, so the copy is left in flight
   unsigned long long *d_total = &f->scalars.ptr->n_clusters;
-  QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr}, EmitRootId{f->bin_cluster.ptr}, f->n_bins,
+  QMCL_TRY(device_scan(s, RootFlag{f->bin_label.ptr, nb_dev}, EmitRootId{f->bin_cluster.ptr}, nb,
                        f->scan_tmp.ptr, d_total));
   QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_NCLUSTERS, d_total, sizeof(unsigned long long), s));
   f->clusters_pending = true;
@@ -785,7 +797,8 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   // and at most the bin count, which is all the host needs here; K14 reads the
   // exact value on the device.
   const bool nc_on_device = f->clusters_pending;
-  const size_t nc_cap = nc_on_device ? f->n_bins : f->n_clusters;
+  const size_t nc_cap =
+      nc_on_device ? (f->bins_pending ? f->n_bins_bound : f->n_bins) : f->n_clusters;
   if (n_any == 0 && nc_cap == 0) return QMCL_OK;  // no clusters: "ALL clusters suck"
   if (n_any > 0 && (!f->bins_built || nc_cap == 0)) {
     set_error("get_estimate: particles have no cluster (call cluster() or resample first)");
@@ -883,6 +896,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
 
 qmcl_status qmcl_filter_num_bins(const qmcl_filter *f, size_t *out) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(const_cast<qmcl_filter *>(f)));
   *out = f->n_bins;
   return QMCL_OK;
 }
@@ -898,6 +912,7 @@ qmcl_status qmcl_filter_copy_bins(const qmcl_filter *fc, int32_t *keys4, int32_t
                                   size_t cap, size_t *n_out) {
   if (!fc) return QMCL_ERR_INVALID_ARG;
   qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  QMCL_TRY(settle(f));
   if (n_out) *n_out = f->n_bins;
   const size_t n = f->n_bins < cap ? f->n_bins : cap;
   if (!n || !keys4 || !labels) return QMCL_OK;

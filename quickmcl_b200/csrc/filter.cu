@@ -180,6 +180,12 @@ void settle_after_sync(qmcl_filter *f) {
     f->total_pending = false;
     apply_total(f, f->h_scalars.ptr[HS_TOTAL], f->pending_n_total);
   }
+  if (f->bins_pending) {
+    f->bins_pending = false;
+    unsigned long long nb;
+    std::memcpy(&nb, &f->h_scalars.ptr[HS_NBINS], sizeof(nb));
+    f->n_bins = nb;
+  }
   if (f->clusters_pending) {
     f->clusters_pending = false;
     unsigned long long nc;
@@ -189,7 +195,7 @@ void settle_after_sync(qmcl_filter *f) {
 }
 
 qmcl_status settle(qmcl_filter *f) {
-  if (!f->total_pending && !f->clusters_pending) return QMCL_OK;
+  if (!f->total_pending && !f->clusters_pending && !f->bins_pending) return QMCL_OK;
   QMCL_TRY(use_device(f->map));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
   settle_after_sync(f);
@@ -343,6 +349,7 @@ qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p) {
   f->theta_lo = static_cast<int>(static_cast<float>(-kPi + 0.001) / p->res_theta);
   f->theta_hi = static_cast<int>(static_cast<float>(kPi - 0.001) / p->res_theta);
   f->n_bins = 0;
+  f->bins_pending = false;
   f->n_clusters = 0;
   f->clusters_pending = false;  // an older count still in flight is void
   f->clusters_valid = false;

@@ -633,6 +633,7 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   out.n = 0;  // output_set->particles.clear()
   f->n_src_index = 0;
   f->n_bins = 0;  // space_partitioning.reset()
+  f->bins_pending = false;
   f->n_clusters = 0;
   f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = true;
@@ -1087,6 +1088,7 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
   const size_t n_max = static_cast<size_t>(f->params.particle_count_max);
   f->n_src_index = 0;
   f->n_bins = 0;
+  f->bins_pending = false;
   f->n_clusters = 0;
   f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = true;

@@ -13,6 +13,7 @@ struct FilterScalars {
   unsigned int pad0;
   unsigned long long n_out;  // KLD output size
   unsigned long long n_clusters;  // label_clusters' count (read on the device by K14)
+  unsigned long long n_bins;      // build_bins' count (read on the device by the labelling)
 };
 
 // quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)
@@ -175,6 +176,8 @@ struct qmcl_filter {
   bool total_pending = false;
   double pending_n_total = 0.0;
   bool clusters_pending = false;
+  bool bins_pending = false;   // n_bins in flight; n_bins_bound sizes launches meanwhile
+  size_t n_bins_bound = 0;
   cudaEvent_t staging_read = nullptr;  // the last H2D copy out of h_beams
   int bbox_hint[6] = {0, 0, 0, 0, 0, 0};  // bin bounds of the set just resampled from
   bool bbox_hint_valid = false;
