@@ -219,11 +219,15 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double odom_new[3]
                                         const double odom_old[3],
                                         const float alpha[4]);
 /* IParticleFilter::update_importance_from_observations
- * (particle_filter.cpp:95-136). cloud_xy = n_points x {float x, y}. */
+ * (particle_filter.cpp:95-136). cloud_xy = n_points x {float x, y}.  The cloud
+ * is copied before the call returns; in the default sync mode
+ * (qmcl_filter_set_sync_mode) the kernels may still be running when it does. */
 qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy,
                                       size_t n_points);
 /* Device-resident variant for benchmarking the kernel alone: the cloud is
- * already in HBM (dev_cloud_xy), nothing is copied to the host. */
+ * already in HBM (dev_cloud_xy), nothing is copied to the host.  dev_cloud_xy
+ * is read by the first kernel enqueued: keep it valid until the next call that
+ * returns a result (get_estimate, a getter, qmcl_filter_synchronize). */
 qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
                                           size_t n_points);
 /* The same update fed with a raw planar LaserScan: the projection
