@@ -5,6 +5,7 @@
 // and the weight helpers of src/quickmcl/particle.cpp:41-64.
 
 #include "filter.cuh"
+#include "cluster.cuh"
 #include "sensor.cuh"
 #include "shard.cuh"
 #include "scan.cuh"
@@ -235,6 +236,15 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   a.rmax = f->beams.ptr + 2 * n_points;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
+  if (ps.n && lazy(f) && f->params.resample_type == QMCL_RESAMPLE_KLD) {
+    // KLD sizes its dense bin table by the bounding box of the set it draws
+    // from.  Taken here, ahead of the sensor kernel, the six numbers are on the
+    // host long before the resampling asks for them.
+    StageScope sc(f, QMCL_STAGE_BINS);
+    QMCL_TRY(launch_bin_bbox(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
+    QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_BBOX_EARLY, f->bbox.ptr, 6 * sizeof(int), s));
+    f->early_bbox_version = f->pose_version;
+  }
   if (ps.n) {
     StageScope sc(f, QMCL_STAGE_SENSOR, 1);
     QMCL_TRY(launch_sensor(m, a));
@@ -266,6 +276,9 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   // before the next resampling, so the copy is left in flight (HS_TOTAL) and
   // folded in at the next synchronisation.
   QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_TOTAL, &f->scalars.ptr->total_weight, sizeof(double), s));
+  if (!f->total_copied)
+    QMCL_CUDA(cudaEventCreateWithFlags(&f->total_copied, cudaEventDisableTiming));
+  QMCL_CUDA(cudaEventRecord(f->total_copied, s));
   f->total_pending = true;
   f->pending_n_total = static_cast<double>(ps.n);
   if (!lazy(f)) QMCL_TRY(settle(f));
@@ -333,6 +346,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->particle_cid.release();
   f->timer.release();
   if (f->staging_read) cudaEventDestroy(f->staging_read);
+  if (f->total_copied) cudaEventDestroy(f->total_copied);
   qmcl_map *map = f->map;
   delete f;
   return qmcl_map_destroy(map);
@@ -344,6 +358,7 @@ qmcl_status qmcl_filter_set_params(qmcl_filter *f, const qmcl_pf_params *p) {
   if (!(p->res_xy > 0) || !(p->res_theta > 0)) return QMCL_ERR_INVALID_ARG;
   if (f->map) QMCL_TRY(settle(f));  // a pending total uses the alphas it was measured under
   f->params = *p;
+  f->early_bbox_version = ~0ull;  // bin resolutions may have changed
   // theta_range: world_to_map of (float)(-pi+0.001) and (float)(pi-0.001):
   // float division then truncation (scaled_map.h:43-48).
   f->theta_lo = static_cast<int>(static_cast<float>(-kPi + 0.001) / p->res_theta);
@@ -388,6 +403,7 @@ qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, si
   f->global_first = 0;
   f->global_n = n;
   f->clusters_valid = false;
+  f->pose_version++;
   if (!n) return QMCL_OK;
   void *stage = nullptr;
   QMCL_TRY(filter_scratch(f, n * sizeof(qmcl_particle), &stage));

@@ -179,6 +179,7 @@ qmcl_status qmcl_filter_initialise_factor(qmcl_filter *f, const float pose[3],
   f->global_first = first;
   f->global_n = global_n;
   f->clusters_valid = false;
+  f->pose_version++;
   if (n) {
     InitParams ip;
     for (int k = 0; k < 3; ++k) ip.mean[k] = pose[k];
@@ -211,6 +212,7 @@ qmcl_status qmcl_filter_global_localization(qmcl_filter *f) {
   f->global_first = first;
   f->global_n = global_n;
   f->clusters_valid = false;
+  f->pose_version++;
   if (n) {
     init_global_kernel<<<div_up(n, 256), 256, 0, f->map->stream>>>(
         ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, n, first, global_n, f->map->free_cells.ptr,
@@ -257,6 +259,7 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double nw[3], cons
     QMCL_LAUNCHED();
   }
   f->clusters_valid = false;
+  f->pose_version++;
   f->step++;
   return QMCL_OK;
 }

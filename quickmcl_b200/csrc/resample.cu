@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256)
 draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
             const float *__restrict__ it, const double *__restrict__ iw,
             const int64_t *__restrict__ pos, const double *__restrict__ incl, size_t P,
+            const unsigned long long *__restrict__ P_dev,
             double w_diff, size_t n_draws, const uint32_t *__restrict__ free_xy,
             unsigned long long n_free, MapGeom g, uint64_t seed, uint32_t step,
             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ ot,
@@ -136,7 +137,11 @@ draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
     return;
   }
   const double rr = uniform53(r[2], r[3]);
-  const int64_t s = pos[running_sum_lookup(incl, P, rr)];
+  // The record count may still be on its way to the host.  Without records
+  // (the host will find out and discard this output) every slot takes
+  // particle 0, which keeps the poses inside the input set's bin bounds.
+  if (P_dev) P = static_cast<size_t>(*P_dev);
+  const int64_t s = P ? pos[running_sum_lookup(incl, P, rr)] : 0;
   ox[m] = ix[s];
   oy[m] = iy[s];
   ot[m] = it[s];
@@ -526,6 +531,34 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
 // bbox_out (optional, single GPU): the bin bounding box of the input set is
 // computed in the same pass and read back with the same synchronisation; it
 // bounds the bins of every draw that copies an input particle.
+// Enqueues the running sum of `in` (in.n > 0): records in f->pos / f->incl, their
+// number in the stable device word scalars->n_records, and copies of that number
+// and of the total weight on their way to HS_RS.  No synchronisation.
+static qmcl_status enqueue_running_sum(qmcl_filter *f, const ParticleSet &in) {
+  cudaStream_t s = f->map->stream;
+  QMCL_TRY(f->cdf.ensure(in.n));
+  QMCL_TRY(f->pos.ensure(in.n));
+  QMCL_TRY(f->incl.ensure(in.n));
+  StageScope sc(f, QMCL_STAGE_CDF);
+  QMCL_TRY(sequential_prefix(f, in.w.ptr, in.n, f->cdf.ptr));
+  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(in.n) + 4));
+  unsigned long long *d_total = &f->scalars.ptr->n_records;
+  QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
+                       in.n, f->scan_tmp.ptr, d_total));
+  double *h = f->h_scalars.ptr + HS_RS;
+  QMCL_CUDA(copy_d2h(h, d_total, sizeof(unsigned long long), s));
+  QMCL_CUDA(copy_d2h(h + 1, f->cdf.ptr + (in.n - 1), sizeof(double), s));
+  return QMCL_OK;
+}
+// What enqueue_running_sum left in HS_RS, once the stream has been synchronised.
+static void read_running_sum(const qmcl_filter *f, size_t *P_out, double *total_out) {
+  const double *h = f->h_scalars.ptr + HS_RS;
+  unsigned long long P;
+  std::memcpy(&P, h, sizeof(P));
+  *P_out = P;
+  *total_out = h[1];
+}
+
 static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size_t *P_out,
                                      double *total_out, int *bbox_out = nullptr) {
   cudaStream_t s = f->map->stream;
@@ -533,29 +566,14 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
   *total_out = 0.0;
   if (bbox_out) bbox_out[0] = 1, bbox_out[3] = 0;  // empty
   if (in.n == 0) return settle(f);
-  QMCL_TRY(f->cdf.ensure(in.n));
-  QMCL_TRY(f->pos.ensure(in.n));
-  QMCL_TRY(f->incl.ensure(in.n));
-  StageScope sc(f, QMCL_STAGE_CDF);
-  QMCL_TRY(sequential_prefix(f, in.w.ptr, in.n, f->cdf.ptr));
-  QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(in.n) + 4));
-  unsigned long long *d_total =
-      scan_total_ptr(f->scan_tmp.ptr, in.n);
-  QMCL_TRY(device_scan(s, PositiveFlag{in.w.ptr}, EmitPositive{f->cdf.ptr, f->pos.ptr, f->incl.ptr},
-                       in.n, f->scan_tmp.ptr, d_total));
-  double *h = f->h_scalars.ptr + HS_RS;
-  QMCL_CUDA(copy_d2h(h, d_total, sizeof(unsigned long long), s));
-  QMCL_CUDA(copy_d2h(h + 1, f->cdf.ptr + (in.n - 1), sizeof(double), s));
+  QMCL_TRY(enqueue_running_sum(f, in));
   if (bbox_out) {
     QMCL_TRY(launch_bin_bbox(f, in.x.ptr, in.y.ptr, in.t.ptr, in.n));
     QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_BBOX, f->bbox.ptr, 6 * sizeof(int), s));
   }
   QMCL_CUDA(cudaStreamSynchronize(s));
   settle_after_sync(f);  // the sensor total (w_slow, w_fast) rides on this synchronisation
-  unsigned long long P;
-  std::memcpy(&P, h, sizeof(P));
-  *P_out = P;
-  *total_out = h[1];
+  read_running_sum(f, P_out, total_out);
   if (bbox_out) std::memcpy(bbox_out, f->h_scalars.ptr + HS_BBOX, 6 * sizeof(int));
   return QMCL_OK;
 }
@@ -566,7 +584,8 @@ static double adaptiveness(const qmcl_filter *f) {
 }
 
 static qmcl_status launch_draws(qmcl_filter *f, const ParticleSet &in, ParticleSet &out, size_t P,
-                                double w_diff, size_t n_draws) {
+                                double w_diff, size_t n_draws,
+                                const unsigned long long *P_dev = nullptr) {
   cudaStream_t s = f->map->stream;
   if (w_diff > 0 && f->map->n_free == 0) {
     set_error("adaptive injection needs a map with free cells");
@@ -575,7 +594,7 @@ static qmcl_status launch_draws(qmcl_filter *f, const ParticleSet &in, ParticleS
   QMCL_TRY(f->src_index.ensure(n_draws));
   StageScope sc(f, QMCL_STAGE_SELECT);
   draw_kernel<<<div_up(n_draws, 256), 256, 0, s>>>(
-      in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr, f->pos.ptr, f->incl.ptr, P, w_diff, n_draws,
+      in.x.ptr, in.y.ptr, in.t.ptr, in.w.ptr, f->pos.ptr, f->incl.ptr, P, P_dev, w_diff, n_draws,
       f->map->free_cells.ptr, f->map->n_free, f->map->geom, f->seed, f->step, out.x.ptr, out.y.ptr,
       out.t.ptr, out.w.ptr, f->src_index.ptr);
   QMCL_LAUNCHED();
@@ -638,26 +657,56 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   f->clusters_pending = false;  // an older count still in flight is void
   f->bins_built = true;
   f->grid = BinGrid{0, 0, 0, 0, 0, 0};
-  size_t P;
-  double total;
-  int in_bbox[6];
-  QMCL_TRY(build_running_sum(f, in, &P, &total, lazy(f) ? in_bbox : nullptr));
-  if (!(total > 0)) return QMCL_OK;
-  if (n_max == 0) return QMCL_OK;
-  if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
-  const double w_diff = adaptiveness(f);  // after the read-back: it settles w_slow / w_fast
-  QMCL_TRY(out.ensure(n_max));
-  QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_max));
-  // The dense bin grid spanned by all candidates.  Without injection every
-  // candidate is a copy of an input particle, so the input set's bounding box
-  // (read back together with the running-sum total) contains it.
-  const int *known_bbox = nullptr;
-  if (lazy(f) && !(w_diff > 0.0) && in_bbox[0] <= in_bbox[3]) {
+  size_t P = 0;
+  double total = 0.0;
+  int in_bbox[6] = {1, 0, 0, 0, 0, 0};  // empty
+  auto bbox_usable = [&]() {
+    if (in_bbox[0] > in_bbox[3]) return false;
     const double cells_in = (static_cast<double>(in_bbox[3]) - in_bbox[0] + 1) *
                             (static_cast<double>(in_bbox[4]) - in_bbox[1] + 1) *
                             (static_cast<double>(in_bbox[5]) - in_bbox[2] + 1);
-    if (cells_in <= static_cast<double>(kMaxTableCells)) known_bbox = in_bbox;
+    return cells_in <= static_cast<double>(kMaxTableCells);
+  };
+  // Streamlined order (single GPU, deferred read-backs): the input set's bin
+  // bounds were taken during the sensor update, so nothing here has to wait for
+  // the running sum — it is enqueued, the host picks up the sensor total as soon
+  // as the sensor kernel is through (an event, not a stream synchronisation) and
+  // goes on enqueueing while the running sum executes.  Whether there was
+  // anything to draw from is checked at the stop-rule read-back below.
+  bool check_later = false;
+  double w_diff = 0.0;
+  if (lazy(f) && in.n && n_max > 0 && n_max <= 0x7fffffffull &&
+      f->early_bbox_version == f->pose_version) {
+    QMCL_TRY(enqueue_running_sum(f, in));
+    if (f->total_pending) {
+      QMCL_CUDA(cudaEventSynchronize(f->total_copied));
+      // everything pending was enqueued before that event
+      settle_after_sync(f);
+    }
+    std::memcpy(in_bbox, f->h_scalars.ptr + HS_BBOX_EARLY, sizeof(in_bbox));
+    w_diff = adaptiveness(f);
+    if (!(w_diff > 0.0) && bbox_usable()) {
+      check_later = true;
+    } else {  // injected poses leave the input set's bounds: wait for the candidates' own
+      QMCL_CUDA(cudaStreamSynchronize(s));
+      settle_after_sync(f);
+      read_running_sum(f, &P, &total);
+    }
+  } else {
+    QMCL_TRY(build_running_sum(f, in, &P, &total, lazy(f) ? in_bbox : nullptr));
+    w_diff = adaptiveness(f);  // after the read-back: it settles w_slow / w_fast
   }
+  if (!check_later && !(total > 0)) return QMCL_OK;
+  if (n_max == 0) return QMCL_OK;
+  if (n_max > 0x7fffffffull) return QMCL_ERR_CAPACITY;
+  QMCL_TRY(out.ensure(n_max));
+  QMCL_TRY(launch_draws(f, in, out, P, w_diff, n_max,
+                        check_later ? &f->scalars.ptr->n_records : nullptr));
+  // The dense bin grid spanned by all candidates.  Without injection every
+  // candidate is a copy of an input particle, so the input set's bounding box
+  // contains it.
+  const int *known_bbox = nullptr;
+  if (lazy(f) && !(w_diff > 0.0) && bbox_usable()) known_bbox = in_bbox;
   QMCL_TRY(build_bins(f, out.x.ptr, out.y.ptr, out.t.ptr, n_max, false, true, known_bbox));
   const BinGrid g = f->grid;
   const size_t cells = static_cast<size_t>(g.nx) * g.ny * g.nt;
@@ -687,6 +736,15 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   QMCL_CUDA(copy_d2h(h + 1, d_total, sizeof(unsigned long long), s));
   QMCL_CUDA(cudaStreamSynchronize(s));
   settle_after_sync(f);
+  if (check_later) {
+    read_running_sum(f, &P, &total);
+    if (!(total > 0)) {  // nothing to draw from: the state of the early return above
+      f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+      f->n_bins = 0;
+      f->bins_built = true;
+      return QMCL_OK;
+    }
+  }
   // no stop (all ones): every candidate is kept and every new-bin flag counts
   const bool stopped = h[0] != ~0ull;
   const size_t n_out = stopped ? static_cast<size_t>(h[0] >> 32) + 1 : n_max;
@@ -1213,6 +1271,7 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
     return QMCL_ERR_INVALID_ARG;
   }
   f->step++;
+  f->pose_version++;
   if (!sharded(f)) {
     f->global_first = 0;
     f->global_n = out.n;

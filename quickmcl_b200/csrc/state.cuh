@@ -14,6 +14,7 @@ struct FilterScalars {
   unsigned long long n_out;  // KLD output size
   unsigned long long n_clusters;  // label_clusters' count (read on the device by K14)
   unsigned long long n_bins;      // build_bins' count (read on the device by the labelling)
+  unsigned long long n_records;   // running-sum records (read on the device by the draws)
 };
 
 // quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)
@@ -138,6 +139,7 @@ enum : int {
   HS_BBOX = 4,       // 6 ints
   HS_STOP = 8,       // KLD: packed stop word, number of new-bin flags
   HS_NBINS = 10,
+  HS_BBOX_EARLY = 12,  // 6 ints: bin bounds taken ahead of the sensor kernel (KLD)
   HS_EST = 16,       // estimate: 13 doubles + invalid flag
   HS_COUNT = 32
 };
@@ -179,6 +181,10 @@ struct qmcl_filter {
   bool bins_pending = false;   // n_bins in flight; n_bins_bound sizes launches meanwhile
   size_t n_bins_bound = 0;
   cudaEvent_t staging_read = nullptr;  // the last H2D copy out of h_beams
+  cudaEvent_t total_copied = nullptr;  // the sensor total has reached HS_TOTAL
+  // Bumped by every call that moves particles or replaces the set; the bin bounds
+  // taken during the sensor update serve the resampling only at the same version.
+  uint64_t pose_version = 0, early_bbox_version = ~0ull;
   int bbox_hint[6] = {0, 0, 0, 0, 0, 0};  // bin bounds of the set just resampled from
   bool bbox_hint_valid = false;
 
