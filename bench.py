@@ -244,6 +244,8 @@ def workload_config(args, wl, n_used_beams):
             "resample": RESAMPLE_NAMES[wl["pf"]["resample_type"]],
             "step": "handle_odometry+update_sensor+resample_and_cluster+get_estimate",
             "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed",
+            "host_waits": ("per value (QMCL_EAGER_SYNC)" if os.environ.get("QMCL_EAGER_SYNC", "0") not in ("", "0")
+                           else "deferred read-backs (qmcl_filter_set_sync_mode default)"),
             "sharding": (f"particles, contiguous global-index blocks; exchanges via {args.transport}"
                          if args.gpus > 1 else "none")}
 
