@@ -60,7 +60,7 @@ for r in rows[2:]:
     a["sm"] += num(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed")
     a["occ"] += num(r, "sm__warps_active.avg.pct_of_peak_sustained_active")
 
-print(f"# {rep}: per-kernel averages over the captured launches (ncu --set full, cold caches, serialised)")
+print(f"# {rep}: per-kernel averages over the captured launches (ncu, cold caches, serialised; under ncu the times are not bench values)")
 print(f"# DRAM GB/s = (dram__bytes_read + dram__bytes_write) / gpu__time_duration; frac = that / {peak} GB/s "
       "(measured copy peak)")
 print(f"{'kernel':44s} {'x':>3s} {'us':>8s} {'grid':>7s} {'blk':>4s} {'regs':>4s} {'DRAM MB':>9s} "
