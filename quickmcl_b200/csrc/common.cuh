@@ -151,6 +151,19 @@ __device__ __forceinline__ uint32_t code_offset(uint32_t x, uint32_t y, uint32_t
   return (x >> 3) * (stride - 8u) + ((y << 3) + x);
 }
 
+// The 1-byte palette map (sensor model's PAL8 path) uses the same construction
+// with strips 16 cells wide: a 128-byte line holds a 16 x 8 block of cells.
+//   offset(x, y) = (x >> 4) * stride + 16 * y + (x & 15),  stride = 16 * round_up(h, 8)
+__host__ __device__ __forceinline__ uint32_t code8_strip_stride(uint32_t h) {
+  return 16u * ((h + 7u) & ~7u);
+}
+__host__ __device__ __forceinline__ size_t code8_map_elems(uint32_t w, uint32_t h) {
+  return static_cast<size_t>((w + 15u) >> 4) * code8_strip_stride(h);
+}
+__device__ __forceinline__ uint32_t code8_offset(uint32_t x, uint32_t y, uint32_t stride) {
+  return (x >> 4) * (stride - 16u) + ((y << 4) + x);
+}
+
 __device__ __forceinline__ int cell_index(float pos, float offset, float res) {
   return __float2int_rz(__fdiv_rn(__fsub_rn(pos, offset), res));
 }

@@ -451,6 +451,9 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->code.release();
   m->pw3_lut.release();
   m->pw3_lut_f32.release();
+  m->code8.release();
+  m->pal8_rank.release();
+  m->pal8_lut.release();
   m->tmp_x.release();
   m->tmp_y.release();
   m->tmp_t.release();
@@ -463,7 +466,7 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
 }
 
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *m, int path) {
-  if (!m || path < 0 || path > 2) return QMCL_ERR_INVALID_ARG;
+  if (!m || path < 0 || path > 3) return QMCL_ERR_INVALID_ARG;
   m->sensor_path = path;
   return QMCL_OK;
 }

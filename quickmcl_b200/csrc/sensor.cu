@@ -33,6 +33,13 @@
 //             case 5e-7 relative, measured ~1e-7, against the 1e-5 bar.  This
 //             is the default when the map was built here; PAL64 and FIELD stay
 //             selectable (qmcl_map_set_sensor_path).
+//  * PAL8   : (opt-in, path 3) far from an obstacle z_hit * p vanishes against
+//             z_rand/max_range, so the float table holds few *distinct* values
+//             over the squared distances that can occur (72 at the defaults,
+//             230 at sigma_hit = 0.2).  When they fit a byte the map is also
+//             kept as one palette index per cell, 16 x 8 cells per 128-byte
+//             line: fewer lines per gather, a 1 KB table instead of 13 KB.
+//             The floats are PAL32's, so are the weights, bit for bit.
 //
 // Division: (m - o) / res is evaluated as q = a*r, q' = fma(fma(q,-res,a), r, q)
 // with r = RN(1/res), which yields the correctly rounded quotient (Markstein);
@@ -43,6 +50,7 @@
 #include "sensor.cuh"
 
 #include <type_traits>
+#include <vector>
 
 namespace qmcl {
 
@@ -81,6 +89,9 @@ struct SensorParams {
   const double *pw3_lut;  // n_codes entries + 1 (out of map)
   const float *pw3_lut_f32;
   int n_codes;
+  const uint8_t *code8;   // PAL8: palette index per cell
+  const float *pal8_lut;  // PAL8: pal8_n + 2 floats
+  int pal8_n;
 };
 
 unsigned sensor_grid(size_t n) { return div_up(n, kParticlesPerBlock); }
@@ -209,7 +220,7 @@ __global__ void fastdiv_check_kernel(SensorParams sp, int *mismatch) {
   if (bad2) atomicExch(mismatch + 1, 1);
 }
 
-enum { PATH_FIELD = 0, PATH_PAL64 = 1, PATH_PAL32 = 2 };
+enum { PATH_FIELD = 0, PATH_PAL64 = 1, PATH_PAL32 = 2, PATH_PAL8 = 3 };
 
 // Shared-memory float table read by byte offset: the code map stores 4 * code,
 // so the lookup needs no address arithmetic.
@@ -218,7 +229,8 @@ __device__ __forceinline__ float lds_f32_at(const float *table, unsigned byte_of
 }
 
 template <int PATH, int DIV>
-__global__ void __launch_bounds__(kSensorThreads, PATH == PATH_PAL32 ? QMCL_SENSOR_MINBLOCKS : 4)
+__global__ void __launch_bounds__(kSensorThreads,
+                                  (PATH == PATH_PAL32 || PATH == PATH_PAL8) ? QMCL_SENSOR_MINBLOCKS : 4)
 sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a) {
   extern __shared__ double s_lut[];  // PAL64: n_codes + 1 doubles; PAL32: floats
   float *s_lut_f32 = reinterpret_cast<float *>(s_lut);
@@ -234,6 +246,8 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   } else if (PATH == PATH_PAL32) {
     for (int k = threadIdx.x; k <= sp.n_codes + 1; k += kSensorThreads)
       s_lut_f32[k] = sp.pw3_lut_f32[k];
+  } else if (PATH == PATH_PAL8) {
+    for (int k = threadIdx.x; k <= sp.pal8_n + 1; k += kSensorThreads) s_lut_f32[k] = sp.pal8_lut[k];
   }
 
   // Lane p prepares particle first+p; the values are then broadcast.
@@ -284,7 +298,7 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   const f32x2 NRES = pack2(sp.neg_res, sp.neg_res);
   const f32x2 TINY = pack2(sp.tiny, sp.tiny);
   const unsigned w = sp.g.w;
-  const unsigned strip = code_strip_stride(sp.g.h);
+  const unsigned strip = PATH == PATH_PAL8 ? code8_strip_stride(sp.g.h) : code_strip_stride(sp.g.h);
   // Software pipeline: the beam for the next step is fetched before this
   // step's arithmetic, and the value gathered in step i is consumed in step
   // i+1, so a full loop body of independent work covers each load's latency.
@@ -294,7 +308,8 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 #pragma unroll
   for (int p = 0; p < kP; ++p) {
     facc[p] = 0.f;
-    code_prev[p] = 4 * (sp.n_codes + 1);  // table entry holding 0 (codes are byte offsets)
+    // table entry holding 0 (uint16 codes are byte offsets, PAL8 codes are indices)
+    code_prev[p] = PATH == PATH_PAL8 ? sp.pal8_n + 1 : 4 * (sp.n_codes + 1);
     pz_prev[p] = -1.0;              // "nothing pending"
   }
   // One step of the walk: this lane's beam b against the kP particles.  The
@@ -343,9 +358,14 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       // 32-bit cell offset (maps are far below 2^32 cells); the code map is
       // stored in 8-cell strips (common.cuh)
       const unsigned cell =
-          PALETTE ? code_offset(static_cast<unsigned>(ix), static_cast<unsigned>(iy), strip)
-                  : static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix);
-      if (PALETTE) {
+          PATH == PATH_PAL8
+              ? code8_offset(static_cast<unsigned>(ix), static_cast<unsigned>(iy), strip)
+              : (PALETTE ? code_offset(static_cast<unsigned>(ix), static_cast<unsigned>(iy), strip)
+                         : static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix));
+      if (PATH == PATH_PAL8) {
+        code_cur[p] = sp.pal8_n;  // outside the map -> p_max entry
+        if (inside) code_cur[p] = __ldg(sp.code8 + cell);
+      } else if (PALETTE) {
         code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry
 #if QMCL_DIAG == 2 || QMCL_DIAG == 3
         if (inside) code_cur[p] = __ldg(sp.code + ((cell & 1u) + 2u * lane + 64u * p + 4096u * (blockIdx.x & 255)));
@@ -369,6 +389,8 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 #else
         facc[p] = __fadd_rn(facc[p], lds_f32_at(s_lut_f32, code_prev[p]));
 #endif
+      } else if (PATH == PATH_PAL8) {
+        facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
       } else if (pz_prev[p] >= 0.0) {
         // z_hit * p is exact in double (two float significands), so the fused
         // form rounds exactly like the reference's mul-then-add.
@@ -381,7 +403,7 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   };
   // float partial sums never hold more than 8 terms
   auto fold = [&]() {
-    if (PATH == PATH_PAL32) {
+    if (PATH == PATH_PAL32 || PATH == PATH_PAL8) {
 #pragma unroll
       for (int p = 0; p < kP; ++p) {
         acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
@@ -423,6 +445,9 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       acc[p] = __dadd_rn(acc[p], s_lut[code_prev[p] >> 2]);
     } else if (PATH == PATH_PAL32) {
       facc[p] = __fadd_rn(facc[p], lds_f32_at(s_lut_f32, code_prev[p]));
+      acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
+    } else if (PATH == PATH_PAL8) {
+      facc[p] = __fadd_rn(facc[p], s_lut_f32[code_prev[p]]);
       acc[p] = __dadd_rn(acc[p], static_cast<double>(facc[p]));
     } else if (pz_prev[p] >= 0.0) {
       const double pw = fma(z_hit, pz_prev[p], zr);
@@ -519,7 +544,77 @@ static SensorParams make_params(const qmcl_map *m) {
   sp.pw3_lut = m->pw3_lut.ptr;
   sp.pw3_lut_f32 = m->pw3_lut_f32.ptr;
   sp.n_codes = m->n_codes;
+  sp.code8 = m->code8.ptr;
+  sp.pal8_lut = m->pal8_lut.ptr;
+  sp.pal8_n = m->pal8_n;
   return sp;
+}
+
+// PAL8: uint16 d^2 code map -> one palette index per cell.  A code the palette
+// does not cover (rank 255) raises the flag; the caller then drops the path.
+__global__ void __launch_bounds__(256)
+code8_build_kernel(const uint16_t *__restrict__ code16, const uint8_t *__restrict__ rank,
+                   uint8_t *__restrict__ code8, uint32_t w, uint32_t h, int *__restrict__ flag) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const unsigned k = code16[code_offset(x, y, code_strip_stride(h))] >> 2;
+  const uint8_t r = rank[k];
+  if (r == 0xff) atomicExch(flag, 1);
+  code8[code8_offset(x, y, code8_strip_stride(h))] = r;
+}
+
+// Builds the one-byte palette for the current float pw^3 table (which must be
+// up to date on the device).  Runs when the table changes — a map load or a
+// parameter change — not per scan: it synchronises.  Leaves pal8_n = 0 when the
+// distinct values do not fit a byte.
+static qmcl_status build_pal8(qmcl_map *m) {
+  m->pal8_valid = true;
+  m->pal8_n = 0;
+  if (!m->has_code || m->n_codes < 2) return QMCL_OK;
+  cudaStream_t s = m->stream;
+  const int n = m->n_codes;  // codes 0 .. kmax and kmax + 1 = "nothing within range"
+  std::vector<float> lut(static_cast<size_t>(n) + 2);
+  QMCL_CUDA(copy_d2h(lut.data(), m->pw3_lut_f32.ptr, lut.size() * sizeof(float), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));
+  // squared distances the exact EDT can produce: a^2 + b^2 <= kmax, and the clip code
+  const int kmax = n - 2;
+  std::vector<uint8_t> reachable(n, 0);
+  for (long a = 0; a * a <= kmax; ++a)
+    for (long b = a; a * a + b * b <= kmax; ++b) reachable[a * a + b * b] = 1;
+  reachable[kmax + 1] = 1;
+  std::vector<uint8_t> rank(n, 0xff);
+  std::vector<float> pal;
+  for (int k = 0; k < n; ++k) {
+    if (!reachable[k]) continue;
+    size_t j = 0;
+    while (j < pal.size() && std::memcmp(&pal[j], &lut[k], sizeof(float)) != 0) ++j;
+    if (j == pal.size()) {
+      if (pal.size() == 254) return QMCL_OK;  // does not fit: PAL32 stays in charge
+      pal.push_back(lut[k]);
+    }
+    rank[k] = static_cast<uint8_t>(j);
+  }
+  const int npal = static_cast<int>(pal.size());
+  pal.push_back(lut[n]);      // outside the map (p_max)
+  pal.push_back(0.0f);        // "nothing pending" entry of the software pipeline
+  QMCL_TRY(m->pal8_rank.ensure(n));
+  QMCL_TRY(m->pal8_lut.ensure(256));
+  QMCL_TRY(m->code8.ensure(code8_map_elems(m->geom.w, m->geom.h)));
+  QMCL_TRY(m->scan_tmp.ensure(8));
+  int *d_flag = reinterpret_cast<int *>(m->scan_tmp.ptr);
+  QMCL_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+  QMCL_CUDA(copy_h2d(m->pal8_rank.ptr, rank.data(), rank.size(), s));
+  QMCL_CUDA(copy_h2d(m->pal8_lut.ptr, pal.data(), pal.size() * sizeof(float), s));
+  dim3 grid(div_up(m->geom.w, 256), m->geom.h);
+  code8_build_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t *>(m->code.ptr),
+                                          m->pal8_rank.ptr, m->code8.ptr, m->geom.w, m->geom.h,
+                                          d_flag);
+  QMCL_LAUNCHED();
+  int flag = 1;
+  QMCL_CUDA(copy_d2h(&flag, d_flag, sizeof(flag), s));
+  QMCL_CUDA(cudaStreamSynchronize(s));  // rank / pal are host vectors: done with them now
+  if (!flag) m->pal8_n = npal;
+  return QMCL_OK;
 }
 
 // Called at map load: decides whether the 3-op division may be used.
@@ -562,7 +657,7 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   int div = m->div_verified;
   if (m->div_forced >= 0) div = std::min(div, m->div_forced);
   int path = PATH_FIELD;
-  if (can_palette && m->sensor_path == 0) path = PATH_PAL32;
+  if (can_palette && (m->sensor_path == 0 || m->sensor_path == 3)) path = PATH_PAL32;
   if (can_palette && m->sensor_path == 2) path = PATH_PAL64;
   if (path != PATH_FIELD) {
     // refresh pw^3 when z_hit / z_rand / max range / p_max changed
@@ -580,6 +675,19 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
       m->lut_z_hit = sp.z_hit;
       m->lut_zr = sp.zr;
       m->lut_p_max = sp.p_max;
+      m->pal8_valid = false;
+    }
+    if (m->sensor_path == 3) {
+      if (!m->pal8_valid) QMCL_TRY(build_pal8(m));
+      if (m->pal8_n > 0) {
+        sp.code8 = m->code8.ptr;
+        sp.pal8_lut = m->pal8_lut.ptr;
+        sp.pal8_n = m->pal8_n;
+        const size_t smem8 = static_cast<size_t>(m->pal8_n + 2) * sizeof(float);
+        if (div == DIV_SPLIT) return launch_variant<PATH_PAL8, DIV_SPLIT>(m, sp, a, smem8);
+        return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL8, DIV_MARKSTEIN>(m, sp, a, smem8)
+                                    : launch_variant<PATH_PAL8, DIV_IEEE>(m, sp, a, smem8);
+      }
     }
     if (path == PATH_PAL64) {
       const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(double);
