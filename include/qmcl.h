@@ -89,10 +89,15 @@ qmcl_status qmcl_map_destroy(qmcl_map *map);
 /* All work of this map (and of filters created on it) is enqueued on
  * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
 qmcl_status qmcl_map_set_stream(qmcl_map *map, void *cuda_stream);
-/* Sensor-model value path: 0 = automatic (uint16 d^2 palette with a float
- * pw^3 table when the map was built by qmcl_map_load, <= 5e-7 relative),
+/* Sensor-model value path: 0 = automatic (for a map built by qmcl_map_load:
+ * path 3 when it applies, else path 4; <= 5e-7 relative),
  * 1 = gather the float32 field and do the reference's double arithmetic per
- * evaluation (exact), 2 = palette with a double pw^3 table (exact). */
+ * evaluation (exact), 2 = uint16 d^2 code per cell with a double pw^3 table
+ * (exact), 3 = one-byte palette index per cell with the float pw^3 values
+ * (exists when those take at most 254 distinct values over the squared
+ * distances that can occur, e.g. sigma_hit <= 0.2 m at 5 cm cells; otherwise
+ * path 4 runs), 4 = uint16 d^2 code per cell with a float pw^3 table.
+ * Paths 3 and 4 produce identical bits. */
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *map, int path);
 /* Cell-index division (m - o) / res of map_base.cpp:66-77.  At load the
  * library checks two multiply-based forms against IEEE division around every

@@ -113,7 +113,8 @@ class MapLikelihood:
               "qmcl_map_set_stream")
 
     def set_sensor_path(self, path):
-        """Test hook: 0 = auto (palette when built here), 1 = float field gather."""
+        """Test hook: 0 = auto (3, else 4, when built here), 1 = float field gather, 2 = uint16
+        codes + double table, 3 = one-byte palette, 4 = uint16 codes + float table."""
         check(self._L.qmcl_map_set_sensor_path(self._h, path), "qmcl_map_set_sensor_path")
 
     def set_division_mode(self, mode):

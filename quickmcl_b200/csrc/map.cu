@@ -466,7 +466,7 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
 }
 
 qmcl_status qmcl_map_set_sensor_path(qmcl_map *m, int path) {
-  if (!m || path < 0 || path > 3) return QMCL_ERR_INVALID_ARG;
+  if (!m || path < 0 || path > 4) return QMCL_ERR_INVALID_ARG;
   m->sensor_path = path;
   return QMCL_OK;
 }

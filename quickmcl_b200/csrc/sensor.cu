@@ -31,9 +31,9 @@
 //             lookup instead of two or more) and summed in float for at most 8
 //             terms before being folded into the double accumulator.  Worst
 //             case 5e-7 relative, measured ~1e-7, against the 1e-5 bar.  This
-//             is the default when the map was built here; PAL64 and FIELD stay
+//             stands in when PAL8 does not apply; PAL64 and FIELD stay
 //             selectable (qmcl_map_set_sensor_path).
-//  * PAL8   : (opt-in, path 3) far from an obstacle z_hit * p vanishes against
+//  * PAL8   : the default when the map was built here.  Far from an obstacle z_hit * p vanishes against
 //             z_rand/max_range, so the float table holds few *distinct* values
 //             over the squared distances that can occur (72 at the defaults,
 //             230 at sigma_hit = 0.2).  When they fit a byte the map is also
@@ -649,7 +649,8 @@ static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, con
 qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   if (a.n == 0) return QMCL_OK;
   SensorParams sp = make_params(m);
-  // sensor_path: 0 auto (PAL32 when the map was built here), 1 FIELD, 2 PAL64
+  // sensor_path: 0 auto (PAL8, else PAL32, when the map was built here), 1 FIELD, 2 PAL64,
+  // 3 PAL8 (same as auto), 4 PAL32
   const bool can_palette =
       m->has_code && static_cast<size_t>(m->n_codes + 2) * sizeof(double) <= 96 * 1024;
   // division: the cheapest form the self-check allowed, or the one forced
@@ -657,8 +658,11 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   int div = m->div_verified;
   if (m->div_forced >= 0) div = std::min(div, m->div_forced);
   int path = PATH_FIELD;
-  if (can_palette && (m->sensor_path == 0 || m->sensor_path == 3)) path = PATH_PAL32;
+  if (can_palette && (m->sensor_path == 0 || m->sensor_path == 3 || m->sensor_path == 4))
+    path = PATH_PAL32;
   if (can_palette && m->sensor_path == 2) path = PATH_PAL64;
+  // 0 (auto) and 3 take the one-byte palette when it exists for these parameters
+  const bool want_pal8 = path == PATH_PAL32 && m->sensor_path != 4;
   if (path != PATH_FIELD) {
     // refresh pw^3 when z_hit / z_rand / max range / p_max changed
     if (!m->lut_params_valid || m->lut_z_hit != sp.z_hit || m->lut_zr != sp.zr ||
@@ -677,7 +681,7 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
       m->lut_p_max = sp.p_max;
       m->pal8_valid = false;
     }
-    if (m->sensor_path == 3) {
+    if (want_pal8) {
       if (!m->pal8_valid) QMCL_TRY(build_pal8(m));
       if (m->pal8_n > 0) {
         sp.code8 = m->code8.ptr;

@@ -54,7 +54,7 @@ struct qmcl_map {
   qmcl::DevBuf<float> pw3_lut_f32;
   bool has_code = false;
   int n_codes = 0;
-  // PAL8 (opt-in, qmcl_map_set_sensor_path(m, 3)): when the float pw^3 table
+  // PAL8 (the default value path when it applies): when the float pw^3 table
   // holds at most 254 distinct values over the d^2 codes that can occur, the
   // map is also kept as one byte per cell (index into that palette), 16 x 8
   // cells per 128-byte line.  Same floats as PAL32, hence the same weights.
@@ -65,7 +65,7 @@ struct qmcl_map {
   bool pal8_valid = false;           // built for the current pw^3 table
   int div_verified = 0;           // cheapest division form verified against IEEE division at load
   int div_forced = -1;            // qmcl_map_set_division_mode: -1 auto, else an upper bound
-  int sensor_path = 0;            // 0 auto, 1 float field, 2 exact double palette, 3 one-byte palette
+  int sensor_path = 0;            // 0 auto (3, else 4), 1 float field, 2 exact double palette, 3 one-byte palette, 4 float table
   bool lut_params_valid = false;
   float lut_z_hit = 0.f, lut_zr = 0.f;
   double lut_p_max = 0.0;

@@ -255,3 +255,35 @@ def test_division_forms_pick_identical_cells(res, origin_shift):
                 assert tt == t0
     gm.set_division_mode(-1)
     gm.set_sensor_path(0)
+
+
+@pytest.mark.parametrize("sigma_hit,res", [(0.1, 0.05), (0.2, 0.05), (0.3, 0.05), (0.1, 0.1)])
+def test_one_byte_palette_identical_to_float_table(sigma_hit, res):
+    """Path 3 (one palette index per cell) and path 4 (uint16 squared-distance code per
+    cell) look the same float pw^3 values up, so the weights must agree bit for bit —
+    on the interior fast path, on the bounds-checked path reaching over the map edge,
+    after a parameter change that rebuilds the table, and when the distinct values do
+    not fit a byte (sigma_hit = 0.3: path 3 then runs path 4)."""
+    occ, _, origin = syn.make_map(600)
+    origin = (origin[0] * res / 0.05, origin[1] * res / 0.05)
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0, sigma_hit=sigma_hit)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**lp))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, 725, 270.0)
+    n = 5003   # ragged: not a multiple of the particles per block
+    for params in (lp, dict(lp, z_hit=0.6, z_rand=0.4, max_laser_distance=20.0)):
+        gm.set_parameters(q.LikelihoodMapParameters(**params))
+        for x, y, t in (syn.gaussian_cloud(pose, n), syn.uniform_cloud(occ, res, origin, n)):
+            got = {}
+            for path in (4, 3, 0):
+                gm.set_sensor_path(path)
+                ps = q.make_particles(x, y, t, np.ones(n))
+                total = gm.update_importance(scan, ps)
+                got[path] = (ps["weight"].copy(), total)
+            assert got[4][0].max() > 0
+            for path in (3, 0):
+                assert np.array_equal(got[path][0].view(np.uint64), got[4][0].view(np.uint64)), path
+                assert got[path][1] == got[4][1]
+    gm.set_sensor_path(0)
