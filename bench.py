@@ -401,9 +401,11 @@ def run_b200(args, wl):
         local_evals = (n / world) * len(scan)
         achieved = local_evals * ALG_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9
         traffic = None
+        traffic_note = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "sensor_traffic.json"))).get(
-                args.workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "sensor_traffic.json")))
+            traffic = tj.get(args.workload)
+            traffic_note = tj.get("_variant")
         except (OSError, ValueError):
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -411,6 +413,8 @@ def run_b200(args, wl):
                     "kernel_ms": k_ms, "kernel_evals_per_s": local_evals / (k_ms * 1e-3),
                     "alg_bytes_per_eval": ALG_BYTES_PER_EVAL, "peak_kind": peak_kind,
                     "launches_timed": sensor_cnt}
+        if traffic is not None and traffic_note:
+            roofline["traffic_note"] = traffic_note
     if rank != 0:
         if dist:
             dist.destroy_process_group()
