@@ -181,6 +181,62 @@ def cpu_cycle_seconds(wl, inputs, steps, warmup):
     return total / steps, evals, {k: v / steps for k, v in stages.items()}
 
 
+def cpu_all_cores(wl, inputs, steps=3):
+    """The same CPU cycle on every host core at once: the particle set is cut into one
+    slice per thread, each slice runs its own full cycle (own filter, shared read-only
+    map).  This is NOT how the reference runs (it is single-threaded, main.cpp:90, and
+    slices resample independently); it bounds what the host could do if it were
+    parallelised over particles.  Returns a dict for the JSON line."""
+    import threading
+    from oracle import binding as ob
+    occ, res, origin, pose, scan, (x, y, t) = inputs
+    threads_n = max(1, min(os.cpu_count() or 1, 64))
+    n = len(x)
+    per = n // threads_n
+    if per < 64:
+        return None
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    om = ob.OracleMap(**lp)
+    om.new_map(occ, res, origin, field_mode=ob.FIELD_BRUSHFIRE)
+    pfp = dict(wl["pf"])
+    sc = per / n
+    pfp["particle_count_min"] = max(1, int(pfp["particle_count_min"] * sc))
+    pfp["particle_count_max"] = max(1, int(pfp["particle_count_max"] * sc))
+    filters = []
+    for k in range(threads_n):
+        of = ob.OracleFilter(om, seed=3 + k)
+        of.set_parameters(**pfp)
+        sl = slice(k * per, (k + 1) * per)
+        filters.append((of, ob.make_particles(x[sl], y[sl], t[sl], np.full(per, 1.0 / per))))
+    barrier = threading.Barrier(threads_n + 1)
+
+    def work(of, init):
+        for it in range(steps + 1):
+            of.set_particles(init)
+            of.set_rng(3, 10 + it)
+            if it == 1:
+                barrier.wait()   # the warm-up step is over everywhere: the clock starts
+            of.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
+            of.update_importance_from_observations(scan)
+            of.resample_and_cluster()
+            of.get_estimated_pose()
+
+    ts = [threading.Thread(target=work, args=fi) for fi in filters]
+    for th in ts:
+        th.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    for th in ts:
+        th.join()
+    sec = (time.perf_counter() - t0) / steps
+    evals = threads_n * per * len(scan)
+    return {"value": evals / sec, "unit": "evals/s", "cores": threads_n,
+            "sample": f"{threads_n} threads x {per} particles x {len(scan)} beams, independent "
+                      f"full cycles per slice, {steps} steps after 1 warm-up",
+            "note": "not reference behaviour (the reference is single-threaded); an upper bound "
+                    "for a particle-parallel host"}
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -213,6 +269,8 @@ def run_reference(args, wl):
         wl_s, (occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])),
         args.steps, args.warmup)
     value = evals / sec
+    all_cores = cpu_all_cores(
+        wl_s, (occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])))
     sample = (f"{n_sample} of {n_full} particles x {len(scan)} beams per step, full update cycle"
               if n_sample < n_full else f"full workload ({n_full} particles x {len(scan)} beams)")
     line = {
@@ -228,7 +286,8 @@ def run_reference(args, wl):
                          "sample": sample, "cpu": cpu_model(), "host_cores": os.cpu_count(),
                          "stage_ms": {k: v * 1e3 for k, v in stages.items()},
                          "note": "CPU restatement of the reference (oracle/); the reference is "
-                                 "single-threaded (main.cpp:90) and cannot be built here"},
+                                 "single-threaded (main.cpp:90) and cannot be built here",
+                         "all_cores": all_cores},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -438,7 +497,9 @@ def run_b200(args, wl):
                    "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
                              f"5 steps after 1 warm-up",
                    "cpu": cpu_model(), "host_cores": os.cpu_count(),
-                   "stage_ms": {k: v * 1e3 for k, v in stages.items()}}
+                   "stage_ms": {k: v * 1e3 for k, v in stages.items()},
+                   "all_cores": cpu_all_cores(
+                       wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])))}
 
     line = {
         "metric": "particle_point_likelihood_evals_per_sec",
