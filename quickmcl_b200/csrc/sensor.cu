@@ -571,6 +571,7 @@ static qmcl_status build_pal8(qmcl_map *m) {
   m->pal8_valid = true;
   m->pal8_n = 0;
   if (!m->has_code || m->n_codes < 2) return QMCL_OK;
+  if (m->geom.h > 65535u) return QMCL_OK;  // the build kernel takes one grid row per map row
   cudaStream_t s = m->stream;
   const int n = m->n_codes;  // codes 0 .. kmax and kmax + 1 = "nothing within range"
   std::vector<float> lut(static_cast<size_t>(n) + 2);
