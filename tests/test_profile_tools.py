@@ -28,3 +28,14 @@ def test_kernel_tables_match_committed():
         got = run("ncu_step_summary.py", os.path.join(ROOT, "profiles", f"r1_kernels_{w}_ncu_raw.csv"))
         want = open(os.path.join(ROOT, "profiles", f"r1_kernels_{w}_ncu.txt")).read()
         assert body(got) == body(want), w
+
+
+def test_k9_lane_summary_model_matches_sequential_sum(tmp_path):
+    """tools/experiments/k9_lanes/model.cpp: the CPU model of the prepared K9 change
+    reproduces the sequential sum bit for bit on its adversarial inputs."""
+    src = os.path.join(ROOT, "tools", "experiments", "k9_lanes", "model.cpp")
+    exe = str(tmp_path / "k9model")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, src], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches 0" in out.stdout
