@@ -515,6 +515,19 @@ def run_b200(args, wl):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "estimate": [float(v) for v in dev["estimate"][1]] if dev["estimate"] else None,
     }
+    if world > 1:
+        # The N = 1 line of the contract is C2; the sharded runs are C4 (strong scaling of
+        # one 16 M-particle filter).  The same workload on ONE GPU, measured earlier with
+        # `bench.py --workload C4` and committed, is attached so that a speed-up can be read
+        # off like with like.
+        try:
+            ref = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_c4_1gpu_final.json")))
+            if ref.get("config", {}).get("workload") == args.workload:
+                line["same_workload_on_one_gpu"] = {
+                    "value": ref["value"], "unit": ref["unit"], "ms_per_step": ref["ms_per_step"],
+                    "source": "profiles/r1_bench_c4_1gpu_final.json (python bench.py --workload C4)"}
+        except (OSError, ValueError, KeyError):
+            pass
     emit(line)
     if dist:
         dist.destroy_process_group()
