@@ -467,11 +467,11 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, siz
   if (!f->map->has_map) return QMCL_ERR_NO_MAP;
   QMCL_TRY(use_device(f->map));
   cudaStream_t s = f->map->stream;
+  QMCL_TRY(staging_free(f));  // before the staging buffer may be reallocated, too
   QMCL_TRY(f->cloud.ensure(2 * n_points + 2));
   QMCL_TRY(f->beams.ensure(2 * n_points + 2));
   QMCL_TRY(f->h_beams.ensure(2 * n_points + 2));
   // stage through pinned memory so the H2D copy is a true async DMA
-  QMCL_TRY(staging_free(f));
   std::memcpy(f->h_beams.ptr, cloud_xy, 2 * n_points * sizeof(float));
   QMCL_CUDA(copy_h2d(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float), s));
   QMCL_CUDA(cudaEventRecord(f->staging_read, s));
@@ -499,11 +499,11 @@ qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, 
   if (!f->map->has_map) return QMCL_ERR_NO_MAP;
   QMCL_TRY(use_device(f->map));
   cudaStream_t s = f->map->stream;
+  QMCL_TRY(staging_free(f));  // before the staging buffer may be reallocated, too
   QMCL_TRY(f->ranges.ensure(n_ranges + 2));
   QMCL_TRY(f->cloud.ensure(2 * n_ranges + 2));
   QMCL_TRY(f->beams.ensure(2 * n_ranges + 2));
   QMCL_TRY(f->h_beams.ensure(2 * n_ranges + 2));
-  QMCL_TRY(staging_free(f));
   std::memcpy(f->h_beams.ptr, ranges, n_ranges * sizeof(float));
   QMCL_CUDA(copy_h2d(f->ranges.ptr, f->h_beams.ptr, n_ranges * sizeof(float), s));
   QMCL_CUDA(cudaEventRecord(f->staging_read, s));
