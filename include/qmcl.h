@@ -35,7 +35,7 @@ typedef enum qmcl_status {
   QMCL_ERR_INVALID_CLUSTER = 5,
   QMCL_ERR_CAPACITY = 6,
   QMCL_ERR_COMM = 7,        /* a qmcl_comm collective failed */
-  QMCL_ERR_UNSUPPORTED = 8  /* not available on a sharded filter yet */
+  QMCL_ERR_UNSUPPORTED = 8  /* the call is not available on a sharded filter */
 } qmcl_status;
 
 /* quickmcl::WeightedParticle (particle.h:32-47): Pose2D<float> + double. */
@@ -254,6 +254,9 @@ qmcl_status qmcl_filter_cluster(qmcl_filter *f);
  * *valid = 1 and pose/cov written when a cluster has weight, else 0. */
 qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3],
                                      double cov[9], int *valid);
+/* effective_particles (particle.cpp:32-39, test_particle.cpp:12-27):
+ * 1 / sum of squared weights of the current set. */
+qmcl_status qmcl_filter_effective_particles(const qmcl_filter *f, double *out);
 /* IParticleFilter::num_particles / get_particles (AoS copy). */
 qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out);
 qmcl_status qmcl_filter_copy_particles(const qmcl_filter *f, qmcl_particle *out,

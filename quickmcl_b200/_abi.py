@@ -96,6 +96,7 @@ SIGNATURES = {
     "qmcl_filter_cluster": [vp],
     "qmcl_filter_get_estimate": [vp, pf64, pf64, C.POINTER(C.c_int)],
     "qmcl_filter_num_particles": [vp, C.POINTER(sz)],
+    "qmcl_filter_effective_particles": [vp, pf64],
     "qmcl_filter_copy_particles": [vp, pP, sz],
     "qmcl_filter_set_particles": [vp, pP, sz],
     "qmcl_filter_set_rng": [vp, u64, u32],

@@ -328,6 +328,13 @@ class ParticleFilter:
         check(self._L.qmcl_filter_num_particles(self._h, C.byref(n)), "qmcl_filter_num_particles")
         return n.value
 
+    def effective_particles(self):
+        """effective_particles(get_particles()) of particle.cpp:32-39: 1 / sum of w^2."""
+        out = C.c_double(0)
+        check(self._L.qmcl_filter_effective_particles(self._h, C.byref(out)),
+              "qmcl_filter_effective_particles")
+        return out.value
+
     # -- test hooks ----------------------------------------------------------
     def initialise_factor(self, starting_point, factor):
         pose = np.asarray(starting_point, np.float32)

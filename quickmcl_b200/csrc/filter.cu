@@ -294,13 +294,26 @@ extern "C" {
 qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) {
   if (!map || !out) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(map));
+  *out = nullptr;
   qmcl_filter *f = new qmcl_filter();
   f->map = map;
-  map->refs++;
   f->seed = seed;
-  QMCL_TRY(f->scalars.ensure(1));
-  QMCL_CUDA(cudaMemsetAsync(f->scalars.ptr, 0, sizeof(FilterScalars), map->stream));
-  QMCL_TRY(f->h_scalars.ensure(HS_COUNT));
+  // the fallible steps come before the map reference is taken, and their
+  // buffers are released again on failure
+  auto init = [&]() -> qmcl_status {
+    QMCL_TRY(f->scalars.ensure(1));
+    QMCL_CUDA(cudaMemsetAsync(f->scalars.ptr, 0, sizeof(FilterScalars), map->stream));
+    QMCL_TRY(f->h_scalars.ensure(HS_COUNT));
+    return QMCL_OK;
+  };
+  const qmcl_status st = init();
+  if (st != QMCL_OK) {
+    f->scalars.release();
+    f->h_scalars.release();
+    delete f;
+    return st;
+  }
+  map->refs++;
   if (const char *e = std::getenv("QMCL_EAGER_SYNC")) f->lazy_sync = !(e[0] && e[0] != '0');
   qmcl_filter_set_params(f, &f->params);
   *out = f;

@@ -231,6 +231,9 @@ struct StopRule {
 // ------------------------------------------------------------------ normalise
 // particle.cpp:41-56: total = sum of weights, w /= total.  The sum is a fixed
 // tree (deterministic); it differs from the sequential sum by rounding only.
+// SQUARE: the sum of squared weights of effective_particles (particle.cpp:32-39),
+// each product rounded before it is added, left in sc->sum_sq.
+template <bool SQUARE>
 __global__ void __launch_bounds__(256)
 weight_sum_kernel(const double *__restrict__ w, size_t n, double *__restrict__ partials,
                   FilterScalars *__restrict__ sc) {
@@ -238,8 +241,10 @@ weight_sum_kernel(const double *__restrict__ w, size_t n, double *__restrict__ p
   __shared__ bool s_last;
   double t = 0.0;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    t = __dadd_rn(t, w[i]);
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const double v = w[i];
+    t = __dadd_rn(t, SQUARE ? __dmul_rn(v, v) : v);
+  }
   t = warp_sum_xor(t);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) s_warp[wid] = t;
@@ -266,7 +271,8 @@ weight_sum_kernel(const double *__restrict__ w, size_t n, double *__restrict__ p
     double tot = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) tot = __dadd_rn(tot, s_warp[i]);
-    sc->post_total = tot;
+    if (SQUARE) sc->sum_sq = tot;
+    else sc->post_total = tot;
     sc->blocks_done = 0;
   }
 }
@@ -291,7 +297,7 @@ static qmcl_status normalise_current(qmcl_filter *f) {
   const unsigned blocks = static_cast<unsigned>(
       std::min<size_t>(std::max<size_t>(div_up(ps.n, 256 * 4), 1), 4 * kSMs));
   QMCL_TRY(f->partials.ensure(blocks));
-  weight_sum_kernel<<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
+  weight_sum_kernel<false><<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
   QMCL_LAUNCHED();
   if (sharded(f)) {
     // Exchange: the normalising total is the sum of the shards' totals.
@@ -578,6 +584,15 @@ static qmcl_status build_running_sum(qmcl_filter *f, const ParticleSet &in, size
   return QMCL_OK;
 }
 
+// particle_filter.cpp:284-290, 338-344: both filters restart after an injection round.
+static void reset_lowpass(qmcl_filter *f) {
+  f->w_slow_before_reset = f->w_slow;
+  f->w_fast_before_reset = f->w_fast;
+  f->lowpass_was_reset = true;
+  f->w_fast = 0;
+  f->w_slow = 0;
+}
+
 static double adaptiveness(const qmcl_filter *f) {
   // particle_filter.cpp:246: std::max(0.0, NaN) is 0.0
   return std::max(0.0, 1.0 - f->w_fast / f->w_slow);
@@ -634,8 +649,7 @@ static qmcl_status resample_adaptive(qmcl_filter *f, const ParticleSet &in, Part
   }
   f->n_src_index = n_out;
   if (w_diff > 0.0) {
-    f->w_fast = 0;
-    f->w_slow = 0;
+    reset_lowpass(f);
   }
   return QMCL_OK;
 }
@@ -752,8 +766,7 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   out.n = n_out;
   f->n_src_index = n_out;
   if (w_diff > 0.0) {
-    f->w_fast = 0;
-    f->w_slow = 0;
+    reset_lowpass(f);
   }
   // the bins the reference holds at this point are those of the kept draws; they
   // lie inside the candidates' bounding box, so the grid is reused
@@ -1091,8 +1104,7 @@ static qmcl_status resample_adaptive_sharded(qmcl_filter *f, const ParticleSet &
     return QMCL_OK;
   }
   if (w_diff > 0.0) {
-    f->w_fast = 0;
-    f->w_slow = 0;
+    reset_lowpass(f);
   }
   return QMCL_OK;
 }
@@ -1214,8 +1226,7 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
   }
   const size_t n_out = (stop >= n_max) ? n_max : static_cast<size_t>(stop) + 1;
   if (w_diff > 0.0) {
-    f->w_fast = 0;
-    f->w_slow = 0;
+    reset_lowpass(f);
   }
   // keep the first n_out slots, then give every rank an equal block again
   std::vector<uint64_t> lo(G), hi(G);
@@ -1243,11 +1254,47 @@ using namespace qmcl;
 
 extern "C" {
 
-// particle_filter.cpp:138-161
+static qmcl_status resample_and_cluster_impl(qmcl_filter *f);
+
+// particle_filter.cpp:138-161.  The reference has no failing path here; this
+// one has (capacity of the dense bin table, injection without free cells, CUDA
+// or exchange errors), so the call is a transaction: the new set replaces the
+// current one only when every step succeeded.  After an error the filter still
+// holds the particles it was called with (their clustering is void).
 qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  const int current = f->current;
+  const uint32_t step = f->step;
+  const uint64_t pose_version = f->pose_version;
+  const size_t global_first = f->global_first, global_n = f->global_n;
+  f->lowpass_was_reset = false;
+  const qmcl_status st = resample_and_cluster_impl(f);
+  if (st == QMCL_OK) return st;
+  // whatever was enqueued no longer matters; the sensor total of the update
+  // before this call still counts (w_slow, w_fast)
+  cudaStreamSynchronize(f->map->stream);
+  settle_after_sync(f);
+  if (f->lowpass_was_reset) {  // the injection round's reset (particle_filter.cpp:284-290) is undone
+    f->w_slow = f->w_slow_before_reset;
+    f->w_fast = f->w_fast_before_reset;
+  }
+  f->current = current;
+  f->step = step;
+  f->pose_version = pose_version + 1;  // bin bounds taken earlier are not trusted any more
+  f->global_first = global_first;
+  f->global_n = global_n;
+  f->n_src_index = 0;
+  f->n_bins = 0;
+  f->n_clusters = 0;
+  f->bins_built = false;
+  f->clusters_valid = false;
+  f->bbox_hint_valid = false;
+  f->grid = BinGrid{0, 0, 0, 0, 0, 0};
+  return st;
+}
 
+static qmcl_status resample_and_cluster_impl(qmcl_filter *f) {
   const ParticleSet &in = f->sets[f->current];
   ParticleSet &out = f->sets[(f->current + 1) % 2];
   f->current = (f->current + 1) % 2;
@@ -1294,6 +1341,39 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
     }
   }
   return normalise_current(f);
+}
+
+// effective_particles (particle.cpp:32-39): 1 / sum of squared weights.  One
+// launch; the sum is a fixed tree over the particle index (deterministic), so it
+// differs from the reference's sequential sum by rounding only.  An empty set
+// gives 1/0 = inf, as the reference's loop does.
+qmcl_status qmcl_filter_effective_particles(const qmcl_filter *fc, double *out) {
+  if (!fc || !out) return QMCL_ERR_INVALID_ARG;
+  qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
+  cudaStream_t s = f->map->stream;
+  const ParticleSet &ps = f->cur();
+  double sum = 0.0;
+  if (ps.n) {
+    const unsigned blocks = static_cast<unsigned>(
+        std::min<size_t>(std::max<size_t>(div_up(ps.n, 256 * 4), 1), 4 * kSMs));
+    QMCL_TRY(f->partials.ensure(blocks));
+    weight_sum_kernel<true><<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
+    QMCL_LAUNCHED();
+  } else if (sharded(f)) {
+    QMCL_CUDA(cudaMemsetAsync(&f->scalars.ptr->sum_sq, 0, sizeof(double), s));
+  }
+  if (sharded(f)) {
+    std::vector<double> sums;
+    QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->sum_sq, &sums));
+    sum = ordered_sum(sums);
+  } else if (ps.n) {
+    QMCL_CUDA(copy_d2h(&sum, &f->scalars.ptr->sum_sq, sizeof(double), s));
+    QMCL_CUDA(cudaStreamSynchronize(s));
+  }
+  *out = 1.0 / sum;
+  return QMCL_OK;
 }
 
 qmcl_status qmcl_filter_copy_resample_indices(const qmcl_filter *fc, int64_t *out, size_t cap,

@@ -41,11 +41,13 @@
 //             line: fewer lines per gather, a 1 KB table instead of 13 KB.
 //             The floats are PAL32's, so are the weights, bit for bit.
 //
-// Division: (m - o) / res is evaluated as q = a*r, q' = fma(fma(q,-res,a), r, q)
-// with r = RN(1/res), which yields the correctly rounded quotient (Markstein);
-// a self-check kernel at map load compares it with IEEE division around every
-// cell boundary of the map and the kernel falls back to __fdiv_rn if any index
-// differs.
+// Division: (m - o) / res is evaluated by the cheapest of three forms that a
+// self-check kernel at map load found to give the same truncated quotient as
+// IEEE division around every cell boundary of the map (fastdiv_check_kernel):
+// DIV_SPLIT, the usual choice, q = fma(a, r_hi, a * r_lo) with r_hi + r_lo =
+// 1/res to 48 bits (two packed ops); DIV_MARKSTEIN, q = a * r, q' =
+// fma(fma(q, -res, a), r, q) with r = RN(1/res), the correctly rounded quotient
+// (three ops); DIV_IEEE, __fdiv_rn, when neither passed.
 
 #include "sensor.cuh"
 
@@ -58,7 +60,10 @@ namespace qmcl {
 #define QMCL_DIAG 0
 #endif
 #ifndef QMCL_SENSOR_FLOOR_FMA
-#define QMCL_SENSOR_FLOOR_FMA 0
+#define QMCL_SENSOR_FLOOR_FMA 1  // interior path: truncation on the FP32 pipe (floor2_nonneg), round 2 A/B
+#endif
+#ifndef QMCL_SENSOR_WIDE_ADDR
+#define QMCL_SENSOR_WIDE_ADDR 1  // palette byte address as one IMAD.WIDE, round 2 A/B
 #endif
 #ifndef QMCL_SENSOR_THREADS
 #define QMCL_SENSOR_THREADS 256
@@ -228,6 +233,24 @@ __device__ __forceinline__ float lds_f32_at(const float *table, unsigned byte_of
   return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(table) + byte_off);
 }
 
+// One palette byte, zero-extended by the load itself: the value is known to fit
+// a byte, so the table index needs no mask afterwards.
+__device__ __forceinline__ unsigned ldg_u8(const uint8_t *p) {
+  unsigned v;
+  asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// base + offset as one IMAD.WIDE (FP32 pipe) instead of an IADD3 pair.
+__device__ __forceinline__ const uint8_t *byte_at(const uint8_t *base, unsigned off) {
+#if QMCL_SENSOR_WIDE_ADDR
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+  return reinterpret_cast<const uint8_t *>(r);
+#else
+  return base + off;
+#endif
+}
+
 template <int PATH, int DIV>
 __global__ void __launch_bounds__(kSensorThreads,
                                   (PATH == PATH_PAL32 || PATH == PATH_PAL8) ? QMCL_SENSOR_MINBLOCKS : 4)
@@ -314,8 +337,11 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
   }
   // One step of the walk: this lane's beam b against the kP particles.  The
   // gathers of this step are consumed in the next one (see above).
-  auto body = [&](auto checked_tag, const float2 b) {
+  // `masked`: the lane may be past the end of the scan (`valid` false); it then
+  // re-evaluates its last beam and contributes the table's zero entry.
+  auto body = [&](auto checked_tag, auto masked_tag, const float2 b, const bool valid) {
     constexpr bool CHECKED = decltype(checked_tag)::value;
+    constexpr bool MASKED = decltype(masked_tag)::value;
     const f32x2 PX = pack2(b.x, b.x), PY = pack2(b.y, b.y);
     int code_cur[kP];
     double pz_cur[kP];
@@ -364,7 +390,8 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
                          : static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix));
       if (PATH == PATH_PAL8) {
         code_cur[p] = sp.pal8_n;  // outside the map -> p_max entry
-        if (inside) code_cur[p] = __ldg(sp.code8 + cell);
+        if (inside) code_cur[p] = static_cast<int>(ldg_u8(byte_at(sp.code8, cell)));
+        if (MASKED && !valid) code_cur[p] = sp.pal8_n + 1;
       } else if (PALETTE) {
         code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry
 #if QMCL_DIAG == 2 || QMCL_DIAG == 3
@@ -374,9 +401,11 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
 #else
         if (inside) code_cur[p] = __ldg(sp.code + cell);
 #endif
+        if (MASKED && !valid) code_cur[p] = 4 * (sp.n_codes + 1);
       } else {
         pz_cur[p] = sp.p_max;
         if (inside) pz_cur[p] = __ldg(sp.field + cell);
+        if (MASKED && !valid) pz_cur[p] = -1.0;
       }
     }
 #pragma unroll
@@ -423,18 +452,34 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       for (int s8 = 0; s8 < 8; ++s8) {
         const int jn = base + 32 * s8 + 32;
         const float2 bn = (jn < n_beams) ? __ldg(beams + jn) : b;
-        body(checked_tag, b);
+        body(checked_tag, std::false_type{}, b, true);
         b = bn;
       }
       fold();
     }
-    int step = 0;
-    for (int j = n_grouped + lane; j < n_beams; j += 32, ++step) {
-      const float2 bn = (j + 32 < n_beams) ? __ldg(beams + j + 32) : b;
-      body(checked_tag, b);
-      if (step == 7) fold();
-      b = bn;
+    // The ragged rest (< 256 beams, i.e. at most 8 steps) as straight-line groups
+    // of 4, 2 and 1 steps in which lanes past the end are masked: the same code
+    // quality as the grouped part instead of a divergent loop.
+    const int rest_steps = (n_beams - n_grouped + 31) >> 5;
+    int j = n_grouped + lane;
+    auto ragged = [&](auto steps_tag) {
+      constexpr int STEPS = decltype(steps_tag)::value;
+#pragma unroll
+      for (int s = 0; s < STEPS; ++s) {
+        const float2 bn = (j + 32 < n_beams) ? __ldg(beams + j + 32) : b;
+        body(checked_tag, std::true_type{}, b, j < n_beams);
+        b = bn;
+        j += 32;
+      }
+    };
+    if (rest_steps & 8) {
+      ragged(std::integral_constant<int, 4>{});
+      ragged(std::integral_constant<int, 4>{});
     }
+    if (rest_steps & 4) ragged(std::integral_constant<int, 4>{});
+    if (rest_steps & 2) ragged(std::integral_constant<int, 2>{});
+    if (rest_steps & 1) ragged(std::integral_constant<int, 1>{});
+    fold();
   };
   if (group_safe) walk(std::false_type{});
   else walk(std::true_type{});

@@ -15,6 +15,7 @@ struct FilterScalars {
   unsigned long long n_clusters;  // label_clusters' count (read on the device by K14)
   unsigned long long n_bins;      // build_bins' count (read on the device by the labelling)
   unsigned long long n_records;   // running-sum records (read on the device by the draws)
+  double sum_sq;                  // sum of squared weights (effective_particles)
 };
 
 // quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)
@@ -176,6 +177,9 @@ struct qmcl_filter {
   // low_pass_filter.h: two host scalars
   double w_slow = 0.0, w_fast = 0.0;
   double last_total = 0.0;
+  // roll-back of a failed resample_and_cluster (resample.cu)
+  bool lowpass_was_reset = false;
+  double w_slow_before_reset = 0.0, w_fast_before_reset = 0.0;
 
   // Deferred 8-byte read-backs (single-GPU filters only).  A value the host
   // needs only later — the sensor total for the two low-pass scalars, the

@@ -66,6 +66,31 @@ def assert_same_particles(gp, op, pose_tol=0.0, w_rel=1e-12):
     assert err.max() <= w_rel, err.max()
 
 
+# ---------------------------------------------------------------- a-10
+def test_effective_particles_reference_vectors_and_oracle():
+    """effective_particles (particle.cpp:32-39): the reference's own known answers
+    (test/quickmcl/test_particle.cpp:12-27) and the oracle on a sensor-weighted cloud."""
+    import ctypes as C
+    occ, res, origin, om, gm, of, gf = make_pair()
+    z = np.zeros(3)
+    gf.set_particles(q.make_particles(z, z, z, np.full(3, 1.0 / 3)))   # equalised
+    assert abs(gf.effective_particles() - 3.0) <= 4 * np.spacing(3.0)
+    gf.set_particles(q.make_particles(z, z, z, np.array([1.0, 0.0, 0.0])))
+    assert gf.effective_particles() == 1.0
+    pose = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, pose, 360, 360.0)
+    for n in (1, 257, 5000, 100_003):
+        x, y, t = syn.gaussian_cloud(pose, n)
+        set_both(of, gf, x, y, t, np.full(n, 1.0 / n))
+        gf.update_importance_from_observations(scan)
+        gp = gf.get_particles()
+        want = ob.lib().orc_effective_particles(gp.ctypes.data_as(C.POINTER(ob.Particle)), n)
+        got = gf.effective_particles()
+        assert abs(got - want) <= 1e-12 * want, (n, got, want)
+    gf.set_particles(q.make_particles(z[:0], z[:0], z[:0], z[:0]))
+    assert math.isinf(gf.effective_particles())                         # 1 / 0, as the loop gives
+
+
 # ---------------------------------------------------------------- K5 / K6
 def test_initialise_matches_oracle():
     _, _, _, om, gm, of, gf = make_pair(particle_count_min=5000)
@@ -426,6 +451,48 @@ def test_sync_modes_agree(rtype, n, inject_at):
         assert np.array_equal(sa[6], sb[6]) and np.array_equal(sa[7], sb[7]), cycle
         assert np.array_equal(sa[8], sb[8]) and sa[9] == sb[9], cycle
         assert sa[10].tobytes() == sb[10].tobytes(), cycle
+
+
+@pytest.mark.parametrize("rtype,how", [(1, "no_free_cells"), (2, "no_free_cells"),
+                                       (0, "capacity"), (2, "capacity")])
+def test_failed_resample_keeps_the_particles(rtype, how):
+    """resample_and_cluster is a transaction: when a step fails (injection without free
+    cells -> QMCL_ERR_NO_MAP; a pose far outside every map -> the dense bin table's
+    QMCL_ERR_CAPACITY) the filter still holds the set it was called with."""
+    from quickmcl_b200._abi import QmclError
+    w, h, res = 64, 64, 0.05
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)))
+    state = np.ones((h, w), np.int8) if how == "no_free_cells" else np.zeros((h, w), np.int8)
+    gm.load_field(np.full((h, w), 0.5, np.float32), state, res, (-1.6, -1.6))
+    gf = q.create_particle_filter(gm, seed=5)
+    p = pf_params(resample_type=rtype, particle_count_min=300, particle_count_max=600)
+    gf.set_parameters(q.ParticleFilterParameters(
+        resample_type=q.ResampleType(rtype), particle_count_min=300, particle_count_max=600,
+        space_partitioning_resolution_xy=p["res_xy"], space_partitioning_resolution_theta=p["res_theta"]))
+    rng = np.random.default_rng(7)
+    n = 400
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    y = rng.uniform(-1, 1, n).astype(np.float32)
+    t = rng.uniform(-3, 3, n).astype(np.float32)
+    wts = rng.uniform(0.1, 1, n)
+    if how == "capacity":
+        x[17] = 3e9          # its bin index saturates: the bounding box exceeds the table
+        wts[17] = 50.0       # ... and it is certain to be drawn
+    wts /= wts.sum()
+    gf.set_particles(q.make_particles(x, y, t, wts))
+    gf.set_lowpass(1.0, 0.5)   # w_diff = 0.5: every second slot would be injected
+    before = gf.get_particles().copy()
+    with pytest.raises(QmclError) as e:
+        gf.resample_and_cluster()
+    assert e.value.status == (4 if how == "no_free_cells" else 6)
+    assert gf.num_particles() == n
+    assert gf.get_particles().tobytes() == before.tobytes()
+    assert tuple(gf.lowpass()) == (1.0, 0.5)
+    if how == "no_free_cells":   # the set is usable: cluster + estimate work on it
+        gf.cluster()
+        ok, pose, cov = gf.get_estimated_pose()
+        assert ok and np.all(np.isfinite(pose))
 
 
 def test_deferred_values_settle_on_read():
