@@ -411,7 +411,11 @@ def run_b200(args, wl):
             tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             total_ms = float(tt.item())
-        return dict(total_ms=total_ms, launches=launches, timing=timing, estimate=est,
+        try:
+            prof = f.tail_profile()
+        except AttributeError:   # the sharded wrapper has no fused tail
+            prof = None
+        return dict(total_ms=total_ms, launches=launches, timing=timing, estimate=est, tail_profile=prof,
                     h2d=(h2d1 - h2d0 - h2d_reset) / steps, d2h=(d2h1 - d2h0 - d2h_reset) / steps)
 
     sampler = ClockSampler(local_rank)
@@ -512,6 +516,11 @@ def run_b200(args, wl):
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                 "ms_per_step": e2e_ms},
         "gpu_launches": dev["launches"],
+        "gpu_launches_per_step": dev["launches"] / args.steps,
+        "stage_ms": {k: ms / cnt for k, (ms, cnt) in dev["timing"].items() if cnt},
+        "tail_phases_us": ({name: ns / 1e3 for name, ns in dev["tail_profile"][0]}
+                           if dev.get("tail_profile") else None),
+        "tail_fallbacks": dev["tail_profile"][1] if dev.get("tail_profile") else None,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "estimate": [float(v) for v in dev["estimate"][1]] if dev["estimate"] else None,
     }

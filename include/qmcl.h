@@ -332,16 +332,24 @@ enum {
   QMCL_STAGE_LABEL = 8,       /* K13 connected components */
   QMCL_STAGE_POST_NORMALISE = 9,
   QMCL_STAGE_MOMENTS = 10,    /* K14 */
-  QMCL_N_STAGES = 11
+  QMCL_STAGE_TAIL = 11,       /* stages 2-10 as one fused launch (default on one GPU) */
+  QMCL_N_STAGES = 12
 };
 const char *qmcl_stage_name(int stage);
-/* level 0 = off, 1 = CUDA events around the sensor kernel only, 2 = around
- * every stage.  Events are recorded on the filter's stream. */
+/* level 0 = off, 1 = CUDA events around the sensor kernel and the fused tail,
+ * 2 = around every stage (the stages then run as separate launches).  Events
+ * are recorded on the filter's stream. */
 qmcl_status qmcl_filter_set_timing(qmcl_filter *f, int level);
 /* Synchronises, then returns accumulated device milliseconds and the number
  * of timed occurrences per stage since the last reset. */
 qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
                                    uint64_t count_out[QMCL_N_STAGES], int reset);
+/* The fused tail (QMCL_STAGE_TAIL): nanoseconds from the kernel's start to the
+ * end of each of its phases (qmcl_tail_phase_name(k), k = 1..14; 0 = phase not
+ * run) for the last fused call this filter completed, and the number of fused
+ * calls that had to be re-run on the multi-launch path so far. */
+qmcl_status qmcl_filter_tail_profile(qmcl_filter *f, uint64_t out[16], uint64_t *fallbacks);
+const char *qmcl_tail_phase_name(int k);
 /* Bytes this library has copied host->device (out[0]) and device->host
  * (out[1]) so far in this process. */
 qmcl_status qmcl_transfer_bytes(uint64_t out[2]);

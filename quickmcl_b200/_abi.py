@@ -118,17 +118,19 @@ SIGNATURES = {
     "qmcl_filter_set_timing": [vp, C.c_int],
     "qmcl_filter_get_timing": [vp, pf64, C.POINTER(u64), C.c_int],
     "qmcl_transfer_bytes": [C.POINTER(u64)],
+    "qmcl_filter_tail_profile": [vp, C.POINTER(u64), C.POINTER(u64)],
 }
 _OTHER = {
     "qmcl_version": (C.c_char_p, []),
     "qmcl_last_error": (C.c_char_p, []),
     "qmcl_kernel_launch_count": (u64, []),
     "qmcl_stage_name": (C.c_char_p, [C.c_int]),
+    "qmcl_tail_phase_name": (C.c_char_p, [C.c_int]),
     "qmcl_shard_slice": (None, [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
     "qmcl_lv_owner_range": (None, [u64, f64, f64, f64, f64, C.c_int, C.c_int, C.POINTER(u64),
                                    C.POINTER(u64)]),
 }
-N_STAGES = 11
+N_STAGES = 12
 
 _lib = None
 

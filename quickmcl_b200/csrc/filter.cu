@@ -167,7 +167,7 @@ static void lowpass_update(double *value, double alpha, double x) {
   else *value = *value + alpha * (x - *value);
 }
 
-static void apply_total(qmcl_filter *f, double total, double n_total) {
+void apply_sensor_total(qmcl_filter *f, double total, double n_total) {
   f->last_total = total;
   if (total > 0) {
     const double avg = total / n_total;
@@ -179,7 +179,7 @@ static void apply_total(qmcl_filter *f, double total, double n_total) {
 void settle_after_sync(qmcl_filter *f) {
   if (f->total_pending) {
     f->total_pending = false;
-    apply_total(f, f->h_scalars.ptr[HS_TOTAL], f->pending_n_total);
+    apply_sensor_total(f, f->h_scalars.ptr[HS_TOTAL], f->pending_n_total);
   }
   if (f->bins_pending) {
     f->bins_pending = false;
@@ -196,10 +196,36 @@ void settle_after_sync(qmcl_filter *f) {
 }
 
 qmcl_status settle(qmcl_filter *f) {
-  if (!f->total_pending && !f->clusters_pending && !f->bins_pending) return QMCL_OK;
+  if (f->normalise_pending && !f->tail_pending) QMCL_TRY(flush_sensor(f));
+  if (!f->total_pending && !f->clusters_pending && !f->bins_pending && !f->tail_pending) return QMCL_OK;
   QMCL_TRY(use_device(f->map));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
   settle_after_sync(f);
+  // the result block of a fused tail; a fall-back re-runs the call here
+  if (f->tail_pending) QMCL_TRY(tail_complete(f));
+  return QMCL_OK;
+}
+
+// K8 and the total's read-back, when sensor_update_common left them to a fused
+// tail that did not come (a getter, a multi-launch resampling, a second sensor
+// update): divide by the pre-penalty total, copy the total for w_slow / w_fast.
+qmcl_status flush_sensor(qmcl_filter *f) {
+  if (!f->normalise_pending) return QMCL_OK;
+  f->normalise_pending = false;
+  QMCL_TRY(use_device(f->map));
+  cudaStream_t s = f->map->stream;
+  ParticleSet &ps = f->cur();
+  if (ps.n) {
+    StageScope sc(f, QMCL_STAGE_NORMALISE);
+    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+    QMCL_LAUNCHED();
+  }
+  QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_TOTAL, &f->scalars.ptr->total_weight, sizeof(double), s));
+  if (!f->total_copied)
+    QMCL_CUDA(cudaEventCreateWithFlags(&f->total_copied, cudaEventDisableTiming));
+  QMCL_CUDA(cudaEventRecord(f->total_copied, s));
+  f->total_pending = true;
+  f->pending_n_total = static_cast<double>(f->normalise_n);
   return QMCL_OK;
 }
 
@@ -219,7 +245,9 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   cudaStream_t s = m->stream;
-  if (f->total_pending) QMCL_TRY(settle(f));  // the slot is about to be reused
+  // a pending total's slot is about to be reused; a deferred normalisation or a
+  // fused tail still in flight belong to the previous update
+  QMCL_TRY(settle(f));
   if (ps.n == 0 && !sharded(f)) {
     f->last_total = 0.0;
     return QMCL_OK;
@@ -236,7 +264,14 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   a.rmax = f->beams.ptr + 2 * n_points;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
-  if (ps.n && lazy(f) && f->params.resample_type == QMCL_RESAMPLE_KLD) {
+  // With the fused tail (tail.cu) K8 and everything after it run in one launch
+  // that reads the total and the bin bounds on the device.
+  const bool defer = tail_enabled(f) && ps.n > 0 && ps.n <= (size_t(1) << 22);
+  if (defer) {
+    StageScope sc(f, QMCL_STAGE_BINS);
+    QMCL_TRY(launch_bin_bbox(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
+    f->early_bbox_version = f->pose_version;
+  } else if (ps.n && lazy(f) && f->params.resample_type == QMCL_RESAMPLE_KLD) {
     // KLD sizes its dense bin table by the bounding box of the set it draws
     // from.  Taken here, ahead of the sensor kernel, the six numbers are on the
     // host long before the resampling asks for them.
@@ -252,6 +287,12 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
     QMCL_CUDA(cudaMemsetAsync(&f->scalars.ptr->total_weight, 0, sizeof(double), s));
   }
   f->clusters_valid = false;
+  f->est_cached = false;
+  if (defer) {
+    f->normalise_pending = true;
+    f->normalise_n = ps.n;
+    return QMCL_OK;
+  }
   if (sharded(f)) {
     // Exchange 1: the pre-penalty total is the sum over shards.
     std::vector<double> totals;
@@ -263,7 +304,7 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
       normalise_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total, n_total);
       QMCL_LAUNCHED();
     }
-    apply_total(f, total, n_total);
+    apply_sensor_total(f, total, n_total);
     return QMCL_OK;
   }
   {
@@ -315,6 +356,7 @@ qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) 
   }
   map->refs++;
   if (const char *e = std::getenv("QMCL_EAGER_SYNC")) f->lazy_sync = !(e[0] && e[0] != '0');
+  if (const char *e = std::getenv("QMCL_TAIL")) f->use_tail = !(e[0] == '0');
   qmcl_filter_set_params(f, &f->params);
   *out = f;
   return QMCL_OK;
@@ -358,6 +400,11 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->cluster_acc.release();
   f->particle_cid.release();
   f->timer.release();
+  f->tail_dev.release();
+  f->tail_scratch.release();
+  f->tail_first.release();
+  f->tail_cluster_w.release();
+  if (f->h_tail) cudaFreeHost(f->h_tail);
   if (f->staging_read) cudaEventDestroy(f->staging_read);
   if (f->total_copied) cudaEventDestroy(f->total_copied);
   qmcl_map *map = f->map;
@@ -393,6 +440,7 @@ qmcl_status qmcl_filter_set_rng(qmcl_filter *f, uint64_t seed, uint32_t step) {
 
 qmcl_status qmcl_filter_num_particles(const qmcl_filter *f, size_t *out) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  if (f->tail_pending) QMCL_TRY(settle(const_cast<qmcl_filter *>(f)));  // the count is still in flight
   *out = sharded(f) ? f->global_n : f->cur().n;
   return QMCL_OK;
 }
@@ -409,6 +457,7 @@ qmcl_status qmcl_filter_set_particles_shard(qmcl_filter *f, const qmcl_particle 
 qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n) {
   if (!f || (!p && n)) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   cudaStream_t s = f->map->stream;
   ParticleSet &ps = f->cur();
   QMCL_TRY(ps.ensure(n));
@@ -416,6 +465,7 @@ qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, si
   f->global_first = 0;
   f->global_n = n;
   f->clusters_valid = false;
+  f->est_cached = false;
   f->pose_version++;
   if (!n) return QMCL_OK;
   void *stage = nullptr;
@@ -431,6 +481,7 @@ qmcl_status qmcl_filter_copy_particles(const qmcl_filter *fc, qmcl_particle *out
   if (!fc || (!out && cap)) return QMCL_ERR_INVALID_ARG;
   qmcl_filter *f = const_cast<qmcl_filter *>(fc);
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   cudaStream_t s = f->map->stream;
   const ParticleSet &ps = f->cur();
   const size_t n = ps.n < cap ? ps.n : cap;
@@ -453,7 +504,12 @@ qmcl_status qmcl_filter_export_markers(const qmcl_filter *fc, float *out5, size_
                                        size_t *n_out, double *max_weight) {
   if (!fc || (!out5 && cap)) return QMCL_ERR_INVALID_ARG;
   qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  if (sharded(f)) {
+    set_error("export_markers: the maximum weight spans all shards; gather the particles instead");
+    return QMCL_ERR_UNSUPPORTED;
+  }
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   cudaStream_t s = f->map->stream;
   const ParticleSet &ps = f->cur();
   const size_t n = ps.n < cap ? ps.n : cap;
@@ -580,6 +636,7 @@ qmcl_status qmcl_filter_set_sync_mode(qmcl_filter *f, int lazy_mode) {
 
 qmcl_status qmcl_filter_set_timing(qmcl_filter *f, int level) {
   if (!f || level < 0 || level > 2) return QMCL_ERR_INVALID_ARG;
+  QMCL_TRY(settle(f));  // level 2 switches the fused tail off
   f->timer.level = level;
   return QMCL_OK;
 }
@@ -588,8 +645,8 @@ qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
                                    uint64_t count_out[QMCL_N_STAGES], int reset) {
   if (!f || !ms_out || !count_out) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
-  settle_after_sync(f);
   f->timer.resolve();
   for (int i = 0; i < QMCL_N_STAGES; ++i) {
     ms_out[i] = f->timer.ms[i];
@@ -605,8 +662,8 @@ qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
 qmcl_status qmcl_filter_synchronize(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   QMCL_CUDA(cudaStreamSynchronize(f->map->stream));
-  settle_after_sync(f);
   return QMCL_OK;
 }
 

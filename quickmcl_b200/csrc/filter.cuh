@@ -18,6 +18,17 @@ qmcl_status launch_export_markers(cudaStream_t s, const float *x, const float *y
 void settle_after_sync(qmcl_filter *f);
 qmcl_status settle(qmcl_filter *f);
 inline bool lazy(const qmcl_filter *f) { return f->lazy_sync && f->n_shards <= 1; }
+// Fused tail (tail.cu).  tail_enabled: the filter defers K8 into the tail;
+// tail_eligible: this call (TAIL_* mode) can run as one fused launch;
+// tail_complete: fold the result in (the stream has been synchronised).
+bool tail_enabled(const qmcl_filter *f);
+bool tail_eligible(const qmcl_filter *f, int mode);
+qmcl_status launch_tail(qmcl_filter *f, int mode);
+qmcl_status tail_complete(qmcl_filter *f);
+// K8 + the total's read-back, when they were deferred (sensor_update_common).
+qmcl_status flush_sensor(qmcl_filter *f);
+// particle_filter.cpp:106-120 on the host: w_slow / w_fast from the sensor total.
+void apply_sensor_total(qmcl_filter *f, double total, double n_total);
 // Grow-only byte scratch of the filter (contents are not preserved).
 qmcl_status filter_scratch(qmcl_filter *f, size_t bytes, void **out);
 

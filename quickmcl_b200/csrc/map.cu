@@ -412,7 +412,7 @@ qmcl_status qmcl_transfer_bytes(uint64_t out[2]) {
 const char *qmcl_stage_name(int stage) {
   static const char *names[QMCL_N_STAGES] = {"motion", "sensor", "normalise", "cdf", "select",
                                              "gather", "kld", "bins", "label",
-                                             "post_normalise", "moments"};
+                                             "post_normalise", "moments", "tail"};
   return (stage >= 0 && stage < QMCL_N_STAGES) ? names[stage] : "?";
 }
 

@@ -170,6 +170,7 @@ qmcl_status qmcl_filter_initialise_factor(qmcl_filter *f, const float pose[3],
                                           const float factor[9]) {
   if (!f || !pose || !factor) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   const size_t global_n = static_cast<size_t>(f->params.particle_count_min);
   size_t first, n;
   shard_slice(f, global_n, &first, &n);
@@ -179,6 +180,7 @@ qmcl_status qmcl_filter_initialise_factor(qmcl_filter *f, const float pose[3],
   f->global_first = first;
   f->global_n = global_n;
   f->clusters_valid = false;
+  f->est_cached = false;
   f->pose_version++;
   if (n) {
     InitParams ip;
@@ -203,6 +205,7 @@ qmcl_status qmcl_filter_global_localization(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   if (!f->map->has_map || f->map->n_free == 0) return QMCL_ERR_NO_MAP;
   QMCL_TRY(use_device(f->map));
+  QMCL_TRY(settle(f));
   const size_t global_n = static_cast<size_t>(f->params.particle_count_max);
   size_t first, n;
   shard_slice(f, global_n, &first, &n);
@@ -212,6 +215,7 @@ qmcl_status qmcl_filter_global_localization(qmcl_filter *f) {
   f->global_first = first;
   f->global_n = global_n;
   f->clusters_valid = false;
+  f->est_cached = false;
   f->pose_version++;
   if (n) {
     init_global_kernel<<<div_up(n, 256), 256, 0, f->map->stream>>>(
@@ -229,6 +233,7 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double nw[3], cons
                                         const float alpha[4]) {
   if (!f || !nw || !od || !alpha) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  if (f->tail_pending) QMCL_TRY(settle(f));  // the particle count is still in flight
   const double xdiff = nw[0] - od[0];
   const double ydiff = nw[1] - od[1];
   const double delta_trans = std::sqrt(xdiff * xdiff + ydiff * ydiff);
@@ -259,6 +264,7 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double nw[3], cons
     QMCL_LAUNCHED();
   }
   f->clusters_valid = false;
+  f->est_cached = false;
   f->pose_version++;
   f->step++;
   return QMCL_OK;

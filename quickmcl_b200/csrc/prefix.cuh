@@ -26,4 +26,10 @@ qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out)
 qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *dev_out);
 bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], double *carry_out);
 
+namespace pfx {
+struct PrefixBuffers;
+}
+qmcl_status plan_prefix_buffers(qmcl_filter *f, size_t n, pfx::PrefixBuffers *pb,
+                                unsigned long long *nc, unsigned long long *nt);
+
 }  // namespace qmcl

@@ -15,6 +15,7 @@
 
 #include "cluster.cuh"
 #include "prefix.cuh"
+#include "resample_dev.cuh"
 #include "scan.cuh"
 #include "shard.cuh"
 
@@ -79,36 +80,6 @@ struct EmitPositive {
   }
 };
 
-// ParticlesRunningSum::lookup_index (particle.h:99-107) over the records
-// (key_t = running sum before positive particle t): the record with the
-// largest key <= r; among records sharing a key the first inserted wins
-// (std::map::insert keeps the existing entry, particle.cpp:77).
-__device__ __forceinline__ size_t running_sum_lookup(const double *__restrict__ incl, size_t P,
-                                                     double r) {
-  // t* = number of t in [1, P) with key_t = incl[t-1] <= r
-  size_t lo = 0, hi = P - 1;
-  while (lo < hi) {
-    const size_t mid = (lo + hi) >> 1;
-    if (incl[mid] <= r) lo = mid + 1;
-    else hi = mid;
-  }
-  const size_t tstar = lo;
-  if (tstar == 0) return 0;
-  const double K = incl[tstar - 1];
-  // first t with key_t == K, i.e. 1 + first j with incl[j] >= K.  Keys repeat
-  // only where a weight was too small to move the sum: one look at the
-  // neighbour (same cache line) settles every other case without a second search.
-  if (tstar == 1 || incl[tstar - 2] < K) return tstar;
-  lo = 0;
-  hi = tstar - 1;
-  while (lo < hi) {
-    const size_t mid = (lo + hi) >> 1;
-    if (incl[mid] < K) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo + 1;
-}
-
 // One adaptive / KLD slot per thread (particle_filter.cpp:261-276, :313-327).
 __global__ void __launch_bounds__(256)
 draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
@@ -150,37 +121,6 @@ draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
 }
 
 // ------------------------------------------------------------------------ KLD
-struct KldParams {
-  float res_xy, res_t;
-  double eps2, z;
-  int32_t nmin, nmax;
-};
-
-// space_partitioning.cpp:52-74, the same double expressions in the same order.
-__device__ __forceinline__ unsigned long long kld_limit(unsigned long long k, const KldParams &kp) {
-  if (k < 2) return static_cast<unsigned long long>(kp.nmax);
-  const double common = 2.0 / static_cast<double>(9 * (k - 1));
-  const double to_be_cubed = 1 - common - sqrt(common) * kp.z;
-  const double result =
-      (static_cast<double>(k - 1) / kp.eps2) * to_be_cubed * to_be_cubed * to_be_cubed;
-  const double c = ceil(result);
-  int32_t fin;
-  if (c >= 2147483647.0) fin = 2147483647;
-  else if (c <= -2147483648.0) fin = static_cast<int32_t>(-2147483647 - 1);
-  else fin = static_cast<int32_t>(c);
-  if (fin < kp.nmin) return static_cast<unsigned long long>(kp.nmin);
-  if (fin > kp.nmax) return static_cast<unsigned long long>(kp.nmax);
-  return static_cast<unsigned long long>(fin);
-}
-
-__device__ __forceinline__ long long kld_cell(float x, float y, float t, const KldParams &kp,
-                                              const BinGrid &g) {
-  const long long ix = static_cast<long long>(cell_index_inf(x, kp.res_xy)) - g.x0;
-  const long long iy = static_cast<long long>(cell_index_inf(y, kp.res_xy)) - g.y0;
-  const long long it = static_cast<long long>(cell_index_inf(t, kp.res_t)) - g.t0;
-  return (ix * g.ny + iy) * g.nt + it;
-}
-
 // table[cell] = smallest draw index that fell into the cell.
 __global__ void __launch_bounds__(256)
 kld_first_kernel(const float *__restrict__ x, const float *__restrict__ y,
@@ -237,40 +177,17 @@ template <bool SQUARE>
 __global__ void __launch_bounds__(256)
 weight_sum_kernel(const double *__restrict__ w, size_t n, double *__restrict__ partials,
                   FilterScalars *__restrict__ sc) {
-  __shared__ double s_warp[8];
   __shared__ bool s_last;
-  double t = 0.0;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const double v = w[i];
-    t = __dadd_rn(t, SQUARE ? __dmul_rn(v, v) : v);
-  }
-  t = warp_sum_xor(t);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) s_warp[wid] = t;
-  __syncthreads();
+  weight_sum_block<SQUARE>(w, n, partials, blockIdx.x, gridDim.x);
   if (threadIdx.x == 0) {
-    double b = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b = __dadd_rn(b, s_warp[i]);
-    partials[blockIdx.x] = b;
     __threadfence();
     s_last = atomicAdd(&sc->blocks_done, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double a = 0.0;
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
-    a = __dadd_rn(a, __ldcg(partials + i));
-  a = warp_sum_xor(a);
-  __syncthreads();
-  if (lane == 0) s_warp[wid] = a;
-  __syncthreads();
+  const double tot = weight_sum_final(partials, gridDim.x);
   if (threadIdx.x == 0) {
-    double tot = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot = __dadd_rn(tot, s_warp[i]);
     if (SQUARE) sc->sum_sq = tot;
     else sc->post_total = tot;
     sc->blocks_done = 0;
@@ -1264,6 +1181,7 @@ static qmcl_status resample_and_cluster_impl(qmcl_filter *f);
 qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
   if (!f) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(use_device(f->map));
+  if (f->tail_pending) QMCL_TRY(settle(f));  // an earlier fused call whose outcome was never read
   const int current = f->current;
   const uint32_t step = f->step;
   const uint64_t pose_version = f->pose_version;
@@ -1295,6 +1213,11 @@ qmcl_status qmcl_filter_resample_and_cluster(qmcl_filter *f) {
 }
 
 static qmcl_status resample_and_cluster_impl(qmcl_filter *f) {
+  // one fused launch for the whole call (and the estimate) when it applies
+  if (f->params.resample_type >= 0 && f->params.resample_type <= 2 &&
+      tail_eligible(f, f->params.resample_type))
+    return launch_tail(f, f->params.resample_type);
+  QMCL_TRY(flush_sensor(f));
   const ParticleSet &in = f->sets[f->current];
   ParticleSet &out = f->sets[(f->current + 1) % 2];
   f->current = (f->current + 1) % 2;
@@ -1380,6 +1303,7 @@ qmcl_status qmcl_filter_copy_resample_indices(const qmcl_filter *fc, int64_t *ou
                                               size_t *n_out) {
   if (!fc) return QMCL_ERR_INVALID_ARG;
   qmcl_filter *f = const_cast<qmcl_filter *>(fc);
+  QMCL_TRY(settle(f));
   if (n_out) *n_out = f->n_src_index;
   const size_t n = f->n_src_index < cap ? f->n_src_index : cap;
   if (!n || !out) return QMCL_OK;

@@ -95,6 +95,13 @@ struct ParticleSet {
   }
 };
 
+namespace qmcl {
+struct TailResult;
+struct TailDev;
+}
+using qmcl::TailDev;
+using qmcl::TailResult;
+
 // Dense bin grid: bounding box of the occupied KLD/cluster bins.
 struct BinGrid {
   int x0, y0, t0;
@@ -188,6 +195,30 @@ struct qmcl_filter {
   // point that synchronises anyway (filter.cu).  lazy_sync = false restores a
   // synchronisation per value (qmcl_filter_set_sync_mode).
   bool lazy_sync = true;
+  // Fused tail (tail.cu): one cooperative launch for everything after the sensor
+  // kernel.  While its result block is in flight the host knows the outcome of
+  // resample_and_cluster / cluster only as an upper bound (tail_pending); every
+  // entry point settles first.
+  bool use_tail = true;
+  bool normalise_pending = false;   // K8 (divide by the sensor total) deferred into the tail
+  size_t normalise_n = 0;           // particles of that sensor update
+  bool tail_pending = false;
+  int tail_mode = 0;
+  bool tail_had_normalise = false;
+  double tail_n_total = 0.0;
+  int tail_prev_current = 0;
+  uint32_t tail_prev_step = 0;
+  unsigned long long tail_serial = 0;
+  uint64_t tail_fallbacks = 0;
+  TailResult *h_tail = nullptr;  // pinned, written by the kernel
+  qmcl::DevBuf<TailDev> tail_dev;
+  qmcl::DevBuf<uint8_t> tail_scratch;
+  qmcl::DevBuf<int32_t> tail_first;
+  qmcl::DevBuf<unsigned long long> tail_cluster_w;
+  // the estimate the last tail computed (valid while clusters_valid)
+  bool est_cached = false;
+  bool est_invalid = false;
+  double est[13] = {};
   bool total_pending = false;
   double pending_n_total = 0.0;
   bool clusters_pending = false;

@@ -485,6 +485,7 @@ def test_failed_resample_keeps_the_particles(rtype, how):
     before = gf.get_particles().copy()
     with pytest.raises(QmclError) as e:
         gf.resample_and_cluster()
+        gf.synchronize()   # a fused call reports at the next call that waits for the device
     assert e.value.status == (4 if how == "no_free_cells" else 6)
     assert gf.num_particles() == n
     assert gf.get_particles().tobytes() == before.tobytes()
