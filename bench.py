@@ -379,6 +379,8 @@ def run_b200(args, wl):
         torch.cuda.synchronize()
         f.set_timing(1)
         f.get_timing(reset=True)
+        if hasattr(f, "tail_profile"):
+            f.tail_profile(reset=True)
         launches0 = q.kernel_launch_count()
         h2d0, d2h0 = q.transfer_bytes()
         h2d_reset = d2h_reset = 0
@@ -520,7 +522,8 @@ def run_b200(args, wl):
         "stage_ms": {k: ms / cnt for k, (ms, cnt) in dev["timing"].items() if cnt},
         "tail_phases_us": ({name: ns / 1e3 for name, ns in dev["tail_profile"][0]}
                            if dev.get("tail_profile") else None),
-        "tail_fallbacks": dev["tail_profile"][1] if dev.get("tail_profile") else None,
+        "tail_calls": dev["tail_profile"][1] if dev.get("tail_profile") else None,
+        "tail_fallbacks": dev["tail_profile"][2] if dev.get("tail_profile") else None,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "estimate": [float(v) for v in dev["estimate"][1]] if dev["estimate"] else None,
     }

@@ -302,7 +302,10 @@ qmcl_status qmcl_filter_num_clusters(const qmcl_filter *f, size_t *out);
 qmcl_status qmcl_filter_get_lowpass(const qmcl_filter *f, double out[2]);
 qmcl_status qmcl_filter_set_lowpass(qmcl_filter *f, double w_slow, double w_fast);
 /* Running-sum kernel selection: 0 = parallel, bit-identical to the sequential
- * loop (default); 1 = the literal one-warp sequential loop (cross-check). */
+ * loop (default); 1 = the literal one-warp sequential loop (cross-check);
+ * 2 = the parallel path with the chunks in which the sum crosses a power of two
+ * resolved lane-wise instead of by 256 literal additions (same bits; measured
+ * slower, kept for A/B). */
 qmcl_status qmcl_filter_set_prefix_mode(qmcl_filter *f, int mode);
 /* out[i] = sequentially rounded running sum of carry_in, w[0..i] (host arrays). */
 qmcl_status qmcl_filter_debug_prefix(qmcl_filter *f, const double *w, size_t n,
@@ -344,11 +347,12 @@ qmcl_status qmcl_filter_set_timing(qmcl_filter *f, int level);
  * of timed occurrences per stage since the last reset. */
 qmcl_status qmcl_filter_get_timing(qmcl_filter *f, double ms_out[QMCL_N_STAGES],
                                    uint64_t count_out[QMCL_N_STAGES], int reset);
-/* The fused tail (QMCL_STAGE_TAIL): nanoseconds from the kernel's start to the
- * end of each of its phases (qmcl_tail_phase_name(k), k = 1..14; 0 = phase not
- * run) for the last fused call this filter completed, and the number of fused
+/* The fused tail (QMCL_STAGE_TAIL): device nanoseconds spent in each of its
+ * phases (qmcl_tail_phase_name(k), k = 1..14), summed over the *calls fused
+ * calls this filter completed since the last reset, and the number of fused
  * calls that had to be re-run on the multi-launch path so far. */
-qmcl_status qmcl_filter_tail_profile(qmcl_filter *f, uint64_t out[16], uint64_t *fallbacks);
+qmcl_status qmcl_filter_tail_profile(qmcl_filter *f, uint64_t out[16], uint64_t *calls,
+                                     uint64_t *fallbacks, int reset);
 const char *qmcl_tail_phase_name(int k);
 /* Bytes this library has copied host->device (out[0]) and device->host
  * (out[1]) so far in this process. */

@@ -118,7 +118,7 @@ SIGNATURES = {
     "qmcl_filter_set_timing": [vp, C.c_int],
     "qmcl_filter_get_timing": [vp, pf64, C.POINTER(u64), C.c_int],
     "qmcl_transfer_bytes": [C.POINTER(u64)],
-    "qmcl_filter_tail_profile": [vp, C.POINTER(u64), C.POINTER(u64)],
+    "qmcl_filter_tail_profile": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.c_int],
 }
 _OTHER = {
     "qmcl_version": (C.c_char_p, []),

@@ -439,15 +439,16 @@ class ParticleFilter:
                 for i in range(_abi.N_STAGES)}
 
 
-    def tail_profile(self):
-        """Phase boundaries of the last fused tail: ([(phase name, ns since kernel start)],
-        number of fused calls re-run on the multi-launch path)."""
+    def tail_profile(self, reset=True):
+        """Mean device time per phase of the fused tail since the last reset:
+        ([(phase name, ns per call)], fused calls, calls re-run on the multi-launch path)."""
         out = np.zeros(16, np.uint64)
-        fb = C.c_uint64(0)
-        check(self._L.qmcl_filter_tail_profile(self._h, ptr(out, C.c_uint64), C.byref(fb)),
-              "qmcl_filter_tail_profile")
-        return ([(self._L.qmcl_tail_phase_name(k).decode(), int(out[k])) for k in range(1, 15)
-                 if out[k]], fb.value)
+        calls, fb = C.c_uint64(0), C.c_uint64(0)
+        check(self._L.qmcl_filter_tail_profile(self._h, ptr(out, C.c_uint64), C.byref(calls),
+                                               C.byref(fb), int(reset)), "qmcl_filter_tail_profile")
+        n = max(calls.value, 1)
+        return ([(self._L.qmcl_tail_phase_name(k).decode(), float(out[k]) / n) for k in range(1, 15)
+                 if out[k]], calls.value, fb.value)
 
 
 def create_likelihood_map(device=-1, stream=None) -> MapLikelihood:

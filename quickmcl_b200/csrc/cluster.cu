@@ -313,6 +313,7 @@ qmcl_status qmcl_filter_cluster(qmcl_filter *f) {
   if (f->tail_pending) QMCL_TRY(settle(f));
   // bins, labels and the estimate in one fused launch when it applies (tail.cu)
   if (tail_eligible(f, 3)) return launch_tail(f, 3);
+  QMCL_TRY(flush_motion(f));
   const ParticleSet &ps = f->cur();
   QMCL_TRY(build_bins(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
   return label_clusters(f);
@@ -338,6 +339,7 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
     }
     return QMCL_OK;
   }
+  QMCL_TRY(flush_motion(f));
   QMCL_TRY(flush_sensor(f));
   const ParticleSet &ps = f->cur();
   // every rank of a sharded filter must take the same branch here

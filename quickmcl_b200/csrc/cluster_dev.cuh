@@ -323,7 +323,7 @@ __device__ __forceinline__ int fixed_point_shift(unsigned long long wmax_bits, s
 }
 
 // One block of 256 particle slots (vblock); all threads of the block must call.
-__device__ __forceinline__ void cluster_weight_block(
+QMCL_PHASE_FN void cluster_weight_block(
     const float *x, const float *y, const float *t, const double *w, size_t n, const BinParams &bp,
     const BinGrid &g, const int32_t *table, const int32_t *label, const int32_t *cluster_of_root,
     int32_t *cid_out, unsigned long long *cluster_w, EstimateScalars *es, int shift, size_t vblock) {
@@ -381,7 +381,7 @@ __device__ __forceinline__ void cluster_weight_block(
 
 // First maximum of the cluster weights (ties -> smallest canonical id).
 // Run by one whole block (any multiple of 32 threads up to 1024).
-__device__ __forceinline__ void best_cluster_block(const unsigned long long *cluster_w,
+QMCL_PHASE_FN void best_cluster_block(const unsigned long long *cluster_w,
                                                    size_t n_clusters, EstimateScalars *es) {
   __shared__ unsigned long long s_w[32];
   __shared__ long long s_i[32];
@@ -474,11 +474,11 @@ __host__ __device__ inline void finalise_estimate(const double *b, const double 
 // result depends on n only, not on scheduling.  partials: [gridDim][2*kMom].
 // When `finalise` is set the last block also writes out[0..13).
 // Partial moments of virtual block `vblock` of `nvblocks` -> partials[vblock][2*kMom].
-__device__ __forceinline__ void moments_block(const float *x, const float *y, const float *t,
+QMCL_PHASE_FN void moments_block(const float *x, const float *y, const float *t,
                                               const double *w, const int32_t *cid, size_t n,
                                               double *partials, int best, unsigned vblock,
                                               unsigned nvblocks) {
-  __shared__ double smem[8];
+  __shared__ double s_mom[2 * kMom][8];
   double vg[kMom], vb[kMom];
 #pragma unroll
   for (int k = 0; k < kMom; ++k) vg[k] = vb[k] = 0.0;
@@ -509,19 +509,30 @@ __device__ __forceinline__ void moments_block(const float *x, const float *y, co
       if (in_best) vb[k] = __dadd_rn(vb[k], v[k]);
     }
   }
+  // block_sum_256 for all twenty sums with one exchange: the warp butterflies, then
+  // the eight warp sums of each moment added in warp order (the same additions)
   double *mine = partials + static_cast<size_t>(vblock) * 2 * kMom;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < kMom; ++k) {
-    const double sg = block_sum_256(vg[k], smem);
-    const double sb = block_sum_256(vb[k], smem);
-    if (threadIdx.x == 0) {
-      mine[k] = sg;
-      mine[kMom + k] = sb;
+    const double sg = warp_sum_xor(vg[k]);
+    const double sb = warp_sum_xor(vb[k]);
+    if (lane == 0) {
+      s_mom[k][wid] = sg;
+      s_mom[kMom + k][wid] = sb;
     }
   }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMom) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t = __dadd_rn(t, s_mom[threadIdx.x][i]);
+    mine[threadIdx.x] = t;
+  }
+  __syncthreads();
 }
 // The block partials added in block order (one block; all its threads call).
-__device__ __forceinline__ void moments_final(const double *partials, unsigned nvblocks,
+QMCL_PHASE_FN void moments_final(const double *partials, unsigned nvblocks,
                                               double *sums_out, double *out, int finalise) {
   __shared__ double s_tot[2 * kMom];
   if (threadIdx.x < 2 * kMom) {

@@ -54,6 +54,20 @@ inline cudaError_t copy_d2h(void *dst, const void *src, size_t bytes, cudaStream
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Phase bodies shared by the stand-alone kernels and the fused tail.  Inlined:
+// out of line (-DQMCL_PHASE_INLINE=0) the bodies read the job's pointers through
+// generic loads from the parameter space instead of the constant bank, which
+// lengthens every dependent chain (measured at C2: tail 156 -> 178 us, the
+// resolve warp alone 41 -> 67 us).
+#ifndef QMCL_PHASE_INLINE
+#define QMCL_PHASE_INLINE 1
+#endif
+#if QMCL_PHASE_INLINE
+#define QMCL_PHASE_FN static __device__ __forceinline__
+#else
+#define QMCL_PHASE_FN static __device__ __noinline__
+#endif
+
 inline unsigned div_up(size_t a, size_t b) { return static_cast<unsigned>((a + b - 1) / b); }
 
 // Grow-only device buffer.

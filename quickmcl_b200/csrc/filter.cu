@@ -6,6 +6,8 @@
 
 #include "filter.cuh"
 #include "cluster.cuh"
+#include "cluster_dev.cuh"
+#include "motion_dev.cuh"
 #include "sensor.cuh"
 #include "shard.cuh"
 #include "scan.cuh"
@@ -196,6 +198,7 @@ void settle_after_sync(qmcl_filter *f) {
 }
 
 qmcl_status settle(qmcl_filter *f) {
+  if (f->motion_pending && !f->tail_pending) QMCL_TRY(flush_motion(f));
   if (f->normalise_pending && !f->tail_pending) QMCL_TRY(flush_sensor(f));
   if (!f->total_pending && !f->clusters_pending && !f->bins_pending && !f->tail_pending) return QMCL_OK;
   QMCL_TRY(use_device(f->map));
@@ -240,14 +243,188 @@ static qmcl_status staging_free(qmcl_filter *f) {
   return QMCL_OK;
 }
 
-// Runs K7 + K8 on the current set with the beams already in f->beams.
-static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_points) {
+// The front kernel of a sensor update on the fused path: one launch for
+//   block 0      the beam selection of map_likelihood.cpp:67-74,92 (subsample_kernel's
+//                job) and the bound of the longest used beam;
+//   blocks 1..   the deferred motion model (K6, odometry.cpp:86-101) over the particles,
+//                grid-stride, and the bin bounds of the moved poses per block; the last
+//                block to finish folds them into bbox[6] for the tail.
+// Replaces motion_kernel + bbox_init_kernel + bin_bbox_kernel + a memset +
+// subsample_kernel (five stream operations) by one.
+struct FrontJob {
+  const float2 *cloud;
+  size_t n_points, step;
+  float2 *beams;
+  int n_used;
+  unsigned *rmax;
+  float *x, *y, *t;
+  size_t n, global_first;
+  int do_motion;
+  MotionParams mp;
+  uint64_t seed;
+  uint32_t rng_step;
+  BinParams bp;
+  int *block_bbox;  // [gridDim.x - 1][6]
+  int *bbox;        // [6]
+  unsigned int *blocks_done;
+};
+
+__global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ FrontJob J) {
+  __shared__ float s_len[8];
+  __shared__ int s_mn[8][3], s_mx[8][3];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (blockIdx.x == 0) {
+    float len = 0.f;
+    for (int j = threadIdx.x; j < J.n_used; j += 256) {
+      float2 p = J.cloud[static_cast<size_t>(j) * J.step];
+      // x86 float->int of a NaN/huge value yields INT_MIN, i.e. "outside the map"
+      if (!(fabsf(p.x) < 1e30f) || !(fabsf(p.y) < 1e30f)) p = make_float2(1e30f, 1e30f);
+      J.beams[j] = p;
+      len = fmaxf(len, __fadd_ru(fabsf(p.x), fabsf(p.y)));  // |p|_1 >= |p|_2, rounded up
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = fmaxf(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) s_len[wid] = len;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int k = 0; k < 8; ++k) m = fmaxf(m, s_len[k]);
+      *J.rmax = __float_as_uint(m);
+    }
+    return;
+  }
+  const unsigned nb = gridDim.x - 1, b = blockIdx.x - 1;
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (size_t i = static_cast<size_t>(b) * 256 + threadIdx.x; i < J.n; i += static_cast<size_t>(nb) * 256) {
+    float px = J.x[i], py = J.y[i], pt = J.t[i];
+    if (J.do_motion) {
+      motion_one(&px, &py, &pt, J.mp, J.seed, J.rng_step, J.global_first + i);
+      J.x[i] = px;
+      J.y[i] = py;
+      J.t[i] = pt;
+    }
+    int k[3];
+    bin_key(px, py, pt, J.bp, &k[0], &k[1], &k[2]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = min(mn[d], k[d]);
+      mx[d] = max(mx[d], k[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      s_mn[wid][d] = mn[d];
+      s_mx[wid][d] = mx[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int k = 0; k < 8; ++k) {
+      lo = min(lo, s_mn[k][threadIdx.x]);
+      hi = max(hi, s_mx[k][threadIdx.x]);
+    }
+    J.block_bbox[b * 6 + threadIdx.x] = lo;
+    J.block_bbox[b * 6 + 3 + threadIdx.x] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(J.blocks_done, 1u) == nb - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block: bounds over all blocks
+  if (threadIdx.x < 6) {
+    const bool is_min = threadIdx.x < 3;
+    int v = is_min ? INT_MAX : INT_MIN;
+    for (unsigned k = 0; k < nb; ++k) {
+      const int e = __ldcg(J.block_bbox + k * 6 + threadIdx.x);
+      v = is_min ? min(v, e) : max(v, e);
+    }
+    J.bbox[threadIdx.x] = v;
+  }
+  if (threadIdx.x == 0) *J.blocks_done = 0;
+}
+
+static qmcl_status launch_front(qmcl_filter *f, const float *dev_cloud_xy, size_t n_points, int *n_used_out) {
+  qmcl_map *m = f->map;
+  ParticleSet &ps = f->cur();
+  // map_likelihood.cpp:67-74
+  size_t step = 1;
+  if (m->params.num_beams) step = n_points / static_cast<size_t>(m->params.num_beams);
+  if (step < 1) step = 1;
+  const size_t n_used = n_points ? (n_points + step - 1) / step : 0;
+  *n_used_out = static_cast<int>(n_used);
+  const unsigned nb = static_cast<unsigned>(std::min<size_t>(div_up(ps.n, 256), 4 * kSMs));
+  QMCL_TRY(f->bbox.ensure(8 + 6 * static_cast<size_t>(4 * kSMs)));
+  FrontJob J;
+  J.cloud = reinterpret_cast<const float2 *>(dev_cloud_xy);
+  J.n_points = n_points;
+  J.step = step;
+  J.beams = reinterpret_cast<float2 *>(f->beams.ptr);
+  J.n_used = static_cast<int>(n_used);
+  J.rmax = reinterpret_cast<unsigned *>(f->beams.ptr + 2 * n_points);
+  J.x = ps.x.ptr;
+  J.y = ps.y.ptr;
+  J.t = ps.t.ptr;
+  J.n = ps.n;
+  J.global_first = f->global_first;
+  J.do_motion = f->motion_pending ? 1 : 0;
+  std::memcpy(&J.mp, f->pending_motion, sizeof(J.mp));
+  J.seed = f->seed;
+  J.rng_step = f->pending_motion_step;
+  J.bp.res_xy = f->params.res_xy;
+  J.bp.res_t = f->params.res_theta;
+  J.bp.theta_lo = f->theta_lo;
+  J.bp.theta_hi = f->theta_hi;
+  J.block_bbox = f->bbox.ptr + 8;
+  J.bbox = f->bbox.ptr;
+  J.blocks_done = &f->scalars.ptr->blocks_done;
+  StageScope sc(f, QMCL_STAGE_MOTION);
+  front_kernel<<<nb + 1, 256, 0, m->stream>>>(J);
+  QMCL_LAUNCHED();
+  f->motion_pending = false;
+  f->early_bbox_version = f->pose_version;
+  return QMCL_OK;
+}
+
+// Runs the beam selection, K7 and K8 on the current set for the cloud at dev_cloud_xy.
+static qmcl_status sensor_update_common(qmcl_filter *f, const float *dev_cloud_xy, size_t n_points) {
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   cudaStream_t s = m->stream;
   // a pending total's slot is about to be reused; a deferred normalisation or a
-  // fused tail still in flight belong to the previous update
-  QMCL_TRY(settle(f));
+  // fused tail still in flight belong to the previous update.  A deferred motion
+  // is ours to apply (front kernel).
+  if (f->tail_pending || f->normalise_pending || f->total_pending || f->bins_pending || f->clusters_pending) {
+    const bool motion = f->motion_pending;
+    f->motion_pending = false;
+    const qmcl_status st = settle(f);
+    f->motion_pending = motion;
+    QMCL_TRY(st);
+  }
+  // With the fused tail (tail.cu) K8 and everything after it run in one launch
+  // that reads the total and the bin bounds on the device.
+  const bool defer = tail_enabled(f) && ps.n > 0 && ps.n <= (size_t(1) << 22);
+  int n_used = 0;
+  if (defer) {
+    QMCL_TRY(launch_front(f, dev_cloud_xy, n_points, &n_used));
+  } else {
+    QMCL_TRY(flush_motion(f));
+    QMCL_TRY(launch_subsample(f->map, dev_cloud_xy, n_points, f->beams.ptr, &n_used));
+  }
   if (ps.n == 0 && !sharded(f)) {
     f->last_total = 0.0;
     return QMCL_OK;
@@ -264,14 +441,7 @@ static qmcl_status sensor_update_common(qmcl_filter *f, int n_used, size_t n_poi
   a.rmax = f->beams.ptr + 2 * n_points;
   a.partials = f->partials.ptr;
   a.scalars = f->scalars.ptr;
-  // With the fused tail (tail.cu) K8 and everything after it run in one launch
-  // that reads the total and the bin bounds on the device.
-  const bool defer = tail_enabled(f) && ps.n > 0 && ps.n <= (size_t(1) << 22);
-  if (defer) {
-    StageScope sc(f, QMCL_STAGE_BINS);
-    QMCL_TRY(launch_bin_bbox(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
-    f->early_bbox_version = f->pose_version;
-  } else if (ps.n && lazy(f) && f->params.resample_type == QMCL_RESAMPLE_KLD) {
+  if (!defer && ps.n && lazy(f) && f->params.resample_type == QMCL_RESAMPLE_KLD) {
     // KLD sizes its dense bin table by the bounding box of the set it draws
     // from.  Taken here, ahead of the sensor kernel, the six numbers are on the
     // host long before the resampling asks for them.
@@ -357,6 +527,7 @@ qmcl_status qmcl_filter_create(qmcl_map *map, uint64_t seed, qmcl_filter **out) 
   map->refs++;
   if (const char *e = std::getenv("QMCL_EAGER_SYNC")) f->lazy_sync = !(e[0] && e[0] != '0');
   if (const char *e = std::getenv("QMCL_TAIL")) f->use_tail = !(e[0] == '0');
+  if (const char *e = std::getenv("QMCL_PREFIX_MODE")) f->prefix_mode = (e[0] == '2') ? 2 : (e[0] == '1');
   qmcl_filter_set_params(f, &f->params);
   *out = f;
   return QMCL_OK;
@@ -544,9 +715,7 @@ qmcl_status qmcl_filter_update_sensor(qmcl_filter *f, const float *cloud_xy, siz
   std::memcpy(f->h_beams.ptr, cloud_xy, 2 * n_points * sizeof(float));
   QMCL_CUDA(copy_h2d(f->cloud.ptr, f->h_beams.ptr, 2 * n_points * sizeof(float), s));
   QMCL_CUDA(cudaEventRecord(f->staging_read, s));
-  int n_used = 0;
-  QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
-  return sensor_update_common(f, n_used, n_points);
+  return sensor_update_common(f, f->cloud.ptr, n_points);
 }
 
 qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud_xy,
@@ -555,9 +724,7 @@ qmcl_status qmcl_filter_update_sensor_dev(qmcl_filter *f, const float *dev_cloud
   if (!f->map->has_map) return QMCL_ERR_NO_MAP;
   QMCL_TRY(use_device(f->map));
   QMCL_TRY(f->beams.ensure(2 * n_points + 2));
-  int n_used = 0;
-  QMCL_TRY(launch_subsample(f->map, dev_cloud_xy, n_points, f->beams.ptr, &n_used));
-  return sensor_update_common(f, n_used, n_points);
+  return sensor_update_common(f, dev_cloud_xy, n_points);
 }
 
 qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, size_t n_ranges,
@@ -588,9 +755,7 @@ qmcl_status qmcl_filter_update_sensor_scan(qmcl_filter *f, const float *ranges, 
   QMCL_CUDA(cudaStreamSynchronize(s));
   f->n_cloud = n_points;
   if (n_points_out) *n_points_out = n_points;
-  int n_used = 0;
-  QMCL_TRY(launch_subsample(f->map, f->cloud.ptr, n_points, f->beams.ptr, &n_used));
-  return sensor_update_common(f, n_used, n_points);
+  return sensor_update_common(f, f->cloud.ptr, n_points);
 }
 
 qmcl_status qmcl_filter_copy_cloud(const qmcl_filter *fc, float *xy_out, size_t cap, size_t *n_out) {

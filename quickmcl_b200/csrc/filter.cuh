@@ -27,6 +27,8 @@ qmcl_status launch_tail(qmcl_filter *f, int mode);
 qmcl_status tail_complete(qmcl_filter *f);
 // K8 + the total's read-back, when they were deferred (sensor_update_common).
 qmcl_status flush_sensor(qmcl_filter *f);
+// K6 of a handle_odometry call left to the next sensor update (motion.cu).
+qmcl_status flush_motion(qmcl_filter *f);
 // particle_filter.cpp:106-120 on the host: w_slow / w_fast from the sensor total.
 void apply_sensor_total(qmcl_filter *f, double total, double n_total);
 // Grow-only byte scratch of the filter (contents are not preserved).

@@ -9,15 +9,11 @@
 // 24 B read+write per particle for motion, 20 B written for init.
 
 #include "filter.cuh"
+#include "motion_dev.cuh"
 
 #include <cmath>
 
 namespace qmcl {
-
-struct MotionParams {
-  double delta_trans, delta_rot1, delta_rot2;
-  double sd_trans, sd_rot1, sd_rot2;
-};
 
 // odometry.cpp:86-101
 __global__ void __launch_bounds__(256)
@@ -25,22 +21,11 @@ motion_kernel(float *__restrict__ x, float *__restrict__ y, float *__restrict__ 
               size_t global_first, MotionParams mp, uint64_t seed, uint32_t step) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t r[4];
-  rng_draw(seed, step, P_MOTION, global_first + i, r);
-  double z0, z1, z2, z3;
-  normal_pair(r[0], r[1], &z0, &z1);
-  normal_pair(r[2], r[3], &z2, &z3);
-  // std::normal_distribution(0, sd) returns z * sd + 0
-  const double trans_hat = mp.delta_trans - z0 * mp.sd_trans;
-  const double rot1_hat = angle_delta(mp.delta_rot1, z1 * mp.sd_rot1);
-  const double rot2_hat = angle_delta(mp.delta_rot2, z2 * mp.sd_rot2);
-  const float th = t[i];
-  double s, c;
-  sincos(static_cast<double>(th) + rot1_hat, &s, &c);
-  x[i] = x[i] + static_cast<float>(trans_hat * c);
-  y[i] = y[i] + static_cast<float>(trans_hat * s);
-  const float th2 = th + static_cast<float>(rot1_hat + rot2_hat);
-  t[i] = normalise_angle_f(th2);
+  float px = x[i], py = y[i], pt = t[i];
+  motion_one(&px, &py, &pt, mp, seed, step, global_first + i);
+  x[i] = px;
+  y[i] = py;
+  t[i] = pt;
 }
 
 struct InitParams {
@@ -150,6 +135,22 @@ void covariance_factor(const float cov[9], float out[9]) {
 
 // Slice [first, first+count) of `global_n` particles owned by this shard:
 // contiguous blocks in global index order.
+// K6 of a handle_odometry call that was left to the next sensor update.
+qmcl_status flush_motion(qmcl_filter *f) {
+  if (!f->motion_pending) return QMCL_OK;
+  f->motion_pending = false;
+  ParticleSet &ps = f->cur();
+  if (!ps.n) return QMCL_OK;
+  QMCL_TRY(use_device(f->map));
+  MotionParams mp;
+  std::memcpy(&mp, f->pending_motion, sizeof(mp));
+  StageScope sc(f, QMCL_STAGE_MOTION);
+  motion_kernel<<<div_up(ps.n, 256), 256, 0, f->map->stream>>>(
+      ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n, f->global_first, mp, f->seed, f->pending_motion_step);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
 void shard_slice(const qmcl_filter *f, size_t global_n, size_t *first, size_t *count) {
   const size_t per = (global_n + f->n_shards - 1) / f->n_shards;
   size_t a = per * f->shard_rank;
@@ -257,7 +258,15 @@ qmcl_status qmcl_filter_handle_odometry(qmcl_filter *f, const double nw[3], cons
   mp.sd_rot1 = std::sqrt(rot1_var);
   mp.sd_rot2 = std::sqrt(rot2_var);
   ParticleSet &ps = f->cur();
-  if (ps.n) {
+  QMCL_TRY(flush_motion(f));  // an earlier motion nobody consumed
+  if (ps.n && tail_enabled(f)) {
+    // The sensor update that follows applies it in its front kernel (filter.cu);
+    // any other reader of the poses makes flush_motion launch it.
+    static_assert(sizeof(MotionParams) == sizeof(f->pending_motion), "pending_motion holds a MotionParams");
+    std::memcpy(f->pending_motion, &mp, sizeof(mp));
+    f->pending_motion_step = f->step;
+    f->motion_pending = true;
+  } else if (ps.n) {
     StageScope sc(f, QMCL_STAGE_MOTION);
     motion_kernel<<<div_up(ps.n, 256), 256, 0, f->map->stream>>>(
         ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n, f->global_first, mp, f->seed, f->step);

@@ -219,6 +219,11 @@ qmcl_status plan_prefix(qmcl_filter *f, size_t n, PrefixPlan *pl) {
   pb.chunk_mode = b + o_cm;
   pb.tile_mode = b + o_tm;
   pb.carry_out = f->prefix_carry.ptr;
+  // prefix mode 2 = binade-crossing chunks resolved lane-wise (lane_chunk) instead of by 256
+  // literal additions.  Bit-identical, but measured slower on the lone resolve warp (57 -> 81 us
+  // at 100 k particles: ~1500 dependent instructions per chunk at one warp's issue rate), so off
+  // by default; kept for A/B.
+  pb.lanes = f->prefix_mode == 2 ? 1 : 0;
   pl->nc = nc;
   pl->nt = nt;
   return QMCL_OK;
@@ -363,7 +368,7 @@ using namespace qmcl;
 extern "C" {
 
 qmcl_status qmcl_filter_set_prefix_mode(qmcl_filter *f, int mode) {
-  if (!f || mode < 0 || mode > 1) return QMCL_ERR_INVALID_ARG;
+  if (!f || mode < 0 || mode > 2) return QMCL_ERR_INVALID_ARG;
   f->prefix_mode = mode;
   return QMCL_OK;
 }

@@ -144,10 +144,11 @@ struct PrefixBuffers {
   uint8_t *chunk_mode;   // nc
   uint8_t *tile_mode;    // nt
   double *carry_out;     // 1
+  int lanes;             // 1: binade-crossing chunks are resolved lane-wise (lane_chunk)
 };
 
 // ---- phase 1: chunk and tile summaries under the guessed binade
-__device__ __forceinline__ void prefix_summaries_tile(const double *w, size_t n, size_t nc,
+QMCL_PHASE_FN void prefix_summaries_tile(const double *w, size_t n, size_t nc,
                                                       const PrefixBuffers &pb, size_t tile) {
   __shared__ unsigned long long s_a0[kTileChunks], s_a1[kTileChunks];
   __shared__ int s_E[kTileChunks];
@@ -197,6 +198,91 @@ __device__ __forceinline__ void prefix_summaries_tile(const double *w, size_t n,
   }
 }
 
+// Phase 2 for a chunk whose summary does not apply because the running sum
+// crosses into the next binade inside it (about log2(N) chunks of a normalised
+// weight array).  Instead of 256 dependent additions the warp evaluates every
+// lane's 8 elements in closed form under the carry's binade E and under E + 1:
+// the lanes before the one in which the sum really crosses follow E, the lanes
+// after it E + 1, and only the crossing lane's 8 elements are added one by one
+// (the same additions on every lane, its elements broadcast by shuffles).  The
+// chunk's running sums are written here.  Returns false — nothing written —
+// when this does not apply (carry not normal, a second crossing, a negative /
+// subnormal / non-finite weight after the crossing); the caller then falls back
+// to the literal additions.  Bit-identical to them whenever it returns true
+// (CPU model of the algorithm: 540 adversarial arrays, round 1; GPU:
+// tests/test_prefix_gpu.py against the one-warp sequential kernel and numpy).
+__device__ __forceinline__ bool lane_chunk(const double *w, size_t n, size_t ch, double c, double *out,
+                                           int lane, double *c_out) {
+  const int cE = biased_exponent_if_normal(c);
+  if (cE == kInvalidE || cE >= 0x7fd) return false;
+  const size_t base = ch * kChunk + static_cast<size_t>(lane) * kLaneItems;
+  double v[kLaneItems];
+  load_items(w, base, n, v);
+  Fn e0[kLaneItems], e1[kLaneItems];
+  Fn F0 = fn_identity(), F1 = fn_identity();
+  bool ok0 = true, ok1 = true;
+#pragma unroll
+  for (int i = 0; i < kLaneItems; ++i) {
+    ok0 &= elem_fn(v[i], cE, &e0[i]);
+    F0 = fn_compose(F0, e0[i]);
+    ok1 &= elem_fn(v[i], cE + 1, &e1[i]);
+    F1 = fn_compose(F1, e1[i]);
+  }
+  const Fn incl = fn_warp_scan(F0, lane);
+  Fn excl = fn_shfl_up(incl, 1);
+  if (lane == 0) excl = fn_identity();
+  const unsigned long long K0 = mantissa_int(c);
+  const unsigned long long Kin = fn_apply(excl, K0), Kout = fn_apply(incl, K0);
+  // weights are >= 0 wherever a closed form exists, so K only grows: a lane is
+  // good iff its own end point is still inside the binade
+  const bool fine = ok0 && Kout < kKLimit;
+  const unsigned int bad = __ballot_sync(0xffffffffu, !fine);
+  int L = 32, myE = cE;
+  double cin;
+  if (bad == 0) {
+    cin = make_double(cE, Kin);
+    *c_out = make_double(cE, __shfl_sync(0xffffffffu, Kout, 31));
+  } else {
+    L = __ffs(bad) - 1;
+    const double cL = make_double(cE, __shfl_sync(0xffffffffu, Kin, L));
+    double cc = cL;  // the crossing lane's 8 elements: true additions (padding zeros add nothing)
+#pragma unroll
+    for (int i = 0; i < kLaneItems; ++i) cc = __dadd_rn(cc, __shfl_sync(0xffffffffu, v[i], L));
+    if (biased_exponent_if_normal(cc) != cE + 1) return false;
+    const Fn G = lane > L ? F1 : fn_identity();
+    const bool okG = lane > L ? ok1 : true;
+    const Fn incl2 = fn_warp_scan(G, lane);
+    Fn excl2 = fn_shfl_up(incl2, 1);
+    if (lane == 0) excl2 = fn_identity();
+    const unsigned long long K1 = mantissa_int(cc);
+    const unsigned long long Kin2 = fn_apply(excl2, K1), Kout2 = fn_apply(incl2, K1);
+    if (!__all_sync(0xffffffffu, okG && Kout2 < kKLimit)) return false;  // e.g. a second crossing
+    cin = lane < L ? make_double(cE, Kin) : (lane == L ? cL : make_double(cE + 1, Kin2));
+    myE = lane < L ? cE : cE + 1;
+    *c_out = make_double(cE + 1, __shfl_sync(0xffffffffu, Kout2, 31));
+  }
+  double r[kLaneItems];
+  if (lane == L) {
+    double cc = cin;
+#pragma unroll
+    for (int i = 0; i < kLaneItems; ++i) {
+      cc = __dadd_rn(cc, v[i]);
+      r[i] = cc;
+    }
+  } else {
+    unsigned long long K = mantissa_int(cin);
+#pragma unroll
+    for (int i = 0; i < kLaneItems; ++i) {
+      K = fn_apply(myE == cE ? e0[i] : e1[i], K);
+      r[i] = make_double(myE, K);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLaneItems; ++i)
+    if (base + i < n) out[base + i] = r[i];
+  return true;
+}
+
 // Exact running sums of one chunk from the exact carry `c` (warp-uniform), for
 // chunks whose summary cannot be used: the literal sequence of double
 // additions.  The warp stages the chunk in shared memory, lane 0 runs the
@@ -241,7 +327,7 @@ __device__ __forceinline__ double exact_chunk(const double *w, size_t e0, int cn
 
 // ---- phase 2: the exact carry through all tiles (one warp)
 // Run by ONE warp (lane = its lane index); only __syncwarp inside.
-__device__ __forceinline__ void prefix_resolve_warp(const double *w, size_t n, size_t nc, size_t nt,
+QMCL_PHASE_FN void prefix_resolve_warp(const double *w, size_t n, size_t nc, size_t nt,
                                                     double carry_in, const PrefixBuffers &pb,
                                                     double *out, int lane) {
   // chunk summaries of the current batch of 32 tiles, staged on demand
@@ -326,6 +412,17 @@ __device__ __forceinline__ void prefix_resolve_warp(const double *w, size_t n, s
             continue;
           }
         }
+        if (pb.lanes) {
+          double c_next;
+          if (lane_chunk(w, n, ch, c, out, lane, &c_next)) {
+            if (lane == 0) {
+              pb.chunk_mode[ch] = MODE_SLOW;  // written here, phase 3 skips it
+              pb.chunk_cin[ch] = c;
+            }
+            c = c_next;
+            continue;
+          }
+        }
         const size_t e0 = ch * kChunk;
         const int cnt = static_cast<int>((e0 + kChunk <= n) ? kChunk : n - e0);
         if (lane == 0) {
@@ -341,7 +438,7 @@ __device__ __forceinline__ void prefix_resolve_warp(const double *w, size_t n, s
 }
 
 // ---- phase 3: expand the carries into the running sums
-__device__ __forceinline__ void prefix_apply_tile(const double *w, size_t n, size_t nc,
+QMCL_PHASE_FN void prefix_apply_tile(const double *w, size_t n, size_t nc,
                                                   const PrefixBuffers &pb, double *out, size_t tile) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t chunk = tile * kTileChunks + wid;

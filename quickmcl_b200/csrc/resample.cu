@@ -1217,6 +1217,7 @@ static qmcl_status resample_and_cluster_impl(qmcl_filter *f) {
   if (f->params.resample_type >= 0 && f->params.resample_type <= 2 &&
       tail_eligible(f, f->params.resample_type))
     return launch_tail(f, f->params.resample_type);
+  QMCL_TRY(flush_motion(f));
   QMCL_TRY(flush_sensor(f));
   const ParticleSet &in = f->sets[f->current];
   ParticleSet &out = f->sets[(f->current + 1) % 2];

@@ -200,6 +200,9 @@ struct qmcl_filter {
   // resample_and_cluster / cluster only as an upper bound (tail_pending); every
   // entry point settles first.
   bool use_tail = true;
+  bool motion_pending = false;      // K6 of the last handle_odometry deferred into the sensor update's front kernel
+  double pending_motion[6] = {};    // its MotionParams (motion_dev.cuh)
+  uint32_t pending_motion_step = 0; // the RNG step it was called at
   bool normalise_pending = false;   // K8 (divide by the sensor total) deferred into the tail
   size_t normalise_n = 0;           // particles of that sensor update
   bool tail_pending = false;
@@ -209,7 +212,10 @@ struct qmcl_filter {
   int tail_prev_current = 0;
   uint32_t tail_prev_step = 0;
   unsigned long long tail_serial = 0;
+  size_t kld_probe = 8192;          // candidates the KLD tail examines first (tail.cu)
   uint64_t tail_fallbacks = 0;
+  uint64_t tail_phase_ns[16] = {};  // per-phase device time, summed over tail_phase_calls calls
+  uint64_t tail_phase_calls = 0;
   TailResult *h_tail = nullptr;  // pinned, written by the kernel
   qmcl::DevBuf<TailDev> tail_dev;
   qmcl::DevBuf<uint8_t> tail_scratch;

@@ -19,18 +19,55 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef QMCL_TAIL_CG_SYNC
+#define QMCL_TAIL_CG_SYNC 0  // 1: cooperative_groups grid.sync() instead of the backing-off barrier
+#endif
+
 namespace qmcl {
 
+constexpr size_t kSoloCells = 2048;  // dense grids up to this size are listed and labelled by one block
+
 // ------------------------------------------------------------------ teams
-struct GridTeam {  // cooperative launch: every block of the grid works on job 0
+// Grid barrier of the cooperative launch.  cooperative_groups' grid.sync() polls
+// its flag without pause; with 295 blocks waiting for one busy warp (the exact
+// carry walk, the single-block labelling) that polling alone slowed the worker
+// down 2-3x (measured: resolve phase 36 us stand-alone, 61 us with 147 waiting
+// blocks, 94 us with 295).  This barrier backs off with nanosleep between polls.
+// The counter only ever grows; every block passes the same number of barriers,
+// so a launch leaves it at a multiple of the grid size.
+struct GridTeam {
+  unsigned long long *counter;
+  __device__ explicit GridTeam(const TailJob &J) : counter(&J.dev->barrier) {}
   __device__ static unsigned rank() { return blockIdx.x; }
   __device__ static unsigned size() { return gridDim.x; }
-  __device__ static void sync() { cg::this_grid().sync(); }
+  // max_sleep_ns: the longest pause between two polls; phases in which one block
+  // works for tens of microseconds pass a larger one.
+  __device__ void sync(unsigned max_sleep_ns = 320) const {
+#if QMCL_TAIL_CG_SYNC
+    cg::this_grid().sync();
+#else
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long n = gridDim.x;
+      const unsigned long long old = atomicAdd(counter, 1ull);
+      const unsigned long long target = (old / n + 1) * n;
+      unsigned ns = 20;
+      while (*reinterpret_cast<volatile unsigned long long *>(counter) < target) {
+        __nanosleep(ns);
+        if (ns < max_sleep_ns) ns *= 2;
+      }
+      __threadfence();
+    }
+    __syncthreads();
+#endif
+  }
 };
 struct BlockTeam {  // one block per job
+  __device__ explicit BlockTeam(const TailJob &) {}
   __device__ static unsigned rank() { return 0; }
   __device__ static unsigned size() { return 1; }
-  __device__ static void sync() { __syncthreads(); }
+  __device__ void sync(unsigned = 0) const { __syncthreads(); }
 };
 
 // ---------------------------------------------------------- block helpers
@@ -102,43 +139,69 @@ __device__ __forceinline__ void lowpass_update_dev(double *value, double alpha, 
 // contiguous items, the geometry of scan.cuh): phase A counts per tile, phase B
 // emits g(i, exclusive_prefix, flag).  Between the two the caller synchronises
 // the team.  Returns (phase B) the grand total to every thread.
+// Items per thread of a compaction over n items: as few as keeps every block of
+// the team busy (each item is a chain of dependent loads), at most 8.
+template <class Team>
+__device__ __forceinline__ int compact_ipt(size_t n) {
+  const size_t per = static_cast<size_t>(Team::size()) * kScanBlock;
+  const size_t want = (n + per - 1) / per;
+  return static_cast<int>(want < 1 ? 1 : (want > kScanItems ? kScanItems : want));
+}
 template <class Team, typename F>
-__device__ __forceinline__ void compact_count(F f, size_t n, uint32_t *tile_cnt) {
-  const size_t tiles = (n + kScanTile - 1) / kScanTile;
+__device__ __forceinline__ void compact_count(F f, size_t n, uint32_t *tile_cnt, int ipt = kScanItems) {
+  const size_t tile_items = static_cast<size_t>(kScanBlock) * ipt;
+  const size_t tiles = (n + tile_items - 1) / tile_items;
   for (size_t tile = Team::rank(); tile < tiles; tile += Team::size()) {
-    const size_t base = (tile * kScanBlock + threadIdx.x) * kScanItems;
+    const size_t base = (tile * kScanBlock + threadIdx.x) * ipt;
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i)
-      if (base + i < n) c += f(base + i);
+      if (i < ipt && base + i < n) c += f(base + i);
     uint32_t total;
     block_excl_scan_u32(c, &total);
     if (threadIdx.x == 0) tile_cnt[tile] = total;
   }
 }
-template <class Team, typename F, typename G>
-__device__ __forceinline__ unsigned long long compact_emit(F f, G g, size_t n, const uint32_t *tile_cnt) {
-  const size_t tiles = (n + kScanTile - 1) / kScanTile;
-  for (size_t tile = Team::rank(); tile < tiles; tile += Team::size()) {
-    const size_t base = (tile * kScanBlock + threadIdx.x) * kScanItems;
-    const unsigned long long excl = block_prefix_of(tile_cnt, tile);
-    uint32_t v[kScanItems];
-    uint32_t c = 0;
+template <typename F, typename G>
+__device__ __forceinline__ void compact_emit_tile(F f, G g, size_t n, const uint32_t *tile_cnt, size_t tile,
+                                                  int ipt = kScanItems) {
+  const size_t base = (tile * kScanBlock + threadIdx.x) * ipt;
+  const unsigned long long excl = block_prefix_of(tile_cnt, tile);
+  uint32_t v[kScanItems];
+  uint32_t c = 0;
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-      v[i] = (base + i < n) ? f(base + i) : 0u;
-      c += v[i];
-    }
-    uint32_t total;
-    uint32_t at = static_cast<uint32_t>(excl) + block_excl_scan_u32(c, &total);
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i)
-      if (base + i < n) {
-        g(base + i, at, v[i]);
-        at += v[i];
-      }
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (i < ipt && base + i < n) ? f(base + i) : 0u;
+    c += v[i];
   }
+  uint32_t total;
+  uint32_t at = static_cast<uint32_t>(excl) + block_excl_scan_u32(c, &total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (i < ipt && base + i < n) {
+      g(base + i, at, v[i]);
+      at += v[i];
+    }
+}
+template <class Team, typename F, typename G>
+__device__ __forceinline__ unsigned long long compact_emit(F f, G g, size_t n, const uint32_t *tile_cnt,
+                                                           int ipt = kScanItems) {
+  const size_t tile_items = static_cast<size_t>(kScanBlock) * ipt;
+  const size_t tiles = (n + tile_items - 1) / tile_items;
+  for (size_t tile = Team::rank(); tile < tiles; tile += Team::size())
+    compact_emit_tile(f, g, n, tile_cnt, tile, ipt);
   return block_prefix_of(tile_cnt, tiles);
+}
+
+// Union-find helpers on a parent array in SHARED memory (the global-memory
+// versions in cluster_dev.cuh read through the L2 with ld.cg).
+__device__ __forceinline__ int uf_root_plain(const int32_t *parent, int v) {
+  int p = parent[v];
+  while (p != v) {
+    v = p;
+    p = parent[v];
+  }
+  return v;
 }
 
 struct TailPositive {
@@ -238,6 +301,7 @@ __device__ void tail_finish(const TailJob &J, unsigned long long status, double 
 template <class Team>
 __device__ void run_tail(const TailJob &J) {
   using namespace pfx;
+  const Team team(J);
   const unsigned rank = Team::rank(), size = Team::size();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   TailDev *D = J.dev;
@@ -303,7 +367,7 @@ __device__ void run_tail(const TailJob &J) {
   // Conditions under which the multi-launch path has to take over; all known
   // before anything is touched.
   if (!grid_ok || (w_diff > 0.0 && J.n_free == 0)) {
-    Team::sync();  // D is initialised before tail_finish reads it
+    team.sync();  // D is initialised before tail_finish reads it
     tail_finish<Team>(J, TAIL_FALLBACK, total, w_diff, g);
     return;
   }
@@ -352,7 +416,7 @@ __device__ void run_tail(const TailJob &J) {
     J.table[i] = 0;
     if (J.mode == TAIL_KLD) J.first[i] = 0x7f7f7f7f;
   }
-  Team::sync();
+  team.sync();
   TAIL_STAMP(TS_NORMALISE);
 
   unsigned long long n_out = n_in;  // cluster-only: the current set
@@ -375,22 +439,26 @@ __device__ void run_tail(const TailJob &J) {
       prefix_summaries_tile(J.iw, n_in, J.nc, J.pb, tile);
       __syncthreads();
     }
-    Team::sync();
+    team.sync();
     TAIL_STAMP(TS_SUMMARIES);
     // ---- phase 2: the exact carry through all tiles (one warp)
     if (rank == 0 && wid == 0) prefix_resolve_warp(J.iw, n_in, J.nc, J.nt, 0.0, J.pb, J.cdf, lane);
-    Team::sync();
+    team.sync(2560);
     TAIL_STAMP(TS_RESOLVE);
     // ---- phase 3: expand into the running sums; records of the positive weights
-    for (size_t tile = rank; tile < J.nt; tile += size) prefix_apply_tile(J.iw, n_in, J.nc, J.pb, J.cdf, tile);
-    if (draws) {
-      Team::sync();  // incl[] reads cdf[] written by other threads of the tile's block
-      const unsigned long long P = compact_emit<Team>(TailPositive{J.iw},
-                                                      TailEmitPositive{J.cdf, J.pos, J.incl}, n_in,
-                                                      J.tile_pos);
-      if (rank == 0 && tid == 0) D->n_records = P;
+    // (a tile's records read only that tile's running sums, which this block has just written)
+    for (size_t tile = rank; tile < J.nt; tile += size) {
+      prefix_apply_tile(J.iw, n_in, J.nc, J.pb, J.cdf, tile);
+      if (draws) {
+        __syncthreads();
+        compact_emit_tile(TailPositive{J.iw}, TailEmitPositive{J.cdf, J.pos, J.incl}, n_in, J.tile_pos, tile);
+      }
     }
-    Team::sync();
+    if (draws && rank == 0) {
+      const unsigned long long P = block_prefix_of(J.tile_pos, J.nt);
+      if (tid == 0) D->n_records = P;
+    }
+    team.sync();
     TAIL_STAMP(TS_APPLY);
 
     const double cdf_total = J.cdf[n_in - 1];
@@ -431,61 +499,81 @@ __device__ void run_tail(const TailJob &J) {
       }
       n_out = M;
     } else {
-      // particle_filter.cpp:261-276, :313-327; KLD: smallest draw index per bin
+      // particle_filter.cpp:261-276, :313-327; KLD: smallest draw index per bin.
+      // KLD looks at the candidates in (at most) two rounds: a probe of the first
+      // J.kld_probe draws, which holds the stop in all but the first cycles of a
+      // tracking filter, then all particle_count_max of them.  Draw m and the
+      // stop test at m depend on draws <= m only, so the outcome is the same.
       const size_t n_draws = static_cast<size_t>(J.mode == TAIL_KLD ? J.n_max : J.n_min);
       const size_t P = static_cast<size_t>(D->n_records);
-      const size_t rounded = (n_draws + 31) & ~static_cast<size_t>(31);
-      for (size_t m = static_cast<size_t>(rank) * kTailThreads + tid; m < rounded;
-           m += static_cast<size_t>(size) * kTailThreads) {
-        long long cell = -1 - static_cast<long long>(lane);  // lanes past the end: distinct, never marked
-        if (m < n_draws) {
-          uint32_t rr4[4];
-          rng_draw(J.seed, J.step, P_DRAW, m, rr4);
-          float x, y, t;
-          double w;
-          int64_t s;
-          if (uniform53(rr4[0], rr4[1]) < w_diff) {
-            uint32_t q[4];
-            rng_draw(J.seed, J.step, P_INJECT, m, q);
-            random_free_pose(J.free_cells, J.n_free, J.geom, q, &x, &y, &t);
-            w = 0.0;  // no influence on the estimate until the next update
-            s = -1;
-          } else {
-            s = J.pos[running_sum_lookup(J.incl, P, uniform53(rr4[2], rr4[3]))];
-            x = J.ix[s];
-            y = J.iy[s];
-            t = J.it[s];
-            w = J.iw[s];
+      size_t done = 0;
+      size_t round_end = n_draws;
+      if (J.mode == TAIL_KLD && J.kld_probe > 0 && J.kld_probe < n_draws) round_end = static_cast<size_t>(J.kld_probe);
+      while (true) {
+        const size_t first_m = done & ~static_cast<size_t>(31);
+        const size_t rounded = (round_end + 31) & ~static_cast<size_t>(31);
+        for (size_t m = first_m + static_cast<size_t>(rank) * kTailThreads + tid; m < rounded;
+             m += static_cast<size_t>(size) * kTailThreads) {
+          long long cell = -1 - static_cast<long long>(lane);  // lanes outside the round: distinct, never marked
+          if (m >= done && m < round_end) {
+            uint32_t rr4[4];
+            rng_draw(J.seed, J.step, P_DRAW, m, rr4);
+            float x, y, t;
+            double w;
+            int64_t sidx;
+            if (uniform53(rr4[0], rr4[1]) < w_diff) {
+              uint32_t q[4];
+              rng_draw(J.seed, J.step, P_INJECT, m, q);
+              random_free_pose(J.free_cells, J.n_free, J.geom, q, &x, &y, &t);
+              w = 0.0;  // no influence on the estimate until the next update
+              sidx = -1;
+            } else {
+              sidx = J.pos[running_sum_lookup(J.incl, P, uniform53(rr4[2], rr4[3]))];
+              x = J.ix[sidx];
+              y = J.iy[sidx];
+              t = J.it[sidx];
+              w = J.iw[sidx];
+            }
+            J.ox[m] = x;
+            J.oy[m] = y;
+            J.ot[m] = t;
+            J.ow[m] = w;
+            J.src[m] = sidx;
+            if (J.mode == TAIL_KLD) cell = kld_cell(x, y, t, J.kp, g);
           }
-          J.ox[m] = x;
-          J.oy[m] = y;
-          J.ot[m] = t;
-          J.ow[m] = w;
-          J.src[m] = s;
-          if (J.mode == TAIL_KLD) cell = kld_cell(x, y, t, J.kp, g);
+          if (J.mode == TAIL_KLD) {
+            const unsigned peers = __match_any_sync(0xffffffffu, cell);
+            if (cell >= 0 && (__ffs(peers) - 1) == lane) atomicMin(J.first + cell, static_cast<int32_t>(m));
+          }
         }
-        if (J.mode == TAIL_KLD) {
-          const unsigned peers = __match_any_sync(0xffffffffu, cell);
-          if (cell >= 0 && (__ffs(peers) - 1) == lane) atomicMin(J.first + cell, static_cast<int32_t>(m));
+        n_out = n_draws;
+        team.sync();
+        if (J.mode != TAIL_KLD) break;
+        if (done == 0) TAIL_STAMP(TS_SELECT);
+        // ---- phases 5, 6: K11 KLD stop rule (particle_filter.cpp:313-335) over [0, round_end)
+        const TailNewBin nb{J.ox, J.oy, J.ot, J.kp, g, J.first};
+        const int ipt = compact_ipt<Team>(round_end);
+        compact_count<Team>(nb, round_end, J.tile_cnt, ipt);
+        team.sync();
+        const unsigned long long n_new =
+            compact_emit<Team>(nb, TailStopRule{J.kp, &D->stop}, round_end, J.tile_cnt, ipt);
+        if (rank == 0 && tid == 0) D->n_new = n_new;
+        team.sync();
+        const unsigned long long stop = *reinterpret_cast<volatile unsigned long long *>(&D->stop);
+        if (stop != ~0ull) {
+          n_out = (stop >> 32) + 1;
+          break;
         }
+        if (round_end == n_draws) break;  // no stop at all: every candidate is kept
+        done = round_end;
+        round_end = n_draws;
       }
-      n_out = n_draws;
+      if (J.mode == TAIL_KLD) TAIL_STAMP(TS_KLD);
+      else TAIL_STAMP(TS_SELECT);
     }
-    Team::sync();
-    TAIL_STAMP(TS_SELECT);
-
-    // ---- phases 5, 6: K11 KLD stop rule (particle_filter.cpp:313-335)
-    if (J.mode == TAIL_KLD) {
-      const size_t n_max = static_cast<size_t>(J.n_max);
-      const TailNewBin nb{J.ox, J.oy, J.ot, J.kp, g, J.first};
-      compact_count<Team>(nb, n_max, J.tile_cnt);
-      Team::sync();
-      const unsigned long long n_new = compact_emit<Team>(nb, TailStopRule{J.kp, &D->stop}, n_max, J.tile_cnt);
-      if (rank == 0 && tid == 0) D->n_new = n_new;
-      Team::sync();
-      const unsigned long long stop = *reinterpret_cast<volatile unsigned long long *>(&D->stop);
-      n_out = (stop != ~0ull) ? (stop >> 32) + 1 : n_max;
-      TAIL_STAMP(TS_KLD);
+    if (J.mode == TAIL_LOW_VARIANCE) {
+      team.sync();
+      TAIL_STAMP(TS_SELECT);
     }
   }
   if (rank == 0 && tid == 0) D->n_out = n_out;
@@ -499,30 +587,111 @@ __device__ void run_tail(const TailJob &J) {
          i += static_cast<size_t>(size) * kTailThreads)
       bin_mark_one(cx, cy, ct, static_cast<size_t>(n_out), J.bp, g, J.table, i);
   }
-  Team::sync();
+  team.sync();
   TAIL_STAMP(TS_MARK);
-  // ---- phase 8: the occupied-bin list (sorted), table -> bin id + 1
-  compact_count<Team>(TailOccupied{J.table}, cells, J.tile_cnt);
-  Team::sync();
-  const unsigned long long n_bins = compact_emit<Team>(
-      TailOccupied{J.table}, TailEmitBin{J.table, J.bin_cell, J.bin_count, J.bin_label}, cells, J.tile_cnt);
-  if (rank == 0 && tid == 0) D->n_bins = n_bins;
-  Team::sync();
-  TAIL_STAMP(TS_BINS);
-  // ---- phases 9-11: K13 connected components (space_partitioning.cpp:89-128)
-  for (size_t b = static_cast<size_t>(rank) * kTailThreads + tid; b < n_bins;
-       b += static_cast<size_t>(size) * kTailThreads)
-    cc_hook_bin(J.table, J.bin_cell, g, J.bp, J.bin_label, static_cast<int>(b));
-  Team::sync();
-  for (size_t b = static_cast<size_t>(rank) * kTailThreads + tid; b < n_bins;
-       b += static_cast<size_t>(size) * kTailThreads)
-    J.bin_label[b] = uf_find_readonly(J.bin_label, static_cast<int>(b));
-  Team::sync();
-  compact_count<Team>(TailRoot{J.bin_label}, n_bins, J.tile_cnt);
-  Team::sync();
-  const unsigned long long n_clusters =
-      compact_emit<Team>(TailRoot{J.bin_label}, TailEmitRoot{J.bin_cluster, J.cluster_w}, n_bins, J.tile_cnt);
-  if (rank == 0 && tid == 0) D->n_clusters = n_clusters;
+  // ---- phases 8-11: the occupied-bin list (sorted), table -> bin id + 1; K13 connected
+  // components (space_partitioning.cpp:89-128); dense cluster ids.  A small grid (a
+  // tracking cloud) is handled by block 0 alone between block barriers, with the
+  // union-find forest in shared memory: six team barriers and the latency of
+  // contended global atomics on a single component go away.
+  unsigned long long n_bins = 0, n_clusters = 0;  // valid on rank 0 (everywhere on the team path)
+  if (cells <= J.solo_cells) {
+    if (rank == 0) {
+      // everything in shared memory: the dense table, the bin list, the union-find forest
+      __shared__ int32_t s_tab[kSoloCells], s_cell[kSoloCells], s_parent[kSoloCells];
+      for (size_t i = tid; i < cells; i += kTailThreads) s_tab[i] = J.table[i];
+      __syncthreads();
+      uint32_t v[kSoloCells / kTailThreads];
+      uint32_t c = 0, total = 0;
+      constexpr int kPer = kSoloCells / kTailThreads;  // contiguous cells per thread
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const size_t idx = static_cast<size_t>(tid) * kPer + i;
+        v[i] = (idx < cells && s_tab[idx] > 0) ? 1u : 0u;
+        c += v[i];
+      }
+      uint32_t at = block_excl_scan_u32(c, &total);
+      n_bins = total;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i)
+        if (v[i]) {
+          const size_t idx = static_cast<size_t>(tid) * kPer + i;
+          J.bin_cell[at] = static_cast<int32_t>(idx);
+          s_cell[at] = static_cast<int32_t>(idx);
+          J.bin_count[at] = s_tab[idx];
+          s_parent[at] = static_cast<int32_t>(at);
+          s_tab[idx] = static_cast<int32_t>(at) + 1;
+          ++at;
+        }
+      __syncthreads();
+      for (size_t b = tid; b < n_bins; b += kTailThreads)
+        cc_hook_bin(s_tab, s_cell, g, J.bp, s_parent, static_cast<int>(b));
+      __syncthreads();
+      int32_t root[kPer];
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const size_t b = static_cast<size_t>(tid) + static_cast<size_t>(i) * kTailThreads;
+        root[i] = b < n_bins ? uf_root_plain(s_parent, static_cast<int>(b)) : -1;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const size_t b = static_cast<size_t>(tid) + static_cast<size_t>(i) * kTailThreads;
+        if (b < n_bins) {
+          s_parent[b] = root[i];
+          J.bin_label[b] = root[i];
+        }
+      }
+      __syncthreads();
+      // dense cluster ids in root order
+      c = 0;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
+        const size_t b = static_cast<size_t>(tid) * kPer + i;
+        v[i] = (b < n_bins && s_parent[b] == static_cast<int32_t>(b)) ? 1u : 0u;
+        c += v[i];
+      }
+      at = block_excl_scan_u32(c, &total);
+      n_clusters = total;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i)
+        if (v[i]) {
+          J.bin_cluster[static_cast<size_t>(tid) * kPer + i] = static_cast<int32_t>(at);
+          J.cluster_w[at] = 0ull;
+          ++at;
+        }
+      for (size_t i = tid; i < cells; i += kTailThreads) J.table[i] = s_tab[i];
+      if (tid == 0) {
+        D->n_bins = n_bins;
+        D->n_clusters = n_clusters;
+      }
+    }
+    TAIL_STAMP(TS_BINS);
+  } else {
+    const int ipt_c = compact_ipt<Team>(cells);
+    compact_count<Team>(TailOccupied{J.table}, cells, J.tile_cnt, ipt_c);
+    team.sync();
+    n_bins = compact_emit<Team>(TailOccupied{J.table},
+                                TailEmitBin{J.table, J.bin_cell, J.bin_count, J.bin_label}, cells, J.tile_cnt,
+                                ipt_c);
+    if (rank == 0 && tid == 0) D->n_bins = n_bins;
+    team.sync();
+    TAIL_STAMP(TS_BINS);
+    for (size_t b = static_cast<size_t>(rank) * kTailThreads + tid; b < n_bins;
+         b += static_cast<size_t>(size) * kTailThreads)
+      cc_hook_bin(J.table, J.bin_cell, g, J.bp, J.bin_label, static_cast<int>(b));
+    team.sync();
+    for (size_t b = static_cast<size_t>(rank) * kTailThreads + tid; b < n_bins;
+         b += static_cast<size_t>(size) * kTailThreads)
+      J.bin_label[b] = uf_find_readonly(J.bin_label, static_cast<int>(b));
+    team.sync();
+    const int ipt_b = compact_ipt<Team>(n_bins);
+    compact_count<Team>(TailRoot{J.bin_label}, n_bins, J.tile_cnt, ipt_b);
+    team.sync();
+    n_clusters = compact_emit<Team>(TailRoot{J.bin_label}, TailEmitRoot{J.bin_cluster, J.cluster_w}, n_bins,
+                                    J.tile_cnt, ipt_b);
+    if (rank == 0 && tid == 0) D->n_clusters = n_clusters;
+  }
   TAIL_STAMP(TS_LABEL);
 
   // ---- phase 12: total of the new set (particle.cpp:41-48) and its largest weight
@@ -543,7 +712,7 @@ __device__ void run_tail(const TailJob &J) {
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0 && m) atomicMax(&D->wmax_raw, m);
   }
-  Team::sync();
+  team.sync(cells <= J.solo_cells ? 1280 : 320);  // block 0 may still be labelling on its own
   TAIL_STAMP(TS_WEIGHT_SUM);
   // ---- phase 13: normalise (particle_filter.cpp:160), cluster weights (K14 step 2)
   {
@@ -568,11 +737,11 @@ __device__ void run_tail(const TailJob &J) {
                            J.particle_cid, J.cluster_w, &D->es, shift, vb);
     }
   }
-  Team::sync();
+  team.sync();
   TAIL_STAMP(TS_CLUSTER_W);
   // ---- phase 14: the cluster with the largest weight (particle_filter.cpp:186-200)
   if (rank == 0) best_cluster_block(J.cluster_w, static_cast<size_t>(n_clusters), &D->es);
-  Team::sync();
+  team.sync();
   TAIL_STAMP(TS_BEST);
   // ---- phases 15, 16: moments of the best cluster and of all particles, estimate
   const unsigned mom_blocks =
@@ -583,7 +752,7 @@ __device__ void run_tail(const TailJob &J) {
     for (unsigned vb = rank; vb < mom_blocks; vb += size)
       moments_block(cx, cy, ct, cw, J.particle_cid, n, mom_partials, best, vb, mom_blocks);
   }
-  Team::sync();
+  team.sync();
   TAIL_STAMP(TS_MOMENTS);
   if (rank == 0) {
     // no clusters ("ALL clusters suck", particle_filter.cpp:206-211): out stays {0}
@@ -593,7 +762,7 @@ __device__ void run_tail(const TailJob &J) {
   tail_finish<Team>(J, TAIL_OK, total, w_diff, g);
 }
 
-__global__ void __launch_bounds__(kTailThreads) tail_grid_kernel(const __grid_constant__ TailJob job) {
+__global__ void __launch_bounds__(kTailThreads, 1) tail_grid_kernel(const __grid_constant__ TailJob job) {
   run_tail<GridTeam>(job);
 }
 __global__ void __launch_bounds__(kTailThreads) tail_batch_kernel(const TailJob *__restrict__ jobs) {
@@ -610,19 +779,19 @@ __global__ void __launch_bounds__(kTailThreads) tail_batch_kernel(const TailJob 
 
 extern "C" {
 
-// Measurement hook: %globaltimer stamps (ns, relative to the kernel's start) of
-// the phase boundaries of the last fused tail this filter completed, in the
-// order of qmcl_tail_phase_name.  0 = phase not run.
-qmcl_status qmcl_filter_tail_profile(qmcl_filter *f, uint64_t out[16], uint64_t *fallbacks) {
+// Measurement hook: device time of every phase of the fused tail (ns, from
+// %globaltimer stamps taken by block 0 at the phase boundaries), summed over the
+// *calls fused calls this filter has completed since the last reset.
+qmcl_status qmcl_filter_tail_profile(qmcl_filter *f, uint64_t out[16], uint64_t *calls,
+                                     uint64_t *fallbacks, int reset) {
   if (!f || !out) return QMCL_ERR_INVALID_ARG;
   QMCL_TRY(qmcl::settle(f));
-  for (int k = 0; k < 16; ++k) out[k] = 0;
+  for (int k = 0; k < 16; ++k) out[k] = f->tail_phase_ns[k];
+  if (calls) *calls = f->tail_phase_calls;
   if (fallbacks) *fallbacks = f->tail_fallbacks;
-  if (!f->h_tail || f->h_tail->serial != f->tail_serial) return QMCL_OK;
-  const unsigned long long t0 = f->h_tail->stamps[qmcl::TS_START];
-  for (int k = 1; k < qmcl::kTailStamps; ++k) {
-    const unsigned long long t = f->h_tail->stamps[k];
-    out[k] = (t > t0) ? t - t0 : 0;
+  if (reset) {
+    for (int k = 0; k < 16; ++k) f->tail_phase_ns[k] = 0;
+    f->tail_phase_calls = 0;
   }
   return QMCL_OK;
 }
@@ -651,7 +820,7 @@ int tail_blocks_per_sm() {
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tail_grid_kernel, kTailThreads, 0) != cudaSuccess)
     occ = 0;
-  int want = 2;
+  int want = 1;  // A/B at C2: one or two blocks per SM time the same; one leaves every register to the block
   if (const char *e = std::getenv("QMCL_TAIL_BLOCKS_PER_SM")) want = std::atoi(e);
   cached = std::max(0, std::min(occ, want));
   return cached;
@@ -677,7 +846,7 @@ void map_bin_bounds(const qmcl_filter *f, int out[6]) {
 }  // namespace
 
 bool tail_enabled(const qmcl_filter *f) {
-  return lazy(f) && f->use_tail && f->timer.level < 2 && f->prefix_mode == 0 && tail_blocks_per_sm() > 0;
+  return lazy(f) && f->use_tail && f->timer.level < 2 && f->prefix_mode != 1 && tail_blocks_per_sm() > 0;
 }
 
 bool tail_eligible(const qmcl_filter *f, int mode) {
@@ -694,6 +863,7 @@ bool tail_eligible(const qmcl_filter *f, int mode) {
 
 qmcl_status launch_tail(qmcl_filter *f, int mode) {
   cudaStream_t s = f->map->stream;
+  QMCL_TRY(flush_motion(f));  // a motion no sensor update consumed
   ParticleSet &in = f->cur();
   const bool resample = mode != TAIL_CLUSTER;
   ParticleSet &out = f->sets[(f->current + 1) % 2];
@@ -733,10 +903,11 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
   QMCL_TRY(f->bin_cluster.ensure(bins_cap));
   QMCL_TRY(f->tail_cluster_w.ensure(bins_cap));
   QMCL_TRY(f->particle_cid.ensure(n_any + 1));
-  QMCL_TRY(f->tail_dev.ensure(1));
+  QMCL_TRY(f->tail_dev.ensure_zero(1));  // the barrier counter starts at zero
   if (!f->h_tail) QMCL_CUDA(cudaMallocHost(reinterpret_cast<void **>(&f->h_tail), sizeof(TailResult)));
   QMCL_TRY(plan_prefix_buffers(f, n_in, &J.pb, &J.nc, &J.nt));
-  const size_t tiles = (std::max(std::max(n_any, table_cap), bins_cap) + kScanTile - 1) / kScanTile + 1;
+  // tiles of the compactions: as small as one item per thread
+  const size_t tiles = (std::max(std::max(n_any, table_cap), bins_cap) + kScanBlock - 1) / kScanBlock + 1;
   size_t off = 0;
   auto carve = [&](size_t bytes) {
     const size_t at = off;
@@ -763,6 +934,16 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
   J.n_in = n_in;
   J.n_min = n_min;
   J.n_max = n_max;
+  J.kld_probe = f->kld_probe;
+  {
+    static long solo = -1;  // QMCL_TAIL_SOLO_CELLS: A/B knob, 0 = always the team-wide labelling
+    if (solo < 0) {
+      const char *e = std::getenv("QMCL_TAIL_SOLO_CELLS");
+      solo = e ? std::min<long>(std::atol(e), static_cast<long>(kSoloCells)) : static_cast<long>(kSoloCells);
+      if (solo < 0) solo = 0;
+    }
+    J.solo_cells = static_cast<unsigned long long>(solo);
+  }
   J.kp.res_xy = f->params.res_xy;
   J.kp.res_t = f->params.res_theta;
   J.kp.eps2 = 2 * f->params.kld_epsilon;  // space_partitioning.cpp:31
@@ -847,6 +1028,17 @@ qmcl_status tail_complete(qmcl_filter *f) {
   }
   const int mode = f->tail_mode;
   const bool resample = mode != TAIL_CLUSTER;
+  {  // phase durations, accumulated for qmcl_filter_tail_profile
+    unsigned long long prev = r.stamps[TS_START];
+    for (int k = 1; k < kTailStamps; ++k) {
+      const unsigned long long t = r.stamps[k];
+      if (t >= prev && t != 0) {
+        f->tail_phase_ns[k] += t - prev;
+        prev = t;
+      }
+    }
+    f->tail_phase_calls++;
+  }
   if (r.status == TAIL_FALLBACK || r.status == TAIL_FALLBACK_NORMALISED) {
     if (resample) {  // undo launch_tail's bookkeeping; the multi-launch path redoes it
       f->current = f->tail_prev_current;
@@ -868,6 +1060,12 @@ qmcl_status tail_complete(qmcl_filter *f) {
   if (resample) {
     cur.n = static_cast<size_t>(r.n_out);
     f->n_src_index = cur.n;
+    if (mode == TAIL_KLD) {
+      // next time, look at twice as many candidates as this stop needed (a power of two)
+      size_t probe = 4096;
+      while (probe < 2 * cur.n) probe *= 2;
+      f->kld_probe = probe;
+    }
     f->global_first = 0;
     f->global_n = cur.n;
     if ((mode == TAIL_ADAPTIVE || mode == TAIL_KLD) && r.status == TAIL_OK && r.w_diff > 0.0) {

@@ -60,6 +60,7 @@ struct TailResult {
 
 // Device-side scalars the phases hand to each other.
 struct TailDev {
+  unsigned long long barrier;     // grid barrier: arrivals so far (never reset)
   unsigned long long stop;        // KLD stop word {m:32, k:32}
   unsigned long long n_new;       // KLD new-bin flags over all candidates
   unsigned long long n_out;
@@ -85,6 +86,8 @@ struct TailJob {
   double *ow;
   unsigned long long n_in;
   unsigned long long n_min, n_max;  // particle_count_min / max
+  unsigned long long kld_probe;     // KLD: candidates examined in the first round (0 = all)
+  unsigned long long solo_cells;    // grids up to this many cells are listed and labelled by block 0 alone
   KldParams kp;
   BinParams bp;
   MapGeom geom;

@@ -28,11 +28,15 @@ def seq_cumsum(w, carry=0.0):
 
 def check(filt, w, carry=0.0, oracle=True):
     w = np.ascontiguousarray(w, np.float64)
-    filt.set_prefix_mode(0)
+    filt.set_prefix_mode(0)          # parallel, binade-crossing chunks by literal additions
     got, co = filt.debug_prefix(w, carry)
-    filt.set_prefix_mode(1)
+    filt.set_prefix_mode(2)          # parallel, binade-crossing chunks resolved lane-wise
+    got2, co2 = filt.debug_prefix(w, carry)
+    filt.set_prefix_mode(1)          # the literal one-warp loop
     seq, co_seq = filt.debug_prefix(w, carry)
     filt.set_prefix_mode(0)
+    assert np.array_equal(got2.view(np.uint64), seq.view(np.uint64)), "mode 2 != sequential"
+    assert np.float64(co2).view(np.uint64) == np.float64(co_seq).view(np.uint64)
     assert np.array_equal(got.view(np.uint64), seq.view(np.uint64)), \
         f"parallel != one-warp sequential at {np.flatnonzero(got.view(np.uint64) != seq.view(np.uint64))[:5]}"
     assert np.float64(co).view(np.uint64) == np.float64(co_seq).view(np.uint64)
