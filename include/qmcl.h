@@ -281,6 +281,28 @@ qmcl_status qmcl_batch_update(qmcl_filter *const *filters, size_t n_filters, int
                               const size_t *n_points, int resample, double *poses_out,
                               double *covs_out, int *valid_out);
 
+/* The same cycle for n filters that live on ONE map handle, in four launches
+ * for the whole batch (motion + beam selection, sensor model, and the fused
+ * tail with one block per filter) and one host wait.  The batch owns its
+ * filters (seeds seed, seed + 1, ...); qmcl_batch_filter lends filter i for the
+ * per-filter calls (initialise, set_particles, getters).  clouds_xy holds the
+ * scans back to back, robot i's points at [cloud_offsets[i], cloud_offsets[i+1])
+ * (offsets in points, n + 1 entries).  Falls back to a per-filter loop on the
+ * same stream when a filter cannot take the fused path (sets above 65536
+ * particles, eager sync mode, stage timing). */
+typedef struct qmcl_batch qmcl_batch;
+qmcl_status qmcl_batch_create(qmcl_map *map, size_t n_filters, uint64_t seed, qmcl_batch **out);
+qmcl_status qmcl_batch_destroy(qmcl_batch *batch);
+qmcl_status qmcl_batch_size(const qmcl_batch *batch, size_t *out);
+qmcl_status qmcl_batch_filter(qmcl_batch *batch, size_t i, qmcl_filter **out);
+qmcl_status qmcl_batch_set_params(qmcl_batch *batch, const qmcl_pf_params *p);
+qmcl_status qmcl_batch_cycle(qmcl_batch *batch, const double *odom_new, const double *odom_old,
+                             const float alpha[4], const float *clouds_xy,
+                             const size_t *cloud_offsets, int resample, double *poses_out,
+                             double *covs_out, int *valid_out);
+/* Cycles that ran fused / as a per-filter loop so far. */
+qmcl_status qmcl_batch_stats(const qmcl_batch *batch, uint64_t *fused_cycles, uint64_t *looped_cycles);
+
 /* ---- test hooks (not part of the reference interface) ---- */
 qmcl_status qmcl_filter_set_particles(qmcl_filter *f, const qmcl_particle *p, size_t n);
 /* Sharded variant: p[0..n) is this rank's block, starting at global index

@@ -113,6 +113,14 @@ SIGNATURES = {
                                    C.POINTER(C.c_size_t), C.POINTER(C.c_double)],
     "qmcl_batch_update": [C.POINTER(vp), sz, C.c_int, pf64, pf64, pf32, C.POINTER(pf32),
                           C.POINTER(sz), C.c_int, pf64, pf64, C.POINTER(C.c_int)],
+    "qmcl_batch_create": [vp, sz, u64, C.POINTER(vp)],
+    "qmcl_batch_destroy": [vp],
+    "qmcl_batch_size": [vp, C.POINTER(sz)],
+    "qmcl_batch_filter": [vp, sz, C.POINTER(vp)],
+    "qmcl_batch_set_params": [vp, C.POINTER(PFParams)],
+    "qmcl_batch_cycle": [vp, pf64, pf64, pf32, pf32, C.POINTER(sz), C.c_int, pf64, pf64,
+                         C.POINTER(C.c_int)],
+    "qmcl_batch_stats": [vp, C.POINTER(u64), C.POINTER(u64)],
     "qmcl_filter_set_prefix_mode": [vp, C.c_int],
     "qmcl_filter_debug_prefix": [vp, pf64, sz, f64, pf64, pf64],
     "qmcl_filter_set_timing": [vp, C.c_int],

@@ -224,9 +224,21 @@ class ParticleFilter:
         self._h = h
         self.parameters = ParticleFilterParameters()
 
+    @classmethod
+    def _borrowed(cls, map_, handle):
+        """A view of a filter owned by someone else (a qmcl_batch): never destroyed from here."""
+        self = cls.__new__(cls)
+        self._L = _abi.lib()
+        self.map = map_
+        self._h = handle
+        self._owned = False
+        self.parameters = ParticleFilterParameters()
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            self._L.qmcl_filter_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._L.qmcl_filter_destroy(self._h)
             self._h = None
 
     def __del__(self):

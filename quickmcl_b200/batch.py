@@ -21,7 +21,7 @@ import torch
 
 from . import _abi
 from ._abi import check, ptr
-from .api import (LikelihoodMapParameters, OccupancyGrid, ParticleFilterParameters,
+from .api import (LikelihoodMapParameters, OccupancyGrid, ParticleFilter, ParticleFilterParameters,
                   create_likelihood_map, create_particle_filter)
 
 
@@ -108,3 +108,76 @@ class FilterBatch:
                 f.cluster()
             return f.get_estimated_pose()
         return self.for_each(one)
+
+
+class FusedBatch:
+    """qmcl_batch: n independent filters on ONE map handle whose scan cycle
+    (laser_handler.cpp:243-276 per robot) runs as four launches for the whole batch —
+    deferred motion + beam selection, sensor model, and the fused tail with one block per
+    filter (csrc/tail.cu) — and one host wait.  `filters[i]` is filter i for the per-filter
+    calls (initialise, set_particles, getters)."""
+
+    def __init__(self, n_filters, grid: OccupancyGrid, map_parameters: LikelihoodMapParameters,
+                 filter_parameters: ParticleFilterParameters, seed=0, device=None, stream=None):
+        self._L = _abi.lib()
+        self.n = int(n_filters)
+        self.device = torch.cuda.current_device() if device is None else device
+        self.map = create_likelihood_map(device=self.device)
+        if stream is not None:
+            self.map.set_stream(stream)
+        self.map.set_parameters(map_parameters)
+        self.map.new_map(grid)
+        h = C.c_void_p()
+        check(self._L.qmcl_batch_create(self.map._h, self.n, seed, C.byref(h)), "qmcl_batch_create")
+        self._h = h
+        self.filters = []
+        for i in range(self.n):
+            fh = C.c_void_p()
+            check(self._L.qmcl_batch_filter(self._h, i, C.byref(fh)), "qmcl_batch_filter")
+            f = ParticleFilter._borrowed(self.map, fh)
+            f.set_parameters(filter_parameters)
+            self.filters.append(f)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for f in self.filters:
+                f.close()
+            self._L.qmcl_batch_destroy(self._h)
+            self._h = None
+            self.map.close()
+
+    def __del__(self):
+        self.close()
+
+    def cycle(self, odom_new, odom_old, alpha, scans, resample=True):
+        """One scan cycle for every robot.  odom_*: [n, 3]; scans: list of float32 [B_i, 2].
+        Returns [(ok, pose, covariance)] per robot."""
+        n = self.n
+        a = np.ascontiguousarray(odom_new, np.float64).reshape(n, 3)
+        b = np.ascontiguousarray(odom_old, np.float64).reshape(n, 3)
+        al = np.asarray(alpha, np.float32)
+        offs = np.zeros(n + 1, np.uint64)
+        offs[1:] = np.cumsum([len(s) for s in scans])
+        packed = np.ascontiguousarray(np.concatenate([np.asarray(s, np.float32).reshape(-1, 2)
+                                                      for s in scans]), np.float32)
+        return self.cycle_packed(a, b, al, packed, offs, resample)
+
+    def cycle_packed(self, odom_new, odom_old, alpha, packed, offsets, resample=True):
+        """The same with the scans already packed back to back (packed: [sum B_i, 2] float32,
+        offsets: [n + 1] uint64 in points)."""
+        n = self.n
+        poses = np.zeros((n, 3))
+        covs = np.zeros((n, 9))
+        valid = np.zeros(n, np.int32)
+        check(self._L.qmcl_batch_cycle(self._h, ptr(odom_new, C.c_double), ptr(odom_old, C.c_double),
+                                       ptr(alpha, C.c_float), ptr(packed, C.c_float),
+                                       offsets.ctypes.data_as(C.POINTER(C.c_size_t)), int(resample),
+                                       ptr(poses, C.c_double), ptr(covs, C.c_double),
+                                       ptr(valid, C.c_int32)), "qmcl_batch_cycle")
+        return [(bool(valid[i]), poses[i], covs[i].reshape(3, 3)) for i in range(n)]
+
+    def stats(self):
+        """(cycles that ran fused, cycles that ran as a per-filter loop)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(self._L.qmcl_batch_stats(self._h, C.byref(a), C.byref(b)), "qmcl_batch_stats")
+        return a.value, b.value

@@ -7,7 +7,7 @@
 #include "filter.cuh"
 #include "cluster.cuh"
 #include "cluster_dev.cuh"
-#include "motion_dev.cuh"
+#include "front.cuh"
 #include "sensor.cuh"
 #include "shard.cuh"
 #include "scan.cuh"
@@ -251,30 +251,13 @@ static qmcl_status staging_free(qmcl_filter *f) {
 //                block to finish folds them into bbox[6] for the tail.
 // Replaces motion_kernel + bbox_init_kernel + bin_bbox_kernel + a memset +
 // subsample_kernel (five stream operations) by one.
-struct FrontJob {
-  const float2 *cloud;
-  size_t n_points, step;
-  float2 *beams;
-  int n_used;
-  unsigned *rmax;
-  float *x, *y, *t;
-  size_t n, global_first;
-  int do_motion;
-  MotionParams mp;
-  uint64_t seed;
-  uint32_t rng_step;
-  BinParams bp;
-  int *block_bbox;  // [gridDim.x - 1][6]
-  int *bbox;        // [6]
-  unsigned int *blocks_done;
-};
-
-__global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ FrontJob J) {
+// Block `bx` of the 1 + nb blocks working on job J.
+__device__ __forceinline__ void front_body(const FrontJob &J, const unsigned bx, const unsigned nb) {
   __shared__ float s_len[8];
   __shared__ int s_mn[8][3], s_mx[8][3];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (blockIdx.x == 0) {
+  if (bx == 0) {
     float len = 0.f;
     for (int j = threadIdx.x; j < J.n_used; j += 256) {
       float2 p = J.cloud[static_cast<size_t>(j) * J.step];
@@ -294,7 +277,7 @@ __global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ Fron
     }
     return;
   }
-  const unsigned nb = gridDim.x - 1, b = blockIdx.x - 1;
+  const unsigned b = bx - 1;
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (size_t i = static_cast<size_t>(b) * 256 + threadIdx.x; i < J.n; i += static_cast<size_t>(nb) * 256) {
     float px = J.x[i], py = J.y[i], pt = J.t[i];
@@ -358,7 +341,25 @@ __global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ Fron
   if (threadIdx.x == 0) *J.blocks_done = 0;
 }
 
-static qmcl_status launch_front(qmcl_filter *f, const float *dev_cloud_xy, size_t n_points, int *n_used_out) {
+__global__ void __launch_bounds__(256) front_kernel(const __grid_constant__ FrontJob J) {
+  front_body(J, blockIdx.x, gridDim.x - 1);
+}
+// Many filters in one launch: blockIdx.y selects the job.
+__global__ void __launch_bounds__(256) front_batch_kernel(const FrontJob *__restrict__ jobs) {
+  __shared__ FrontJob s_job;
+  for (unsigned k = threadIdx.x; k < sizeof(FrontJob) / 8; k += blockDim.x)
+    reinterpret_cast<uint64_t *>(&s_job)[k] = reinterpret_cast<const uint64_t *>(jobs + blockIdx.y)[k];
+  __syncthreads();
+  const unsigned nb = static_cast<unsigned>(min(static_cast<size_t>((s_job.n + 255) / 256),
+                                                static_cast<size_t>(4 * kSMs)));
+  if (blockIdx.x > nb) return;
+  front_body(s_job, blockIdx.x, nb);
+}
+
+// Fills the front job of filter f for the cloud at dev_cloud_xy and does the
+// host-side bookkeeping of its launch (the caller launches it, alone or in a batch).
+qmcl_status front_prepare(qmcl_filter *f, const float *dev_cloud_xy, size_t n_points, FrontJob *Jp,
+                          int *n_used_out) {
   qmcl_map *m = f->map;
   ParticleSet &ps = f->cur();
   // map_likelihood.cpp:67-74
@@ -367,9 +368,9 @@ static qmcl_status launch_front(qmcl_filter *f, const float *dev_cloud_xy, size_
   if (step < 1) step = 1;
   const size_t n_used = n_points ? (n_points + step - 1) / step : 0;
   *n_used_out = static_cast<int>(n_used);
-  const unsigned nb = static_cast<unsigned>(std::min<size_t>(div_up(ps.n, 256), 4 * kSMs));
   QMCL_TRY(f->bbox.ensure(8 + 6 * static_cast<size_t>(4 * kSMs)));
-  FrontJob J;
+  FrontJob &J = *Jp;
+  std::memset(&J, 0, sizeof(J));
   J.cloud = reinterpret_cast<const float2 *>(dev_cloud_xy);
   J.n_points = n_points;
   J.step = step;
@@ -392,11 +393,50 @@ static qmcl_status launch_front(qmcl_filter *f, const float *dev_cloud_xy, size_
   J.block_bbox = f->bbox.ptr + 8;
   J.bbox = f->bbox.ptr;
   J.blocks_done = &f->scalars.ptr->blocks_done;
-  StageScope sc(f, QMCL_STAGE_MOTION);
-  front_kernel<<<nb + 1, 256, 0, m->stream>>>(J);
-  QMCL_LAUNCHED();
   f->motion_pending = false;
   f->early_bbox_version = f->pose_version;
+  return QMCL_OK;
+}
+
+unsigned front_blocks(size_t n_particles) {
+  return static_cast<unsigned>(std::min<size_t>(div_up(n_particles, 256), 4 * kSMs));
+}
+
+static qmcl_status launch_front(qmcl_filter *f, const float *dev_cloud_xy, size_t n_points, int *n_used_out) {
+  FrontJob J;
+  QMCL_TRY(front_prepare(f, dev_cloud_xy, n_points, &J, n_used_out));
+  StageScope sc(f, QMCL_STAGE_MOTION, 1);
+  front_kernel<<<front_blocks(J.n) + 1, 256, 0, f->map->stream>>>(J);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+qmcl_status launch_front_batch(qmcl_map *m, const FrontJob *dev_jobs, unsigned n_jobs, size_t max_particles) {
+  if (!n_jobs) return QMCL_OK;
+  front_batch_kernel<<<dim3(front_blocks(max_particles) + 1, n_jobs), 256, 0, m->stream>>>(dev_jobs);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// The sensor job of filter f after front_prepare (fused path only): K7's
+// arguments, and the bookkeeping of a launch whose K8 is left to the tail.
+qmcl_status sensor_prepare_deferred(qmcl_filter *f, int n_used, size_t n_points, SensorLaunch *a) {
+  ParticleSet &ps = f->cur();
+  QMCL_TRY(f->partials.ensure(sensor_grid(ps.n) + 1));
+  a->x = ps.x.ptr;
+  a->y = ps.y.ptr;
+  a->t = ps.t.ptr;
+  a->w = ps.w.ptr;
+  a->n = ps.n;
+  a->beams = f->beams.ptr;
+  a->n_beams = n_used;
+  a->rmax = f->beams.ptr + 2 * n_points;
+  a->partials = f->partials.ptr;
+  a->scalars = f->scalars.ptr;
+  f->clusters_valid = false;
+  f->est_cached = false;
+  f->normalise_pending = true;
+  f->normalise_n = ps.n;
   return QMCL_OK;
 }
 

@@ -11,10 +11,10 @@ namespace qmcl {
 // (key_t = running sum before positive particle t): the record with the
 // largest key <= r; among records sharing a key the first inserted wins
 // (std::map::insert keeps the existing entry, particle.cpp:77).
-__device__ __forceinline__ size_t running_sum_lookup(const double *incl, size_t P,
-                                                     double r) {
+// lo/hi: a window [lo, hi] known to contain t* (the whole list: 0, P - 1).
+__device__ __forceinline__ size_t running_sum_lookup_in(const double *incl, size_t P, double r, size_t lo,
+                                                        size_t hi) {
   // t* = number of t in [1, P) with key_t = incl[t-1] <= r
-  size_t lo = 0, hi = P - 1;
   while (lo < hi) {
     const size_t mid = (lo + hi) >> 1;
     if (incl[mid] <= r) lo = mid + 1;
@@ -35,6 +35,29 @@ __device__ __forceinline__ size_t running_sum_lookup(const double *incl, size_t 
     else hi = mid;
   }
   return lo + 1;
+}
+__device__ __forceinline__ size_t running_sum_lookup(const double *incl, size_t P, double r) {
+  return running_sum_lookup_in(incl, P, r, 0, P - 1);
+}
+// The same with the first levels of the search served from shared memory:
+// samp[j] = incl[j * stride] for j < n_samp, j * stride < P - 1 (every stride-th
+// key).  Narrows the window to one stride, then searches incl itself: the same
+// t* (incl is non-decreasing), with log2(stride) dependent global loads instead
+// of log2(P).
+__device__ __forceinline__ size_t running_sum_lookup_sampled(const double *incl, size_t P, double r,
+                                                             const double *samp, size_t n_samp,
+                                                             size_t stride) {
+  size_t a = 0, b = n_samp;  // J = number of samples <= r
+  while (a < b) {
+    const size_t mid = (a + b) >> 1;
+    if (samp[mid] <= r) a = mid + 1;
+    else b = mid;
+  }
+  if (a == 0) return running_sum_lookup_in(incl, P, r, 0, 0);  // incl[0] > r (or no samples): t* = 0
+  const size_t lo = (a - 1) * stride + 1;
+  size_t hi = a * stride;
+  if (hi > P - 1) hi = P - 1;
+  return running_sum_lookup_in(incl, P, r, lo, hi);
 }
 
 struct KldParams {

@@ -251,17 +251,19 @@ __device__ __forceinline__ const uint8_t *byte_at(const uint8_t *base, unsigned 
 #endif
 }
 
+// The kernel body for block `bx` of the `nbx` blocks working on job `a` (one
+// filter's particle set).  sensor_kernel runs it for a single filter,
+// sensor_batch_kernel for many filters in one launch (blockIdx.y = filter).
 template <int PATH, int DIV>
-__global__ void __launch_bounds__(kSensorThreads,
-                                  (PATH == PATH_PAL32 || PATH == PATH_PAL8) ? QMCL_SENSOR_MINBLOCKS : 4)
-sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a) {
+__device__ __forceinline__ void sensor_body(const int8_t *__restrict__ state, const SensorParams &sp,
+                                            const SensorLaunch &a, const unsigned bx, const unsigned nbx) {
   extern __shared__ double s_lut[];  // PAL64: n_codes + 1 doubles; PAL32: floats
   float *s_lut_f32 = reinterpret_cast<float *>(s_lut);
   constexpr bool PALETTE = PATH != PATH_FIELD;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const size_t first =
-      (static_cast<size_t>(blockIdx.x) * kSensorWarps + warp_in_block) * kP;
+      (static_cast<size_t>(bx) * kSensorWarps + warp_in_block) * kP;
 
   // table: [0, n_codes) codes, n_codes = outside the map, n_codes+1 = 0
   if (PATH == PATH_PAL64) {
@@ -395,7 +397,7 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
       } else if (PALETTE) {
         code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry
 #if QMCL_DIAG == 2 || QMCL_DIAG == 3
-        if (inside) code_cur[p] = __ldg(sp.code + ((cell & 1u) + 2u * lane + 64u * p + 4096u * (blockIdx.x & 255)));
+        if (inside) code_cur[p] = __ldg(sp.code + ((cell & 1u) + 2u * lane + 64u * p + 4096u * (bx & 255)));
 #elif QMCL_DIAG == 4
         if (inside) code_cur[p] = (cell & 0x3ffu) << 2;
 #else
@@ -528,17 +530,17 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     double t = 0.0;
 #pragma unroll
     for (int i = 0; i < kSensorWarps; ++i) t = __dadd_rn(t, s_warp[i]);
-    a.partials[blockIdx.x] = t;
+    a.partials[bx] = t;
     __threadfence();
     const unsigned done = atomicAdd(&a.scalars->blocks_done, 1u);
-    s_last = (done == gridDim.x - 1);
+    s_last = (done == nbx - 1);
   }
   __syncthreads();
   if (!s_last) return;
   // Last block: deterministic reduction of the block partials.
   __threadfence();
   double t = 0.0;
-  for (unsigned i = threadIdx.x; i < gridDim.x; i += kSensorThreads)
+  for (unsigned i = threadIdx.x; i < nbx; i += kSensorThreads)
     t = __dadd_rn(t, __ldcg(a.partials + i));
   t = warp_sum_xor(t);
   __syncthreads();
@@ -551,6 +553,31 @@ sensor_kernel(const int8_t *__restrict__ state, SensorParams sp, SensorLaunch a)
     a.scalars->total_weight = tot;
     a.scalars->blocks_done = 0;
   }
+}
+
+template <int PATH, int DIV>
+__global__ void __launch_bounds__(kSensorThreads,
+                                  (PATH == PATH_PAL32 || PATH == PATH_PAL8) ? QMCL_SENSOR_MINBLOCKS : 4)
+sensor_kernel(const int8_t *__restrict__ state, const __grid_constant__ SensorParams sp,
+              const __grid_constant__ SensorLaunch a) {
+  sensor_body<PATH, DIV>(state, sp, a, blockIdx.x, gridDim.x);
+}
+
+// Many filters on one map in one launch: blockIdx.y selects the job, whose
+// particle set may need fewer blocks than the grid is wide.
+template <int PATH, int DIV>
+__global__ void __launch_bounds__(kSensorThreads,
+                                  (PATH == PATH_PAL32 || PATH == PATH_PAL8) ? QMCL_SENSOR_MINBLOCKS : 4)
+sensor_batch_kernel(const int8_t *__restrict__ state, const __grid_constant__ SensorParams sp,
+                    const SensorLaunch *__restrict__ jobs) {
+  __shared__ SensorLaunch s_a;
+  if (threadIdx.x < sizeof(SensorLaunch) / 8)
+    reinterpret_cast<uint64_t *>(&s_a)[threadIdx.x] =
+        reinterpret_cast<const uint64_t *>(jobs + blockIdx.y)[threadIdx.x];
+  __syncthreads();
+  const unsigned nbx = static_cast<unsigned>((s_a.n + kParticlesPerBlock - 1) / kParticlesPerBlock);
+  if (blockIdx.x >= nbx) return;
+  sensor_body<PATH, DIV>(state, sp, s_a, blockIdx.x, nbx);
 }
 
 qmcl_status launch_subsample(const qmcl_map *m, const float *dev_cloud_xy, size_t n_points,
@@ -680,9 +707,25 @@ qmcl_status sensor_prepare_map(qmcl_map *m) {
   return QMCL_OK;
 }
 
+// A batch launch: dev_jobs[n_jobs] (device memory), the widest job needs grid_x blocks.
+struct SensorBatch {
+  const SensorLaunch *dev_jobs = nullptr;
+  unsigned n_jobs = 0, grid_x = 0;
+};
+
 template <int PATH, int DIV>
 static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, const SensorLaunch &a,
-                                  size_t smem) {
+                                  size_t smem, const SensorBatch &batch) {
+  if (batch.dev_jobs) {
+    auto kern = sensor_batch_kernel<PATH, DIV>;
+    if (smem > 48 * 1024)
+      QMCL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    kern<<<dim3(batch.grid_x, batch.n_jobs), kSensorThreads, smem, m->stream>>>(m->state.ptr, sp,
+                                                                                batch.dev_jobs);
+    QMCL_LAUNCHED();
+    return QMCL_OK;
+  }
   auto kern = sensor_kernel<PATH, DIV>;
   if (smem > 48 * 1024)
     QMCL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -692,8 +735,26 @@ static qmcl_status launch_variant(const qmcl_map *m, const SensorParams &sp, con
   return QMCL_OK;
 }
 
+static qmcl_status launch_sensor_impl(qmcl_map *m, const SensorLaunch &a, const SensorBatch &batch);
+
 qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
   if (a.n == 0) return QMCL_OK;
+  return launch_sensor_impl(m, a, SensorBatch{});
+}
+
+// K7 for n_jobs filters that share map `m` in one launch (dev_jobs in device
+// memory; max_particles = the largest particle count among them).
+qmcl_status launch_sensor_batch(qmcl_map *m, const SensorLaunch *dev_jobs, unsigned n_jobs,
+                                size_t max_particles) {
+  if (!n_jobs || !max_particles) return QMCL_OK;
+  SensorBatch b;
+  b.dev_jobs = dev_jobs;
+  b.n_jobs = n_jobs;
+  b.grid_x = sensor_grid(max_particles);
+  return launch_sensor_impl(m, SensorLaunch{}, b);
+}
+
+static qmcl_status launch_sensor_impl(qmcl_map *m, const SensorLaunch &a, const SensorBatch &batch) {
   SensorParams sp = make_params(m);
   // sensor_path: 0 auto (PAL8, else PAL32, when the map was built here), 1 FIELD, 2 PAL64,
   // 3 PAL8 (same as auto), 4 PAL32
@@ -734,23 +795,23 @@ qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a) {
         sp.pal8_lut = m->pal8_lut.ptr;
         sp.pal8_n = m->pal8_n;
         const size_t smem8 = static_cast<size_t>(m->pal8_n + 2) * sizeof(float);
-        if (div == DIV_SPLIT) return launch_variant<PATH_PAL8, DIV_SPLIT>(m, sp, a, smem8);
-        return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL8, DIV_MARKSTEIN>(m, sp, a, smem8)
-                                    : launch_variant<PATH_PAL8, DIV_IEEE>(m, sp, a, smem8);
+        if (div == DIV_SPLIT) return launch_variant<PATH_PAL8, DIV_SPLIT>(m, sp, a, smem8, batch);
+        return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL8, DIV_MARKSTEIN>(m, sp, a, smem8, batch)
+                                    : launch_variant<PATH_PAL8, DIV_IEEE>(m, sp, a, smem8, batch);
       }
     }
     if (path == PATH_PAL64) {
       const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(double);
-      return div >= DIV_MARKSTEIN ? launch_variant<PATH_PAL64, DIV_MARKSTEIN>(m, sp, a, smem)
-                                  : launch_variant<PATH_PAL64, DIV_IEEE>(m, sp, a, smem);
+      return div >= DIV_MARKSTEIN ? launch_variant<PATH_PAL64, DIV_MARKSTEIN>(m, sp, a, smem, batch)
+                                  : launch_variant<PATH_PAL64, DIV_IEEE>(m, sp, a, smem, batch);
     }
     const size_t smem = static_cast<size_t>(m->n_codes + 2) * sizeof(float);
-    if (div == DIV_SPLIT) return launch_variant<PATH_PAL32, DIV_SPLIT>(m, sp, a, smem);
-    return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL32, DIV_MARKSTEIN>(m, sp, a, smem)
-                                : launch_variant<PATH_PAL32, DIV_IEEE>(m, sp, a, smem);
+    if (div == DIV_SPLIT) return launch_variant<PATH_PAL32, DIV_SPLIT>(m, sp, a, smem, batch);
+    return div == DIV_MARKSTEIN ? launch_variant<PATH_PAL32, DIV_MARKSTEIN>(m, sp, a, smem, batch)
+                                : launch_variant<PATH_PAL32, DIV_IEEE>(m, sp, a, smem, batch);
   }
-  return div >= DIV_MARKSTEIN ? launch_variant<PATH_FIELD, DIV_MARKSTEIN>(m, sp, a, 0)
-                              : launch_variant<PATH_FIELD, DIV_IEEE>(m, sp, a, 0);
+  return div >= DIV_MARKSTEIN ? launch_variant<PATH_FIELD, DIV_MARKSTEIN>(m, sp, a, 0, batch)
+                              : launch_variant<PATH_FIELD, DIV_IEEE>(m, sp, a, 0, batch);
 }
 
 }  // namespace qmcl

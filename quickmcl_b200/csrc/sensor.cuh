@@ -23,6 +23,9 @@ unsigned sensor_grid(size_t n_particles);
 qmcl_status launch_subsample(const qmcl_map *m, const float *dev_cloud_xy, size_t n_points,
                              float *dev_beams, int *n_used_out);
 qmcl_status launch_sensor(qmcl_map *m, const SensorLaunch &a);
+// The same for n_jobs filters sharing map `m`, one launch (dev_jobs: device memory).
+qmcl_status launch_sensor_batch(qmcl_map *m, const SensorLaunch *dev_jobs, unsigned n_jobs,
+                                size_t max_particles);
 // After the map's field/geometry changed: verify the fast division, drop the LUT.
 qmcl_status sensor_prepare_map(qmcl_map *m);
 

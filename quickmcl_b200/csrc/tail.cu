@@ -25,6 +25,7 @@ namespace cg = cooperative_groups;
 
 namespace qmcl {
 
+constexpr size_t kLookupSamples = 1024;
 constexpr size_t kSoloCells = 2048;  // dense grids up to this size are listed and labelled by one block
 
 // ------------------------------------------------------------------ teams
@@ -506,6 +507,15 @@ __device__ void run_tail(const TailJob &J) {
       // stop test at m depend on draws <= m only, so the outcome is the same.
       const size_t n_draws = static_cast<size_t>(J.mode == TAIL_KLD ? J.n_max : J.n_min);
       const size_t P = static_cast<size_t>(D->n_records);
+      // every 2^k-th key of the record list in shared memory: the first ten levels of each search
+      __shared__ double s_samp[kLookupSamples];
+      size_t samp_stride = 1, n_samp = 0;
+      if (P > 1) {
+        samp_stride = (P - 1 + kLookupSamples - 1) / kLookupSamples;
+        n_samp = (P - 1 + samp_stride - 1) / samp_stride;
+        for (size_t j = tid; j < n_samp; j += kTailThreads) s_samp[j] = J.incl[j * samp_stride];
+      }
+      __syncthreads();
       size_t done = 0;
       size_t round_end = n_draws;
       if (J.mode == TAIL_KLD && J.kld_probe > 0 && J.kld_probe < n_draws) round_end = static_cast<size_t>(J.kld_probe);
@@ -528,7 +538,8 @@ __device__ void run_tail(const TailJob &J) {
               w = 0.0;  // no influence on the estimate until the next update
               sidx = -1;
             } else {
-              sidx = J.pos[running_sum_lookup(J.incl, P, uniform53(rr4[2], rr4[3]))];
+              sidx = J.pos[running_sum_lookup_sampled(J.incl, P, uniform53(rr4[2], rr4[3]), s_samp, n_samp,
+                                                      samp_stride)];
               x = J.ix[sidx];
               y = J.iy[sidx];
               t = J.it[sidx];
@@ -861,8 +872,10 @@ bool tail_eligible(const qmcl_filter *f, int mode) {
   return true;
 }
 
-qmcl_status launch_tail(qmcl_filter *f, int mode) {
-  cudaStream_t s = f->map->stream;
+// Fills the tail job of filter f (buffers sized, every pointer set) and does the
+// host-side bookkeeping of its launch: the caller launches it — tail_grid_kernel
+// for one filter, tail_batch_kernel for many — right after.
+qmcl_status tail_prepare(qmcl_filter *f, int mode, TailJob *Jp) {
   QMCL_TRY(flush_motion(f));  // a motion no sensor update consumed
   ParticleSet &in = f->cur();
   const bool resample = mode != TAIL_CLUSTER;
@@ -873,7 +886,7 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
   const size_t n_draws = mode == TAIL_KLD ? n_max : (mode == TAIL_ADAPTIVE ? n_min : n_in);
   const size_t n_any = std::max(n_in, n_draws);
 
-  TailJob J;
+  TailJob &J = *Jp;
   std::memset(&J, 0, sizeof(J));
   J.mode = mode;
   J.normalise_pending = f->normalise_pending ? 1 : 0;
@@ -983,14 +996,6 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
   J.result = f->h_tail;
   J.serial = ++f->tail_serial;
 
-  {
-    StageScope sc(f, QMCL_STAGE_TAIL, 1);
-    void *args[] = {&J};
-    const unsigned blocks = static_cast<unsigned>(kSMs * tail_blocks_per_sm());
-    QMCL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(tail_grid_kernel), dim3(blocks),
-                                          dim3(kTailThreads), args, 0, s));
-    QMCL_LAUNCHED();
-  }
   g_d2h_bytes.fetch_add(sizeof(TailResult), std::memory_order_relaxed);  // written by the kernel itself
 
   // bookkeeping of a call whose outcome the host has not seen yet
@@ -1011,6 +1016,26 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
     f->pose_version++;
     out.n = n_draws;  // an upper bound until the result arrives
   }
+  return QMCL_OK;
+}
+
+qmcl_status launch_tail(qmcl_filter *f, int mode) {
+  TailJob J;
+  QMCL_TRY(tail_prepare(f, mode, &J));
+  StageScope sc(f, QMCL_STAGE_TAIL, 1);
+  void *args[] = {&J};
+  const unsigned blocks = static_cast<unsigned>(kSMs * tail_blocks_per_sm());
+  QMCL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(tail_grid_kernel), dim3(blocks),
+                                        dim3(kTailThreads), args, 0, f->map->stream));
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// One block per job: the batch form (jobs in device memory).
+qmcl_status launch_tail_batch(qmcl_map *m, const TailJob *dev_jobs, unsigned n_jobs) {
+  if (!n_jobs) return QMCL_OK;
+  tail_batch_kernel<<<n_jobs, kTailThreads, 0, m->stream>>>(dev_jobs);
+  QMCL_LAUNCHED();
   return QMCL_OK;
 }
 

@@ -123,6 +123,11 @@ struct TailJob {
   unsigned long long serial;
 };
 
+// Host side (tail.cu): fill / launch.  tail_prepare does the bookkeeping of a
+// launch, so the kernel must follow on the filter's stream.
+qmcl_status tail_prepare(qmcl_filter *f, int mode, TailJob *J);
+qmcl_status launch_tail_batch(qmcl_map *m, const TailJob *dev_jobs, unsigned n_jobs);
+
 constexpr unsigned kTailThreads = 256;
 // doubles `partials` must hold
 constexpr size_t kTailPartials = 4 * 148 + static_cast<size_t>(4 * 148) * 2 * kMom;
