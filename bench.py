@@ -284,6 +284,7 @@ def run_reference(args, wl):
         "config": workload_config(args, wl, len(scan)),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port",
                          "sample": sample, "cpu": cpu_model(), "host_cores": os.cpu_count(),
+                         "field": "brushfire (the reference's own field build)",
                          "stage_ms": {k: v * 1e3 for k, v in stages.items()},
                          "note": "CPU restatement of the reference (oracle/); the reference is "
                                  "single-threaded (main.cpp:90) and cannot be built here",
@@ -302,14 +303,234 @@ def workload_config(args, wl, n_used_beams):
             "beams_hit": n_used_beams, "num_beams": 0,
             "resample": RESAMPLE_NAMES[wl["pf"]["resample_type"]],
             "step": "handle_odometry+update_sensor+resample_and_cluster+get_estimate",
-            "l2": "flushed between steps (256 MiB write); per-step CUDA-event pairs summed",
+            "l2": "flushed between steps (256 MiB write); one CUDA-event pair per step, summed "
+                  "(median and p95 alongside)",
             "host_waits": ("per value (QMCL_EAGER_SYNC)" if os.environ.get("QMCL_EAGER_SYNC", "0") not in ("", "0")
-                           else "deferred read-backs (qmcl_filter_set_sync_mode default)"),
+                           else ("one: the estimate (fused front + sensor + tail launches)" if args.gpus == 1
+                                 else "deferred read-backs (qmcl_filter_set_sync_mode default)")),
             "sharding": (f"particles, contiguous global-index blocks; exchanges via {args.transport}"
                          if args.gpus > 1 else "none")}
 
 
 # ------------------------------------------------------------------ GPU arm
+class Harness:
+    """One workload on one filter (single GPU or one shard of a sharded filter): builds the
+    map and the filter, and times update steps with CUDA events on the filter's stream."""
+
+    def __init__(self, q, torch, wl_name, device, stream, dist=None, transport="nccl", sharded=False):
+        self.q, self.torch, self.name, self.dist = q, torch, wl_name, dist
+        self.wl = wl = WORKLOADS[wl_name]
+        self.stream = stream
+        self.inputs = make_inputs(wl)
+        occ, res, origin, pose, scan, (x, y, t) = self.inputs
+        self.scan = scan
+        self.n = wl["particles"]
+        self.gm = q.create_likelihood_map(device=device)
+        self.gm.set_stream(stream.cuda_stream)
+        self.gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)))
+        self.gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+        pfp = q.ParticleFilterParameters(**wl["pf"])
+        pfp.resample_type = q.ResampleType(wl["pf"]["resample_type"])
+        if sharded:
+            from quickmcl_b200.sharded import ShardedParticleFilter
+            self.f = ShardedParticleFilter(self.gm, seed=3, group=dist.group.WORLD, transport=transport)
+        else:
+            self.f = q.create_particle_filter(self.gm, seed=3)
+        self.sharded = sharded
+        self.f.set_parameters(pfp)
+        self.init = q.make_particles(x, y, t, np.full(self.n, 1.0 / self.n))
+        self.d_scan = torch.from_numpy(scan).cuda()
+        self.h_scan = torch.from_numpy(scan).pin_memory().numpy()
+        self.evals = self.n * len(scan)
+
+    def close(self):
+        self.f.close()
+        self.gm.close()
+
+    def reset(self, it, flush):
+        self.f.set_particles(self.init)   # untimed: same initial cloud for every step
+        self.f.set_rng(3, 10 + it)
+        if flush is not None:
+            flush.zero_()                 # evict the map from L2
+
+    def step(self, host):
+        f = self.f
+        f.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
+        if host:
+            f.update_importance_from_observations(self.h_scan)
+        else:
+            f.update_importance_from_device_cloud(self.d_scan.data_ptr(), len(self.scan))
+        f.resample_and_cluster()
+        return f.get_estimated_pose()
+
+    def timed_loop(self, host, steps, warmup, it0, flush):
+        q, torch, f, dist = self.q, self.torch, self.f, self.dist if self.sharded else None
+        for i in range(warmup):
+            self.reset(it0 + i, flush)
+            self.step(host)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        f.set_timing(1)
+        f.get_timing(reset=True)
+        if hasattr(f, "tail_profile") and not self.sharded:
+            f.tail_profile(reset=True)
+        launches = 0
+        h2d = d2h = 0
+        per_step = []
+        est = None
+        for i in range(steps):
+            self.reset(it0 + warmup + i, flush)
+            a0, b0 = q.transfer_bytes()
+            l0 = q.kernel_launch_count()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            est = self.step(host)
+            e1.record(self.stream)
+            e1.synchronize()
+            per_step.append(e0.elapsed_time(e1))
+            launches += q.kernel_launch_count() - l0
+            a1, b1 = q.transfer_bytes()
+            h2d += a1 - a0
+            d2h += b1 - b0
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        timing = f.get_timing(reset=True)
+        f.set_timing(0)
+        prof = f.tail_profile() if hasattr(f, "tail_profile") and not self.sharded else None
+        total_ms = float(sum(per_step))
+        if dist:
+            tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_ms = float(tt.item())
+        ps = np.asarray(per_step)
+        return dict(total_ms=total_ms, steps=steps, ms_per_step=total_ms / steps, median_ms=float(np.median(ps)),
+                    p95_ms=float(np.percentile(ps, 95)), min_ms=float(ps.min()),
+                    launches=launches, timing=timing, estimate=est, tail_profile=prof,
+                    h2d=h2d / steps, d2h=d2h / steps)
+
+    def summary(self, dev, e2e, world=1):
+        """The per-workload block of the JSON line."""
+        out = {"workload": self.name, "particles": self.n, "beams_hit": len(self.scan),
+               "resample": RESAMPLE_NAMES[self.wl["pf"]["resample_type"]],
+               "ms_per_step": dev["ms_per_step"], "median_ms": dev["median_ms"], "p95_ms": dev["p95_ms"],
+               "evals_per_s": self.evals / (dev["ms_per_step"] * 1e-3),
+               "gpu_launches_per_step": dev["launches"] / dev["steps"],
+               "stage_ms": {k: ms / cnt for k, (ms, cnt) in dev["timing"].items() if cnt}}
+        if e2e:
+            out["e2e_ms_per_step"] = e2e["ms_per_step"]
+        sm, sc = dev["timing"]["sensor"]
+        if sc:
+            k_ms = sm / sc
+            local_evals = (self.n / world) * len(self.scan)
+            out["k7_ms"] = k_ms
+            out["k7_evals_per_s"] = local_evals / (k_ms * 1e-3)
+            out["k7_roofline_frac"] = local_evals * ALG_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9 / peak_gbs()[0]
+        if dev.get("tail_profile"):
+            out["tail_phases_us"] = {name: ns / 1e3 for name, ns in dev["tail_profile"][0]}
+            out["tail_fallbacks"] = dev["tail_profile"][2]
+        return out
+
+
+def peak_gbs():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def particle_checksum(particles, first):
+    """Order-sensitive 64-bit checksum of a block of the particle set: slot (first + i) weighs
+    the bit patterns of pose i.  Summed over blocks it identifies the whole set slot by slot."""
+    u = np.ascontiguousarray(np.stack([particles["x"], particles["y"], particles["theta"]], 1)).view(np.uint32)
+    h = (u[:, 0].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+         ^ u[:, 1].astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+         ^ u[:, 2].astype(np.uint64) * np.uint64(0x165667B19E3779F9))
+    idx = np.arange(first + 1, first + 1 + len(h), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum(h * idx, dtype=np.uint64))
+
+
+def measure_field_rebuild(q, torch, stream, width=8192, reps=5):
+    """configs[4]: the likelihood-field rebuild (exact EDT + Gaussian table + free-cell list) of a
+    width x width map, end to end through the plugin call with a pinned host occupancy grid."""
+    occ, res, origin = syn.make_map(width)
+    occ = torch.from_numpy(occ).pin_memory().numpy()
+    gm = q.create_likelihood_map()
+    gm.set_stream(stream.cuda_stream)
+    gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)))
+    grid = q.OccupancyGrid(occ, res, origin[0], origin[1])
+    gm.new_map(grid)                      # first call allocates
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        gm.new_map(grid)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    gm.close()
+    cells = width * width
+    ms = 1e3 * float(np.median(ts))
+    return {"workload": f"C5 field rebuild {width}x{width}", "ms_end_to_end_incl_h2d": ms,
+            "h2d_bytes": cells, "algorithmic_bytes": 6 * cells,
+            "roofline_frac_end_to_end": 6 * cells / (ms * 1e-3) / 1e9 / peak_gbs()[0],
+            "reps": reps}
+
+
+def measure_batch(q, torch, stream, n_filters=256, n_particles=2000, cycles=20):
+    """configs[4]: the multi-robot batch — n_filters independent filters at QuickMCL's default
+    size (C1 settings) on one map, one fused batch cycle (qmcl_batch_cycle) per step."""
+    from quickmcl_b200 import batch
+    occ, res, origin = syn.make_map(400)
+    pf = q.ParticleFilterParameters(resample_type=q.ResampleType.low_variance,
+                                    particle_count_min=n_particles, particle_count_max=n_particles)
+    truth = syn.pick_truth_pose(occ, res, origin)
+    scan = syn.make_scan(occ, res, origin, truth, 360, 360.0)
+    cov = np.diag([0.25, 0.25, 0.01]).astype(np.float32)
+    fb = batch.FusedBatch(n_filters, q.OccupancyGrid(occ, res, origin[0], origin[1]),
+                          q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)), pf,
+                          seed=7, stream=stream.cuda_stream)
+    for f in fb.filters:
+        f.initialise(truth.astype(np.float32), cov)
+    odo_new = np.tile([0.02, 0.01, 0.01], (n_filters, 1)).astype(np.float64)
+    odo_old = np.zeros((n_filters, 3))
+    al = np.asarray(syn.NODE_ALPHA, np.float32)
+    offs = np.arange(n_filters + 1, dtype=np.uint64) * len(scan)
+    packed = np.ascontiguousarray(np.tile(scan, (n_filters, 1)), np.float32)
+    for _ in range(3):
+        fb.cycle_packed(odo_new, odo_old, al, packed, offs)
+    torch.cuda.synchronize()
+    wall, devt = [], []
+    l0 = q.kernel_launch_count()
+    for _ in range(cycles):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        fb.cycle_packed(odo_new, odo_old, al, packed, offs)   # host scans in, host estimates out
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - t0)
+        devt.append(e0.elapsed_time(e1))
+    launches = (q.kernel_launch_count() - l0) / cycles
+    stats = fb.stats()
+    fb.close()
+    ms = 1e3 * float(np.median(wall))
+    return {"workload": f"C5 batch {n_filters} filters x {n_particles} particles x {len(scan)} beams, low variance",
+            "ms_per_batch_update_e2e": ms, "p95_ms": 1e3 * float(np.percentile(wall, 95)),
+            "ms_per_batch_update_device": float(np.median(devt)),
+            "filter_updates_per_s": n_filters / (ms * 1e-3),
+            "evals_per_s": n_filters * n_particles * len(scan) / (ms * 1e-3),
+            "gpu_launches_per_batch_update": launches, "cycles_fused_looped": list(stats)}
+
+
 def run_b200(args, wl):
     import torch
     import quickmcl_b200 as q
@@ -326,147 +547,106 @@ def run_b200(args, wl):
         import torch.distributed as dist
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=120))
+                                timeout=datetime.timedelta(seconds=180))
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
-
-    inputs = make_inputs(wl)
-    occ, res, origin, pose, scan, (x, y, t) = inputs
-    n = wl["particles"]
     stream = torch.cuda.current_stream()
-    gm = q.create_likelihood_map(device=local_rank)
-    gm.set_stream(stream.cuda_stream)
-    gm.set_parameters(q.LikelihoodMapParameters(**dict(syn.NODE_LIKELIHOOD, num_beams=0)))
-    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
-    pfp = q.ParticleFilterParameters(**wl["pf"])
-    pfp.resample_type = q.ResampleType(wl["pf"]["resample_type"])
-    if world > 1:
-        from quickmcl_b200.sharded import ShardedParticleFilter
-        f = ShardedParticleFilter(gm, seed=3, group=dist.group.WORLD, transport=args.transport)
-    else:
-        f = q.create_particle_filter(gm, seed=3)
-    f.set_parameters(pfp)
-    init = q.make_particles(x, y, t, np.full(n, 1.0 / n))
-    d_scan = torch.from_numpy(scan).cuda()
-    h_scan = torch.from_numpy(scan).pin_memory().numpy()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    evals = n * len(scan)
+    PARITY_IT = 5000
 
-    def reset(it):
-        f.set_particles(init)        # untimed: same initial cloud for every step
-        f.set_rng(3, 10 + it)
-        flush.zero_()                # evict the map from L2
+    # N > 1: the same workload on ONE GPU first (rank 0, in this process), so that the speed-up
+    # and the parity of the NCCL path are read off like with like.
+    one_gpu = None
+    if world > 1 and rank == 0 and not args.no_one_gpu_anchor:
+        h1 = Harness(q, torch, args.workload, local_rank, stream)
+        d1 = h1.timed_loop(False, min(args.steps, 5), 2, 0, flush)
+        h1.reset(PARITY_IT, flush)
+        est1 = h1.step(False)
+        p1 = h1.f.get_particles()
+        one_gpu = {"ms_per_step": d1["ms_per_step"], "median_ms": d1["median_ms"],
+                   "value": h1.evals / (d1["ms_per_step"] * 1e-3), "unit": "evals/s",
+                   "steps": min(args.steps, 5), "stage_ms": {k: ms / c for k, (ms, c) in d1["timing"].items() if c},
+                   "source": "measured in this run on rank 0 before the sharded run",
+                   "_estimate": est1, "_checksum": particle_checksum(p1, 0), "_n": len(p1)}
+        del p1
+        h1.close()
+        del h1
+        torch.cuda.empty_cache()
+    if dist:
+        dist.barrier()
 
-    def step_device():
-        f.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
-        f.update_importance_from_device_cloud(d_scan.data_ptr(), len(scan))
-        f.resample_and_cluster()
-        return f.get_estimated_pose()
-
-    def step_host():
-        f.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
-        f.update_importance_from_observations(h_scan)
-        f.resample_and_cluster()
-        return f.get_estimated_pose()
-
-    def timed_loop(step_fn, steps, warmup, it0):
-        for i in range(warmup):
-            reset(it0 + i)
-            step_fn()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        f.set_timing(1)
-        f.get_timing(reset=True)
-        if hasattr(f, "tail_profile"):
-            f.tail_profile(reset=True)
-        launches0 = q.kernel_launch_count()
-        h2d0, d2h0 = q.transfer_bytes()
-        h2d_reset = d2h_reset = 0
-        total_ms = 0.0
-        est = None
-        for i in range(steps):
-            a0, b0 = q.transfer_bytes()
-            l0 = q.kernel_launch_count()
-            reset(it0 + warmup + i)
-            a1, b1 = q.transfer_bytes()
-            h2d_reset += a1 - a0
-            d2h_reset += b1 - b0
-            launches0 += q.kernel_launch_count() - l0  # exclude the untimed restore
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            est = step_fn()
-            e1.record(stream)
-            e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        timing = f.get_timing(reset=True)
-        f.set_timing(0)
-        launches = q.kernel_launch_count() - launches0
-        h2d1, d2h1 = q.transfer_bytes()
-        if dist:
-            tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            total_ms = float(tt.item())
-        try:
-            prof = f.tail_profile()
-        except AttributeError:   # the sharded wrapper has no fused tail
-            prof = None
-        return dict(total_ms=total_ms, launches=launches, timing=timing, estimate=est, tail_profile=prof,
-                    h2d=(h2d1 - h2d0 - h2d_reset) / steps, d2h=(d2h1 - d2h0 - d2h_reset) / steps)
-
+    h = Harness(q, torch, args.workload, local_rank, stream, dist=dist, transport=args.transport,
+                sharded=world > 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev = timed_loop(step_device, args.steps, args.warmup, 0)
-    e2e = timed_loop(step_host, args.steps, max(3, args.warmup // 2), 1000)
+    dev = h.timed_loop(False, args.steps, args.warmup, 0, flush)
+    e2e = h.timed_loop(True, args.steps, max(3, args.warmup // 2), 1000, flush)
+
+    # hardware parity of the sharded (NCCL) path against the one-GPU run: estimate and the
+    # resampled set slot by slot (checksum of pose bits weighted by global slot index)
+    parity = None
+    if world > 1:
+        h.reset(PARITY_IT, flush)
+        est = h.step(False)
+        first, count, total = h.f.shard_range()
+        loc = h.f.get_particles()
+        cs = torch.tensor([np.int64(np.uint64(particle_checksum(loc, first)))], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        cs_all = int(np.uint64(np.int64(cs.item())))
+        if rank == 0 and one_gpu is not None:
+            e1 = one_gpu.pop("_estimate")
+            d_pose = float(np.max(np.abs(np.asarray(est[1]) - np.asarray(e1[1]))))
+            d_cov = float(np.max(np.abs(np.asarray(est[2]) - np.asarray(e1[2]))))
+            parity = {"resampled_set_checksum_equal": cs_all == one_gpu.pop("_checksum"),
+                      "particles": [int(total), one_gpu.pop("_n")],
+                      "estimate_max_abs_diff": max(d_pose, d_cov), "estimate_valid": [bool(est[0]), bool(e1[0])]}
+            parity["ok"] = bool(parity["resampled_set_checksum_equal"] and parity["estimate_max_abs_diff"] <= 1e-9
+                                and parity["particles"][0] == parity["particles"][1])
+
+    secondary = None
+    if world == 1 and not args.no_secondary and args.workload == "C2":
+        secondary = {}
+        for name, st, wu in (("C1", 50, 5), ("C3", 20, 3)):
+            hs = Harness(q, torch, name, local_rank, stream)
+            ds = hs.timed_loop(False, st, wu, 0, flush)
+            es = hs.timed_loop(True, max(5, st // 2), 2, 1000, flush)
+            secondary[name] = hs.summary(ds, es)
+            hs.close()
+        secondary["C5_field_rebuild"] = measure_field_rebuild(q, torch, stream)
+        secondary["C5_batch"] = measure_batch(q, torch, stream)
     clocks = sampler.stop() if rank == 0 else None
 
-    # optional per-stage breakdown (untimed extra pass, stderr only)
+    # optional per-stage breakdown (untimed extra pass, stderr only): level 2 runs the stages as
+    # separate launches, i.e. the multi-launch path
     if args.breakdown:   # every rank takes part (the steps contain collectives)
+        f = h.f
         f.set_timing(2)
         f.get_timing(reset=True)
-        for i in range(args.steps):
-            reset(2000 + i)
-            step_device()
+        for i in range(min(args.steps, 20)):
+            h.reset(2000 + i, flush)
+            h.step(False)
         tb = f.get_timing(reset=True)
         f.set_timing(0)
         if rank == 0:
-            log("stage breakdown (device ms per step, CUDA events inside the library):")
+            log("stage breakdown (device ms per step, CUDA events inside the library, multi-launch path):")
             for k, (ms, cnt) in tb.items():
                 if cnt:
-                    log(f"  {k:15s} {ms / args.steps:9.4f} ms  ({cnt / args.steps:.1f} scopes/step)")
-            try:
-                log(f"  after the last step: {f.num_clusters()} clusters")
-            except Exception as e:  # noqa: BLE001 (diagnostic only)
-                log(f"  cluster count unavailable: {e}")
+                    log(f"  {k:15s} {ms / min(args.steps, 20):9.4f} ms  ({cnt / min(args.steps, 20):.1f} scopes/step)")
 
-    global_n = n
-    evals_job = global_n * len(scan)
-    ms_per_step = dev["total_ms"] / args.steps
+    n, scan = h.n, h.scan
+    evals_job = n * len(scan)
+    ms_per_step = dev["ms_per_step"]
     value = evals_job / (ms_per_step * 1e-3)
-    e2e_ms = e2e["total_ms"] / args.steps
+    e2e_ms = e2e["ms_per_step"]
     sensor_ms, sensor_cnt = dev["timing"]["sensor"]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except (OSError, ValueError):
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
-        "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak, peak_kind = peak_gbs()
     roofline = None
     if sensor_cnt:
         k_ms = sensor_ms / sensor_cnt
         local_evals = (n / world) * len(scan)
         achieved = local_evals * ALG_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9
-        traffic = None
-        traffic_note = None
+        traffic = traffic_note = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "sensor_traffic.json")))
             traffic = tj.get(args.workload)
@@ -480,14 +660,26 @@ def run_b200(args, wl):
                     "launches_timed": sensor_cnt}
         if traffic is not None and traffic_note:
             roofline["traffic_note"] = traffic_note
+        try:
+            gp = json.load(open(os.path.join(ROOT, "profiles", "r2_probe_gather.json")))
+            best = max(r["gathers_per_s"] for r in gp["results"]
+                       if r["pattern"] == "random" and r["elem_bytes"] == 1 and r["table_bytes"] == 4 << 20)
+            roofline["vs_measured_l2_random_gather"] = {
+                "peak_gathers_per_s": best, "kernel_evals_over_peak": local_evals / (k_ms * 1e-3) / best,
+                "source": "profiles/r2_probe_gather.json: independent random 1-byte gathers into a 4 MB "
+                          "L2-resident table; K7 exceeds it because consecutive beams share cache lines"}
+        except (OSError, ValueError, KeyError):
+            pass
     if rank != 0:
+        h.close()
         if dist:
             dist.destroy_process_group()
         return 0
 
     cpu = None
-    if world == 1 or rank == 0:
+    if not args.no_cpu_baseline:
         # bounded CPU sample: a slice of the particle set, full cycle, one thread
+        occ, res, origin, pose, _, (x, y, t) = h.inputs
         n_cpu = int(min(n, max(2000, 2.0e9 / 6 // len(scan))))
         wl_s = dict(wl)
         pf = dict(wl["pf"])
@@ -496,16 +688,17 @@ def run_b200(args, wl):
             pf["particle_count_min"] = max(1, int(pf["particle_count_min"] * sc))
             pf["particle_count_max"] = max(1, int(pf["particle_count_max"] * sc))
         wl_s["pf"] = pf
-        if not args.no_cpu_baseline:
-            sec, ev, stages = cpu_cycle_seconds(
-                wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])), 5, 1)
-            cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": "port",
-                   "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
-                             f"5 steps after 1 warm-up",
-                   "cpu": cpu_model(), "host_cores": os.cpu_count(),
-                   "stage_ms": {k: v * 1e3 for k, v in stages.items()},
-                   "all_cores": cpu_all_cores(
-                       wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])))}
+        sec, ev, stages = cpu_cycle_seconds(
+            wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])), 5, 1)
+        cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": "port",
+               "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
+                         f"5 steps after 1 warm-up",
+               "field": "brushfire (the reference's own field build; the GPU arm uses the exact EDT "
+                        "north_star asks for — same cost per evaluation)",
+               "cpu": cpu_model(), "host_cores": os.cpu_count(),
+               "stage_ms": {k: v * 1e3 for k, v in stages.items()},
+               "all_cores": cpu_all_cores(
+                   wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])))}
 
     line = {
         "metric": "particle_point_likelihood_evals_per_sec",
@@ -514,35 +707,34 @@ def run_b200(args, wl):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, wl, len(scan)),
         "update_latency_ms": ms_per_step,
+        "update_latency_median_ms": dev["median_ms"], "update_latency_p95_ms": dev["p95_ms"],
         "e2e": {"value": evals_job / (e2e_ms * 1e-3), "unit": "evals/s",
                 "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                "ms_per_step": e2e_ms},
+                "ms_per_step": e2e_ms, "median_ms": e2e["median_ms"], "p95_ms": e2e["p95_ms"]},
         "gpu_launches": dev["launches"],
         "gpu_launches_per_step": dev["launches"] / args.steps,
         "stage_ms": {k: ms / cnt for k, (ms, cnt) in dev["timing"].items() if cnt},
         "tail_phases_us": ({name: ns / 1e3 for name, ns in dev["tail_profile"][0]}
                            if dev.get("tail_profile") else None),
-        "tail_calls": dev["tail_profile"][1] if dev.get("tail_profile") else None,
         "tail_fallbacks": dev["tail_profile"][2] if dev.get("tail_profile") else None,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "estimate": [float(v) for v in dev["estimate"][1]] if dev["estimate"] else None,
     }
+    if secondary is not None:
+        line["secondary"] = secondary
     if world > 1:
-        # The N = 1 line of the contract is C2; the sharded runs are C4 (strong scaling of
-        # one 16 M-particle filter).  The same workload on ONE GPU, measured earlier with
-        # `bench.py --workload C4` and committed, is attached so that a speed-up can be read
-        # off like with like.
-        try:
-            ref = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_c4_1gpu_final.json")))
-            if ref.get("config", {}).get("workload") == args.workload:
-                line["same_workload_on_one_gpu"] = {
-                    "value": ref["value"], "unit": ref["unit"], "ms_per_step": ref["ms_per_step"],
-                    "source": "profiles/r1_bench_c4_1gpu_final.json (python bench.py --workload C4)"}
-        except (OSError, ValueError, KeyError):
-            pass
+        if one_gpu is not None:
+            one_gpu = {k: v for k, v in one_gpu.items() if not k.startswith("_")}
+            one_gpu["speedup_of_this_run"] = one_gpu["ms_per_step"] / ms_per_step
+            line["same_workload_on_one_gpu"] = one_gpu
+        line["parity_vs_one_gpu"] = parity
     emit(line)
+    h.close()
     if dist:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        log("bench.py: the sharded run does not reproduce the one-GPU run:", parity)
+        return 1
     return 0
 
 
@@ -567,13 +759,17 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--breakdown", action="store_true",
                     help="extra untimed pass with per-stage CUDA events, printed to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="N=1: skip the C1 / C3 / C5 measurements that ride along in `secondary`")
+    ap.add_argument("--no-one-gpu-anchor", action="store_true",
+                    help="N>1: skip the one-GPU run of the same workload on rank 0 (and the parity check)")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "torch"],
                     help="sharded exchanges: the library's built-in NCCL table or torch.distributed")
     args = ap.parse_args()

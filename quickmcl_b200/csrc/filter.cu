@@ -457,9 +457,12 @@ static qmcl_status sensor_update_common(qmcl_filter *f, const float *dev_cloud_x
   }
   // With the fused tail (tail.cu) K8 and everything after it run in one launch
   // that reads the total and the bin bounds on the device.
-  const bool defer = tail_enabled(f) && ps.n > 0 && ps.n <= (size_t(1) << 22);
+  // The front kernel (deferred motion + beam selection + bin bounds) serves every
+  // single-GPU filter in lazy mode; K8 is left to the tail only for sets it will take.
+  const bool front = tail_enabled(f) && ps.n > 0;
+  const bool defer = front && ps.n <= kTailMaxParticles;
   int n_used = 0;
-  if (defer) {
+  if (front) {
     QMCL_TRY(launch_front(f, dev_cloud_xy, n_points, &n_used));
   } else {
     QMCL_TRY(flush_motion(f));
@@ -486,7 +489,7 @@ static qmcl_status sensor_update_common(qmcl_filter *f, const float *dev_cloud_x
     // from.  Taken here, ahead of the sensor kernel, the six numbers are on the
     // host long before the resampling asks for them.
     StageScope sc(f, QMCL_STAGE_BINS);
-    QMCL_TRY(launch_bin_bbox(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
+    if (!front) QMCL_TRY(launch_bin_bbox(f, ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n));
     QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_BBOX_EARLY, f->bbox.ptr, 6 * sizeof(int), s));
     f->early_bbox_version = f->pose_version;
   }

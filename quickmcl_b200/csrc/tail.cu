@@ -776,6 +776,10 @@ __device__ void run_tail(const TailJob &J) {
 __global__ void __launch_bounds__(kTailThreads, 1) tail_grid_kernel(const __grid_constant__ TailJob job) {
   run_tail<GridTeam>(job);
 }
+// A small filter alone: one block, block barriers, an ordinary launch.
+__global__ void __launch_bounds__(kTailThreads) tail_block_kernel(const __grid_constant__ TailJob job) {
+  run_tail<BlockTeam>(job);
+}
 __global__ void __launch_bounds__(kTailThreads) tail_batch_kernel(const TailJob *__restrict__ jobs) {
   __shared__ TailJob s_job;
   // the job is read through shared memory: one copy per block instead of per thread
@@ -822,8 +826,8 @@ namespace qmcl {
 
 namespace {
 
-constexpr size_t kTailMaxParticles = size_t(1) << 22;  // beyond this the multi-launch path streams better
 constexpr size_t kTailMaxCells = size_t(1) << 26;      // dense tables: 2 x 256 MiB at most
+constexpr size_t kTailOneBlock = 8192;                 // sets up to this size: the tail runs in one block
 
 int tail_blocks_per_sm() {
   static int cached = -1;
@@ -1023,6 +1027,14 @@ qmcl_status launch_tail(qmcl_filter *f, int mode) {
   TailJob J;
   QMCL_TRY(tail_prepare(f, mode, &J));
   StageScope sc(f, QMCL_STAGE_TAIL, 1);
+  if (J.n_in <= kTailOneBlock && (mode == TAIL_CLUSTER || mode == TAIL_LOW_VARIANCE ||
+                                  (mode == TAIL_KLD ? J.n_max : J.n_min) <= kTailOneBlock)) {
+    // small sets (QuickMCL's defaults): one block between block barriers beats 148 blocks
+    // between grid barriers, and leaves the other SMs to concurrent filters
+    tail_block_kernel<<<1, kTailThreads, 0, f->map->stream>>>(J);
+    QMCL_LAUNCHED();
+    return QMCL_OK;
+  }
   void *args[] = {&J};
   const unsigned blocks = static_cast<unsigned>(kSMs * tail_blocks_per_sm());
   QMCL_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(tail_grid_kernel), dim3(blocks),

@@ -55,7 +55,37 @@ pf = q.ParticleFilterParameters(resample_type=q.ResampleType.low_variance,
 truth = syn.pick_truth_pose(occ1, res1, origin1)
 scan = syn.make_scan(occ1, res1, origin1, truth, 360, 360.0)
 cov = np.diag([0.25, 0.25, 0.01]).astype(np.float32)
-for lanes in (1, 8, 16, 32):
+# the fused batch (qmcl_batch): one map handle, four launches per cycle for all robots
+fb = batch.FusedBatch(n_filters, q.OccupancyGrid(occ1, res1, origin1[0], origin1[1]),
+                      q.LikelihoodMapParameters(**lp1), pf, seed=7, stream=stream.cuda_stream)
+for f in fb.filters:
+    f.initialise(truth.astype(np.float32), cov)
+odo_new = np.tile([0.02, 0.01, 0.01], (n_filters, 1)).astype(np.float64)
+odo_old = np.zeros((n_filters, 3))
+al = np.asarray(syn.NODE_ALPHA, np.float32)
+offs = np.arange(n_filters + 1, dtype=np.uint64) * len(scan)
+packed = np.ascontiguousarray(np.tile(scan, (n_filters, 1)), np.float32)
+for _ in range(3):
+    fb.cycle_packed(odo_new, odo_old, al, packed, offs)
+torch.cuda.synchronize()
+ts, td = [], []
+for _ in range(20):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    fb.cycle_packed(odo_new, odo_old, al, packed, offs)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ts.append(time.perf_counter() - t0)
+    td.append(e0.elapsed_time(e1))
+ms = 1e3 * float(np.median(ts))
+out["batch256_fused"] = {"ms_per_batch_update_wall": ms, "ms_per_batch_update_device": float(np.median(td)),
+                         "p95_wall_ms": 1e3 * float(np.percentile(ts, 95)),
+                         "filter_updates_per_s": n_filters / (ms * 1e-3),
+                         "evals_per_s": n_filters * n_particles * len(scan) / (ms * 1e-3),
+                         "cycles_fused_looped": fb.stats(), "launches_per_cycle": 3}
+fb.close()
+for lanes in ((16,) if os.environ.get("C5_QUICK") else (1, 8, 16, 32)):
     b = batch.FilterBatch(n_filters, q.OccupancyGrid(occ1, res1, origin1[0], origin1[1]),
                           q.LikelihoodMapParameters(**lp1), pf, lanes=lanes, seed=7)
     poses = np.tile(truth.astype(np.float32), (n_filters, 1))
