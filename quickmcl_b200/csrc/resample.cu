@@ -649,9 +649,8 @@ static qmcl_status resample_kld(qmcl_filter *f, const ParticleSet &in, ParticleS
   kp.nmin = f->params.particle_count_min;
   kp.nmax = f->params.particle_count_max;
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(n_max) + 8));
-  unsigned long long *d_total =
-      scan_total_ptr(f->scan_tmp.ptr, n_max);
-  unsigned long long *d_stop = d_total + 1;
+  unsigned long long *d_total = &f->scalars.ptr->kld_new;
+  unsigned long long *d_stop = &f->scalars.ptr->kld_stop;
   {
     StageScope sc(f, QMCL_STAGE_KLD);
     QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0x7f, cells * sizeof(int32_t), s));

@@ -16,6 +16,11 @@ struct FilterScalars {
   unsigned long long n_bins;      // build_bins' count (read on the device by the labelling)
   unsigned long long n_records;   // running-sum records (read on the device by the draws)
   double sum_sq;                  // sum of squared weights (effective_particles)
+  // Results of the multi-launch KLD scan.  They live here, not behind the scan's
+  // status words: a later, longer scan over the same buffer would read a stop
+  // word {m:32, k:32} left there as a tile status.
+  unsigned long long kld_new;     // new-bin flags over all candidates
+  unsigned long long kld_stop;    // stop word
 };
 
 // quickmcl::MapLikelihood (map_likelihood.h:35-93) + MapBase (map_base.h:31-69)

@@ -184,6 +184,58 @@ std::vector<CudaParticleFilter::Marker> CudaParticleFilter::export_markers(doubl
   return out;
 }
 
+ScanCycle::Result ScanCycle::on_scan(const Pose2D<double> &odom_new, const LaserPointCloud &cloud) {
+  Result r;
+  if (!have_odom_) {  // laser_handler.cpp:196-199
+    odom_at_last_filter_run_ = odom_new;
+    have_odom_ = true;
+    r.recompute_transform = true;
+  }
+  // :205-210: diff.normalise() wraps the heading difference (utils.h:28-35)
+  const double two_pi = 2 * 3.14159265358979323846;
+  const double dx = odom_new.x - odom_at_last_filter_run_.x;
+  const double dy = odom_new.y - odom_at_last_filter_run_.y;
+  double dt = odom_new.theta - odom_at_last_filter_run_.theta;
+  dt = dt - two_pi * std::floor((dt + two_pi / 2) / two_pi);
+  const bool has_moved = std::fabs(dx) > motion.min_trans || std::fabs(dy) > motion.min_trans ||
+                         std::fabs(dt) > motion.min_rot;
+  auto estimate = [&]() {
+    calls.push_back("get_estimated_pose");
+    r.pose_ok = filter_->get_estimated_pose(&r.pose, &r.covariance);
+  };
+  if (!pose_reset_ && !has_moved) {  // :212-219
+    calls.push_back("cluster");
+    filter_->cluster();
+    estimate();
+    return r;
+  }
+  if (pose_reset_) r.recompute_transform = true;
+  pose_reset_ = false;
+  r.processed = true;
+  if (filter_->num_particles() == 0) {  // get_particles().empty() without the copy (:236-241)
+    calls.push_back("global_localization");
+    filter_->global_localization();
+    r.recompute_transform = true;
+    r.global_localization = true;
+  }
+  calls.push_back("handle_odometry");
+  filter_->handle_odometry(odom_new, odom_at_last_filter_run_, motion.alpha);  // :243-251
+  odom_at_last_filter_run_ = odom_new;
+  calls.push_back("update_importance_from_observations");
+  filter_->update_importance_from_observations(cloud);  // :252-256
+  if (resample_counter_++ % static_cast<uint32_t>(resample_count_)) {  // :259-270
+    r.recompute_transform = true;
+    r.resampled = true;
+    calls.push_back("resample_and_cluster");
+    filter_->resample_and_cluster();
+  } else {
+    calls.push_back("cluster");
+    filter_->cluster();
+  }
+  estimate();
+  return r;
+}
+
 std::vector<double> PoseCheckpoint::store() const {
   Pose2D<double> pose;
   Matrix3d cov;

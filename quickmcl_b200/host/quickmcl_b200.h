@@ -19,6 +19,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <memory>
+#include <string>
 #include <vector>
 
 struct qmcl_map;
@@ -195,6 +196,46 @@ private:
 // no estimate), restore() re-initialises the filter from them with the
 // reference's defaults for missing / NaN entries; restore(nullptr) is the "no
 // parameter" case (pose 0, identity covariance).
+// LaserHandler::Impl::cloud_callback (src/quickmcl_node/laser_handler.cpp:179-288)
+// without ROS: the moved-enough gate, the fall-back to global
+// localisation when the set is empty, motion -> sensor -> resample-or-cluster
+// with the reference's cadence (it resamples when `counter++ % resample_count`
+// is NON-zero, :259-260), and the estimate Publishing::publish_estimated_pose
+// (publishing.cpp:157-227) turns into the map->odom transform.  Drives any
+// IParticleFilter; `calls` records the interface calls made, in order.
+class ScanCycle {
+public:
+  struct MotionModel {  // Parameters::MotionModel (parameters.h:40-50), the node's cfg defaults
+    float alpha[4] = {0.05f, 0.1f, 0.02f, 0.05f};
+    double min_trans = 0.2;
+    double min_rot = 3.14159265358979323846 / 6;
+  };
+  struct Result {
+    bool processed = false;            // false: "Skipping laser scan: haven't moved"
+    bool resampled = false;
+    bool global_localization = false;  // the set was empty and was re-seeded
+    bool recompute_transform = false;  // what publish_estimated_pose is told
+    bool pose_ok = false;              // get_estimated_pose's return value
+    Pose2D<double> pose;
+    Matrix3d covariance;
+  };
+  explicit ScanCycle(const std::shared_ptr<IParticleFilter> &filter, int resample_count = 2)
+      : filter_(filter), resample_count_(resample_count) {}
+  MotionModel motion;
+  std::vector<std::string> calls;
+  //! LaserHandler::force_pose_reset: the next scan is processed even without motion.
+  void force_pose_reset() { pose_reset_ = true; }
+  Result on_scan(const Pose2D<double> &odom_new, const LaserPointCloud &cloud);
+
+private:
+  std::shared_ptr<IParticleFilter> filter_;
+  int resample_count_;
+  bool have_odom_ = false;
+  Pose2D<double> odom_at_last_filter_run_;
+  bool pose_reset_ = false;
+  uint32_t resample_counter_ = 0;
+};
+
 class PoseCheckpoint {
 public:
   explicit PoseCheckpoint(const std::shared_ptr<IParticleFilter> &filter) : filter_(filter) {}

@@ -225,6 +225,34 @@ int main(int argc, char **argv) {
     EXPECT(std::fabs(cov(1, 1) - 0.25) <= 0.05 && std::fabs(cov(0, 0) - stored[3]) <= 0.2 * stored[3] + 1e-3);
     std::printf("checkpoint: restored around (%.3f, %.3f, %.3f)\n", est.x, est.y, est.theta);
   }
+  {
+    // ScanCycle (laser_handler.cpp:179-288): gate, cadence, call order on the CUDA filter
+    ScanCycle cycle(pf, 2);
+    const auto cloud2 = make_scan(*grid, 1.0, -2.0, 0.3);
+    auto r0 = cycle.on_scan(Pose2D<double>{0.0, 0.0, 0.0}, cloud2);       // first odometry: no motion yet
+    EXPECT(!r0.processed && r0.recompute_transform && r0.pose_ok);
+    auto r1 = cycle.on_scan(Pose2D<double>{0.05, 0.0, 0.0}, cloud2);      // below min_trans: skipped
+    EXPECT(!r1.processed && !r1.recompute_transform);
+    auto r2 = cycle.on_scan(Pose2D<double>{0.3, 0.0, 0.0}, cloud2);       // moved: counter 0 -> cluster only
+    EXPECT(r2.processed && !r2.resampled && r2.pose_ok);
+    auto r3 = cycle.on_scan(Pose2D<double>{0.6, 0.05, 0.0}, cloud2);      // counter 1 -> resample
+    EXPECT(r3.processed && r3.resampled && r3.recompute_transform && r3.pose_ok);
+    auto r4 = cycle.on_scan(Pose2D<double>{0.6, 0.05, 0.7}, cloud2);      // rotation alone passes the gate
+    EXPECT(r4.processed && !r4.resampled);
+    cycle.force_pose_reset();
+    auto r5 = cycle.on_scan(Pose2D<double>{0.6, 0.05, 0.7}, cloud2);      // forced although nothing moved
+    EXPECT(r5.processed && r5.resampled && r5.recompute_transform);
+    const std::vector<std::string> want = {
+        "cluster", "get_estimated_pose", "cluster", "get_estimated_pose",
+        "handle_odometry", "update_importance_from_observations", "cluster", "get_estimated_pose",
+        "handle_odometry", "update_importance_from_observations", "resample_and_cluster", "get_estimated_pose",
+        "handle_odometry", "update_importance_from_observations", "cluster", "get_estimated_pose",
+        "handle_odometry", "update_importance_from_observations", "resample_and_cluster", "get_estimated_pose"};
+    EXPECT(cycle.calls == want);
+    EXPECT(std::isfinite(r5.pose.x) && std::isfinite(r5.covariance(0, 0)));
+    std::printf("scan cycle: %zu interface calls, last estimate (%.3f, %.3f, %.3f)\n", cycle.calls.size(),
+                r5.pose.x, r5.pose.y, r5.pose.theta);
+  }
   EXPECT(qmcl_kernel_launch_count() > 20);
   orc_filter_destroy(of);
   orc_map_destroy(om);
