@@ -392,7 +392,15 @@ __device__ __forceinline__ void sensor_body(const int8_t *__restrict__ state, co
                          : static_cast<unsigned>(iy) * w + static_cast<unsigned>(ix));
       if (PATH == PATH_PAL8) {
         code_cur[p] = sp.pal8_n;  // outside the map -> p_max entry
+#if QMCL_DIAG == 4
+        // upper bound of any map-staging scheme (shared-memory / TMA window): no gather at all
+        if (inside) code_cur[p] = static_cast<int>(cell & 63u);
+#elif QMCL_DIAG == 5
+        // every gather hits one L1-resident 4 KB window
+        if (inside) code_cur[p] = static_cast<int>(ldg_u8(byte_at(sp.code8, cell & 4095u)));
+#else
         if (inside) code_cur[p] = static_cast<int>(ldg_u8(byte_at(sp.code8, cell)));
+#endif
         if (MASKED && !valid) code_cur[p] = sp.pal8_n + 1;
       } else if (PALETTE) {
         code_cur[p] = 4 * sp.n_codes;  // outside the map -> p_max entry

@@ -14,10 +14,10 @@ build() {  # name source macros...
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/lib$name.so $OTHERS build/variants/sensor_$name.o -ldl -lpthread
 }
 pids=""
-if [ -f /tmp/base/csrc/sensor.cu ]; then cp /tmp/base/csrc/sensor.cu build/variants/sensor_prev.cu; build prev build/variants/sensor_prev.cu & pids="$pids $!"; fi
 build cur sensor.cu & pids="$pids $!"
-build floor sensor.cu -DQMCL_SENSOR_FLOOR_FMA=1 & pids="$pids $!"
-build wide sensor.cu -DQMCL_SENSOR_WIDE_ADDR=1 & pids="$pids $!"
-build floorwide sensor.cu -DQMCL_SENSOR_FLOOR_FMA=1 -DQMCL_SENSOR_WIDE_ADDR=1 & pids="$pids $!"
+build nogather sensor.cu -DQMCL_DIAG=4 & pids="$pids $!"
+build l1window sensor.cu -DQMCL_DIAG=5 & pids="$pids $!"
+build blocks6 sensor.cu -DQMCL_SENSOR_MINBLOCKS=6 & pids="$pids $!"
+build blocks4 sensor.cu -DQMCL_SENSOR_MINBLOCKS=4 & pids="$pids $!"
 for p in $pids; do wait $p; done
 ls -la ../variants
