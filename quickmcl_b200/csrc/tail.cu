@@ -302,6 +302,8 @@ __device__ void tail_finish(const TailJob &J, unsigned long long status, double 
 template <class Team>
 __device__ void run_tail(const TailJob &J) {
   using namespace pfx;
+  // block 0's scratch for the single-block phases (KLD stop rule, bin list + labelling)
+  __shared__ int32_t s_solo[3 * kSoloCells];
   const Team team(J);
   const unsigned rank = Team::rank(), size = Team::size();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -562,14 +564,72 @@ __device__ void run_tail(const TailJob &J) {
         if (J.mode != TAIL_KLD) break;
         if (done == 0) TAIL_STAMP(TS_SELECT);
         // ---- phases 5, 6: K11 KLD stop rule (particle_filter.cpp:313-335) over [0, round_end)
-        const TailNewBin nb{J.ox, J.oy, J.ot, J.kp, g, J.first};
-        const int ipt = compact_ipt<Team>(round_end);
-        compact_count<Team>(nb, round_end, J.tile_cnt, ipt);
-        team.sync();
-        const unsigned long long n_new =
-            compact_emit<Team>(nb, TailStopRule{J.kp, &D->stop}, round_end, J.tile_cnt, ipt);
-        if (rank == 0 && tid == 0) D->n_new = n_new;
-        team.sync();
+        if (cells <= J.solo_cells) {
+          // A small table (a tracking cloud): the stop follows from the table alone.  With the
+          // first-draw indices of the occupied cells sorted, f_1 < f_2 < ... < f_K, the number of
+          // bins after draw m is k(m) = #{j : f_j <= m}; on [f_j, f_j+1) it is j, so the first m
+          // of that stretch with m >= limit(j) is max(f_j, limit(j)), and the stop is the smallest
+          // such m over all j.  One block, K values: no pass over the candidates at all.
+          if (rank == 0) {
+            int32_t *s_first = s_solo;
+            constexpr int kPer = kSoloCells / kTailThreads;
+            int32_t fv[kPer];
+            uint32_t c = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+              const size_t idx = static_cast<size_t>(tid) * kPer + i;
+              fv[i] = idx < cells ? J.first[idx] : 0x7f7f7f7f;
+              c += (fv[i] != 0x7f7f7f7f) ? 1u : 0u;
+            }
+            uint32_t at = block_excl_scan_u32(c, &total);
+            const uint32_t K = total;
+            uint32_t n2 = 32;
+            while (n2 < K) n2 <<= 1;
+            for (uint32_t i = tid; i < n2; i += kTailThreads) s_first[i] = 0x7fffffff;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kPer; ++i)
+              if (fv[i] != 0x7f7f7f7f) s_first[at++] = fv[i];
+            __syncthreads();
+            for (uint32_t k = 2; k <= n2; k <<= 1)
+              for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < n2; i += kTailThreads) {
+                  const uint32_t l = i ^ j;
+                  if (l > i) {
+                    const int32_t a = s_first[i], b = s_first[l];
+                    if ((a > b) == ((i & k) == 0)) {
+                      s_first[i] = b;
+                      s_first[l] = a;
+                    }
+                  }
+                }
+                __syncthreads();
+              }
+            unsigned long long best = ~0ull;
+            for (uint32_t j = tid; j < K; j += kTailThreads) {
+              const unsigned long long fj = static_cast<unsigned long long>(s_first[j]);
+              const unsigned long long upper =
+                  (j + 1 < K) ? static_cast<unsigned long long>(s_first[j + 1]) : round_end;
+              const unsigned long long lim = kld_limit(j + 1, J.kp);
+              const unsigned long long m = fj > lim ? fj : lim;
+              if (m < upper) best = min(best, (m << 32) | (j + 1));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0 && best != ~0ull) atomicMin(&D->stop, best);
+            if (tid == 0) D->n_new = K;
+          }
+          team.sync(640);
+        } else {
+          const TailNewBin nb{J.ox, J.oy, J.ot, J.kp, g, J.first};
+          const int ipt = compact_ipt<Team>(round_end);
+          compact_count<Team>(nb, round_end, J.tile_cnt, ipt);
+          team.sync();
+          const unsigned long long n_new =
+              compact_emit<Team>(nb, TailStopRule{J.kp, &D->stop}, round_end, J.tile_cnt, ipt);
+          if (rank == 0 && tid == 0) D->n_new = n_new;
+          team.sync();
+        }
         const unsigned long long stop = *reinterpret_cast<volatile unsigned long long *>(&D->stop);
         if (stop != ~0ull) {
           n_out = (stop >> 32) + 1;
@@ -609,7 +669,7 @@ __device__ void run_tail(const TailJob &J) {
   if (cells <= J.solo_cells) {
     if (rank == 0) {
       // everything in shared memory: the dense table, the bin list, the union-find forest
-      __shared__ int32_t s_tab[kSoloCells], s_cell[kSoloCells], s_parent[kSoloCells];
+      int32_t *s_tab = s_solo, *s_cell = s_solo + kSoloCells, *s_parent = s_solo + 2 * kSoloCells;
       for (size_t i = tid; i < cells; i += kTailThreads) s_tab[i] = J.table[i];
       __syncthreads();
       uint32_t v[kSoloCells / kTailThreads];
