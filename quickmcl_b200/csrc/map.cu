@@ -6,8 +6,10 @@
 // transform (separable, integer d^2), K3 Gaussian table through a d^2 LUT,
 // K4 free-cell compaction.  All HBM-bound; see DESIGN.md for the byte counts.
 
+#include "scan.cuh"
 #include "sensor.cuh"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -45,10 +47,10 @@ constexpr int kSegLen = 128;     // rows per column segment in pass 1
 // Warp lanes are adjacent columns, so every load/store is coalesced.
 __global__ void __launch_bounds__(128)
 edt_columns_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
-                   uint16_t *__restrict__ g, int w, int h, int R) {
+                   uint16_t *__restrict__ g, int w, int h, int R, int seg_first) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
-  const int y0 = blockIdx.y * kSegLen;
+  const int y0 = (seg_first + blockIdx.y) * kSegLen;
   const int y1 = min(h, y0 + kSegLen);
   int d = kEdtInf;
   for (int y = max(0, y0 - R); y < y1; ++y) {
@@ -91,11 +93,11 @@ __device__ __forceinline__ int8_t tri_state(int v) {
 }
 __global__ void __launch_bounds__(kColThreads)
 edt_columns4_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
-                    uint16_t *__restrict__ g, int w, int h, int R) {
+                    uint16_t *__restrict__ g, int w, int h, int R, int seg_first) {
   __shared__ uchar4 s_down[kColSeg][kColThreads];
   const int x = (blockIdx.x * kColThreads + threadIdx.x) * 4;
   if (x >= w) return;
-  const int y0 = blockIdx.y * kColSeg;
+  const int y0 = (seg_first + blockIdx.y) * kColSeg;
   const int y1 = min(h, y0 + kColSeg);
   int d0 = 255, d1 = 255, d2 = 255, d3 = 255;
 #pragma unroll 4
@@ -160,10 +162,10 @@ constexpr int kRowChunk = 256;
 __global__ void __launch_bounds__(kRowChunk)
 edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_dist,
                 const float *__restrict__ lut_field, float *__restrict__ distance,
-                float *__restrict__ field, uint16_t *__restrict__ code, int w, int h, int R,
-                int kmax) {
+                float *__restrict__ field, uint16_t *__restrict__ code, int w, int h, int y_first,
+                int R, int kmax) {
   extern __shared__ int sG[];  // kRowChunk + 2R entries
-  const int y = blockIdx.y;
+  const int y = y_first + blockIdx.y;
   const int x0 = blockIdx.x * kRowChunk;
   const int span = kRowChunk + 2 * R;
   const int big = 1 << 28;
@@ -204,6 +206,97 @@ edt_rows_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_di
   if (code) code[code_offset(x, y, code_strip_stride(h))] = static_cast<uint16_t>(4 * k);
 }
 
+// K2 pass 2 + K3, two cells per thread on 16-bit lanes.  The candidates d^2 + G
+// fit 16 bits (R <= 74 cells: G <= R^2, "none" = kInf16, sums below 65536), so a
+// pair of adjacent cells shares every instruction: VIADDMNMX.U16x2 (DPX, native
+// on sm_100a) adds the step's d^2 to both lanes and folds the minimum, and an
+// odd offset's pair is one funnel shift of the two aligned words around it.  Per
+// two outward steps and two cells: 2 LDS, 2 SHF, 4 VIADDMNMX — half the
+// instructions per cell-candidate of edt_rows_kernel.  Same results (the minimum
+// over the same window of the same integers).
+constexpr int kRow2Cells = 512;  // cells per block: 256 threads x 2
+constexpr unsigned kInf16 = 60000u;
+constexpr int kRow2MaxR = 74;
+__global__ void __launch_bounds__(256)
+edt_rows2_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_dist,
+                 const float *__restrict__ lut_field, float *__restrict__ distance,
+                 float *__restrict__ field, uint16_t *__restrict__ code, int w, int h, int y_first,
+                 int R, int kmax) {
+  extern __shared__ unsigned sW[];  // (kRow2Cells + 2 Rp) / 2 + 2 words of uint16 pairs
+  uint16_t *sG16 = reinterpret_cast<uint16_t *>(sW);
+  const int Rp = (R + 1) & ~1;  // even halo: every thread's pair is word-aligned
+  const int y = y_first + blockIdx.y;
+  const int x0 = blockIdx.x * kRow2Cells;
+  const int span = kRow2Cells + 2 * Rp + 4;
+  for (int i = threadIdx.x; i < span; i += 256) {
+    const int xx = x0 - Rp + i;
+    unsigned v = kInf16;
+    if (xx >= 0 && xx < w) {
+      const int gy = g[static_cast<size_t>(y) * w + xx];
+      if (gy <= R) v = static_cast<unsigned>(gy * gy);
+    }
+    sG16[i] = static_cast<uint16_t>(v);
+  }
+  __syncthreads();
+  // anything within reach of this warp's 64 cells?
+  const int lane = threadIdx.x & 31, wbase = (threadIdx.x & ~31) * 2;
+  int any = 0;
+  for (int i = lane; i < (64 + 2 * Rp) / 2; i += 32) {
+    const unsigned p = sW[wbase / 2 + i];
+    any |= (p & 0xffffu) != kInf16 || (p >> 16) != kInf16;
+  }
+  any = __any_sync(0xffffffffu, any);
+  const int x = x0 + 2 * threadIdx.x;
+  if (x >= w) return;
+  const int cw = (Rp + 2 * threadIdx.x) / 2;  // word holding this thread's two cells
+  unsigned best2 = sW[cw];
+  if (any) {
+    unsigned Rw = best2, Lw = best2;
+    for (int k = 0;; ++k) {
+      const unsigned mx = max(best2 & 0xffffu, best2 >> 16);
+      if (k >= 1) {
+        const int d = 2 * k;
+        const unsigned dd = static_cast<unsigned>(d * d);
+        if (d > R || dd >= mx) break;
+        const unsigned dd2 = dd | (dd << 16);
+        best2 = __viaddmin_u16x2(Rw, dd2, best2);
+        best2 = __viaddmin_u16x2(Lw, dd2, best2);
+      }
+      const int d = 2 * k + 1;
+      const unsigned dd = static_cast<unsigned>(d * d);
+      if (d > R || dd >= mx) break;
+      const unsigned dd2 = dd | (dd << 16);
+      const unsigned Rn = sW[cw + k + 1], Ln = sW[cw - k - 1];
+      best2 = __viaddmin_u16x2(__funnelshift_r(Rw, Rn, 16), dd2, best2);  // cells x+d, x+1+d
+      best2 = __viaddmin_u16x2(__funnelshift_r(Ln, Lw, 16), dd2, best2);  // cells x-d, x+1-d
+      Rw = Rn;
+      Lw = Ln;
+    }
+  }
+  const int b0 = static_cast<int>(best2 & 0xffffu), b1 = static_cast<int>(best2 >> 16);
+  const int k0 = (b0 > kmax) ? (kmax + 1) : b0;
+  const int k1 = (b1 > kmax) ? (kmax + 1) : b1;
+  const size_t i = static_cast<size_t>(y) * w + x;
+  const bool two = x + 1 < w;
+  if (two && (i & 1) == 0) {
+    *reinterpret_cast<float2 *>(field + i) = make_float2(__ldg(lut_field + k0), __ldg(lut_field + k1));
+    if (distance) *reinterpret_cast<float2 *>(distance + i) = make_float2(__ldg(lut_dist + k0), __ldg(lut_dist + k1));
+  } else {
+    field[i] = __ldg(lut_field + k0);
+    if (distance) distance[i] = __ldg(lut_dist + k0);
+    if (two) {
+      field[i + 1] = __ldg(lut_field + k1);
+      if (distance) distance[i + 1] = __ldg(lut_dist + k1);
+    }
+  }
+  if (code) {
+    // x is even, so both cells sit in one 8-cell strip, next to each other
+    const uint32_t off = code_offset(x, y, code_strip_stride(h));
+    if (two) *reinterpret_cast<ushort2 *>(code + off) = make_ushort2(static_cast<uint16_t>(4 * k0), static_cast<uint16_t>(4 * k1));
+    else code[off] = static_cast<uint16_t>(4 * k0);
+  }
+}
+
 // Distance field on demand (qmcl_map_copy_distance): code -> metres.
 __global__ void __launch_bounds__(256)
 distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__restrict__ lut_dist,
@@ -212,118 +305,6 @@ distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__rest
   if (i >= static_cast<size_t>(w) * h) return;
   const uint32_t y = static_cast<uint32_t>(i / w), x = static_cast<uint32_t>(i - size_t(y) * w);
   out[i] = __ldg(lut_dist + (code[code_offset(x, y, code_strip_stride(h))] >> 2));
-}
-
-// K4: free-cell compaction (map_base.cpp:46-55), order = row-major.
-// Phase A: per-block count.  Phase B: single-block exclusive scan of the
-// counts.  Phase C: in-block scan + scatter.
-constexpr int kCompactBlock = 256;
-constexpr int kCompactItems = 16;  // contiguous cells per thread
-
-__device__ __forceinline__ int block_exclusive_scan_256(int v, int *total) {
-  __shared__ int warp_tot[kCompactBlock / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
-  }
-  if (lane == 31) warp_tot[wid] = incl;
-  __syncthreads();
-  int offset = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < kCompactBlock / 32; ++i) {
-    const int t = warp_tot[i];
-    if (i < wid) offset += t;
-    tot += t;
-  }
-  __syncthreads();
-  *total = tot;
-  return offset + incl - v;
-}
-
-// 16 consecutive state bytes as a 16-bit "is free" mask (one 16-byte load when
-// the run is inside the map and aligned).
-__device__ __forceinline__ unsigned free_mask16(const int8_t *__restrict__ state, size_t base,
-                                                size_t n) {
-  unsigned mask = 0;
-  if (base + 16 <= n && (reinterpret_cast<uintptr_t>(state + base) & 15u) == 0) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(state + base));
-    const unsigned wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (((wds[k] >> (8 * j)) & 0xffu) == 0) mask |= 1u << (4 * k + j);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (base + i < n && state[base + i] == 0) mask |= 1u << i;
-  }
-  return mask;
-}
-
-__global__ void __launch_bounds__(kCompactBlock)
-free_count_kernel(const int8_t *__restrict__ state, size_t n, uint32_t *__restrict__ counts) {
-  const size_t base =
-      (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
-  const int c = __popc(free_mask16(state, base, n));
-  int total;
-  block_exclusive_scan_256(c, &total);
-  if (threadIdx.x == 0) counts[blockIdx.x] = static_cast<uint32_t>(total);
-}
-
-// Exclusive scan of `n` uint32 in place by ONE block; grand total -> out_total.
-__global__ void __launch_bounds__(1024)
-scan_counts_kernel(uint32_t *__restrict__ counts, size_t n, unsigned long long *out_total) {
-  __shared__ unsigned long long warp_excl[32];
-  __shared__ unsigned long long chunk_total;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned long long carry = 0;
-  for (size_t base = 0; base < n; base += 1024) {
-    const size_t i = base + threadIdx.x;
-    const unsigned long long v = (i < n) ? counts[i] : 0;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    if (lane == 31) warp_excl[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      const unsigned long long t = warp_excl[lane];
-      unsigned long long ti = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, ti, o);
-        if (lane >= o) ti += up;
-      }
-      warp_excl[lane] = ti - t;
-      if (lane == 31) chunk_total = ti;
-    }
-    __syncthreads();
-    if (i < n) counts[i] = static_cast<uint32_t>(carry + warp_excl[wid] + incl - v);
-    carry += chunk_total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && out_total) *out_total = carry;
-}
-
-// The free-cell list holds linear cell indices (y * w + x, 4 bytes) in
-// row-major order, which is the order of map_base.cpp:46-55.
-__global__ void __launch_bounds__(kCompactBlock)
-free_scatter_kernel(const int8_t *__restrict__ state, size_t n,
-                    const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ out_idx) {
-  const size_t base =
-      (static_cast<size_t>(blockIdx.x) * kCompactBlock + threadIdx.x) * kCompactItems;
-  const unsigned mask = free_mask16(state, base, n);
-  int total;
-  size_t pos = block_offsets[blockIdx.x] + block_exclusive_scan_256(__popc(mask), &total);
-#pragma unroll
-  for (int i = 0; i < kCompactItems; ++i)
-    if (mask & (1u << i)) out_idx[pos++] = static_cast<uint32_t>(base + i);
 }
 
 // qmcl_map_copy_free_cells: (x, y) pairs as the reference's Vector2i list.
@@ -361,28 +342,35 @@ __global__ void random_pose_kernel(const uint32_t *__restrict__ free_xy, unsigne
 
 // ---------------------------------------------------------------- host side
 
+// K4: the free-cell list (map_base.cpp:46-55, row-major order) by one single-pass
+// compaction (scan.cuh, decoupled look-back).  The count stays on the device
+// until the caller's next synchronisation (read_free_count).
+struct FreeFlag {
+  const int8_t *state;
+  __device__ uint32_t operator()(size_t i) const { return state[i] == 0 ? 1u : 0u; }
+};
+struct EmitFree {
+  uint32_t *out;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+    if (flag) out[pos] = static_cast<uint32_t>(i);
+  }
+};
+// (One scan item per cell.  Eight cells per item — one 8-byte load, up to eight
+// indices written by one thread — was tried and is slower: 0.35 -> ~0.9 ms at
+// 8192^2, the stores of a warp then spread over 32 x 256 bytes.)
 static qmcl_status rebuild_free_cells(qmcl_map *m) {
   const size_t n = static_cast<size_t>(m->geom.w) * m->geom.h;
-  const unsigned blocks = div_up(n, static_cast<size_t>(kCompactBlock) * kCompactItems);
-  QMCL_TRY(m->scan_tmp.ensure(blocks + 4));
-  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(
-      m->scan_tmp.ptr + ((blocks + 1) & ~1u));
-  free_count_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(m->state.ptr, n, m->scan_tmp.ptr);
-  QMCL_LAUNCHED();
-  scan_counts_kernel<<<1, 1024, 0, m->stream>>>(m->scan_tmp.ptr, blocks, d_total);
-  QMCL_LAUNCHED();
-  unsigned long long total = 0;
-  QMCL_CUDA(copy_d2h(&total, d_total, sizeof(total), m->stream));
-  QMCL_CUDA(cudaStreamSynchronize(m->stream));
-  m->n_free = total;
-  QMCL_TRY(m->free_cells.ensure(total + 2));
-  if (total) {
-    free_scatter_kernel<<<blocks, kCompactBlock, 0, m->stream>>>(m->state.ptr, n, m->scan_tmp.ptr,
-                                                                 m->free_cells.ptr);
-    QMCL_LAUNCHED();
-  }
+  QMCL_TRY(m->free_cells.ensure(n + 2));  // worst case: every cell is free
+  QMCL_TRY(m->scan_tmp.ensure_zero(scan_tmp_words(n) + 8));
+  QMCL_TRY(m->h_count.ensure(2));
+  unsigned long long *d_total = scan_total_ptr(m->scan_tmp.ptr, n);
+  QMCL_TRY(device_scan(m->stream, FreeFlag{m->state.ptr}, EmitFree{m->free_cells.ptr}, n, m->scan_tmp.ptr,
+                       d_total));
+  QMCL_CUDA(copy_d2h(m->h_count.ptr, d_total, sizeof(unsigned long long), m->stream));
+  m->n_free = 0;  // read_free_count fills it in after the next synchronisation
   return QMCL_OK;
 }
+static void read_free_count(qmcl_map *m) { m->n_free = m->h_count.ptr[0]; }
 
 static void set_geometry(qmcl_map *m, uint32_t w, uint32_t h, float res, double ox, double oy) {
   // map_base.cpp:37-40: offset = (float)origin, res = (float)resolution
@@ -461,6 +449,9 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->tmp_aos.release();
   m->tmp_cloud.release();
   m->tmp_scalars.release();
+  m->h_count.release();
+  for (cudaEvent_t e : m->slab_events) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   delete m;
   return QMCL_OK;
 }
@@ -525,41 +516,84 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   const bool with_code = 4 * (kmax + 4) <= 65535;
   if (with_code) QMCL_TRY(m->code.ensure(code_map_elems(width, height)));
   else QMCL_TRY(m->distance.ensure(n));  // with codes the distance field is derived on demand
-  QMCL_CUDA(copy_h2d(m->occ.ptr, occ, n, m->stream));
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
   float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
-
   edt_lut_kernel<<<div_up(kmax + 2, 256), 256, 0, m->stream>>>(lut_dist, lut_field, kmax + 2,
                                                                resolution, max_dist, m->z_hit_pre);
   QMCL_LAUNCHED();
-  if (width % 4 == 0 && R <= 253) {
-    dim3 grid1(div_up(width, 4 * kColThreads), div_up(height, kColSeg));
-    edt_columns4_kernel<<<grid1, kColThreads, 0, m->stream>>>(
-        m->occ.ptr, m->state.ptr, g, static_cast<int>(width), static_cast<int>(height), R);
-  } else {
-    dim3 grid1(div_up(width, 128), div_up(height, kSegLen));
-    edt_columns_kernel<<<grid1, 128, 0, m->stream>>>(m->occ.ptr, m->state.ptr, g,
-                                                     static_cast<int>(width),
-                                                     static_cast<int>(height), R);
+  // The occupancy grid crosses PCIe in row slabs on a second stream while the
+  // slabs already here are transformed: a slab's column pass needs R rows of the
+  // next one, so it waits for that slab's copy; its row pass follows it.
+  const bool vec4 = width % 4 == 0 && R <= 253;
+  const int seg = vec4 ? kColSeg : kSegLen;
+  int n_slabs = static_cast<int>(std::min<uint32_t>(16, std::max<uint32_t>(1, height / 1024)));
+  int slab_rows = static_cast<int>(div_up(div_up(height, n_slabs), seg)) * seg;
+  if (slab_rows < R + seg) {  // a slab must cover the halo of its neighbour
+    n_slabs = 1;
+    slab_rows = static_cast<int>(div_up(height, seg)) * seg;
   }
-  QMCL_LAUNCHED();
-  dim3 grid2(div_up(width, kRowChunk), height);
-  const size_t smem = (kRowChunk + 2 * static_cast<size_t>(R)) * sizeof(int);
-  if (smem > 200 * 1024) return QMCL_ERR_INVALID_ARG;
-  if (smem > 48 * 1024)
-    QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-  edt_rows_kernel<<<grid2, kRowChunk, smem, m->stream>>>(
-      g, lut_dist, lut_field, with_code ? nullptr : m->distance.ptr, m->field.ptr,
-      with_code ? m->code.ptr : nullptr,
-      static_cast<int>(width), static_cast<int>(height), R, kmax);
-  QMCL_LAUNCHED();
+  n_slabs = static_cast<int>(div_up(height, slab_rows));
+  if (!m->copy_stream) QMCL_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  while (m->slab_events.size() < static_cast<size_t>(n_slabs) + 1) {
+    cudaEvent_t e = nullptr;
+    QMCL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->slab_events.push_back(e);
+  }
+  // the copies may not overtake work already queued on the map's stream that reads `occ`
+  QMCL_CUDA(cudaEventRecord(m->slab_events[n_slabs], m->stream));
+  QMCL_CUDA(cudaStreamWaitEvent(m->copy_stream, m->slab_events[n_slabs], 0));
+  for (int sl = 0; sl < n_slabs; ++sl) {
+    const size_t r0 = static_cast<size_t>(sl) * slab_rows;
+    const size_t r1 = std::min<size_t>(height, r0 + slab_rows);
+    QMCL_CUDA(copy_h2d(m->occ.ptr + r0 * width, occ + r0 * width, (r1 - r0) * width, m->copy_stream));
+    QMCL_CUDA(cudaEventRecord(m->slab_events[sl], m->copy_stream));
+  }
+  const bool rows2 = R <= kRow2MaxR;
+  const size_t smem2 = ((kRow2Cells + 2 * static_cast<size_t>((R + 1) & ~1)) / 2 + 4) * sizeof(unsigned);
+  const size_t smem1 = (kRowChunk + 2 * static_cast<size_t>(R)) * sizeof(int);
+  if (!rows2) {
+    if (smem1 > 200 * 1024) return QMCL_ERR_INVALID_ARG;
+    if (smem1 > 48 * 1024)
+      QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem1)));
+  }
+  for (int sl = 0; sl < n_slabs; ++sl) {
+    const int r0 = sl * slab_rows;
+    const int r1 = static_cast<int>(std::min<size_t>(height, static_cast<size_t>(r0) + slab_rows));
+    QMCL_CUDA(cudaStreamWaitEvent(m->stream, m->slab_events[std::min(sl + 1, n_slabs - 1)], 0));
+    const unsigned segs = div_up(r1 - r0, seg);
+    if (vec4) {
+      dim3 grid1(div_up(width, 4 * kColThreads), segs);
+      edt_columns4_kernel<<<grid1, kColThreads, 0, m->stream>>>(
+          m->occ.ptr, m->state.ptr, g, static_cast<int>(width), static_cast<int>(height), R, r0 / seg);
+    } else {
+      dim3 grid1(div_up(width, 128), segs);
+      edt_columns_kernel<<<grid1, 128, 0, m->stream>>>(m->occ.ptr, m->state.ptr, g,
+                                                       static_cast<int>(width),
+                                                       static_cast<int>(height), R, r0 / seg);
+    }
+    QMCL_LAUNCHED();
+    if (rows2) {
+      dim3 grid2(div_up(width, kRow2Cells), r1 - r0);
+      edt_rows2_kernel<<<grid2, 256, smem2, m->stream>>>(
+          g, lut_dist, lut_field, with_code ? nullptr : m->distance.ptr, m->field.ptr,
+          with_code ? m->code.ptr : nullptr, static_cast<int>(width), static_cast<int>(height), r0, R, kmax);
+    } else {
+      dim3 grid2(div_up(width, kRowChunk), r1 - r0);
+      edt_rows_kernel<<<grid2, kRowChunk, smem1, m->stream>>>(
+          g, lut_dist, lut_field, with_code ? nullptr : m->distance.ptr, m->field.ptr,
+          with_code ? m->code.ptr : nullptr, static_cast<int>(width), static_cast<int>(height), r0, R, kmax);
+    }
+    QMCL_LAUNCHED();
+  }
   QMCL_TRY(rebuild_free_cells(m));
   m->has_map = true;
   m->has_distance = true;
   m->has_code = with_code;
   m->n_codes = kmax + 2;
-  return sensor_prepare_map(m);
+  QMCL_TRY(sensor_prepare_map(m));  // synchronises: the free-cell count has arrived with it
+  read_free_count(m);
+  return QMCL_OK;
 }
 
 qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *state,
@@ -579,7 +613,9 @@ qmcl_status qmcl_map_load_field(qmcl_map *m, const float *field, const int8_t *s
   m->has_distance = false;
   m->has_code = false;
   m->n_codes = 0;
-  return sensor_prepare_map(m);
+  QMCL_TRY(sensor_prepare_map(m));  // synchronises: the free-cell count has arrived with it
+  read_free_count(m);
+  return QMCL_OK;
 }
 
 qmcl_status qmcl_map_size(const qmcl_map *m, uint32_t *width, uint32_t *height) {

@@ -76,6 +76,12 @@ struct qmcl_map {
   float lut_z_hit = 0.f, lut_zr = 0.f;
   double lut_p_max = 0.0;
 
+  // qmcl_map_load: the occupancy grid is copied in row slabs on copy_stream while
+  // earlier slabs are being transformed on `stream`
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> slab_events;
+  qmcl::PinnedBuf<unsigned long long> h_count;  // free-cell count read-back
+
   int refs = 1;  // the creator + one per filter
 
   // scratch for the host-vector update_importance overload

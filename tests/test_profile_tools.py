@@ -31,9 +31,10 @@ def test_kernel_tables_match_committed():
 
 
 def test_k9_lane_summary_model_matches_sequential_sum(tmp_path):
-    """tools/experiments/k9_lanes/model.cpp: the CPU model of the prepared K9 change
+    """tools/k9_lanes_model.cpp: the CPU model of the lane-wise resolution of binade-crossing chunks
+    (prefix mode 2, prefix_dev.cuh lane_chunk)
     reproduces the sequential sum bit for bit on its adversarial inputs."""
-    src = os.path.join(ROOT, "tools", "experiments", "k9_lanes", "model.cpp")
+    src = os.path.join(ROOT, "tools", "k9_lanes_model.cpp")
     exe = str(tmp_path / "k9model")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, src], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
