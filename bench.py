@@ -334,6 +334,7 @@ class Harness:
         if sharded:
             from quickmcl_b200.sharded import ShardedParticleFilter
             self.f = ShardedParticleFilter(self.gm, seed=3, group=dist.group.WORLD, transport=transport)
+            self.f.set_rebalance_threshold(0.05)   # equal blocks are restored only beyond 5 % drift
         else:
             self.f = q.create_particle_filter(self.gm, seed=3)
         self.sharded = sharded

@@ -195,6 +195,10 @@ qmcl_status qmcl_filter_set_comm(qmcl_filter *f, const qmcl_comm *comm);
 /* After a sharded resampling, move particles so that every rank again owns an
  * equal contiguous block (default 1 = on). */
 qmcl_status qmcl_filter_set_rebalance(qmcl_filter *f, int enabled);
+/* ... but only when some rank holds more than (1 + t) or less than (1 - t)
+ * times its equal share ("an optional all-to-all rebalances when the
+ * imbalance exceeds a threshold").  Default 0: after every resampling. */
+qmcl_status qmcl_filter_set_rebalance_threshold(qmcl_filter *f, double relative_imbalance);
 /* This shard's block: first global index and local count. */
 qmcl_status qmcl_filter_shard_range(const qmcl_filter *f, uint64_t *first, uint64_t *count,
                                     uint64_t *global_count);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "qmcl_nccl_comm_create": [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, vp],
     "qmcl_nccl_comm_destroy": [vp],
     "qmcl_filter_set_rebalance": [vp, C.c_int],
+    "qmcl_filter_set_rebalance_threshold": [vp, f64],
     "qmcl_filter_shard_range": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
     "qmcl_filter_set_particles_shard": [vp, pP, sz, u64, u64],
     "qmcl_filter_set_params": [vp, C.POINTER(PFParams)],

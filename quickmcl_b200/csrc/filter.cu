@@ -278,6 +278,10 @@ __device__ __forceinline__ void front_body(const FrontJob &J, const unsigned bx,
     return;
   }
   const unsigned b = bx - 1;
+  // L2 prefetch of the sensor kernel's map (one request per 128-byte line, spread over the grid)
+  for (size_t line = static_cast<size_t>(b) * 256 + threadIdx.x; line * 128 < J.prefetch_bytes;
+       line += static_cast<size_t>(nb) * 256)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(J.prefetch + line * 128));
   int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
   for (size_t i = static_cast<size_t>(b) * 256 + threadIdx.x; i < J.n; i += static_cast<size_t>(nb) * 256) {
     float px = J.x[i], py = J.y[i], pt = J.t[i];
@@ -393,6 +397,14 @@ qmcl_status front_prepare(qmcl_filter *f, const float *dev_cloud_xy, size_t n_po
   J.block_bbox = f->bbox.ptr + 8;
   J.bbox = f->bbox.ptr;
   J.blocks_done = &f->scalars.ptr->blocks_done;
+  // the palette map when it is the sensor path in use and fits L2 comfortably
+  if (m->pal8_valid && m->pal8_n > 0 && (m->sensor_path == 0 || m->sensor_path == 3)) {
+    const size_t bytes = code8_map_elems(m->geom.w, m->geom.h);
+    if (bytes <= (size_t(32) << 20)) {
+      J.prefetch = m->code8.ptr;
+      J.prefetch_bytes = bytes;
+    }
+  }
   f->motion_pending = false;
   f->early_bbox_version = f->pose_version;
   return QMCL_OK;

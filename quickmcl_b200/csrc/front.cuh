@@ -24,6 +24,10 @@ struct FrontJob {
   int *block_bbox;  // [gridDim.x - 1][6]
   int *bbox;        // [6]
   unsigned int *blocks_done;
+  // the map the sensor kernel is about to gather from (one-byte palette): its
+  // lines are requested into L2 while the motion model runs
+  const uint8_t *prefetch;
+  size_t prefetch_bytes;
 };
 
 

@@ -345,6 +345,23 @@ qmcl_status rebalance_blocks(qmcl_filter *f, ParticleSet &set, const std::vector
     balanced &= (lo[r] == a && hi[r] == a + c);
   }
   if (!f->rebalance || balanced) return QMCL_OK;
+  // Only worth an all-to-all when some rank has drifted from its equal share by more than the
+  // threshold (every rank evaluates the same table, so all take the same branch).  Blocks stay
+  // contiguous and in rank order either way; unequal blocks are what the no-rebalance mode runs on.
+  if (f->rebalance_threshold > 0.0) {
+    double worst = 0.0;
+    for (int r = 0; r < G; ++r) {
+      size_t a, c;
+      shard_slice_of(M, r, G, &a, &c);
+      const double have = static_cast<double>(hi[r] - lo[r]);
+      const double want = static_cast<double>(std::max<size_t>(c, 1));
+      worst = std::max(worst, std::fabs(have - want) / want);
+    }
+    if (worst <= f->rebalance_threshold) {
+      f->n_rebalance_skipped++;
+      return QMCL_OK;
+    }
+  }
   StageScope sc(f, QMCL_STAGE_GATHER);
   const size_t n_have = static_cast<size_t>(hi[me] - lo[me]);
   size_t my_a, my_c;

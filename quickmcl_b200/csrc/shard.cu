@@ -88,6 +88,12 @@ qmcl_status qmcl_filter_set_rebalance(qmcl_filter *f, int enabled) {
   return QMCL_OK;
 }
 
+qmcl_status qmcl_filter_set_rebalance_threshold(qmcl_filter *f, double relative_imbalance) {
+  if (!f || !(relative_imbalance >= 0.0)) return QMCL_ERR_INVALID_ARG;
+  f->rebalance_threshold = relative_imbalance;
+  return QMCL_OK;
+}
+
 qmcl_status qmcl_filter_shard_range(const qmcl_filter *f, uint64_t *first, uint64_t *count,
                                     uint64_t *global_count) {
   if (!f) return QMCL_ERR_INVALID_ARG;

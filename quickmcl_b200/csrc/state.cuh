@@ -182,6 +182,8 @@ struct qmcl_filter {
   int shard_rank = 0, n_shards = 1;
   qmcl_comm comm{0, 1, nullptr, nullptr, nullptr, nullptr};
   bool rebalance = true;
+  double rebalance_threshold = 0.0;  // relative imbalance below which the all-to-all is skipped (0: never)
+  uint64_t n_rebalance_skipped = 0;
   qmcl::DevBuf<uint8_t> xchg;        // collective payloads
   qmcl::DevBuf<uint8_t> xchg_send, xchg_recv;  // particle rebalancing (AoS)
   uint64_t n_collectives = 0;

@@ -214,6 +214,11 @@ class ShardedParticleFilter(ParticleFilter):
     def world_size(self):
         return self._size
 
+    def set_rebalance_threshold(self, relative_imbalance):
+        """Skip the rebalancing all-to-all while every rank is within this fraction of its share."""
+        check(self._L.qmcl_filter_set_rebalance_threshold(self._h, float(relative_imbalance)),
+              "qmcl_filter_set_rebalance_threshold")
+
     def set_rebalance(self, enabled):
         check(self._L.qmcl_filter_set_rebalance(self._h, int(enabled)),
               "qmcl_filter_set_rebalance")

@@ -138,7 +138,8 @@ def test_init_motion_sensor_match_oracle(G):
                                                  (3, 40_001, "global", True),
                                                  (8, 40_001, "global", False),
                                                  (4, 7, "tracking", True),
-                                                 (8, 300_000, "tracking", True)])
+                                                 (8, 300_000, "tracking", True),
+                                                 (4, 40_001, "global", "threshold")])
 def test_low_variance_resample_cluster_estimate_match_oracle(G, n, cloud, rebalance):
     s = Setup(particle_count_min=n, particle_count_max=n)
     if cloud == "tracking":
@@ -157,7 +158,10 @@ def test_low_variance_resample_cluster_estimate_match_oracle(G, n, cloud, rebala
 
     def body(f, rank):
         f.set_parameters(s.gpu_params())
-        check(f._L.qmcl_filter_set_rebalance(f._h, int(rebalance)), "rebalance")
+        check(f._L.qmcl_filter_set_rebalance(f._h, int(bool(rebalance))), "rebalance")
+        if rebalance == "threshold":   # the skewed weights move every rank far from its share: the
+            # all-to-all is skipped only under a threshold as loose as this one
+            check(f._L.qmcl_filter_set_rebalance_threshold(f._h, 100.0), "rebalance threshold")
         set_block(f, rank, G, start)
         f.set_rng(3, 5)
         f.resample_and_cluster()
@@ -175,10 +179,12 @@ def test_low_variance_resample_cluster_estimate_match_oracle(G, n, cloud, rebala
         assert np.array_equal(got[k], want[k]), k        # slot by slot the same source particle
     # the normalising total is a fixed tree sum here, a sequential sum in the reference
     assert rel_err(got["weight"], want["weight"]) <= 1e-11
-    if rebalance:
+    if rebalance is True:
         for rank, r in enumerate(res):
             first, count = sharded.shard_slice(n, rank, G)
             assert r[0][0] == first and len(r[0][1]) == count
+    if rebalance == "threshold":   # skipped: the blocks are the owner ranges, not the equal shares
+        assert any(len(r[0][1]) != sharded.shard_slice(n, rank, G)[1] for rank, r in enumerate(res))
     ok, o_pose, o_cov = of.get_estimated_pose()
     okeys, olabels = of.bins()
     for r in res:

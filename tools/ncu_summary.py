@@ -1,12 +1,13 @@
 """Prints the metrics of an .ncu-rep that the profiles/ summaries quote, and the
 warp-stall samples aggregated by code region (regions = runs of SASS lines with
-the same execution count).  Usage: python tools/ncu_summary.py report.ncu-rep"""
+the same execution count).  Usage: python tools/ncu_summary.py report.ncu-rep [kernel-name regex]"""
 import csv
 import io
 import subprocess
 import sys
 
 rep = sys.argv[1]
+KFILT = ["-k", "regex:" + sys.argv[2]] if len(sys.argv) > 2 else []   # optional kernel-name filter
 WANT = """gpu__time_duration.sum launch__grid_size launch__block_size launch__registers_per_thread
 sm__warps_active.avg.pct_of_peak_sustained_active dram__bytes_read.sum dram__bytes_write.sum
 lts__t_sector_hit_rate.pct l1tex__t_sector_hit_rate.pct lts__throughput.avg.pct_of_peak_sustained_elapsed
@@ -19,7 +20,7 @@ sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed sm__inst_execu
 sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active
 sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active smsp__warps_eligible.avg.per_cycle_active
 smsp__warps_active.avg.per_cycle_active sm__cycles_elapsed.max smsp__cycles_active.avg""".split()
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep] + KFILT + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h, units = rows[0], rows[1]
 for name in WANT:
@@ -33,7 +34,7 @@ for i, name in enumerate(h):
         v = [float(r[i]) for r in rows[2:]]
         if max(v) >= 0.3:
             print(f"{name:72s} " + " | ".join(f"{x:.2f}" for x in v))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + KFILT + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 k = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[k]
