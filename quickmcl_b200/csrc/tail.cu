@@ -892,8 +892,11 @@ constexpr size_t kTailOneBlock = 8192;                 // sets up to this size: 
 int tail_blocks_per_sm() {
   static int cached = -1;
   if (cached >= 0) return cached;
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tail_grid_kernel, kTailThreads, 0) != cudaSuccess)
+  int occ = 0, dev = 0, coop = 0;
+  // without cooperative launch (some virtualised devices) the multi-launch path serves every call
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tail_grid_kernel, kTailThreads, 0) != cudaSuccess)
     occ = 0;
   int want = 1;  // A/B at C2: one or two blocks per SM time the same; one leaves every register to the block
   if (const char *e = std::getenv("QMCL_TAIL_BLOCKS_PER_SM")) want = std::atoi(e);
