@@ -303,8 +303,10 @@ def workload_config(args, wl, n_used_beams):
             "beams_hit": n_used_beams, "num_beams": 0,
             "resample": RESAMPLE_NAMES[wl["pf"]["resample_type"]],
             "step": "handle_odometry+update_sensor+resample_and_cluster+get_estimate",
-            "l2": "flushed between steps (256 MiB write); one CUDA-event pair per step, summed "
-                  "(median and p95 alongside)",
+            "l2": ("NOT FLUSHED (QMCL_BENCH_NO_FLUSH diagnostic run: not a bench value)"
+                   if os.environ.get("QMCL_BENCH_NO_FLUSH") else
+                   "flushed between steps (256 MiB write); one CUDA-event pair per step, summed "
+                   "(median and p95 alongside)"),
             "host_waits": ("per value (QMCL_EAGER_SYNC)" if os.environ.get("QMCL_EAGER_SYNC", "0") not in ("", "0")
                            else ("one: the estimate (fused front + sensor + tail launches)" if args.gpus == 1
                                  else "deferred read-backs (qmcl_filter_set_sync_mode default)")),
@@ -553,6 +555,8 @@ def run_b200(args, wl):
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if os.environ.get("QMCL_BENCH_NO_FLUSH"):   # diagnostic only: such a line is not a bench value
+        flush = None
     PARITY_IT = 5000
 
     # N > 1: the same workload on ONE GPU first (rank 0, in this process), so that the speed-up

@@ -29,7 +29,10 @@
 //            Chunks that fail the check — the ones in which the sum crosses
 //            into the next binade, the very first chunk, and anything with a
 //            negative / subnormal / non-finite weight — are evaluated with
-//            true sequential double additions (256 adds each)
+//            true sequential double additions (256 adds each), except that a
+//            crossing predicted by phase 1 from the approximate carry (which
+//            element crosses) is verified with the exact carry and then costs
+//            one addition (prefix_dev.cuh)
 //   phase 3  every fast chunk expands its carry-in into the 256 running sums
 //            with integer arithmetic and writes them as doubles
 //
@@ -103,7 +106,8 @@ prefix_summaries_kernel(const double *__restrict__ w, size_t n, size_t nc, Prefi
 __global__ void __launch_bounds__(32)
 prefix_resolve_kernel(const double *__restrict__ w, size_t n, size_t nc, size_t nt, double carry_in,
                       PrefixBuffers pb, double *__restrict__ out) {
-  prefix_resolve_warp(w, n, nc, nt, carry_in, pb, out, threadIdx.x);
+  __shared__ ResolveScratch scratch;
+  prefix_resolve_warp(w, n, nc, nt, carry_in, pb, out, threadIdx.x, &scratch);
 }
 
 __global__ void __launch_bounds__(256)
@@ -127,7 +131,7 @@ prefix_shard_summary_kernel(PrefixBuffers pb, size_t nt, unsigned long long *__r
   Fn f = fn_identity();
   int E = -2;  // -2: nothing yet
   for (size_t t = t0; t < t1; ++t) {
-    const int tE = pb.tile_E[t];
+    const int tE = pb.tile_jx[t] >= 0 ? kInvalidE : pb.tile_E[t];  // a crossing: no plain summary
     if (E == -2) E = tE;
     else if (tE != E) E = kInvalidE;
     f = fn_compose(f, Fn{pb.tile_a0[t], pb.tile_a1[t]});
@@ -200,9 +204,12 @@ qmcl_status plan_prefix(qmcl_filter *f, size_t n, PrefixPlan *pl) {
     return at;
   };
   const size_t o_sum = carve(nc * 8), o_apx = carve(nc * 8), o_ca0 = carve(nc * 8),
-               o_ca1 = carve(nc * 8), o_ccin = carve(nc * 8), o_ta0 = carve(nt * 8),
-               o_ta1 = carve(nt * 8), o_tcin = carve(nt * 8), o_cE = carve(nc * 2),
-               o_tE = carve(nt * 2), o_cm = carve(nc), o_tm = carve(nt);
+               o_ca1 = carve(nc * 8), o_cb0 = carve(nc * 8), o_cb1 = carve(nc * 8),
+               o_cwx = carve(nc * 8), o_ccin = carve(nc * 8), o_ta0 = carve(nt * 8),
+               o_ta1 = carve(nt * 8), o_tb0 = carve(nt * 8), o_tb1 = carve(nt * 8),
+               o_twx = carve(nt * 8), o_tcin = carve(nt * 8), o_cE = carve(nc * 2),
+               o_cjx = carve(nc * 2), o_tE = carve(nt * 2), o_tjx = carve(nt * 2), o_cm = carve(nc),
+               o_tm = carve(nt);
   QMCL_TRY(f->prefix_scratch.ensure(off + 16));
   uint8_t *b = f->prefix_scratch.ptr;
   PrefixBuffers &pb = pl->pb;
@@ -210,20 +217,26 @@ qmcl_status plan_prefix(qmcl_filter *f, size_t n, PrefixPlan *pl) {
   pb.approx_in = reinterpret_cast<double *>(b + o_apx);
   pb.chunk_a0 = reinterpret_cast<unsigned long long *>(b + o_ca0);
   pb.chunk_a1 = reinterpret_cast<unsigned long long *>(b + o_ca1);
+  pb.chunk_b0 = reinterpret_cast<unsigned long long *>(b + o_cb0);
+  pb.chunk_b1 = reinterpret_cast<unsigned long long *>(b + o_cb1);
+  pb.chunk_wx = reinterpret_cast<double *>(b + o_cwx);
   pb.chunk_cin = reinterpret_cast<double *>(b + o_ccin);
   pb.tile_a0 = reinterpret_cast<unsigned long long *>(b + o_ta0);
   pb.tile_a1 = reinterpret_cast<unsigned long long *>(b + o_ta1);
+  pb.tile_b0 = reinterpret_cast<unsigned long long *>(b + o_tb0);
+  pb.tile_b1 = reinterpret_cast<unsigned long long *>(b + o_tb1);
+  pb.tile_wx = reinterpret_cast<double *>(b + o_twx);
   pb.tile_cin = reinterpret_cast<double *>(b + o_tcin);
   pb.chunk_E = reinterpret_cast<int16_t *>(b + o_cE);
+  pb.chunk_jx = reinterpret_cast<int16_t *>(b + o_cjx);
   pb.tile_E = reinterpret_cast<int16_t *>(b + o_tE);
+  pb.tile_jx = reinterpret_cast<int16_t *>(b + o_tjx);
   pb.chunk_mode = b + o_cm;
   pb.tile_mode = b + o_tm;
   pb.carry_out = f->prefix_carry.ptr;
-  // prefix mode 2 = binade-crossing chunks resolved lane-wise (lane_chunk) instead of by 256
-  // literal additions.  Bit-identical, but measured slower on the lone resolve warp (57 -> 81 us
-  // at 100 k particles: ~1500 dependent instructions per chunk at one warp's issue rate), so off
-  // by default; kept for A/B.
-  pb.lanes = f->prefix_mode == 2 ? 1 : 0;
+  // prefix mode 2 = no predicted crossings: every binade-crossing chunk is added literally
+  // (bit-identical; kept for A/B and as a cross-check of the speculation).
+  pb.speculate = f->prefix_mode == 2 ? 0 : 1;
   pl->nc = nc;
   pl->nt = nt;
   return QMCL_OK;

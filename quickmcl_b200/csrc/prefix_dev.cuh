@@ -17,7 +17,7 @@ constexpr unsigned long long kImplicit = 1ull << 52;
 constexpr unsigned long long kKLimit = 1ull << 53;
 constexpr int kInvalidE = -1;
 
-enum : uint8_t { MODE_FAST = 0, MODE_SLOW = 1, MODE_MIXED = 2 };
+enum : uint8_t { MODE_FAST = 0, MODE_SLOW = 1, MODE_MIXED = 2, MODE_CROSS = 3 };
 
 // Parity-dependent offset: K -> K + (K even ? a0 : a1).
 struct Fn {
@@ -58,6 +58,8 @@ __device__ __forceinline__ Fn fn_warp_scan(Fn v, int lane) {
 
 // Increment of one weight for a running sum in the binade with biased
 // exponent Eb.  Returns false when the closed form does not apply.
+#ifdef QMCL_ELEM_FN_INT
+// Integer form (round 1): shifts of the mantissa.  ~45 instructions.
 __device__ __forceinline__ bool elem_fn(double w, int Eb, Fn *out) {
   const long long bits = __double_as_longlong(w);
   *out = fn_identity();
@@ -82,6 +84,33 @@ __device__ __forceinline__ bool elem_fn(double w, int Eb, Fn *out) {
   }
   return true;
 }
+#else
+// The same in double arithmetic, a third of the instructions.  x = w / ulp is
+// exact (a power-of-two scaling; x < 2^52).  K + x rounded to nearest-even is
+// K + rint(x) unless x lies exactly half-way between two integers; then an even
+// K takes the even neighbour of x, which is rint(x), and an odd K the other one.
+// x - rint(x) is exact (at most 1/2 in magnitude and a multiple of ulp(x)), so
+// the tie test is exact too.  Binades below 2^-971 (Eb < 52: the scale factor
+// would overflow) get no closed form.  Checked against the integer form on 2e7
+// random / tie / boundary cases (tools/k9_model.cpp).
+__device__ __forceinline__ bool elem_fn(double w, int Eb, Fn *out) {
+  *out = fn_identity();
+  if (w == 0.0) return true;  // +-0 adds nothing
+  const double top = __longlong_as_double(static_cast<long long>(Eb) << 52);  // 2^E: w >= it leaves the binade
+  // negative, subnormal, inf, nan all fail one of the two comparisons
+  if (!(w >= 2.2250738585072014e-308 && w < top) || Eb < 52) return false;
+  const double scale = __longlong_as_double(static_cast<long long>(2098 - Eb) << 52);  // 2^(52 - E)
+  const double x = __dmul_rn(w, scale);
+  const double r = rint(x);
+  const double d = __dadd_rn(x, -r);
+  const unsigned long long a0 = static_cast<unsigned long long>(__double2ll_rn(r));
+  unsigned long long a1 = a0;
+  if (fabs(d) == 0.5) a1 = d > 0.0 ? a0 + 1ull : a0 - 1ull;
+  out->a0 = a0;
+  out->a1 = a1;
+  return true;
+}
+#endif
 
 __device__ __forceinline__ int biased_exponent_if_normal(double c) {
   const long long bits = __double_as_longlong(c);
@@ -132,165 +161,197 @@ __device__ __forceinline__ void prefix_chunk_sums_tile(const double *w, size_t n
   if (lane == 0) chunk_sum[chunk] = s;
 }
 
+// A summary is {E, a} — "in binade E the integer sum grows by a(parity)" — or,
+// with a predicted crossing (jx >= 0), {E, a, wx, b}: a over the elements before
+// element jx, then the literal addition of wx, which must take the sum into
+// binade E + 1, then b over the elements after it.  Tiles: jx is the index of
+// the crossing CHUNK inside the tile.
 struct PrefixBuffers {
   double *chunk_sum;     // nc
   double *approx_in;     // nc
-  unsigned long long *chunk_a0, *chunk_a1;  // nc
+  unsigned long long *chunk_a0, *chunk_a1, *chunk_b0, *chunk_b1;  // nc
+  double *chunk_wx;      // nc
   double *chunk_cin;     // nc   (phase 2, MIXED tiles only)
-  unsigned long long *tile_a0, *tile_a1;    // nt
+  unsigned long long *tile_a0, *tile_a1, *tile_b0, *tile_b1;      // nt
+  double *tile_wx;       // nt
   double *tile_cin;      // nt
   int16_t *chunk_E;      // nc   biased exponent guess, -1 = no closed form
+  int16_t *chunk_jx;     // nc   predicted crossing element (index inside the chunk), -1 = none
   int16_t *tile_E;       // nt
+  int16_t *tile_jx;      // nt   chunk (index inside the tile) with the predicted crossing, -1 = none
   uint8_t *chunk_mode;   // nc
   uint8_t *tile_mode;    // nt
   double *carry_out;     // 1
-  int lanes;             // 1: binade-crossing chunks are resolved lane-wise (lane_chunk)
+  int speculate;         // 1: predicted crossings are summarised; 0: such chunks are added literally
 };
 
+// Shared memory of the resolving warp: one chunk of weights / sums for the literal
+// additions.  The fused tail lends it from a buffer of a later phase.
+struct ResolveScratch {
+  double w[kChunk], o[kChunk];
+  // the summaries of the 32 tiles being walked
+  unsigned long long ta0[33], ta1[33], tb0[32], tb1[32];  // 33: the walk fetches one tile ahead
+  double twx[32];
+  int tE[33], tjx[33];
+};
+
+// One summary applied to the exact carry c (binade cE, valid).  True and *c_out
+// set when it holds: the sum is inside the binade at the end of `a` — weights
+// are >= 0 wherever a summary exists, so that bounds everything before — and,
+// with a crossing, right after wx it is one binade up and stays there through b.
+__device__ __forceinline__ bool apply_summary(double c, int cE, const Fn &a, int jx, double wx, const Fn &b,
+                                              double *c_out) {
+  const unsigned long long K1 = fn_apply(a, mantissa_int(c));
+  if (K1 >= kKLimit) return false;
+  if (jx < 0) {
+    *c_out = make_double(cE, K1);
+    return true;
+  }
+  const double c2 = __dadd_rn(make_double(cE, K1), wx);
+  if (biased_exponent_if_normal(c2) != cE + 1) return false;
+  const unsigned long long K3 = fn_apply(b, mantissa_int(c2));
+  if (K3 >= kKLimit) return false;
+  *c_out = make_double(cE + 1, K3);
+  return true;
+}
+
 // ---- phase 1: chunk and tile summaries under the guessed binade
+// The chunk in which the running sum crosses into the next binade (about
+// log2(N) chunks of a normalised weight array) has no summary of the plain
+// kind: where it crosses depends on the exact carry.  But the approximate
+// carry-in is good to a few thousand ulps while one weight is worth ~2^53 / N
+// of them, so the crossing ELEMENT can be predicted, and phase 2 checks the
+// prediction with the exact carry before using it (apply_summary).  A wrong
+// prediction only costs the literal additions of that chunk.
 QMCL_PHASE_FN void prefix_summaries_tile(const double *w, size_t n, size_t nc,
                                                       const PrefixBuffers &pb, size_t tile) {
-  __shared__ unsigned long long s_a0[kTileChunks], s_a1[kTileChunks];
-  __shared__ int s_E[kTileChunks];
+  __shared__ unsigned long long s_a0[kTileChunks], s_a1[kTileChunks], s_b0[kTileChunks], s_b1[kTileChunks];
+  __shared__ double s_wx[kTileChunks];
+  __shared__ int s_E[kTileChunks], s_jx[kTileChunks];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t chunk = tile * kTileChunks + wid;
-  int Eb = kInvalidE;
-  Fn f = fn_identity();
+  int Eb = kInvalidE, jx = -1;
+  Fn f = fn_identity(), tail = fn_identity();
+  double wx = 0.0;
   if (chunk < nc) {
-    Eb = biased_exponent_if_normal(pb.approx_in[chunk]);
+    const double approx = pb.approx_in[chunk];
+    Eb = biased_exponent_if_normal(approx);
     const size_t base = chunk * kChunk + static_cast<size_t>(lane) * kLaneItems;
     double v[kLaneItems];
     load_items(w, base, n, v);
+    Fn e[kLaneItems];
     bool ok = Eb != kInvalidE;
     if (ok) {
 #pragma unroll
       for (int i = 0; i < kLaneItems; ++i) {
-        Fn e;
-        ok &= elem_fn(v[i], Eb, &e);
-        f = fn_compose(f, e);
+        ok &= elem_fn(v[i], Eb, &e[i]);
+        f = fn_compose(f, e[i]);
       }
     }
     if (!__all_sync(0xffffffffu, ok)) Eb = kInvalidE;
     f = fn_warp_scan(f, lane);
+    if (Eb != kInvalidE && Eb < 0x7fd && pb.speculate) {
+      const unsigned long long K = mantissa_int(approx);  // approximate, like the carry it stands for
+      const unsigned int over = __ballot_sync(0xffffffffu, fn_apply(f, K) >= kKLimit);
+      if (over) {
+        // the lane, then the element, at which the approximate sum leaves the binade
+        const int L = __ffs(over) - 1;
+        Fn excl = fn_shfl_up(f, 1);
+        if (lane == 0) excl = fn_identity();
+        unsigned long long k = fn_apply(excl, K);
+        int ix = kLaneItems;
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < kLaneItems; ++i) {
+          k = fn_apply(e[i], k);
+          if (ix == kLaneItems && k >= kKLimit) {
+            ix = i;
+            mine = v[i];
+          }
+        }
+        ix = __shfl_sync(0xffffffffu, ix, L);
+        wx = __shfl_sync(0xffffffffu, mine, L);
+        jx = L * kLaneItems + ix;
+        Fn head = fn_identity();
+#pragma unroll
+        for (int i = 0; i < kLaneItems; ++i) {
+          const int idx = lane * kLaneItems + i;
+          if (idx < jx) {
+            head = fn_compose(head, e[i]);
+          } else if (idx > jx) {
+            Fn e1;
+            elem_fn(v[i], Eb + 1, &e1);  // valid under E, hence under E + 1
+            tail = fn_compose(tail, e1);
+          }
+        }
+        f = fn_warp_scan(head, lane);
+        tail = fn_warp_scan(tail, lane);
+      }
+    }
     if (lane == 31) {
       pb.chunk_a0[chunk] = f.a0;
       pb.chunk_a1[chunk] = f.a1;
+      pb.chunk_b0[chunk] = tail.a0;
+      pb.chunk_b1[chunk] = tail.a1;
+      pb.chunk_wx[chunk] = wx;
       pb.chunk_E[chunk] = static_cast<int16_t>(Eb);
+      pb.chunk_jx[chunk] = static_cast<int16_t>(jx);
     }
   }
   if (lane == 31) {
     s_a0[wid] = f.a0;
     s_a1[wid] = f.a1;
+    s_b0[wid] = tail.a0;
+    s_b1[wid] = tail.a1;
+    s_wx[wid] = wx;
     s_E[wid] = (chunk < nc) ? Eb : -2;  // -2: chunk beyond the end (identity)
+    s_jx[wid] = jx;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    Fn t = fn_identity();
-    int E = s_E[0];
-    for (int k = 0; k < kTileChunks; ++k) {
+    // the tile's summary: its chunks' in order; at most one crossing, after which the
+    // guesses must be one binade up
+    Fn a = fn_identity(), b = fn_identity();
+    int E = s_E[0], kx = -1;
+    double twx = 0.0;
+    for (int k = 0; k < kTileChunks && E != kInvalidE; ++k) {
       if (s_E[k] == -2) break;
-      if (s_E[k] != E) E = kInvalidE;
-      t = fn_compose(t, Fn{s_a0[k], s_a1[k]});
+      const Fn ca{s_a0[k], s_a1[k]};
+      if (kx < 0) {
+        if (s_E[k] != E) {
+          E = kInvalidE;
+        } else if (s_jx[k] < 0) {
+          a = fn_compose(a, ca);
+        } else {
+          a = fn_compose(a, ca);
+          twx = s_wx[k];
+          b = Fn{s_b0[k], s_b1[k]};
+          kx = k;
+        }
+      } else if (s_E[k] != E + 1 || s_jx[k] >= 0) {
+        E = kInvalidE;
+      } else {
+        b = fn_compose(b, ca);
+      }
     }
-    pb.tile_a0[tile] = t.a0;
-    pb.tile_a1[tile] = t.a1;
+    pb.tile_a0[tile] = a.a0;
+    pb.tile_a1[tile] = a.a1;
+    pb.tile_b0[tile] = b.a0;
+    pb.tile_b1[tile] = b.a1;
+    pb.tile_wx[tile] = twx;
     pb.tile_E[tile] = static_cast<int16_t>(E);
+    pb.tile_jx[tile] = static_cast<int16_t>(kx);
   }
-}
-
-// Phase 2 for a chunk whose summary does not apply because the running sum
-// crosses into the next binade inside it (about log2(N) chunks of a normalised
-// weight array).  Instead of 256 dependent additions the warp evaluates every
-// lane's 8 elements in closed form under the carry's binade E and under E + 1:
-// the lanes before the one in which the sum really crosses follow E, the lanes
-// after it E + 1, and only the crossing lane's 8 elements are added one by one
-// (the same additions on every lane, its elements broadcast by shuffles).  The
-// chunk's running sums are written here.  Returns false — nothing written —
-// when this does not apply (carry not normal, a second crossing, a negative /
-// subnormal / non-finite weight after the crossing); the caller then falls back
-// to the literal additions.  Bit-identical to them whenever it returns true
-// (CPU model of the algorithm: 540 adversarial arrays, round 1; GPU:
-// tests/test_prefix_gpu.py against the one-warp sequential kernel and numpy).
-__device__ __forceinline__ bool lane_chunk(const double *w, size_t n, size_t ch, double c, double *out,
-                                           int lane, double *c_out) {
-  const int cE = biased_exponent_if_normal(c);
-  if (cE == kInvalidE || cE >= 0x7fd) return false;
-  const size_t base = ch * kChunk + static_cast<size_t>(lane) * kLaneItems;
-  double v[kLaneItems];
-  load_items(w, base, n, v);
-  Fn e0[kLaneItems], e1[kLaneItems];
-  Fn F0 = fn_identity(), F1 = fn_identity();
-  bool ok0 = true, ok1 = true;
-#pragma unroll
-  for (int i = 0; i < kLaneItems; ++i) {
-    ok0 &= elem_fn(v[i], cE, &e0[i]);
-    F0 = fn_compose(F0, e0[i]);
-    ok1 &= elem_fn(v[i], cE + 1, &e1[i]);
-    F1 = fn_compose(F1, e1[i]);
-  }
-  const Fn incl = fn_warp_scan(F0, lane);
-  Fn excl = fn_shfl_up(incl, 1);
-  if (lane == 0) excl = fn_identity();
-  const unsigned long long K0 = mantissa_int(c);
-  const unsigned long long Kin = fn_apply(excl, K0), Kout = fn_apply(incl, K0);
-  // weights are >= 0 wherever a closed form exists, so K only grows: a lane is
-  // good iff its own end point is still inside the binade
-  const bool fine = ok0 && Kout < kKLimit;
-  const unsigned int bad = __ballot_sync(0xffffffffu, !fine);
-  int L = 32, myE = cE;
-  double cin;
-  if (bad == 0) {
-    cin = make_double(cE, Kin);
-    *c_out = make_double(cE, __shfl_sync(0xffffffffu, Kout, 31));
-  } else {
-    L = __ffs(bad) - 1;
-    const double cL = make_double(cE, __shfl_sync(0xffffffffu, Kin, L));
-    double cc = cL;  // the crossing lane's 8 elements: true additions (padding zeros add nothing)
-#pragma unroll
-    for (int i = 0; i < kLaneItems; ++i) cc = __dadd_rn(cc, __shfl_sync(0xffffffffu, v[i], L));
-    if (biased_exponent_if_normal(cc) != cE + 1) return false;
-    const Fn G = lane > L ? F1 : fn_identity();
-    const bool okG = lane > L ? ok1 : true;
-    const Fn incl2 = fn_warp_scan(G, lane);
-    Fn excl2 = fn_shfl_up(incl2, 1);
-    if (lane == 0) excl2 = fn_identity();
-    const unsigned long long K1 = mantissa_int(cc);
-    const unsigned long long Kin2 = fn_apply(excl2, K1), Kout2 = fn_apply(incl2, K1);
-    if (!__all_sync(0xffffffffu, okG && Kout2 < kKLimit)) return false;  // e.g. a second crossing
-    cin = lane < L ? make_double(cE, Kin) : (lane == L ? cL : make_double(cE + 1, Kin2));
-    myE = lane < L ? cE : cE + 1;
-    *c_out = make_double(cE + 1, __shfl_sync(0xffffffffu, Kout2, 31));
-  }
-  double r[kLaneItems];
-  if (lane == L) {
-    double cc = cin;
-#pragma unroll
-    for (int i = 0; i < kLaneItems; ++i) {
-      cc = __dadd_rn(cc, v[i]);
-      r[i] = cc;
-    }
-  } else {
-    unsigned long long K = mantissa_int(cin);
-#pragma unroll
-    for (int i = 0; i < kLaneItems; ++i) {
-      K = fn_apply(myE == cE ? e0[i] : e1[i], K);
-      r[i] = make_double(myE, K);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kLaneItems; ++i)
-    if (base + i < n) out[base + i] = r[i];
-  return true;
 }
 
 // Exact running sums of one chunk from the exact carry `c` (warp-uniform), for
 // chunks whose summary cannot be used: the literal sequence of double
 // additions.  The warp stages the chunk in shared memory, lane 0 runs the
 // dependent chain (bound by the DADD latency, the loads are issued ahead in
-// groups of 16), the warp writes the result back coalesced.  (A closed-form
-// variant that re-summarised the lanes around the crossing was tried; on one
-// latency-bound warp its ~800 instructions per round were slower than these
-// 256 additions.)
+// groups of 16), the warp writes the result back coalesced: 1.8 us per chunk on
+// the B200 (profiles/r2_resolve_trace.txt).  A closed-form variant that
+// re-summarised the lanes around the crossing inside this phase was tried twice;
+// on one latency-bound warp its ~1500 instructions took 4.4 us.
 __device__ __forceinline__ double exact_chunk(const double *w, size_t e0, int cnt, double c, double *out,
                                               int lane, double *s_w, double *s_o) {
 #pragma unroll
@@ -326,27 +387,55 @@ __device__ __forceinline__ double exact_chunk(const double *w, size_t e0, int cn
 }
 
 // ---- phase 2: the exact carry through all tiles (one warp)
+#ifdef QMCL_RESOLVE_TRACE
+// Diagnostic build only: (event id, %globaltimer) pairs of the resolving warp (tools/resolve_trace.py).
+static __device__ unsigned long long g_resolve_trace[4096];
+static __device__ unsigned int g_resolve_trace_n;
+#define RTRACE(id)                                                                 \
+  do {                                                                             \
+    if (lane == 0) {                                                               \
+      unsigned long long t_;                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                       \
+      const unsigned k_ = g_resolve_trace_n;                                       \
+      if (k_ + 2 <= 4096) {                                                        \
+        g_resolve_trace[k_] = (id);                                                \
+        g_resolve_trace[k_ + 1] = t_;                                              \
+        g_resolve_trace_n = k_ + 2;                                                \
+      }                                                                            \
+    }                                                                              \
+  } while (0)
+#else
+#define RTRACE(id) do { } while (0)
+#endif
 // Run by ONE warp (lane = its lane index); only __syncwarp inside.
 QMCL_PHASE_FN void prefix_resolve_warp(const double *w, size_t n, size_t nc, size_t nt,
                                                     double carry_in, const PrefixBuffers &pb,
-                                                    double *out, int lane) {
-  // chunk summaries of the current batch of 32 tiles, staged on demand
-  __shared__ unsigned long long s_a0[32 * kTileChunks], s_a1[32 * kTileChunks];
-  __shared__ int16_t s_E[32 * kTileChunks];
-  __shared__ double s_w[kChunk], s_o[kChunk];
+                                                    double *out, int lane, ResolveScratch *S) {
   double c = carry_in;  // uniform across the warp
+#ifdef QMCL_RESOLVE_TRACE
+  if (lane == 0) g_resolve_trace_n = 0;
+#endif
+  RTRACE(1);
   for (size_t base = 0; base < nt; base += 32) {
+    // the summaries of 32 tiles, one per lane
     const size_t t = base + lane;
-    Fn f = fn_identity();
-    int E = -2;
+    Fn f = fn_identity(), g = fn_identity();
+    double twx = 0.0;
+    int E = -2, tjx = -1;
     if (t < nt) {
       f.a0 = pb.tile_a0[t];
       f.a1 = pb.tile_a1[t];
+      g.a0 = pb.tile_b0[t];
+      g.a1 = pb.tile_b1[t];
+      twx = pb.tile_wx[t];
       E = pb.tile_E[t];
+      tjx = pb.tile_jx[t];
     }
+    RTRACE(2);
     const int Ec = biased_exponent_if_normal(c);
-    const bool lane_ok = (E == -2) || (E == Ec && Ec != kInvalidE);
+    const bool lane_ok = (E == -2) || (E == Ec && Ec != kInvalidE && tjx < 0);
     if (__all_sync(0xffffffffu, lane_ok)) {
+      // no crossing expected in any of them: one scan
       const Fn incl = fn_warp_scan(f, lane);
       const Fn total = fn_shfl(incl, 31);
       const unsigned long long K = mantissa_int(c);
@@ -359,67 +448,96 @@ QMCL_PHASE_FN void prefix_resolve_warp(const double *w, size_t n, size_t nc, siz
           pb.tile_mode[t] = MODE_FAST;
         }
         c = make_double(Ec, Kend);
+        RTRACE(3);
         continue;
       }
     }
-    // Walk these (up to) 32 tiles one by one; stage their chunk summaries first.
-    const size_t t_end = (base + 32 < nt) ? base + 32 : nt;
-    {
-      const size_t cb = base * kTileChunks;
-      for (int i = lane; i < 32 * kTileChunks; i += 32) {
-        const size_t ch = cb + i;
-        if (ch < nc) {
-          s_a0[i] = pb.chunk_a0[ch];
-          s_a1[i] = pb.chunk_a1[ch];
-          s_E[i] = pb.chunk_E[ch];
-        }
-      }
-      __syncwarp();
-    }
-    for (size_t tt = base; tt < t_end; ++tt) {
-      const Fn tf = fn_shfl(f, static_cast<int>(tt - base));
-      const int tE = __shfl_sync(0xffffffffu, E, static_cast<int>(tt - base));
-      int cE = biased_exponent_if_normal(c);
-      if (tE != kInvalidE && tE == cE) {
-        const unsigned long long Kend = fn_apply(tf, mantissa_int(c));
-        if (Kend < kKLimit) {
-          if (lane == 0) {
-            pb.tile_cin[tt] = c;
-            pb.tile_mode[tt] = MODE_FAST;
-          }
-          c = make_double(cE, Kend);
-          continue;
-        }
-      }
-      if (lane == 0) {
-        pb.tile_cin[tt] = c;
-        pb.tile_mode[tt] = MODE_MIXED;
-      }
-      const size_t ch0 = tt * kTileChunks;
-      const size_t ch1 = (ch0 + kTileChunks < nc) ? ch0 + kTileChunks : nc;
-      for (size_t ch = ch0; ch < ch1; ++ch) {
-        const int si = static_cast<int>(ch - base * kTileChunks);
-        cE = biased_exponent_if_normal(c);
-        const int chE = s_E[si];
-        if (chE != kInvalidE && chE == cE) {
-          const unsigned long long Kend = fn_apply(Fn{s_a0[si], s_a1[si]}, mantissa_int(c));
-          if (Kend < kKLimit) {
-            if (lane == 0) {
-              pb.chunk_cin[ch] = c;
-              pb.chunk_mode[ch] = MODE_FAST;
-            }
-            c = make_double(cE, Kend);
+    RTRACE(3);
+    // Walk these (up to) 32 tiles one by one, every lane alike.  A lone warp issues one
+    // instruction every ~5 cycles whatever it is (measured: profiles/r2_resolve_trace.txt), so
+    // the step of the common kind is kept to a couple of dozen instructions: the carry travels
+    // as (cE, K), the next tile's summary is fetched from shared memory ahead of its use, and
+    // each lane just remembers the carry of "its" tile — the carries are stored after the walk.
+    __syncwarp();
+    S->ta0[lane] = f.a0;
+    S->ta1[lane] = f.a1;
+    S->tb0[lane] = g.a0;
+    S->tb1[lane] = g.a1;
+    S->twx[lane] = twx;
+    S->tE[lane] = E;
+    S->tjx[lane] = tjx;
+    __syncwarp();
+    const int n_win = static_cast<int>(((base + 32 < nt) ? base + 32 : nt) - base);
+    int cE = biased_exponent_if_normal(c);
+    unsigned long long K = mantissa_int(c);
+    int nE = S->tE[0], nj = S->tjx[0];
+    unsigned long long na0 = S->ta0[0], na1 = S->ta1[0];
+    double my_cin = 0.0;
+    uint8_t my_mode = MODE_MIXED;
+    for (int i = 0; i < n_win; ++i) {
+      const int tE = nE, tj = nj;
+      const unsigned long long a0 = na0, a1 = na1;
+      nE = S->tE[i + 1];
+      nj = S->tjx[i + 1];
+      na0 = S->ta0[i + 1];
+      na1 = S->ta1[i + 1];
+      if (lane == i) my_cin = c;
+      if (tE == cE && cE != kInvalidE) {
+        const unsigned long long K1 = K + ((K & 1ull) ? a1 : a0);
+        if (K1 < kKLimit) {
+          if (tj < 0) {
+            if (lane == i) my_mode = MODE_FAST;
+            K = K1;
+            c = make_double(cE, K1);
             continue;
           }
+          // predicted crossing: one literal addition, then the rest of the tile one binade up
+          const double c2 = __dadd_rn(make_double(cE, K1), S->twx[i]);
+          if (biased_exponent_if_normal(c2) == cE + 1) {
+            const unsigned long long K3 = fn_apply(Fn{S->tb0[i], S->tb1[i]}, mantissa_int(c2));
+            if (K3 < kKLimit) {
+              if (lane == i) my_mode = MODE_CROSS;
+              ++cE;
+              K = K3;
+              c = make_double(cE, K3);
+              continue;
+            }
+          }
         }
-        if (pb.lanes) {
+      }
+      const size_t tt = base + i;
+      // open the tile (my_mode stays MODE_MIXED): its chunks' summaries, one per lane
+      RTRACE(5);
+      const size_t ch0 = tt * kTileChunks;
+      const size_t ch1 = (ch0 + kTileChunks < nc) ? ch0 + kTileChunks : nc;
+      Fn ca = fn_identity(), cb = fn_identity();
+      double cwx = 0.0;
+      int chE = kInvalidE, cjx = -1;
+      if (ch0 + lane < ch1) {
+        const size_t ch = ch0 + lane;
+        ca.a0 = pb.chunk_a0[ch];
+        ca.a1 = pb.chunk_a1[ch];
+        cb.a0 = pb.chunk_b0[ch];
+        cb.a1 = pb.chunk_b1[ch];
+        cwx = pb.chunk_wx[ch];
+        chE = pb.chunk_E[ch];
+        cjx = pb.chunk_jx[ch];
+      }
+      RTRACE(4);
+      for (size_t ch = ch0; ch < ch1; ++ch) {
+        const int k = static_cast<int>(ch - ch0);
+        cE = biased_exponent_if_normal(c);
+        const int kE = __shfl_sync(0xffffffffu, chE, k);
+        const int kj = __shfl_sync(0xffffffffu, cjx, k);
+        if (kE != kInvalidE && kE == cE) {
           double c_next;
-          if (lane_chunk(w, n, ch, c, out, lane, &c_next)) {
+          if (apply_summary(c, cE, fn_shfl(ca, k), kj, __shfl_sync(0xffffffffu, cwx, k), fn_shfl(cb, k), &c_next)) {
             if (lane == 0) {
-              pb.chunk_mode[ch] = MODE_SLOW;  // written here, phase 3 skips it
               pb.chunk_cin[ch] = c;
+              pb.chunk_mode[ch] = kj < 0 ? MODE_FAST : MODE_CROSS;
             }
             c = c_next;
+            RTRACE(6);
             continue;
           }
         }
@@ -429,11 +547,19 @@ QMCL_PHASE_FN void prefix_resolve_warp(const double *w, size_t n, size_t nc, siz
           pb.chunk_mode[ch] = MODE_SLOW;  // written here, phase 3 skips it
           pb.chunk_cin[ch] = c;
         }
-        c = exact_chunk(w, e0, cnt, c, out, lane, s_w, s_o);
+        RTRACE(7);
+        c = exact_chunk(w, e0, cnt, c, out, lane, S->w, S->o);
+        RTRACE(8);
       }
-      __syncwarp();
+      cE = biased_exponent_if_normal(c);
+      K = mantissa_int(c);
+    }
+    if (lane < n_win) {
+      pb.tile_cin[base + lane] = my_cin;
+      pb.tile_mode[base + lane] = my_mode;
     }
   }
+  RTRACE(9);
   if (lane == 0) *pb.carry_out = c;
 }
 
@@ -443,41 +569,86 @@ QMCL_PHASE_FN void prefix_apply_tile(const double *w, size_t n, size_t nc,
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t chunk = tile * kTileChunks + wid;
   if (chunk >= nc) return;
-  int Eb;
+  // the chunk's exact carry-in (Eb, K) and its crossing element, if phase 2 confirmed one
+  int Eb, jx = kChunk;
   unsigned long long K;
-  if (pb.tile_mode[tile] == MODE_FAST) {
+  const uint8_t tmode = pb.tile_mode[tile];
+  if (tmode != MODE_MIXED) {
+    // from the tile's carry-in through the summaries of the chunks before this one
     Eb = pb.tile_E[tile];
-    K = mantissa_int(pb.tile_cin[tile]);
-    Fn lane_cf = fn_identity();
+    const int kx = tmode == MODE_CROSS ? pb.tile_jx[tile] : -1;
+    double c = pb.tile_cin[tile];
+    Fn a = fn_identity(), b = fn_identity();
+    double cwx = 0.0;
     if (lane < wid) {
-      lane_cf.a0 = pb.chunk_a0[tile * kTileChunks + lane];
-      lane_cf.a1 = pb.chunk_a1[tile * kTileChunks + lane];
+      const size_t ch = tile * kTileChunks + lane;
+      a.a0 = pb.chunk_a0[ch];
+      a.a1 = pb.chunk_a1[ch];
+      if (lane == kx) {
+        b.a0 = pb.chunk_b0[ch];
+        b.a1 = pb.chunk_b1[ch];
+        cwx = pb.chunk_wx[ch];
+      }
     }
-    for (int j = 0; j < wid; ++j) K = fn_apply(fn_shfl(lane_cf, j), K);
+    for (int j = 0; j < wid; ++j) {
+      unsigned long long k = fn_apply(fn_shfl(a, j), mantissa_int(c));
+      if (j == kx) {
+        const double c2 = __dadd_rn(make_double(Eb, k), __shfl_sync(0xffffffffu, cwx, j));
+        k = fn_apply(fn_shfl(b, j), mantissa_int(c2));
+        ++Eb;
+      }
+      c = make_double(Eb, k);
+    }
+    K = mantissa_int(c);
+    if (wid == kx) jx = pb.chunk_jx[chunk];
   } else {
-    if (pb.chunk_mode[chunk] == MODE_SLOW) return;  // written by phase 2
+    const uint8_t mode = pb.chunk_mode[chunk];
+    if (mode == MODE_SLOW) return;  // written by phase 2
     Eb = pb.chunk_E[chunk];
     K = mantissa_int(pb.chunk_cin[chunk]);
+    if (mode == MODE_CROSS) jx = pb.chunk_jx[chunk];
   }
   const size_t base = chunk * kChunk + static_cast<size_t>(lane) * kLaneItems;
   double v[kLaneItems];
   load_items(w, base, n, v);
+  // elements before jx under Eb, element jx added literally, elements after it under Eb + 1
   Fn e[kLaneItems];
-  Fn f = fn_identity();
+  Fn head = fn_identity(), tail = fn_identity();
+  double mine = 0.0;
 #pragma unroll
   for (int i = 0; i < kLaneItems; ++i) {
-    elem_fn(v[i], Eb, &e[i]);
-    f = fn_compose(f, e[i]);
+    const int idx = lane * kLaneItems + i;
+    e[i] = fn_identity();
+    if (idx == jx) mine = v[i];
+    else elem_fn(v[i], idx < jx ? Eb : Eb + 1, &e[i]);
+    if (idx < jx) head = fn_compose(head, e[i]);
+    else tail = fn_compose(tail, e[i]);
   }
-  const Fn incl = fn_warp_scan(f, lane);
-  Fn excl = fn_shfl_up(incl, 1);
-  if (lane == 0) excl = fn_identity();
-  unsigned long long Kl = fn_apply(excl, K);
+  const Fn hs = fn_warp_scan(head, lane);
+  Fn hx = fn_shfl_up(hs, 1);
+  if (lane == 0) hx = fn_identity();
+  unsigned long long Kh = fn_apply(hx, K), Kt = 0;
+  double c2 = 0.0;
+  if (jx < kChunk) {
+    const Fn ts = fn_warp_scan(tail, lane);
+    Fn tx = fn_shfl_up(ts, 1);
+    if (lane == 0) tx = fn_identity();
+    c2 = __dadd_rn(make_double(Eb, fn_apply(fn_shfl(hs, 31), K)), __shfl_sync(0xffffffffu, mine, jx / kLaneItems));
+    Kt = fn_apply(tx, mantissa_int(c2));
+  }
   double r[kLaneItems];
 #pragma unroll
   for (int i = 0; i < kLaneItems; ++i) {
-    Kl = fn_apply(e[i], Kl);
-    r[i] = make_double(Eb, Kl);
+    const int idx = lane * kLaneItems + i;
+    if (idx < jx) {
+      Kh = fn_apply(e[i], Kh);
+      r[i] = make_double(Eb, Kh);
+    } else if (idx > jx) {
+      Kt = fn_apply(e[i], Kt);
+      r[i] = make_double(Eb + 1, Kt);
+    } else {
+      r[i] = c2;
+    }
   }
   if (base + kLaneItems <= n && (reinterpret_cast<uintptr_t>(out + base) & 15u) == 0) {
     double2 *p = reinterpret_cast<double2 *>(out + base);

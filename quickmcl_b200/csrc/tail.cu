@@ -303,7 +303,7 @@ template <class Team>
 __device__ void run_tail(const TailJob &J) {
   using namespace pfx;
   // block 0's scratch for the single-block phases (KLD stop rule, bin list + labelling)
-  __shared__ int32_t s_solo[3 * kSoloCells];
+  __shared__ __align__(16) int32_t s_solo[3 * kSoloCells];
   const Team team(J);
   const unsigned rank = Team::rank(), size = Team::size();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -445,7 +445,9 @@ __device__ void run_tail(const TailJob &J) {
     team.sync();
     TAIL_STAMP(TS_SUMMARIES);
     // ---- phase 2: the exact carry through all tiles (one warp)
-    if (rank == 0 && wid == 0) prefix_resolve_warp(J.iw, n_in, J.nc, J.nt, 0.0, J.pb, J.cdf, lane);
+    static_assert(sizeof(ResolveScratch) <= sizeof(s_solo), "the resolve scratch is lent from s_solo");
+    if (rank == 0 && wid == 0)
+      prefix_resolve_warp(J.iw, n_in, J.nc, J.nt, 0.0, J.pb, J.cdf, lane, reinterpret_cast<ResolveScratch *>(s_solo));
     team.sync(2560);
     TAIL_STAMP(TS_RESOLVE);
     // ---- phase 3: expand into the running sums; records of the positive weights
@@ -853,6 +855,19 @@ __global__ void __launch_bounds__(kTailThreads) tail_batch_kernel(const TailJob 
 }  // namespace qmcl
 
 extern "C" {
+
+#ifdef QMCL_RESOLVE_TRACE
+// Diagnostic build only: the resolving warp's event trace of the last fused tail (prefix_dev.cuh).
+qmcl_status qmcl_debug_resolve_trace(unsigned long long *out, size_t cap, size_t *n_out) {
+  unsigned int n = 0;
+  QMCL_CUDA(cudaDeviceSynchronize());
+  QMCL_CUDA(cudaMemcpyFromSymbol(&n, qmcl::pfx::g_resolve_trace_n, sizeof(n)));
+  if (n > cap) n = static_cast<unsigned int>(cap);
+  if (n) QMCL_CUDA(cudaMemcpyFromSymbol(out, qmcl::pfx::g_resolve_trace, n * sizeof(unsigned long long)));
+  *n_out = n;
+  return QMCL_OK;
+}
+#endif
 
 // Measurement hook: device time of every phase of the fused tail (ns, from
 // %globaltimer stamps taken by block 0 at the phase boundaries), summed over the

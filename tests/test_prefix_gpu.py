@@ -28,9 +28,9 @@ def seq_cumsum(w, carry=0.0):
 
 def check(filt, w, carry=0.0, oracle=True):
     w = np.ascontiguousarray(w, np.float64)
-    filt.set_prefix_mode(0)          # parallel, binade-crossing chunks by literal additions
+    filt.set_prefix_mode(0)          # parallel, predicted binade crossings summarised
     got, co = filt.debug_prefix(w, carry)
-    filt.set_prefix_mode(2)          # parallel, binade-crossing chunks resolved lane-wise
+    filt.set_prefix_mode(2)          # parallel, every binade-crossing chunk by literal additions
     got2, co2 = filt.debug_prefix(w, carry)
     filt.set_prefix_mode(1)          # the literal one-warp loop
     seq, co_seq = filt.debug_prefix(w, carry)
@@ -128,3 +128,55 @@ def test_degenerate_inputs_fall_back_to_true_additions(filt):
     z = np.zeros(10_000)
     z[7777] = 1.0
     check(filt, z)
+
+
+ULP = 2.0 ** -53      # of the binade [0.5, 1)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_crossing_at_every_element_of_a_chunk(filt, seed):
+    # carry 0.5 + dust, then one weight that takes the sum across 1.0 at element j of chunk 3,
+    # for every j; ties on both sides of the crossing (odd multiples of ulp/2 before it, of ulp
+    # after it), zeros sprinkled in
+    rng = np.random.default_rng(seed)
+    for j in list(range(0, 256, 5)) + [1, 254, 255]:
+        n = 2048 + int(rng.integers(0, 300))
+        w = (2 * rng.integers(0, 1 << 12, n) + 1).astype(np.float64) * (ULP / 2)
+        w[rng.random(n) < 0.1] = 0.0
+        at = 3 * 256 + j
+        w[at] = 0.5 - w[:at].sum() + float(rng.integers(0, 3)) * ULP
+        w[at + 1:] = (2 * rng.integers(0, 1 << 12, n - at - 1) + 1).astype(np.float64) * ULP
+        w[at + 1::7] = 0.0
+        got = check(filt, w, carry=0.5)
+        assert got[at - 1] < 1.0 <= got[at] or got[at] < 1.0    # the crossing is at `at` or just after
+
+
+def test_mispredicted_crossings_fall_back(filt):
+    # (a) dust that the sequential sum absorbs but a tree sum accumulates: the approximate carry
+    # runs ahead, the crossing is predicted too early
+    dust = np.full(200_000, 2.0 ** -55)
+    near = np.array([0.5 - 1000 * ULP])
+    steps = np.full(40, 100 * ULP)
+    w = np.concatenate([dust, near, steps, np.full(3000, 2.0 ** -30)])
+    got = check(filt, w, carry=0.5)
+    assert got[len(dust)] < 1.0 and got[len(dust) + 11] >= 1.0
+    # (b) every addition rounds up (0.75 ulp -> 1 ulp): the approximate carry lags, the crossing
+    # comes earlier than predicted
+    up = np.full(100_000, 0.75 * ULP)
+    near = np.array([0.5 - 90_000 * ULP])
+    w = np.concatenate([up, near, np.full(4000, 1000 * ULP)])
+    got = check(filt, w, carry=0.5)
+    assert got[len(up) - 1] < 1.0 <= got[len(up)]
+    # (c) two crossings inside one chunk, and a crossing in the very last (partial) chunk
+    w = np.concatenate([np.full(300, 2.0 ** -20), [0.5, 1.0], np.full(100, 2.0 ** -20)])
+    check(filt, w, carry=0.5)
+    w = np.concatenate([np.full(2048 + 17, 2.0 ** -20), [0.5 - 1000 * 2.0 ** -20], np.full(5, 2.0 ** -20)])
+    check(filt, w, carry=0.5)
+
+
+def test_crossings_with_the_largest_exponents(filt):
+    # the binade above the carry's must exist: sums near the top of the double range
+    w = np.full(5000, 2.0 ** 1010)
+    check(filt, w, carry=2.0 ** 1022)
+    w = np.full(5000, 2.0 ** 1000)
+    check(filt, w, carry=2.0 ** 1021)
