@@ -10,6 +10,7 @@
 #include "sensor.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -297,6 +298,351 @@ edt_rows2_kernel(const uint16_t *__restrict__ g, const float *__restrict__ lut_d
   }
 }
 
+// ---- fast path of the field build (width % 4 == 0, R <= 74) -----------------
+// The column distances fit a byte, the two sweeps of a column segment run on
+// different warps of one block (half the dependent chain each), their loads are
+// issued eight rows at a time, and the row pass takes eight rows per block so
+// that its fixed costs (staging, barrier, stores) are paid once per 4096 cells.
+
+constexpr int kColBSeg = 16;       // rows per column segment
+constexpr int kColBThreads = 128;  // x 4 columns; the block has 2 x 128 threads (down / up sweep)
+constexpr int kColBBatch = 8;      // rows loaded ahead of the dependent chain
+
+// 0x80 in every byte of v that holds an occupied cell (v > 65 as int8,
+// distance_calculator.cpp:200): low seven bits + 62 carry into bit 7 iff they are
+// >= 66, and the sign bit must be clear.
+__device__ __forceinline__ unsigned occupied_mask4(unsigned v) {
+  return ((v & 0x7f7f7f7fu) + 0x3e3e3e3eu) & ~v & 0x80808080u;
+}
+// One sweep step on four columns: distance + 1, 0 on an obstacle.  "No obstacle
+// yet" starts at 128 and a sweep is at most kColBSeg + R <= 90 rows long, so the
+// bytes never carry and everything >= 128 means out of reach.
+__device__ __forceinline__ unsigned sweep_step4(unsigned d, unsigned v) {
+  const unsigned m = occupied_mask4(v);
+  const unsigned keep = ~((m >> 7) * 0xffu);
+  return (d + 0x01010101u) & keep;
+}
+
+__global__ void __launch_bounds__(2 * kColBThreads)
+edt_columns_u8_kernel(const int8_t *__restrict__ occ, int8_t *__restrict__ state,
+                      uint8_t *__restrict__ g8, int w, int R, int row_first, int row_end, int h) {
+  __shared__ unsigned s_d[2][kColBSeg][kColBThreads];
+  const int t = threadIdx.x & (kColBThreads - 1);
+  const int up = threadIdx.x >> 7;  // warp-uniform
+  const int x = (blockIdx.x * kColBThreads + t) * 4;
+  const int y0 = row_first + blockIdx.y * kColBSeg;
+  const int y1 = min(row_end, y0 + kColBSeg);
+  if (x < w) {
+    const unsigned *occ4 = reinterpret_cast<const unsigned *>(occ + x);
+    const size_t w4 = static_cast<size_t>(w) >> 2;
+    unsigned d = 0x80808080u;
+    if (!up) {
+      const int ya = max(0, y0 - R);
+      for (int yb = ya; yb < y1; yb += kColBBatch) {
+        unsigned v[kColBBatch];
+#pragma unroll
+        for (int j = 0; j < kColBBatch; ++j)
+          v[j] = (yb + j < y1) ? __ldg(occ4 + static_cast<size_t>(yb + j) * w4) : 0u;
+#pragma unroll
+        for (int j = 0; j < kColBBatch; ++j) {
+          const int y = yb + j;
+          if (y < y1) {
+            d = sweep_step4(d, v[j]);
+            if (y >= y0) {
+              s_d[0][y - y0][t] = d;
+              const char4 c = *reinterpret_cast<const char4 *>(&v[j]);
+              *reinterpret_cast<char4 *>(state + static_cast<size_t>(y) * w + x) =
+                  make_char4(tri_state(c.x), tri_state(c.y), tri_state(c.z), tri_state(c.w));
+            }
+          }
+        }
+      }
+    } else {
+      const int ya = min(h, y1 + R) - 1;
+      for (int yb = ya; yb >= y0; yb -= kColBBatch) {
+        unsigned v[kColBBatch];
+#pragma unroll
+        for (int j = 0; j < kColBBatch; ++j)
+          v[j] = (yb - j >= y0) ? __ldg(occ4 + static_cast<size_t>(yb - j) * w4) : 0u;
+#pragma unroll
+        for (int j = 0; j < kColBBatch; ++j) {
+          const int y = yb - j;
+          if (y >= y0) {
+            d = sweep_step4(d, v[j]);
+            if (y < y1) s_d[1][y - y0][t] = d;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (y1 - y0) * kColBThreads; i += 2 * kColBThreads) {
+    const int r = i / kColBThreads, c = i % kColBThreads;
+    const int xx = (blockIdx.x * kColBThreads + c) * 4;
+    if (xx < w)
+      *reinterpret_cast<unsigned *>(g8 + static_cast<size_t>(y0 + r) * w + xx) =
+          __vminu4(s_d[0][r][c], s_d[1][r][c]);
+  }
+}
+
+// Row pass of the fast path: edt_rows2_kernel's search on 16-bit lanes, four cells
+// (two lane pairs A = x, x+1 and B = x+2, x+3) per thread and eight rows of 512
+// cells per block.  g arrives as bytes and is squared while it is staged.  B's
+// candidates at step d are A's at step d + 2, so one new word per side and
+// iteration feeds both pairs; the exit test runs once per two outward steps (extra
+// candidates inside the window never change the minimum).  A warp first marks which
+// 4-cell groups of its window hold a column distance within reach at all (one ballot
+// bit per group) and every thread starts its search at the nearest such group
+// instead of walking through cells that cannot contribute.  The uint16 codes leave
+// through shared memory so that every 128-byte line of the strip layout (8 x 8
+// cells) is written whole.
+constexpr int kRowBRows = 8;
+constexpr int kRowBCells = 512;
+constexpr int kRowBThreads = 256;  // two halves of 128 threads, four cells per thread
+// 64 bits of the 128-bit value {hi, lo} starting at bit s (0 <= s < 128)
+__device__ __forceinline__ unsigned long long bits_from128(unsigned long long lo, unsigned long long hi, int s) {
+  if (s == 0) return lo;
+  if (s < 64) return (lo >> s) | (hi << (64 - s));
+  return hi >> (s - 64);
+}
+__device__ __forceinline__ bool pair_finite(unsigned p) {
+  return (p & 0xffffu) != kInf16 || (p >> 16) != kInf16;
+}
+__global__ void __launch_bounds__(kRowBThreads)
+edt_rows_u8_kernel(const uint8_t *__restrict__ g8, const float *__restrict__ lut_dist,
+                   const float *__restrict__ lut_field, float *__restrict__ distance,
+                   float *__restrict__ field, uint16_t *__restrict__ code, int w, int h,
+                   int row_first, int row_end, int R, int kmax) {
+  extern __shared__ unsigned sW[];  // kRowBRows x wpr words of uint16 pairs, then the code tile
+  const int Rq = (R + 3) & ~3;      // halo in cells, a multiple of 4
+  const int wpr = (kRowBCells + 2 * Rq) / 2;
+  uint16_t *s_code = reinterpret_cast<uint16_t *>(sW + kRowBRows * wpr);  // [strip 64][row 8][8]
+  const int x0 = blockIdx.x * kRowBCells;
+  const int y0 = row_first + blockIdx.y * kRowBRows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    // warp r stages rows r and r + 4: one 4-cell word of g per lane and step
+    const int gw = (kRowBCells + 2 * Rq) / 4;
+    for (int rr = warp; rr < kRowBRows; rr += kRowBThreads / 32) {
+      const int y = y0 + rr;
+      for (int j = lane; j < gw; j += 32) {
+        const int xx = x0 - Rq + 4 * j;
+        unsigned v = 0xffffffffu;
+        if (y < row_end && xx >= 0 && xx < w)
+          v = __ldg(reinterpret_cast<const unsigned *>(g8 + static_cast<size_t>(y) * w + xx));
+        unsigned G[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const unsigned gb = (v >> (8 * b)) & 0xffu;
+          G[b] = (gb <= static_cast<unsigned>(R)) ? gb * gb : kInf16;
+        }
+        *reinterpret_cast<uint2 *>(sW + rr * wpr + 2 * j) =
+            make_uint2(G[0] | (G[1] << 16), G[2] | (G[3] << 16));
+      }
+    }
+  }
+  __syncthreads();
+  // threads 0-127 take rows 0-3 of the tile, threads 128-255 rows 4-7
+  const int tx = threadIdx.x & (kRowBThreads / 2 - 1), half = threadIdx.x / (kRowBThreads / 2);
+  const int x = x0 + 4 * tx;
+  const int c0 = Rq / 2 + 2 * tx;  // word of pair A; pair B is the next one
+  const uint32_t stride = code_strip_stride(h);
+  const int k_full = R >> 1;       // iterations k <= k_full take both steps 2k-1 and 2k
+  const int wlane = tx >> 5;       // this warp's 128-cell stretch of the row
+#pragma unroll 1
+  for (int r = half * (kRowBRows / 2); r < (half + 1) * (kRowBRows / 2); ++r) {
+    const int y = y0 + r;
+    if (y >= row_end) break;  // warp-uniform
+    const unsigned *Wr = sW + r * wpr;
+    // one bit per 4-cell group of this warp's window: bit i = words 64 * wlane + 2i, 2i + 1
+    // (i < 32 + Rq / 2 <= 70)
+    unsigned fm[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = 32 * q + lane;
+      bool fin = false;
+      if (i < 32 + Rq / 2) {
+        const uint2 p = *reinterpret_cast<const uint2 *>(Wr + 64 * wlane + 2 * i);
+        fin = pair_finite(p.x) || pair_finite(p.y);
+      }
+      fm[q] = __ballot_sync(0xffffffffu, fin);
+    }
+    unsigned bestA = Wr[c0], bestB = Wr[c0 + 1];
+    const unsigned long long M01 = fm[0] | (static_cast<unsigned long long>(fm[1]) << 32);
+    const unsigned long long M23 = fm[2];
+    const int b = Rq / 4 + lane;  // this thread's group in the window, 1 <= b <= 50
+    const unsigned long long right = bits_from128(M01, M23, b + 1);
+    const unsigned long long left = M01 << (64 - b);
+    const int jR = right ? __ffsll(static_cast<long long>(right)) : 1000;
+    const int jL = left ? __clzll(static_cast<long long>(left)) + 1 : 1000;
+    // group at offset j is first seen at step 4j - 3, i.e. in iteration 2j - 1; a
+    // group that holds a distance itself starts at step 1 (its cells are each other's
+    // neighbours)
+    const bool own = pair_finite(bestA) || pair_finite(bestB);
+    int kk = own ? 1 : 2 * min(jR, jL) - 1;
+    if (2 * kk - 1 <= R) {
+      const unsigned *pr = Wr + c0 + kk + 1, *pl = Wr + c0 - kk;  // next words outward
+      unsigned r0 = pr[-2], r1 = pr[-1], l1 = pl[1], l2 = pl[2];
+      const unsigned d0 = static_cast<unsigned>(2 * kk - 1);
+      unsigned po = d0 * d0 * 0x10001u;         // d^2 on both lanes, odd step d = 2k-1
+      unsigned inc = (2 * d0 + 1) * 0x10001u;   // (d+1)^2 - d^2
+      // steps 2k-1 and 2k; the exit test sees the odd step's d^2 (ties walk one more
+      // iteration: harmless)
+#define QMCL_EDT_STEP2(R0, R1, R2, L0, L1, L2)                                   \
+      {                                                                          \
+        const unsigned m = __vimax3_u16x2(bestA, bestB, bestB);                          \
+        if ((po & 0xffffu) >= max(m & 0xffffu, m >> 16)) break;                  \
+        R2 = *pr++;                                                              \
+        L0 = *pl--;                                                              \
+        bestA = __viaddmin_u16x2(__funnelshift_r(R0, R1, 16), po, bestA);        \
+        bestB = __viaddmin_u16x2(__funnelshift_r(R1, R2, 16), po, bestB);        \
+        bestA = __viaddmin_u16x2(__funnelshift_r(L0, L1, 16), po, bestA);        \
+        bestB = __viaddmin_u16x2(__funnelshift_r(L1, L2, 16), po, bestB);        \
+        const unsigned pe = po + inc;                                            \
+        bestA = __viaddmin_u16x2(R1, pe, bestA);                                 \
+        bestB = __viaddmin_u16x2(R2, pe, bestB);                                 \
+        bestA = __viaddmin_u16x2(L0, pe, bestA);                                 \
+        bestB = __viaddmin_u16x2(L1, pe, bestB);                                 \
+        po = pe + inc + 0x20002u;                                                \
+        inc += 0x40004u;                                                         \
+      }
+      unsigned r2, l0;
+      // three iterations per trip: the word registers rotate by renaming
+      while (true) {
+        if (kk > k_full) break;
+        QMCL_EDT_STEP2(r0, r1, r2, l0, l1, l2)
+        if (++kk > k_full) break;
+        QMCL_EDT_STEP2(r1, r2, r0, l2, l0, l1)
+        if (++kk > k_full) break;
+        QMCL_EDT_STEP2(r2, r0, r1, l1, l2, l0)
+        ++kk;
+      }
+#undef QMCL_EDT_STEP2
+      // R odd: the last outward step stands alone
+      if ((R & 1) && kk == k_full + 1) {
+        const unsigned m = __vimax3_u16x2(bestA, bestB, bestB);
+        if ((po & 0xffffu) < max(m & 0xffffu, m >> 16)) {
+          const unsigned *qr = Wr + c0 + kk, *ql = Wr + c0 - kk;
+          bestA = __viaddmin_u16x2(__funnelshift_r(qr[-1], qr[0], 16), po, bestA);
+          bestB = __viaddmin_u16x2(__funnelshift_r(qr[0], qr[1], 16), po, bestB);
+          bestA = __viaddmin_u16x2(__funnelshift_r(ql[0], ql[1], 16), po, bestA);
+          bestB = __viaddmin_u16x2(__funnelshift_r(ql[1], ql[2], 16), po, bestB);
+        }
+      }
+    }
+    int k[4] = {static_cast<int>(bestA & 0xffffu), static_cast<int>(bestA >> 16),
+                static_cast<int>(bestB & 0xffffu), static_cast<int>(bestB >> 16)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = (k[i] > kmax) ? (kmax + 1) : k[i];
+    if (code)  // tile in output order: strip, row, cell
+      *reinterpret_cast<uint2 *>(s_code + (tx >> 1) * 64 + r * 8 + 4 * (tx & 1)) =
+          make_uint2((4u * k[0]) | ((4u * k[1]) << 16), (4u * k[2]) | ((4u * k[3]) << 16));
+    if (x < w) {  // w % 4 == 0: all four cells exist, 16-byte aligned
+      const size_t i = static_cast<size_t>(y) * w + x;
+      *reinterpret_cast<float4 *>(field + i) = make_float4(__ldg(lut_field + k[0]), __ldg(lut_field + k[1]),
+                                                           __ldg(lut_field + k[2]), __ldg(lut_field + k[3]));
+      if (distance)
+        *reinterpret_cast<float4 *>(distance + i) = make_float4(__ldg(lut_dist + k[0]), __ldg(lut_dist + k[1]),
+                                                                __ldg(lut_dist + k[2]), __ldg(lut_dist + k[3]));
+    }
+  }
+  if (code) {
+    __syncthreads();
+    // 64 strips x 128 bytes; y0 is a multiple of 8, so a strip's eight rows are one line
+    const int rows = min(kRowBRows, row_end - y0);
+    for (int i = threadIdx.x; i < 64 * 8; i += kRowBThreads) {
+      const int strip = i >> 3, part = i & 7;  // part = row inside the strip's line
+      const int xs = x0 + 8 * strip;
+      if (xs < w && part < rows)
+        *reinterpret_cast<uint4 *>(code + static_cast<size_t>(xs >> 3) * stride +
+                                   8 * static_cast<size_t>(y0 + part)) =
+            *reinterpret_cast<const uint4 *>(s_code + strip * 64 + part * 8);
+    }
+  }
+}
+
+// K4 of the fast path: free cells of rows [first, end) appended to the list.  16
+// cells per thread (one 16-byte load), zero bytes counted with bit tricks, the
+// tile's indices compacted in shared memory and written out contiguously; tile
+// prefixes by decoupled look-back as in scan.cuh.  Slabs chain through *base_in.
+constexpr int kFreeTile = 4096;
+__device__ __forceinline__ unsigned zero_bytes4(unsigned v) {  // 0x80 in every zero byte
+  return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v | 0x7f7f7f7fu);
+}
+__global__ void __launch_bounds__(256)
+free_cells_u8_kernel(const int8_t *__restrict__ state, size_t first, size_t end,
+                     uint32_t *__restrict__ out, unsigned long long *__restrict__ status,
+                     uint32_t epoch, const unsigned long long *__restrict__ base_in,
+                     unsigned long long *__restrict__ total_out) {
+  __shared__ uint32_t s_idx[kFreeTile];
+  __shared__ uint32_t s_prefix;
+  const unsigned tile = blockIdx.x;
+  const size_t cell0 = first + static_cast<size_t>(tile) * kFreeTile + threadIdx.x * 16;
+  unsigned v[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
+  if (cell0 + 16 <= end) {
+    const uint4 q = *reinterpret_cast<const uint4 *>(state + cell0);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else if (cell0 < end) {
+    for (int b = 0; b < 16 && cell0 + b < end; ++b)
+      if (state[cell0 + b] == 0) v[b >> 2] &= ~(0xffu << (8 * (b & 3)));
+  }
+  unsigned z[4];
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    z[k] = zero_bytes4(v[k]);
+    c += __popc(z[k]);
+  }
+  uint32_t total;
+  uint32_t pos = block_excl_scan_u32(c, &total);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long *st = status;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      if (base_in) excl = static_cast<uint32_t>(*base_in);
+      if (lane == 0) st[0] = scan_pack(epoch, kScanInclusive, excl + total);
+    } else {
+      if (lane == 0) st[tile] = scan_pack(epoch, kScanAggregate, total);
+      __threadfence();
+      int hi = static_cast<int>(tile) - 1;
+      while (true) {
+        const int t = hi - lane;
+        unsigned long long wd = 0;
+        bool ready;
+        do {
+          wd = (t >= 0) ? st[t] : scan_pack(epoch, kScanInclusive, 0u);
+          ready = (wd >> 34) == epoch && (wd & (3ull << 32)) != 0;
+        } while (!__all_sync(0xffffffffu, ready));
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, (wd & kScanInclusive) != 0);
+        const int stop = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+        uint32_t part = (lane <= stop) ? static_cast<uint32_t>(wd) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        excl += part;
+        if (incl_mask) break;
+        hi -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        st[tile] = scan_pack(epoch, kScanInclusive, excl + total);
+      }
+    }
+    if (lane == 0) {
+      s_prefix = excl;
+      if (tile == gridDim.x - 1) *total_out = static_cast<unsigned long long>(excl) + total;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (z[k] & (0x80u << (8 * b))) s_idx[pos++] = static_cast<uint32_t>(cell0 + 4 * k + b);
+  __syncthreads();
+  uint32_t *dst = out + s_prefix;
+  for (uint32_t i = threadIdx.x; i < total; i += 256) dst[i] = s_idx[i];
+}
+
 // Distance field on demand (qmcl_map_copy_distance): code -> metres.
 __global__ void __launch_bounds__(256)
 distance_from_code_kernel(const uint16_t *__restrict__ code, const float *__restrict__ lut_dist,
@@ -372,6 +718,12 @@ static qmcl_status rebuild_free_cells(qmcl_map *m) {
 }
 static void read_free_count(qmcl_map *m) { m->n_free = m->h_count.ptr[0]; }
 
+static int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  const int v = e ? std::atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+
 static void set_geometry(qmcl_map *m, uint32_t w, uint32_t h, float res, double ox, double oy) {
   // map_base.cpp:37-40: offset = (float)origin, res = (float)resolution
   m->geom.w = w;
@@ -435,6 +787,7 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->occ.release();
   m->edt_g.release();
   m->scan_tmp.release();
+  m->free_totals.release();
   m->lut.release();
   m->code.release();
   m->pw3_lut.release();
@@ -451,7 +804,10 @@ qmcl_status qmcl_map_destroy(qmcl_map *m) {
   m->tmp_scalars.release();
   m->h_count.release();
   for (cudaEvent_t e : m->slab_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->col_events) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->col_stream) cudaStreamDestroy(m->col_stream);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   delete m;
   return QMCL_OK;
 }
@@ -518,48 +874,141 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
   else QMCL_TRY(m->distance.ensure(n));  // with codes the distance field is derived on demand
   uint16_t *g = reinterpret_cast<uint16_t *>(m->edt_g.ptr);
   float *lut_dist = m->lut.ptr, *lut_field = m->lut.ptr + (kmax + 2);
-  edt_lut_kernel<<<div_up(kmax + 2, 256), 256, 0, m->stream>>>(lut_dist, lut_field, kmax + 2,
-                                                               resolution, max_dist, m->z_hit_pre);
-  QMCL_LAUNCHED();
   // The occupancy grid crosses PCIe in row slabs on a second stream while the
   // slabs already here are transformed: a slab's column pass needs R rows of the
-  // next one, so it waits for that slab's copy; its row pass follows it.
+  // next one, so it waits for that slab's copy; its row pass and its share of the
+  // free-cell list follow it.  The last slab is split further so that little work
+  // is left once the final bytes have arrived.
   const bool vec4 = width % 4 == 0 && R <= 253;
-  const int seg = vec4 ? kColSeg : kSegLen;
-  int n_slabs = static_cast<int>(std::min<uint32_t>(16, std::max<uint32_t>(1, height / 1024)));
-  int slab_rows = static_cast<int>(div_up(div_up(height, n_slabs), seg)) * seg;
-  if (slab_rows < R + seg) {  // a slab must cover the halo of its neighbour
-    n_slabs = 1;
-    slab_rows = static_cast<int>(div_up(height, seg)) * seg;
+  const bool fast = width % 4 == 0 && R <= kRow2MaxR;
+  const int seg = fast ? kColBSeg : (vec4 ? kColSeg : kSegLen);
+  const int slab_pref = env_int("QMCL_MAP_SLAB_ROWS", 512);
+  const int tail_pref = env_int("QMCL_MAP_TAIL_ROWS", 256);
+  const int min_rows = static_cast<int>(div_up(R + seg, seg)) * seg;  // a slab covers its neighbour's halo
+  std::vector<int> bounds{0};
+  {
+    int rows = std::max(min_rows, static_cast<int>(div_up(std::max(slab_pref, seg), seg)) * seg);
+    if (static_cast<int>(div_up(height, rows)) > 30) rows = static_cast<int>(div_up(div_up(height, 30), seg)) * seg;
+    int y = 0;
+    while (static_cast<int>(height) - y > rows + min_rows) bounds.push_back(y += rows);
+    // the rest [y, height): halved down to the tail size
+    const int tail_rows = std::max(min_rows, static_cast<int>(div_up(std::max(tail_pref, seg), seg)) * seg);
+    int rest = static_cast<int>(height) - y;
+    while (fast && rest >= 2 * tail_rows) {
+      const int half = static_cast<int>(div_up(rest / 2, seg)) * seg;
+      bounds.push_back(y += half);
+      rest = static_cast<int>(height) - y;
+    }
+    bounds.push_back(static_cast<int>(height));
   }
-  n_slabs = static_cast<int>(div_up(height, slab_rows));
+  const int n_slabs = static_cast<int>(bounds.size()) - 1;
   if (!m->copy_stream) QMCL_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   while (m->slab_events.size() < static_cast<size_t>(n_slabs) + 1) {
     cudaEvent_t e = nullptr;
     QMCL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     m->slab_events.push_back(e);
   }
+  QMCL_TRY(m->h_count.ensure(2));
+  QMCL_TRY(m->free_totals.ensure(static_cast<size_t>(n_slabs) + 2));
+  // QMCL_MAP_TRACE=1: timestamps of every slab's copy and kernels on stderr (profiling aid)
+  const bool trace = env_int("QMCL_MAP_TRACE", 0) != 0;
+  std::vector<cudaEvent_t> tr_copy, tr_kern;
+  cudaEvent_t tr_start = nullptr;
+  if (trace) {
+    QMCL_CUDA(cudaEventCreate(&tr_start));
+    for (int i = 0; i < n_slabs; ++i) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      QMCL_CUDA(cudaEventCreate(&a));
+      QMCL_CUDA(cudaEventCreate(&b));
+      tr_copy.push_back(a);
+      tr_kern.push_back(b);
+    }
+    QMCL_CUDA(cudaEventRecord(tr_start, m->stream));
+  }
   // the copies may not overtake work already queued on the map's stream that reads `occ`
   QMCL_CUDA(cudaEventRecord(m->slab_events[n_slabs], m->stream));
   QMCL_CUDA(cudaStreamWaitEvent(m->copy_stream, m->slab_events[n_slabs], 0));
+  cudaStream_t cs = m->stream, as = m->stream;  // streams of the column pass and of the free-cell list
+  if (fast) {
+    if (!m->col_stream) QMCL_CUDA(cudaStreamCreateWithFlags(&m->col_stream, cudaStreamNonBlocking));
+    if (!m->aux_stream) QMCL_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+    while (m->col_events.size() < static_cast<size_t>(n_slabs) + 1) {
+      cudaEvent_t e = nullptr;
+      QMCL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      m->col_events.push_back(e);
+    }
+    // QMCL_MAP_STREAMS: 2 = everything on the map's stream, 3 = column pass + free-cell
+    // list on a second one, 4 = one stream each
+    const int n_streams = env_int("QMCL_MAP_STREAMS", 3);
+    cs = n_streams >= 3 ? m->col_stream : m->stream;
+    as = n_streams >= 4 ? m->aux_stream : cs;
+    if (cs != m->stream) QMCL_CUDA(cudaStreamWaitEvent(cs, m->slab_events[n_slabs], 0));
+    if (as != cs) QMCL_CUDA(cudaStreamWaitEvent(as, m->slab_events[n_slabs], 0));
+  }
+  // the tables and the division self-check only need the parameters and the geometry:
+  // they run under the first copy
+  edt_lut_kernel<<<div_up(kmax + 2, 256), 256, 0, m->stream>>>(lut_dist, lut_field, kmax + 2,
+                                                               resolution, max_dist, m->z_hit_pre);
+  QMCL_LAUNCHED();
+  QMCL_TRY(sensor_prepare_map_launch(m));
   for (int sl = 0; sl < n_slabs; ++sl) {
-    const size_t r0 = static_cast<size_t>(sl) * slab_rows;
-    const size_t r1 = std::min<size_t>(height, r0 + slab_rows);
+    const size_t r0 = bounds[sl], r1 = bounds[sl + 1];
     QMCL_CUDA(copy_h2d(m->occ.ptr + r0 * width, occ + r0 * width, (r1 - r0) * width, m->copy_stream));
     QMCL_CUDA(cudaEventRecord(m->slab_events[sl], m->copy_stream));
+    if (trace) QMCL_CUDA(cudaEventRecord(tr_copy[sl], m->copy_stream));
   }
   const bool rows2 = R <= kRow2MaxR;
   const size_t smem2 = ((kRow2Cells + 2 * static_cast<size_t>((R + 1) & ~1)) / 2 + 4) * sizeof(unsigned);
   const size_t smem1 = (kRowChunk + 2 * static_cast<size_t>(R)) * sizeof(int);
+  const size_t smemB = static_cast<size_t>(kRowBRows) * ((kRowBCells + 2 * ((R + 3) & ~3)) / 2) * sizeof(unsigned) +
+                       static_cast<size_t>(kRowBRows) * kRowBCells * sizeof(uint16_t);
   if (!rows2) {
     if (smem1 > 200 * 1024) return QMCL_ERR_INVALID_ARG;
     if (smem1 > 48 * 1024)
       QMCL_CUDA(cudaFuncSetAttribute(edt_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem1)));
   }
+  if (fast) {
+    QMCL_TRY(m->free_cells.ensure(n + 2));  // worst case: every cell is free
+    QMCL_TRY(m->scan_tmp.ensure_zero(scan_tmp_words(n) + 8 + 2 * static_cast<size_t>(n_slabs)));
+  }
+  size_t tile_base = 0;  // status words used by the free-cell kernels of earlier slabs
   for (int sl = 0; sl < n_slabs; ++sl) {
-    const int r0 = sl * slab_rows;
-    const int r1 = static_cast<int>(std::min<size_t>(height, static_cast<size_t>(r0) + slab_rows));
+    const int r0 = bounds[sl], r1 = bounds[sl + 1];
+    if (fast) {
+      // three streams: the column pass of a slab starts as soon as the next slab's copy
+      // has landed (its halo); the row pass and the slab's share of the free-cell list
+      // follow the column pass side by side.  Every kernel here is at most one wave of
+      // blocks, so the overlap is what fills the device.
+      QMCL_CUDA(cudaStreamWaitEvent(cs, m->slab_events[std::min(sl + 1, n_slabs - 1)], 0));
+      uint8_t *g8 = reinterpret_cast<uint8_t *>(m->edt_g.ptr);
+      dim3 grid1(div_up(width, 4 * kColBThreads), div_up(r1 - r0, kColBSeg));
+      edt_columns_u8_kernel<<<grid1, 2 * kColBThreads, 0, cs>>>(
+          m->occ.ptr, m->state.ptr, g8, static_cast<int>(width), R, r0, r1, static_cast<int>(height));
+      QMCL_LAUNCHED();
+      if (cs != m->stream) {
+        QMCL_CUDA(cudaEventRecord(m->col_events[sl], cs));
+        QMCL_CUDA(cudaStreamWaitEvent(m->stream, m->col_events[sl], 0));
+      }
+      dim3 grid2(div_up(width, kRowBCells), div_up(r1 - r0, kRowBRows));
+      edt_rows_u8_kernel<<<grid2, kRowBThreads, smemB, m->stream>>>(
+          g8, lut_dist, lut_field, with_code ? nullptr : m->distance.ptr, m->field.ptr,
+          with_code ? m->code.ptr : nullptr, static_cast<int>(width), static_cast<int>(height), r0, r1, R, kmax);
+      QMCL_LAUNCHED();
+      const size_t first = static_cast<size_t>(r0) * width, last = static_cast<size_t>(r1) * width;
+      const unsigned tiles = div_up(last - first, kFreeTile);
+      uint32_t epoch = g_scan_epoch.fetch_add(1, std::memory_order_relaxed) & 0x3fffffffu;
+      if (epoch == 0) epoch = g_scan_epoch.fetch_add(1, std::memory_order_relaxed) & 0x3fffffffu;
+      if (as != cs) QMCL_CUDA(cudaStreamWaitEvent(as, m->col_events[sl], 0));
+      free_cells_u8_kernel<<<tiles, 256, 0, as>>>(
+          m->state.ptr, first, last, m->free_cells.ptr,
+          reinterpret_cast<unsigned long long *>(m->scan_tmp.ptr) + tile_base, epoch,
+          sl ? m->free_totals.ptr + (sl - 1) : nullptr, m->free_totals.ptr + sl);
+      QMCL_LAUNCHED();
+      tile_base += tiles;
+      if (trace) QMCL_CUDA(cudaEventRecord(tr_kern[sl], m->stream));
+      continue;
+    }
     QMCL_CUDA(cudaStreamWaitEvent(m->stream, m->slab_events[std::min(sl + 1, n_slabs - 1)], 0));
     const unsigned segs = div_up(r1 - r0, seg);
     if (vec4) {
@@ -586,13 +1035,35 @@ qmcl_status qmcl_map_load(qmcl_map *m, const int8_t *occ, uint32_t width, uint32
     }
     QMCL_LAUNCHED();
   }
-  QMCL_TRY(rebuild_free_cells(m));
+  if (fast) {
+    if (as != m->stream) {
+      QMCL_CUDA(cudaEventRecord(m->col_events[n_slabs], as));
+      QMCL_CUDA(cudaStreamWaitEvent(m->stream, m->col_events[n_slabs], 0));
+    }
+    QMCL_CUDA(copy_d2h(m->h_count.ptr, m->free_totals.ptr + (n_slabs - 1), sizeof(unsigned long long), m->stream));
+    m->n_free = 0;
+  } else {
+    QMCL_TRY(rebuild_free_cells(m));
+  }
   m->has_map = true;
   m->has_distance = true;
   m->has_code = with_code;
   m->n_codes = kmax + 2;
-  QMCL_TRY(sensor_prepare_map(m));  // synchronises: the free-cell count has arrived with it
+  QMCL_TRY(sensor_prepare_map_finish(m));  // synchronises: the free-cell count has arrived with it
   read_free_count(m);
+  if (trace && fast) {
+    cudaStreamSynchronize(m->copy_stream);
+    for (int i = 0; i < n_slabs; ++i) {
+      float tc = 0.f, tk = 0.f;
+      cudaEventElapsedTime(&tc, tr_start, tr_copy[i]);
+      cudaEventElapsedTime(&tk, tr_start, tr_kern[i]);
+      fprintf(stderr, "slab %2d rows %5d-%5d  copy done %8.1f us  kernels done %8.1f us\n", i, bounds[i],
+              bounds[i + 1], 1e3 * tc, 1e3 * tk);
+      cudaEventDestroy(tr_copy[i]);
+      cudaEventDestroy(tr_kern[i]);
+    }
+    cudaEventDestroy(tr_start);
+  }
   return QMCL_OK;
 }
 

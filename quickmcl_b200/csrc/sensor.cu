@@ -698,21 +698,32 @@ static qmcl_status build_pal8(qmcl_map *m) {
   return QMCL_OK;
 }
 
-// Called at map load: decides whether the 3-op division may be used.
-qmcl_status sensor_prepare_map(qmcl_map *m) {
+// Called at map load: decides whether the 3-op division may be used.  The check
+// depends on the geometry only, so the load launches it ahead of its own work
+// (_launch) and picks the verdict up at its final synchronisation (_finish).
+qmcl_status sensor_prepare_map_launch(qmcl_map *m) {
   SensorParams sp = make_params(m);
-  QMCL_TRY(m->scan_tmp.ensure(8));
-  int *d_flag = reinterpret_cast<int *>(m->scan_tmp.ptr);
+  QMCL_TRY(m->h_count.ensure(2));
+  QMCL_TRY(m->free_totals.ensure(2));
+  int *d_flag = reinterpret_cast<int *>(m->free_totals.ptr + (m->free_totals.cap - 1));  // last word: never a slab total
   QMCL_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), m->stream));
   const unsigned threads = (std::max(m->geom.w, m->geom.h) + 8) * 9;
   fastdiv_check_kernel<<<div_up(threads, 256), 256, 0, m->stream>>>(sp, d_flag);
   QMCL_LAUNCHED();
-  int flag[2] = {1, 1};
-  QMCL_CUDA(copy_d2h(flag, d_flag, sizeof(flag), m->stream));
+  QMCL_CUDA(copy_d2h(m->h_count.ptr + 1, d_flag, 2 * sizeof(int), m->stream));
+  return QMCL_OK;
+}
+qmcl_status sensor_prepare_map_finish(qmcl_map *m) {
   QMCL_CUDA(cudaStreamSynchronize(m->stream));
+  int flag[2];
+  memcpy(flag, m->h_count.ptr + 1, sizeof(flag));
   m->div_verified = flag[0] ? DIV_IEEE : (flag[1] ? DIV_MARKSTEIN : DIV_SPLIT);
   m->lut_params_valid = false;
   return QMCL_OK;
+}
+qmcl_status sensor_prepare_map(qmcl_map *m) {
+  QMCL_TRY(sensor_prepare_map_launch(m));
+  return sensor_prepare_map_finish(m);
 }
 
 // A batch launch: dev_jobs[n_jobs] (device memory), the widest job needs grid_x blocks.

@@ -28,5 +28,7 @@ qmcl_status launch_sensor_batch(qmcl_map *m, const SensorLaunch *dev_jobs, unsig
                                 size_t max_particles);
 // After the map's field/geometry changed: verify the fast division, drop the LUT.
 qmcl_status sensor_prepare_map(qmcl_map *m);
+qmcl_status sensor_prepare_map_launch(qmcl_map *m);
+qmcl_status sensor_prepare_map_finish(qmcl_map *m);
 
 }  // namespace qmcl

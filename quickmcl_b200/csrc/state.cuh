@@ -78,9 +78,11 @@ struct qmcl_map {
 
   // qmcl_map_load: the occupancy grid is copied in row slabs on copy_stream while
   // earlier slabs are being transformed on `stream`
-  cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> slab_events;
-  qmcl::PinnedBuf<unsigned long long> h_count;  // free-cell count read-back
+  // (fast path: column passes on col_stream, row passes on `stream`, free-cell list on aux_stream)
+  cudaStream_t copy_stream = nullptr, col_stream = nullptr, aux_stream = nullptr;
+  std::vector<cudaEvent_t> slab_events, col_events;
+  qmcl::PinnedBuf<unsigned long long> h_count;  // [0] free-cell count, [1] division self-check flags
+  qmcl::DevBuf<unsigned long long> free_totals; // running free-cell count after each slab, then the flags
 
   int refs = 1;  // the creator + one per filter
 

@@ -99,3 +99,31 @@ def test_state_at_and_random_pose():
         assert occ[cy, cx] == 0 or (0 <= occ[cy, cx] < 35)
         assert -np.pi <= p[2] < np.pi
         assert ((free[:, 0] == cx) & (free[:, 1] == cy)).any()
+
+
+@pytest.mark.parametrize("shape,slab,tail", [((333, 404), 64, 32), ((1001, 520), 128, 64),
+                                             ((130, 1028), 48, 16)])
+def test_fast_path_slabs_chain_exactly(monkeypatch, shape, slab, tail):
+    """The byte-distance fast path (width % 4 == 0) with the load cut into many small
+    row slabs: column halos across slab borders, ragged last rows, and the free-cell
+    list appended slab by slab must reproduce the oracle bit for bit."""
+    monkeypatch.setenv("QMCL_MAP_SLAB_ROWS", str(slab))
+    monkeypatch.setenv("QMCL_MAP_TAIL_ROWS", str(tail))
+    rng = np.random.default_rng(shape[0])
+    occ = rng.choice(np.array([-1, 0, 20, 34, 35, 65, 66, 100, 127, -128], np.int8), size=shape,
+                     p=[.05, .85, .03, .02, .01, .01, .01, .01, .005, .005])
+    occ[shape[0] // 3:shape[0] // 3 + 90, 40:200] = 0     # an empty region wider than the reach
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    om = ob.OracleMap(**lp)
+    om.new_map(occ, 0.05, (-1.0, 2.0), field_mode=ob.FIELD_EXACT_EDT)
+    gm = gpu_map(occ, 0.05, (-1.0, 2.0), **lp)
+    assert np.array_equal(gm.state(), om.state())
+    assert np.array_equal(gm.distance(), om.distance())
+    assert np.array_equal(gm.field(), om.field())
+    assert np.array_equal(gm.free_cells(), om.free_cells())
+    # a second load on the same handle (status words of the first one are still there)
+    occ2 = np.ascontiguousarray(occ[::-1])
+    om.new_map(occ2, 0.05, (-1.0, 2.0), field_mode=ob.FIELD_EXACT_EDT)
+    gm.new_map(q.OccupancyGrid(occ2, 0.05, -1.0, 2.0))
+    assert np.array_equal(gm.distance(), om.distance())
+    assert np.array_equal(gm.free_cells(), om.free_cells())
