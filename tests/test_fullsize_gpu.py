@@ -1,6 +1,12 @@
 """BASELINE.json's full sizes (C2: 100 k particles / 2000^2 map / 1081 beams /
-KLD; C3: 1 M particles / 4000^2 map / adaptive) through size-independent
-properties, because the oracle cannot run them whole in test time:
+KLD; C3: 1 M particles / 4000^2 map / adaptive; C4: 16 M particles).
+
+Whole cycles against the oracle (it needs 0.3 s for a C2 update and a few seconds
+for a C3 one on one core): every weight, every resampled slot, the bins and the
+estimate at 100 k and at 1 M particles, and the resampling + clustering + estimate
+of a 16 M-particle set (test_whole_cycle_*, test_sixteen_million_*).
+
+And size-independent properties:
 
 * per-particle weights are independent of the rest of the set, so a random
   subset re-evaluated by the oracle must match the GPU's weights;
@@ -178,3 +184,114 @@ def test_sharded_equals_single_gpu_at_one_million():
     assert same.mean() > 0.9999, same.mean()
     ok2, pose2, cov2 = parts[0][2]
     assert ok1 and ok2 and np.max(np.abs(pose1 - pose2)) <= 1e-6
+
+
+def _pf(rtype, nmin, nmax):
+    return dict(resample_type=rtype, particle_count_min=nmin, particle_count_max=nmax,
+                res_theta=RES_THETA), \
+        q.ParticleFilterParameters(resample_type=q.ResampleType(rtype), particle_count_min=nmin,
+                                   particle_count_max=nmax,
+                                   space_partitioning_resolution_theta=RES_THETA)
+
+
+@pytest.mark.parametrize("width,n,cloud,rtype,inject", [
+    (2000, 100_000, "tracking", 2, False),      # C2: KLD
+    (4000, 1_000_000, "global", 1, True),       # C3: adaptive with injected random poses
+])
+def test_whole_cycle_at_full_size_matches_oracle(width, n, cloud, rtype, inject):
+    """One whole update at BASELINE.json's sizes on the path bench.py times (map built
+    by the library, one-byte palette, front kernel, fused tail where it applies) against
+    the oracle on the same field: every particle's pose after the motion model, every
+    weight, then - from identical weights - every resampled slot, bin, label and the
+    estimate."""
+    occ, res, origin, lp, gm, scan, start = setup(width, n, cloud)
+    om = ob.OracleMap(**lp)
+    om.load_field(gm.field(), gm.state(), res, origin)
+    of = ob.OracleFilter(om, seed=3)
+    of.set_trig_mode(ob.TRIG_CR)
+    gf = q.create_particle_filter(gm, seed=3)
+    po, pg = _pf(rtype, 100 if rtype == 2 else n, n)
+    of.set_parameters(**po)
+    gf.set_parameters(pg)
+    of.set_particles(start.view(ob.PARTICLE_DTYPE))
+    gf.set_particles(start)
+    for f in (of, gf):
+        f.set_rng(3, 5)
+        f.handle_odometry((0.25, 0.05, 0.1), (0.0, 0.0, 0.0), syn.NODE_ALPHA)
+        f.update_importance_from_observations(scan)
+    g, o = gf.get_particles(), of.get_particles()
+    for k in ("x", "y", "theta"):
+        assert np.max(np.abs(g[k].astype(np.float64) - o[k])) <= 1e-6, k
+    # the motion model differs in the last bit for a few particles per thousand; weights
+    # are compared where the poses agree exactly (the others moved by one ulp)
+    same = (g["x"] == o["x"]) & (g["y"] == o["y"]) & (g["theta"] == o["theta"])
+    assert same.mean() > 0.99
+    nz = o["weight"] > 0
+    assert np.array_equal(nz[same], (g["weight"] > 0)[same])
+    rel = np.abs(g["weight"] - o["weight"])[same & nz] / o["weight"][same & nz]
+    assert rel.max() <= 1e-5, rel.max()
+    assert abs(gf.last_total_weight() - of.last_total_weight()) <= 1e-5 * of.last_total_weight()
+    # identical weights are the premise of the bit-exactness claim
+    gf.set_particles(o.view(q.api.PARTICLE_DTYPE))
+    for f in (of, gf):
+        if inject:
+            f.set_lowpass(1.0, 0.8)
+        f.set_rng(3, 6)
+        f.resample_and_cluster()
+    assert gf.num_particles() == of.num_particles()
+    assert np.array_equal(gf.resample_indices(), of.resample_indices())
+    g, o = gf.get_particles(), of.get_particles()
+    for k in ("x", "y", "theta"):
+        assert np.array_equal(g[k], o[k]), k
+    assert np.max(np.abs(g["weight"] - o["weight"])) <= 1e-12 * np.max(o["weight"])
+    gk, gl = gf.bins()
+    ok_, ol = of.bins()
+    assert np.array_equal(gk, ok_)
+    assert np.array_equal(gl, ol)
+    assert gf.num_clusters() == of.num_clusters()
+    g_ok, g_pose, g_cov = gf.get_estimated_pose()
+    o_ok, o_pose, o_cov = of.get_estimated_pose()
+    assert g_ok and o_ok == 1
+    assert np.max(np.abs(g_pose[:2] - o_pose[:2])) <= 1e-4
+    assert abs(math.remainder(g_pose[2] - o_pose[2], 2 * math.pi)) <= 1e-4
+    assert np.max(np.abs(g_cov - o_cov)) <= 1e-6
+    print(f"{n} particles -> {gf.num_particles()}, {len(gk)} bins, {gf.num_clusters()} clusters, "
+          f"max weight error {rel.max():.2e}, estimate error {np.max(np.abs(g_pose - o_pose)):.2e}")
+
+
+def test_sixteen_million_resample_cluster_estimate_match_oracle():
+    """C4's particle count on one GPU: low-variance resampling, 5.8 M bins, labels and the
+    estimate of a 16 M-particle global cloud, slot for slot against the oracle (the sensor
+    model has no dependence on the set size and is covered above; the sharded run is
+    checked against this single-GPU path in bench.py --gpus N)."""
+    n = 16_000_000
+    occ, res, origin = syn.make_map(4000)
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    gm = q.create_likelihood_map()
+    gm.set_parameters(q.LikelihoodMapParameters(**lp))
+    gm.new_map(q.OccupancyGrid(occ, res, origin[0], origin[1]))
+    om = ob.OracleMap(**lp)
+    om.load_field(gm.field(), gm.state(), res, origin)
+    x, y, t = syn.uniform_cloud(occ, res, origin, n)
+    w = np.random.default_rng(0).random(n)
+    w[::7] = 0.0                                        # penalised particles
+    w /= w.sum()
+    of = ob.OracleFilter(om, seed=3)
+    gf = q.create_particle_filter(gm, seed=3)
+    po, pg = _pf(0, n, n)
+    of.set_parameters(**po)
+    gf.set_parameters(pg)
+    of.set_particles(ob.make_particles(x, y, t, w))
+    gf.set_particles(q.make_particles(x, y, t, w))
+    for f in (of, gf):
+        f.set_rng(3, 2)
+        f.resample_and_cluster()
+    assert gf.num_particles() == of.num_particles() == n
+    assert np.array_equal(gf.resample_indices(), of.resample_indices())
+    assert gf.num_clusters() == of.num_clusters()
+    g_ok, g_pose, g_cov = gf.get_estimated_pose()
+    o_ok, o_pose, o_cov = of.get_estimated_pose()
+    assert g_ok and o_ok == 1
+    assert np.max(np.abs(g_pose[:2] - o_pose[:2])) <= 1e-4
+    assert abs(math.remainder(g_pose[2] - o_pose[2], 2 * math.pi)) <= 1e-4
+    assert np.max(np.abs(g_cov - o_cov)) <= 1e-6
