@@ -168,7 +168,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f);
  * Every buffer is a DEVICE pointer.  A call must be ordered after the work
  * already enqueued on `stream` (the filter's cudaStream_t) and the filter's
  * later work on that stream must see its result.  Return 0 on success. */
-enum { QMCL_DT_I32 = 0, QMCL_DT_I64 = 1, QMCL_DT_F64 = 2 };
+enum { QMCL_DT_I32 = 0, QMCL_DT_I64 = 1, QMCL_DT_F64 = 2, QMCL_DT_U8 = 3 };
 enum { QMCL_OP_SUM = 0, QMCL_OP_MIN = 1, QMCL_OP_MAX = 2 };
 typedef struct qmcl_comm {
   int rank, size;

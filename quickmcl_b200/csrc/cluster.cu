@@ -38,6 +38,20 @@ bin_mark_kernel(const float *__restrict__ x, const float *__restrict__ y,
 }
 
 __global__ void __launch_bounds__(256)
+bin_mark_occupancy_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                          const float *__restrict__ t, size_t n, BinParams bp, BinGrid g,
+                          unsigned *__restrict__ occ_words) {
+  bin_mark_occupancy(x, y, t, n, bp, g, occ_words, static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256)
+bin_count_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                 const float *__restrict__ t, size_t n, BinParams bp, BinGrid g,
+                 const int32_t *__restrict__ table, int32_t *__restrict__ bin_count) {
+  bin_count_one(x, y, t, n, bp, g, table, bin_count, static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256)
 cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bin_cell,
                size_t n_bins, const unsigned long long *__restrict__ n_bins_dev, BinGrid g,
                BinParams bp, int32_t *__restrict__ parent) {
@@ -91,6 +105,89 @@ best_cluster_kernel(const unsigned long long *__restrict__ cluster_w, size_t n_c
   // the count may still be on its way to the host (label_clusters, deferred)
   if (n_clusters_dev) n_clusters = static_cast<size_t>(*n_clusters_dev);
   best_cluster_block(cluster_w, n_clusters, es);
+}
+
+// The same over many blocks, for cluster lists of a global cloud (tens of
+// thousands of clusters and more; one block needs 24 us for 47 k of them): block
+// maxima into scratch, the last block to finish folds them.  Integer comparisons
+// with the index as the tie-break: the result does not depend on the order.
+__global__ void __launch_bounds__(256)
+best_cluster_multi_kernel(const unsigned long long *__restrict__ cluster_w, size_t n_clusters,
+                          const unsigned long long *__restrict__ n_clusters_dev,
+                          EstimateScalars *__restrict__ es, unsigned long long *__restrict__ part_w,
+                          long long *__restrict__ part_i) {
+  __shared__ unsigned long long s_w[8];
+  __shared__ long long s_i[8];
+  __shared__ bool s_last;
+  if (n_clusters_dev) n_clusters = static_cast<size_t>(*n_clusters_dev);
+  auto better = [](unsigned long long w1, long long i1, unsigned long long w2, long long i2) {
+    if (i1 < 0) return false;
+    if (i2 < 0) return true;
+    return w1 > w2 || (w1 == w2 && i1 < i2);
+  };
+  auto warp_best = [&](unsigned long long &bw, long long &bi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ow = __shfl_xor_sync(0xffffffffu, bw, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ow, oi, bw, bi)) {
+        bw = ow;
+        bi = oi;
+      }
+    }
+  };
+  unsigned long long bw = 0;
+  long long bi = -1;
+  for (size_t c = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < n_clusters;
+       c += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long v = cluster_w[c];
+    if (bi < 0 || v > bw) {
+      bw = v;
+      bi = static_cast<long long>(c);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  warp_best(bw, bi);
+  if (lane == 0) {
+    s_w[wid] = bw;
+    s_i[wid] = bi;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    bw = lane < 8 ? s_w[lane] : 0ull;
+    bi = lane < 8 ? s_i[lane] : -1ll;
+    warp_best(bw, bi);
+    if (lane == 0) {
+      part_w[blockIdx.x] = bw;
+      part_i[blockIdx.x] = bi;
+      __threadfence();
+      s_last = atomicAdd(&es->pad, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!s_last || wid != 0) return;
+  __threadfence();
+  bw = 0;
+  bi = -1;
+  for (unsigned b = lane; b < gridDim.x; b += 32) {
+    const unsigned long long v = __ldcg(part_w + b);
+    const long long i = __ldcg(part_i + b);
+    if (better(v, i, bw, bi)) {
+      bw = v;
+      bi = i;
+    }
+  }
+  warp_best(bw, bi);
+  if (lane == 0) {
+    es->best = static_cast<int>(bi);
+    es->best_w = bw;
+    es->pad = 0;
+  }
+}
+
+// sharded estimate: the "a bin has no cluster" flag as a double behind the moment sums
+__global__ void pack_invalid_kernel(const EstimateScalars *__restrict__ es, double *__restrict__ out) {
+  *out = es->invalid ? 1.0 : 0.0;
 }
 
 // statistics.cpp:23-41 for the best cluster and for all particles: block
@@ -229,28 +326,44 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     f->bins_built = true;
     return QMCL_OK;
   }
-  QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0, cells * sizeof(int32_t), s));
-  if (n) {
-    bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);
-    QMCL_LAUNCHED();
-  }
   size_t n_all = n;
-  if (sharded(f)) {
-    // Exchange: bin occupancy counts summed over the shards; the occupied-bin
-    // list and the labels are then computed identically on every rank.
-    QMCL_TRY(shard_allreduce(f, f->table.ptr, cells, QMCL_DT_I32, QMCL_OP_SUM));
-    n_all = f->global_n;
-  }
-  const size_t max_bins = std::min(n_all, cells);
-  QMCL_TRY(f->bin_cell.ensure(max_bins));
-  QMCL_TRY(f->bin_count.ensure(max_bins));
-  QMCL_TRY(f->bin_label.ensure(max_bins));
-  QMCL_TRY(f->bin_cluster.ensure(max_bins));
+  const size_t max_bins_local = std::min(sharded(f) ? f->global_n : n, cells);
+  QMCL_TRY(f->bin_cell.ensure(max_bins_local));
+  QMCL_TRY(f->bin_count.ensure(max_bins_local));
+  QMCL_TRY(f->bin_label.ensure(max_bins_local));
+  QMCL_TRY(f->bin_cluster.ensure(max_bins_local));
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(cells) + 4));
   unsigned long long *d_total = &f->scalars.ptr->n_bins;  // stable: the labelling reads it
-  QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
-                       EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
-                       cells, f->scan_tmp.ptr, d_total));
+  if (sharded(f)) {
+    // Exchange: bin OCCUPANCY, one byte per cell, max-reduced over the shards (a
+    // quarter of the count table's bytes); the occupied-bin list and the labels are
+    // then computed identically on every rank.  Counts: bin_counts_on_demand.
+    const size_t words = (cells + 3) / 4;
+    QMCL_TRY(f->occ8.ensure(4 * words));
+    QMCL_CUDA(cudaMemsetAsync(f->occ8.ptr, 0, 4 * words, s));
+    if (n) {
+      bin_mark_occupancy_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g,
+                                                               reinterpret_cast<unsigned *>(f->occ8.ptr));
+      QMCL_LAUNCHED();
+    }
+    QMCL_TRY(shard_allreduce(f, f->occ8.ptr, 4 * words, QMCL_DT_U8, QMCL_OP_MAX));
+    n_all = f->global_n;
+    QMCL_TRY(device_scan(s, OccupiedByte{f->occ8.ptr},
+                         EmitBinOccupancy{f->table.ptr, f->bin_cell.ptr, f->bin_label.ptr}, cells,
+                         f->scan_tmp.ptr, d_total));
+    f->bin_counts_valid = false;
+  } else {
+    QMCL_CUDA(cudaMemsetAsync(f->table.ptr, 0, cells * sizeof(int32_t), s));
+    if (n) {
+      bin_mark_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g, f->table.ptr);
+      QMCL_LAUNCHED();
+    }
+    QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
+                         EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
+                         cells, f->scan_tmp.ptr, d_total));
+    f->bin_counts_valid = true;
+  }
+  const size_t max_bins = std::min(n_all, cells);
   if (known_bins >= 0 && !sharded(f)) {
     // the caller counted the bins already (KLD: new-bin flags up to the stop)
     f->n_bins = static_cast<size_t>(known_bins);
@@ -260,7 +373,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_NBINS, d_total, sizeof(unsigned long long), s));
     f->bins_pending = true;
     f->n_bins_bound = max_bins;
-    if (!lazy(f)) QMCL_TRY(settle(f));
+    if (!defer_counts(f)) QMCL_TRY(settle(f));
   }
   f->bins_built = true;
   return QMCL_OK;
@@ -295,7 +408,7 @@ qmcl_status label_clusters(qmcl_filter *f) {
                        f->scan_tmp.ptr, d_total));
   QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_NCLUSTERS, d_total, sizeof(unsigned long long), s));
   f->clusters_pending = true;
-  if (!lazy(f)) QMCL_TRY(settle(f));
+  if (!defer_counts(f)) QMCL_TRY(settle(f));
   f->clusters_valid = true;
   return QMCL_OK;
 }
@@ -396,8 +509,17 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   // Exchange: cluster weights are integers, so their sum over shards is exact
   // and order-independent.
   if (sharded(f)) QMCL_TRY(shard_allreduce(f, cluster_w, f->n_clusters, QMCL_DT_I64, QMCL_OP_SUM));
-  best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, nc_cap,
-                                         nc_on_device ? &f->scalars.ptr->n_clusters : nullptr, es);
+  if (nc_cap >= 8192 && blocks >= 32) {
+    // scratch: the moments' block partials (written after this kernel)
+    const unsigned nb = std::min<unsigned>(kSMs, div_up(nc_cap, 1024));
+    unsigned long long *part_w = reinterpret_cast<unsigned long long *>(base + o_part);
+    best_cluster_multi_kernel<<<nb, 256, 0, s>>>(cluster_w, nc_cap,
+                                                 nc_on_device ? &f->scalars.ptr->n_clusters : nullptr, es,
+                                                 part_w, reinterpret_cast<long long *>(part_w + kSMs));
+  } else {
+    best_cluster_kernel<<<1, 1024, 0, s>>>(cluster_w, nc_cap,
+                                           nc_on_device ? &f->scalars.ptr->n_clusters : nullptr, es);
+  }
   QMCL_LAUNCHED();
   moments_kernel<<<blocks, 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, f->particle_cid.ptr,
                                         ps.n, base + o_part, es, base + o_sums, d_out,
@@ -407,13 +529,12 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   int flag = 0;
   if (sharded(f)) {
     // Exchange: moments of the best cluster and of all particles, summed in rank order.
-    struct Part { double sums[2 * kMom]; double invalid; } mine;
-    QMCL_CUDA(copy_d2h(mine.sums, base + o_sums, sizeof(mine.sums), s));
-    QMCL_CUDA(copy_d2h(&flag, &es->invalid, sizeof(int), s));
-    QMCL_CUDA(cudaStreamSynchronize(s));
-    mine.invalid = flag;
+    // (the flag joins the sums on the device: one exchange, one host wait)
+    struct Part { double sums[2 * kMom]; double invalid; };
+    pack_invalid_kernel<<<1, 1, 0, s>>>(es, base + o_sums + 2 * kMom);
+    QMCL_LAUNCHED();
     std::vector<Part> parts(f->n_shards);
-    QMCL_TRY(shard_gather(f, &mine, false, sizeof(Part), parts.data()));
+    QMCL_TRY(shard_gather(f, base + o_sums, true, sizeof(Part), parts.data()));
     double tot[2 * kMom] = {0};
     flag = 0;
     for (const Part &pt : parts) {
@@ -469,6 +590,19 @@ qmcl_status qmcl_filter_copy_bins(const qmcl_filter *fc, int32_t *keys4, int32_t
   if (!n || !keys4 || !labels) return QMCL_OK;
   QMCL_TRY(use_device(f->map));
   cudaStream_t s = f->map->stream;
+  if (!f->bin_counts_valid) {
+    // A sharded filter exchanged occupancy only (build_bins): the counts are made now,
+    // from every rank's particles - on a sharded filter this call is collective.
+    const ParticleSet &ps = f->cur();
+    QMCL_CUDA(cudaMemsetAsync(f->bin_count.ptr, 0, f->n_bins * sizeof(int32_t), s));
+    if (ps.n) {
+      bin_count_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.n, bin_params(f),
+                                                         f->grid, f->table.ptr, f->bin_count.ptr);
+      QMCL_LAUNCHED();
+    }
+    if (sharded(f)) QMCL_TRY(shard_allreduce(f, f->bin_count.ptr, f->n_bins, QMCL_DT_I32, QMCL_OP_SUM));
+    f->bin_counts_valid = true;
+  }
   void *stage = nullptr;
   QMCL_TRY(filter_scratch(f, n * 5 * sizeof(int32_t), &stage));
   int32_t *d_keys = static_cast<int32_t *>(stage);

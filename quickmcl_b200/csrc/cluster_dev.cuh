@@ -100,6 +100,53 @@ __device__ __forceinline__ void bin_mark_one(const float *x, const float *y, con
     atomicAdd(table + idx, __popc(peers));
 }
 
+// Sharded filters exchange bin *occupancy* only: one byte per cell, max-reduced
+// over the ranks (a quarter of the int32 count table; the per-bin counts are
+// made on demand, qmcl_filter_copy_bins).  Bytes are set through the word that
+// holds them.
+__device__ __forceinline__ void bin_mark_occupancy(const float *x, const float *y, const float *t, size_t n,
+                                                   const BinParams &bp, const BinGrid &g,
+                                                   unsigned *occ_words, size_t i) {
+  if (i >= n) return;
+  int kx, ky, kt;
+  bin_key(x[i], y[i], t[i], bp, &kx, &ky, &kt);
+  const long long idx = grid_index(g, kx, ky, kt);
+  const unsigned peers = __match_any_sync(__activemask(), idx);
+  if (idx >= 0 && (__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31))
+    atomicOr(occ_words + (idx >> 2), 1u << (8 * static_cast<unsigned>(idx & 3)));
+}
+struct OccupiedByte {
+  const uint8_t *occ;
+  __device__ uint32_t operator()(size_t i) const { return occ[i] ? 1u : 0u; }
+};
+// Compacted bin list from the occupancy bytes; every cell of the table is written
+// (cell -> bin id + 1, 0 for an empty cell), so the table needs no clearing.
+struct EmitBinOccupancy {
+  int32_t *table;
+  int32_t *bin_cell;
+  int32_t *parent;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+    table[i] = flag ? static_cast<int32_t>(pos) + 1 : 0;
+    if (!flag) return;
+    bin_cell[pos] = static_cast<int32_t>(i);
+    parent[pos] = static_cast<int32_t>(pos);
+  }
+};
+// Per-bin particle counts of this rank's particles (table: cell -> bin id + 1).
+__device__ __forceinline__ void bin_count_one(const float *x, const float *y, const float *t, size_t n,
+                                              const BinParams &bp, const BinGrid &g, const int32_t *table,
+                                              int32_t *bin_count, size_t i) {
+  if (i >= n) return;
+  int kx, ky, kt;
+  bin_key(x[i], y[i], t[i], bp, &kx, &ky, &kt);
+  const long long idx = grid_index(g, kx, ky, kt);
+  const unsigned peers = __match_any_sync(__activemask(), idx);
+  if (idx >= 0 && (__ffs(peers) - 1) == static_cast<int>(threadIdx.x & 31)) {
+    const int b = table[idx] - 1;
+    if (b >= 0) atomicAdd(bin_count + b, __popc(peers));
+  }
+}
+
 struct OccupiedFlag {
   const int32_t *table;
   __device__ uint32_t operator()(size_t i) const { return table[i] > 0 ? 1u : 0u; }

@@ -48,11 +48,11 @@ __global__ void soa_to_aos_kernel(const float *__restrict__ x, const float *__re
 // K8: particle.cpp:50-64 as used by particle_filter.cpp:101-120 — divide by the
 // pre-penalty total when it is positive, otherwise equalise to 1/N.
 __global__ void normalise_by_total_kernel(double *__restrict__ w, size_t n,
-                                          const FilterScalars *__restrict__ sc) {
+                                          const FilterScalars *__restrict__ sc, double n_total) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double total = sc->total_weight;
-  w[i] = (total > 0) ? __ddiv_rn(w[i], total) : __ddiv_rn(1.0, static_cast<double>(n));
+  w[i] = (total > 0) ? __ddiv_rn(w[i], total) : __ddiv_rn(1.0, n_total);
 }
 
 qmcl_status launch_aos_to_soa(cudaStream_t s, const qmcl_particle *dev_in, size_t n, float *x,
@@ -220,7 +220,8 @@ qmcl_status flush_sensor(qmcl_filter *f) {
   ParticleSet &ps = f->cur();
   if (ps.n) {
     StageScope sc(f, QMCL_STAGE_NORMALISE);
-    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr,
+                                                                static_cast<double>(ps.n));
     QMCL_LAUNCHED();
   }
   QMCL_CUDA(copy_d2h(f->h_scalars.ptr + HS_TOTAL, &f->scalars.ptr->total_weight, sizeof(double), s));
@@ -518,23 +519,15 @@ static qmcl_status sensor_update_common(qmcl_filter *f, const float *dev_cloud_x
     f->normalise_n = ps.n;
     return QMCL_OK;
   }
+  const double n_total = static_cast<double>(sharded(f) ? f->global_n : ps.n);
   if (sharded(f)) {
-    // Exchange 1: the pre-penalty total is the sum over shards.
-    std::vector<double> totals;
-    QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->total_weight, &totals));
-    const double total = ordered_sum(totals);
-    const double n_total = static_cast<double>(f->global_n);
-    if (ps.n) {
-      StageScope sc(f, QMCL_STAGE_NORMALISE);
-      normalise_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total, n_total);
-      QMCL_LAUNCHED();
-    }
-    apply_sensor_total(f, total, n_total);
-    return QMCL_OK;
+    // Exchange 1: the pre-penalty total is the sum over the shards, taken
+    // in rank order on the device; the host picks it up like a single-GPU filter does.
+    QMCL_TRY(shard_sum_f64_device(f, &f->scalars.ptr->total_weight));
   }
-  {
+  if (ps.n) {
     StageScope sc(f, QMCL_STAGE_NORMALISE);
-    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
+    normalise_by_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr, n_total);
     QMCL_LAUNCHED();
   }
   // The host keeps the two low-pass scalars (w_slow, w_fast), so it needs the
@@ -546,8 +539,8 @@ static qmcl_status sensor_update_common(qmcl_filter *f, const float *dev_cloud_x
     QMCL_CUDA(cudaEventCreateWithFlags(&f->total_copied, cudaEventDisableTiming));
   QMCL_CUDA(cudaEventRecord(f->total_copied, s));
   f->total_pending = true;
-  f->pending_n_total = static_cast<double>(ps.n);
-  if (!lazy(f)) QMCL_TRY(settle(f));
+  f->pending_n_total = n_total;
+  if (!defer_counts(f)) QMCL_TRY(settle(f));
   return QMCL_OK;
 }
 
@@ -619,6 +612,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f) {
   f->table.release();
   f->bin_cell.release();
   f->bin_count.release();
+  f->occ8.release();
   f->bin_label.release();
   f->bin_cluster.release();
   f->scan_tmp.release();

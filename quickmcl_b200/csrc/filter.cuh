@@ -18,6 +18,10 @@ qmcl_status launch_export_markers(cudaStream_t s, const float *x, const float *y
 void settle_after_sync(qmcl_filter *f);
 qmcl_status settle(qmcl_filter *f);
 inline bool lazy(const qmcl_filter *f) { return f->lazy_sync && f->n_shards <= 1; }
+// Sharded filters defer the same three read-backs (sensor total, bin count, cluster
+// count): every host-synchronising exchange (shard_gather) folds them in, and the
+// sharded adaptive / KLD resamplers settle before they read w_slow / w_fast.
+inline bool defer_counts(const qmcl_filter *f) { return f->lazy_sync; }
 // Fused tail (tail.cu).  tail_enabled: the filter defers K8 into the tail;
 // tail_eligible: this call (TAIL_* mode) can run as one fused launch;
 // tail_complete: fold the result in (the stream has been synchronised).

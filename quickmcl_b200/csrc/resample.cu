@@ -91,6 +91,20 @@ draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
             float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ ot,
             double *__restrict__ ow, int64_t *__restrict__ src) {
   const size_t m = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // The record count may still be on its way to the host.  Without records
+  // (the host will find out and discard this output) every slot takes
+  // particle 0, which keeps the poses inside the input set's bin bounds.
+  if (P_dev) P = static_cast<size_t>(*P_dev);
+  // every 2^k-th key of the record list in shared memory: the first ten levels of
+  // each search come from there instead of from L2 (as in the fused tail)
+  __shared__ double s_samp[kLookupSamples];
+  size_t samp_stride = 1, n_samp = 0;
+  if (P > 4 * kLookupSamples) {
+    samp_stride = (P - 1 + kLookupSamples - 1) / kLookupSamples;
+    n_samp = (P - 1 + samp_stride - 1) / samp_stride;
+    for (size_t j = threadIdx.x; j < n_samp; j += blockDim.x) s_samp[j] = incl[j * samp_stride];
+    __syncthreads();
+  }
   if (m >= n_draws) return;
   uint32_t r[4];
   rng_draw(seed, step, P_DRAW, m, r);
@@ -108,11 +122,9 @@ draw_kernel(const float *__restrict__ ix, const float *__restrict__ iy,
     return;
   }
   const double rr = uniform53(r[2], r[3]);
-  // The record count may still be on its way to the host.  Without records
-  // (the host will find out and discard this output) every slot takes
-  // particle 0, which keeps the poses inside the input set's bin bounds.
-  if (P_dev) P = static_cast<size_t>(*P_dev);
-  const int64_t s = P ? pos[running_sum_lookup(incl, P, rr)] : 0;
+  const int64_t s = !P ? 0
+                       : pos[n_samp ? running_sum_lookup_sampled(incl, P, rr, s_samp, n_samp, samp_stride)
+                                    : running_sum_lookup(incl, P, rr)];
   ox[m] = ix[s];
   oy[m] = iy[s];
   ot[m] = it[s];
@@ -216,17 +228,10 @@ static qmcl_status normalise_current(qmcl_filter *f) {
   QMCL_TRY(f->partials.ensure(blocks));
   weight_sum_kernel<false><<<blocks, 256, 0, s>>>(ps.w.ptr, ps.n, f->partials.ptr, f->scalars.ptr);
   QMCL_LAUNCHED();
-  if (sharded(f)) {
-    // Exchange: the normalising total is the sum of the shards' totals.
-    std::vector<double> totals;
-    QMCL_TRY(shard_gather_f64(f, &f->scalars.ptr->post_total, &totals));
-    const double total = ordered_sum(totals);
-    if (ps.n) {
-      divide_by_value_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, total);
-      QMCL_LAUNCHED();
-    }
-    return QMCL_OK;
-  }
+  // Exchange (sharded): the normalising total is the sum of the shards' totals, taken in
+  // rank order on the device.
+  if (sharded(f)) QMCL_TRY(shard_sum_f64_device(f, &f->scalars.ptr->post_total));
+  if (!ps.n) return QMCL_OK;
   divide_by_post_total_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(ps.w.ptr, ps.n, f->scalars.ptr);
   QMCL_LAUNCHED();
   return QMCL_OK;
@@ -278,6 +283,12 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
   return QMCL_OK;
 }
 
+__global__ void pack_info_kernel(const double *__restrict__ approx_total, double count,
+                                 double *__restrict__ out) {
+  out[0] = *approx_total;
+  out[1] = count;
+}
+
 // The exact (sequentially rounded) running sum of a sharded weight array:
 // f->cdf[i] = global running sum after local particle i.  carry[r] = running
 // sum before shard r's first particle (carry[G] = grand total), the same bits
@@ -292,11 +303,11 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   struct Info { double approx_total; double count; };
   std::vector<Info> info(G);
   QMCL_TRY(prefix_local_total(f, w, n));
-  Info mine;
-  QMCL_CUDA(copy_d2h(&mine.approx_total, f->prefix_carry.ptr + 1, sizeof(double), s));
-  QMCL_CUDA(cudaStreamSynchronize(s));
-  mine.count = static_cast<double>(n);
-  QMCL_TRY(shard_gather(f, &mine, false, sizeof(Info), info.data()));
+  // (the count joins the total on the device: one exchange, one host wait)
+  QMCL_TRY(f->partials.ensure(8));
+  pack_info_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr + 1, static_cast<double>(n), f->partials.ptr);
+  QMCL_LAUNCHED();
+  QMCL_TRY(shard_gather(f, f->partials.ptr, true, sizeof(Info), info.data()));
   double approx_in = 0.0;
   for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
   QMCL_TRY(prefix_summaries(f, w, n, approx_in));
@@ -1015,6 +1026,7 @@ static qmcl_status resample_draws_sharded(qmcl_filter *f, const ParticleSet &in,
 // particle_filter.cpp:241-291, sharded.
 static qmcl_status resample_adaptive_sharded(qmcl_filter *f, const ParticleSet &in,
                                              ParticleSet &out) {
+  QMCL_TRY(settle(f));  // the sensor total of the last update feeds w_slow / w_fast
   const double w_diff = adaptiveness(f);
   const size_t n_out = static_cast<size_t>(f->params.particle_count_min);
   bool ok = false;
@@ -1087,6 +1099,7 @@ static qmcl_status resample_kld_sharded(qmcl_filter *f, const ParticleSet &in, P
   cudaStream_t s = f->map->stream;
   const int G = f->n_shards, me = f->shard_rank;
   *clustered = false;
+  QMCL_TRY(settle(f));  // the sensor total of the last update feeds w_slow / w_fast
   const double w_diff = adaptiveness(f);
   const size_t n_max = static_cast<size_t>(f->params.particle_count_max);
   f->n_src_index = 0;

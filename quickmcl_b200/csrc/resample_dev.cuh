@@ -39,6 +39,8 @@ __device__ __forceinline__ size_t running_sum_lookup_in(const double *incl, size
 __device__ __forceinline__ size_t running_sum_lookup(const double *incl, size_t P, double r) {
   return running_sum_lookup_in(incl, P, r, 0, P - 1);
 }
+// samples of the record list kept in shared memory by the searching kernels
+constexpr size_t kLookupSamples = 1024;
 // The same with the first levels of the search served from shared memory:
 // samp[j] = incl[j * stride] for j < n_samp, j * stride < P - 1 (every stride-th
 // key).  Narrows the window to one stride, then searches incl itself: the same

@@ -24,6 +24,40 @@ qmcl_status shard_gather(qmcl_filter *f, const void *src, bool src_on_device, si
   f->n_collectives++;
   QMCL_CUDA(copy_d2h(host_out, f->xchg.ptr, G * bytes, s));
   QMCL_CUDA(cudaStreamSynchronize(s));
+  settle_after_sync(f);  // read-backs left in flight (sensor total, bin and cluster counts) have arrived too
+  return QMCL_OK;
+}
+
+// The same exchange with the result left on the device (rank order, in f->xchg): the
+// consumer is the next kernel on the stream, the host does not wait.  The buffer is
+// reused by the next exchange, which stream order puts behind that consumer.
+qmcl_status shard_gather_device(qmcl_filter *f, const void *dev_src, size_t bytes, void **dev_out) {
+  cudaStream_t s = f->map->stream;
+  const size_t G = static_cast<size_t>(f->n_shards);
+  QMCL_TRY(f->xchg.ensure(G * bytes + 16));
+  uint8_t *mine = f->xchg.ptr + static_cast<size_t>(f->shard_rank) * bytes;
+  QMCL_CUDA(cudaMemcpyAsync(mine, dev_src, bytes, cudaMemcpyDeviceToDevice, s));
+  if (f->comm.allgather(f->comm.ctx, f->xchg.ptr, bytes, s) != 0) {
+    set_error("qmcl_comm.allgather failed");
+    return QMCL_ERR_COMM;
+  }
+  f->n_collectives++;
+  *dev_out = f->xchg.ptr;
+  return QMCL_OK;
+}
+
+// out = v[0] + v[1] + ... in rank order: the same bits on every rank (and the bits
+// ordered_sum gives on the host).
+__global__ void sum_in_rank_order_kernel(const double *__restrict__ v, int n, double *__restrict__ out) {
+  double t = 0.0;
+  for (int i = 0; i < n; ++i) t = __dadd_rn(t, v[i]);
+  *out = t;
+}
+qmcl_status shard_sum_f64_device(qmcl_filter *f, double *dev_scalar) {
+  void *g = nullptr;
+  QMCL_TRY(shard_gather_device(f, dev_scalar, sizeof(double), &g));
+  sum_in_rank_order_kernel<<<1, 1, 0, f->map->stream>>>(static_cast<const double *>(g), f->n_shards, dev_scalar);
+  QMCL_LAUNCHED();
   return QMCL_OK;
 }
 

@@ -282,6 +282,8 @@ struct qmcl_filter {
   qmcl::DevBuf<int32_t> table;        // cell -> bin id + 1 (0 = empty)
   qmcl::DevBuf<int32_t> bin_cell;     // bin -> dense cell index (ascending)
   qmcl::DevBuf<int32_t> bin_count;    // particles per bin
+  qmcl::DevBuf<uint8_t> occ8;         // sharded filters: bin occupancy, one byte per cell (the exchanged form)
+  bool bin_counts_valid = true;       // false: bin_count is made on demand (qmcl_filter_copy_bins)
   qmcl::DevBuf<int32_t> bin_label;    // union-find parent, then component root
   qmcl::DevBuf<int32_t> bin_cluster;  // root bin -> dense cluster id
   qmcl::DevBuf<uint32_t> scan_tmp;     // status words of the single-pass scans (+ results)

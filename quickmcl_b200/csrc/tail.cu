@@ -25,7 +25,6 @@ namespace cg = cooperative_groups;
 
 namespace qmcl {
 
-constexpr size_t kLookupSamples = 1024;
 constexpr size_t kSoloCells = 2048;  // dense grids up to this size are listed and labelled by one block
 
 // ------------------------------------------------------------------ teams

@@ -83,6 +83,12 @@ def _worker(rank, world, port, n, seed, errors):
             assert np.array_equal(b, -np.arange(5).astype(dt))
             assert np.array_equal(c, np.arange(5).astype(dt))
 
+        # bin occupancy bytes (QMCL_DT_U8), max-reduced
+        occ = np.zeros(9, np.uint8)
+        occ[rank::world] = rank + 1
+        assert st.allreduce(None, occ.ctypes.data, 9, 3, 2, None) == 0
+        assert np.array_equal(occ, np.array([(i % world) + 1 for i in range(9)], np.uint8))
+
         # ---- 2. sharded low-variance resampling against the oracle
         from oracle import binding as ob
         w = _make_weights(n, seed)
