@@ -168,7 +168,7 @@ qmcl_status qmcl_filter_destroy(qmcl_filter *f);
  * Every buffer is a DEVICE pointer.  A call must be ordered after the work
  * already enqueued on `stream` (the filter's cudaStream_t) and the filter's
  * later work on that stream must see its result.  Return 0 on success. */
-enum { QMCL_DT_I32 = 0, QMCL_DT_I64 = 1, QMCL_DT_F64 = 2, QMCL_DT_U8 = 3 };
+enum { QMCL_DT_I32 = 0, QMCL_DT_I64 = 1, QMCL_DT_F64 = 2 };
 enum { QMCL_OP_SUM = 0, QMCL_OP_MIN = 1, QMCL_OP_MAX = 2 };
 typedef struct qmcl_comm {
   int rank, size;
@@ -202,6 +202,11 @@ qmcl_status qmcl_filter_set_rebalance_threshold(qmcl_filter *f, double relative_
 /* This shard's block: first global index and local count. */
 qmcl_status qmcl_filter_shard_range(const qmcl_filter *f, uint64_t *first, uint64_t *count,
                                     uint64_t *global_count);
+/* Exchange counters of a sharded filter since it was created: out[0] = collectives
+ * enqueued, out[1] = carry-chain rounds of the running sum that needed an exchange of
+ * their own (a shard without a closed-form summary), out[2] = rebalancing all-to-alls
+ * skipped under the threshold. */
+qmcl_status qmcl_filter_shard_stats(const qmcl_filter *f, uint64_t out[3]);
 /* Pure host helpers of the sharded path (no device needed; used by the CPU
  * tests of the multi-rank logic).
  * qmcl_shard_slice: block [first, first+count) of rank `rank` of `size` over n.

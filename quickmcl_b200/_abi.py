@@ -83,6 +83,7 @@ SIGNATURES = {
     "qmcl_filter_set_rebalance": [vp, C.c_int],
     "qmcl_filter_set_rebalance_threshold": [vp, f64],
     "qmcl_filter_shard_range": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)],
+    "qmcl_filter_shard_stats": [vp, C.POINTER(u64)],
     "qmcl_filter_set_particles_shard": [vp, pP, sz, u64, u64],
     "qmcl_filter_set_params": [vp, C.POINTER(PFParams)],
     "qmcl_filter_initialise": [vp, pf32, pf32],

@@ -335,9 +335,12 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(cells) + 4));
   unsigned long long *d_total = &f->scalars.ptr->n_bins;  // stable: the labelling reads it
   if (sharded(f)) {
-    // Exchange: bin OCCUPANCY, one byte per cell, max-reduced over the shards (a
-    // quarter of the count table's bytes); the occupied-bin list and the labels are
-    // then computed identically on every rank.  Counts: bin_counts_on_demand.
+    // Exchange: bin OCCUPANCY, one 0/1 byte per cell - a quarter of the count table's
+    // bytes.  The bytes are summed four at a time as int32 words: with at most 255
+    // ranks no byte can carry into its neighbour, and an int32 sum is the reduction
+    // NCCL runs inside the NVSwitch (a uint8 maximum takes the ring).  The
+    // occupied-bin list and the labels are then computed identically on every rank;
+    // the per-bin counts are made on demand (qmcl_filter_copy_bins).
     const size_t words = (cells + 3) / 4;
     QMCL_TRY(f->occ8.ensure(4 * words));
     QMCL_CUDA(cudaMemsetAsync(f->occ8.ptr, 0, 4 * words, s));
@@ -346,7 +349,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
                                                                reinterpret_cast<unsigned *>(f->occ8.ptr));
       QMCL_LAUNCHED();
     }
-    QMCL_TRY(shard_allreduce(f, f->occ8.ptr, 4 * words, QMCL_DT_U8, QMCL_OP_MAX));
+    QMCL_TRY(shard_allreduce(f, f->occ8.ptr, words, QMCL_DT_I32, QMCL_OP_SUM));
     n_all = f->global_n;
     QMCL_TRY(device_scan(s, OccupiedByte{f->occ8.ptr},
                          EmitBinOccupancy{f->table.ptr, f->bin_cell.ptr, f->bin_label.ptr}, cells,

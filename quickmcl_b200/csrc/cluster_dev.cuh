@@ -100,10 +100,10 @@ __device__ __forceinline__ void bin_mark_one(const float *x, const float *y, con
     atomicAdd(table + idx, __popc(peers));
 }
 
-// Sharded filters exchange bin *occupancy* only: one byte per cell, max-reduced
-// over the ranks (a quarter of the int32 count table; the per-bin counts are
-// made on demand, qmcl_filter_copy_bins).  Bytes are set through the word that
-// holds them.
+// Sharded filters exchange bin *occupancy* only: one 0/1 byte per cell, summed
+// over the ranks word-wise (a quarter of the int32 count table; the per-bin
+// counts are made on demand, qmcl_filter_copy_bins).  Bytes are set through the
+// word that holds them.
 __device__ __forceinline__ void bin_mark_occupancy(const float *x, const float *y, const float *t, size_t n,
                                                    const BinParams &bp, const BinGrid &g,
                                                    unsigned *occ_words, size_t i) {

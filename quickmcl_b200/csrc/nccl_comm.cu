@@ -86,10 +86,7 @@ int cb_allgather(void *ctx, void *dev_buf, size_t bytes_per_rank, void *stream) 
 
 int cb_allreduce(void *ctx, void *dev_buf, size_t count, int dtype, int op, void *stream) {
   NcclCtx *c = static_cast<NcclCtx *>(ctx);
-  const ncclDataType_t dt = dtype == QMCL_DT_I32   ? ncclInt32
-                            : dtype == QMCL_DT_I64 ? ncclInt64
-                            : dtype == QMCL_DT_U8  ? ncclUint8
-                                                   : ncclFloat64;
+  const ncclDataType_t dt = dtype == QMCL_DT_I32 ? ncclInt32 : dtype == QMCL_DT_I64 ? ncclInt64 : ncclFloat64;
   const ncclRedOp_t ro = op == QMCL_OP_SUM ? ncclSum : op == QMCL_OP_MIN ? ncclMin : ncclMax;
   const ncclResult_t r =
       nccl().AllReduce(dev_buf, dev_buf, count, dt, ro, c->comm, static_cast<cudaStream_t>(stream));

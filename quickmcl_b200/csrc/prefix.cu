@@ -116,48 +116,85 @@ prefix_apply_kernel(const double *__restrict__ w, size_t n, size_t nc, PrefixBuf
   prefix_apply_tile(w, n, nc, pb, out, blockIdx.x);
 }
 
-// Summary of a whole shard: the composition of its tile summaries, usable only
-// if every tile was summarised under one and the same binade.  out[0] = binade
-// (biased exponent, -1 = no closed form), out[1], out[2] = a0, a1.
+// Summary of a whole shard: the composition of its tile summaries, in the same form
+// as a tile's: {E, a} when every tile was summarised under one binade, or - with
+// one predicted crossing in one of the tiles - {E, a, wx, b}: a up to the crossing
+// element, the literal addition of wx (which must take the sum into binade E + 1),
+// b over everything after it (tiles summarised under E + 1).  Two crossings, or a
+// tile without a summary: no closed form.
+//   out[0] = binade (biased exponent; -1 = no closed form, -2 = empty shard)
+//   out[1], out[2] = a0, a1     out[3] = 1 with a crossing
+//   out[4] = bits of wx         out[5], out[6] = b0, b1
+struct ShardPiece {
+  int E;    // binade at the start; -2 = identity (nothing yet), -1 = no closed form
+  int x;    // 1: holds a crossing
+  Fn a, b;
+  double wx;
+};
+__device__ __forceinline__ ShardPiece piece_identity() {
+  return ShardPiece{-2, 0, fn_identity(), fn_identity(), 0.0};
+}
+// p first, then q
+__device__ __forceinline__ ShardPiece piece_compose(const ShardPiece &p, const ShardPiece &q) {
+  if (p.E == -2) return q;
+  if (q.E == -2) return p;
+  ShardPiece r = p;
+  if (p.E == kInvalidE || q.E == kInvalidE) {
+    r.E = kInvalidE;
+  } else if (!p.x) {
+    if (q.E != p.E) {
+      r.E = kInvalidE;
+    } else {
+      r.a = fn_compose(p.a, q.a);
+      r.x = q.x;
+      r.wx = q.wx;
+      r.b = q.b;
+    }
+  } else if (q.x || q.E != p.E + 1) {
+    r.E = kInvalidE;
+  } else {
+    r.b = fn_compose(p.b, q.a);
+  }
+  return r;
+}
 __global__ void __launch_bounds__(256)
 prefix_shard_summary_kernel(PrefixBuffers pb, size_t nt, unsigned long long *__restrict__ out) {
-  __shared__ unsigned long long s_a0[8], s_a1[8];
-  __shared__ int s_E[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // thread t composes a contiguous run of tiles, in order
+  __shared__ ShardPiece s_piece[256];
+  // thread t composes a contiguous run of tiles, in order; thread 0 then composes the runs
   const size_t per = (nt + blockDim.x - 1) / blockDim.x;
   const size_t t0 = static_cast<size_t>(threadIdx.x) * per;
   const size_t t1 = (t0 + per < nt) ? t0 + per : nt;
-  Fn f = fn_identity();
-  int E = -2;  // -2: nothing yet
+  ShardPiece acc = piece_identity();
   for (size_t t = t0; t < t1; ++t) {
-    const int tE = pb.tile_jx[t] >= 0 ? kInvalidE : pb.tile_E[t];  // a crossing: no plain summary
-    if (E == -2) E = tE;
-    else if (tE != E) E = kInvalidE;
-    f = fn_compose(f, Fn{pb.tile_a0[t], pb.tile_a1[t]});
+    ShardPiece q;
+    q.E = pb.tile_E[t];
+    q.x = pb.tile_jx[t] >= 0 ? 1 : 0;
+    q.a = Fn{pb.tile_a0[t], pb.tile_a1[t]};
+    q.b = Fn{pb.tile_b0[t], pb.tile_b1[t]};
+    q.wx = pb.tile_wx[t];
+    acc = piece_compose(acc, q);
   }
-  // combine E across the warp / block: all non-empty must agree
-  auto merge_E = [](int a, int b) { return a == -2 ? b : (b == -2 ? a : (a == b ? a : kInvalidE)); };
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) E = merge_E(E, __shfl_xor_sync(0xffffffffu, E, o));
-  f = fn_warp_scan(f, lane);
-  if (lane == 31) {
-    s_a0[wid] = f.a0;
-    s_a1[wid] = f.a1;
-  }
-  if (lane == 0) s_E[wid] = E;
+  s_piece[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    Fn tot = fn_identity();
-    int Eb = -2;
-    for (int k = 0; k < 8; ++k) {
-      tot = fn_compose(tot, Fn{s_a0[k], s_a1[k]});
-      Eb = merge_E(Eb, s_E[k]);
-    }
-    out[0] = static_cast<unsigned long long>(static_cast<long long>(Eb < 0 ? -1 : Eb));
-    out[1] = tot.a0;
-    out[2] = tot.a1;
+    ShardPiece tot = piece_identity();
+    for (int k = 0; k < 256; ++k) tot = piece_compose(tot, s_piece[k]);
+    out[0] = static_cast<unsigned long long>(static_cast<long long>(tot.E == -2 ? -2 : (tot.E < 0 ? -1 : tot.E)));
+    out[1] = tot.a.a0;
+    out[2] = tot.a.a1;
+    out[3] = tot.x ? 1ull : 0ull;
+    out[4] = static_cast<unsigned long long>(__double_as_longlong(tot.wx));
+    out[5] = tot.b.a0;
+    out[6] = tot.b.a1;
   }
+}
+// A shard whose exact carry-out is known already (the first one: its carry-in is 0):
+// out[0] = -3, out[1] = bits of the carry-out.
+__global__ void prefix_exact_summary_kernel(const double *__restrict__ carry_out,
+                                            unsigned long long *__restrict__ out) {
+  out[0] = static_cast<unsigned long long>(-3ll);
+  out[1] = static_cast<unsigned long long>(__double_as_longlong(*carry_out));
+  for (int k = 2; k < 7; ++k) out[k] = 0ull;
 }
 
 // The literal loop on one warp: coalesced loads of 32 weights, lane-uniform
@@ -287,13 +324,13 @@ qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double a
   return QMCL_OK;
 }
 
-// After prefix_summaries: the shard's summary {binade, a0, a1} as three 64-bit
-// words in dev_out (device memory).
+// After prefix_summaries: the shard's summary as kShardSummaryWords 64-bit words in
+// dev_out (device memory); layout at prefix_shard_summary_kernel.
 qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *dev_out) {
   cudaStream_t s = f->map->stream;
   if (!n) {
     // an empty shard adds nothing under any binade: mark as "identity"
-    const unsigned long long ident[3] = {~0ull - 1, 0ull, 0ull};  // binade word -2
+    const unsigned long long ident[kShardSummaryWords] = {~0ull - 1, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};  // binade word -2
     QMCL_CUDA(cudaMemcpyAsync(dev_out, ident, sizeof(ident), cudaMemcpyHostToDevice, s));
     QMCL_CUDA(cudaStreamSynchronize(s));
     return QMCL_OK;
@@ -305,12 +342,27 @@ qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *d
   return QMCL_OK;
 }
 
-// Host replay of one summary on an exact carry: true and *carry_out set when
-// the carry is in the summary's binade and stays there.
-bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], double *carry_out) {
+// After prefix_resolve: the "summary" of a shard whose exact carry-out is known.
+qmcl_status prefix_exact_summary(qmcl_filter *f, unsigned long long *dev_out) {
+  prefix_exact_summary_kernel<<<1, 1, 0, f->map->stream>>>(f->prefix_carry.ptr, dev_out);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// Host replay of one summary on an exact carry (apply_summary of prefix_dev.cuh in
+// host arithmetic: the same integer operations, and one IEEE double addition for a
+// crossing): true and *carry_out set when the carry is in the summary's binade and
+// the summary's conditions hold.
+bool prefix_apply_summary(double carry_in, const unsigned long long summary[kShardSummaryWords],
+                          double *carry_out) {
   const long long Eb = static_cast<long long>(summary[0]);
   if (Eb == -2) {  // empty shard
     *carry_out = carry_in;
+    return true;
+  }
+  if (Eb == -3) {  // resolved by its owner already (the first shard, carry-in 0)
+    if (carry_in != 0.0) return false;
+    std::memcpy(carry_out, &summary[1], sizeof(double));
     return true;
   }
   if (Eb < 0) return false;
@@ -320,9 +372,26 @@ bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], 
   const long long ce = static_cast<long long>(bits >> 52);
   if (ce == 0 || ce == 0x7ff || ce != Eb) return false;
   const unsigned long long K = (bits & kMantMask) | kImplicit;
-  const unsigned long long Kend = K + ((K & 1ull) ? summary[2] : summary[1]);
-  if (Kend >= kKLimit || Kend < K) return false;
-  const unsigned long long ob = (static_cast<unsigned long long>(Eb) << 52) | (Kend & kMantMask);
+  const unsigned long long K1 = K + ((K & 1ull) ? summary[2] : summary[1]);
+  if (K1 >= kKLimit || K1 < K) return false;
+  const unsigned long long b1 = (static_cast<unsigned long long>(Eb) << 52) | (K1 & kMantMask);
+  if (!summary[3]) {
+    std::memcpy(carry_out, &b1, sizeof(b1));
+    return true;
+  }
+  // the crossing: one literal addition, which must land exactly one binade up
+  double c1, wx;
+  std::memcpy(&c1, &b1, sizeof(c1));
+  std::memcpy(&wx, &summary[4], sizeof(wx));
+  volatile double c2v = c1 + wx;  // a rounded IEEE addition (never contracted, never extended)
+  const double c2 = c2v;
+  unsigned long long b2;
+  std::memcpy(&b2, &c2, sizeof(b2));
+  if ((b2 >> 63) || static_cast<long long>(b2 >> 52) != Eb + 1 || Eb + 1 >= 0x7ff) return false;
+  const unsigned long long K2 = (b2 & kMantMask) | kImplicit;
+  const unsigned long long K3 = K2 + ((K2 & 1ull) ? summary[6] : summary[5]);
+  if (K3 >= kKLimit || K3 < K2) return false;
+  const unsigned long long ob = (static_cast<unsigned long long>(Eb + 1) << 52) | (K3 & kMantMask);
   std::memcpy(carry_out, &ob, sizeof(ob));
   return true;
 }

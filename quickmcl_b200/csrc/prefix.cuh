@@ -20,11 +20,16 @@ qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double a
 qmcl_status prefix_resolve(qmcl_filter *f, const double *w, size_t n, double *out,
                            double carry_in);
 qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out);
-// Shard-level shortcut for the carry chain: {binade, a0, a1} of the whole
-// shard (three 64-bit words, device memory; binade -1 = no closed form, -2 =
-// empty shard), and its replay on an exact carry on the host.
+// Shard-level shortcut for the carry chain: the closed-form summary of the whole
+// shard - {binade, a} or, with one predicted binade crossing, {binade, a, wx, b} -
+// as kShardSummaryWords 64-bit words in device memory (binade -1 = no closed form,
+// -2 = empty shard, -3 = the exact carry-out of a shard that has been resolved
+// already, prefix_exact_summary), and its replay on an exact carry on the host.
+constexpr int kShardSummaryWords = 7;
 qmcl_status prefix_shard_summary(qmcl_filter *f, size_t n, unsigned long long *dev_out);
-bool prefix_apply_summary(double carry_in, const unsigned long long summary[3], double *carry_out);
+qmcl_status prefix_exact_summary(qmcl_filter *f, unsigned long long *dev_out);
+bool prefix_apply_summary(double carry_in, const unsigned long long summary[kShardSummaryWords],
+                          double *carry_out);
 
 namespace pfx {
 struct PrefixBuffers;

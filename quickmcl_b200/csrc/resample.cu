@@ -284,7 +284,8 @@ __global__ void pack_info_kernel(const double *__restrict__ approx_total, double
 // sum before shard r's first particle (carry[G] = grand total), the same bits
 // on every rank; count[r] = particles of shard r.
 qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
-                                 std::vector<double> *carry_out, std::vector<double> *count_out) {
+                                 std::vector<double> *carry_out, std::vector<double> *count_out,
+                                 bool need_total = true) {
   cudaStream_t s = f->map->stream;
   const int G = f->n_shards, me = f->shard_rank;
   QMCL_TRY(f->cdf.ensure(n + 1));
@@ -301,25 +302,45 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   double approx_in = 0.0;
   for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
   QMCL_TRY(prefix_summaries(f, w, n, approx_in));
-  // The exact carry, shard after shard.  A shard whose particles all fall into
-  // one binade of the running sum publishes a closed-form summary, which every
-  // rank replays locally; only shards without one (the first, and those in
-  // which the sum crosses a power of two) cost a round of the chain.
-  struct Summary { unsigned long long w[3]; };
+  // The exact carry, shard after shard.  A shard publishes a closed-form summary -
+  // its particles all fall into one binade of the running sum, or the sum crosses
+  // into the next binade once, at a predicted element - which every rank replays
+  // locally.  The first shard starts from 0 and runs through dozens of binades: it
+  // resolves itself right away and publishes its exact carry-out instead.  Only
+  // shards without either (two crossings, a failed prediction) cost a round of the
+  // chain: at 8 ranks usually none (3-4 rounds before the crossing form existed).
+  struct Summary { unsigned long long w[kShardSummaryWords]; };
   std::vector<Summary> summaries(G);
   QMCL_TRY(f->partials.ensure(8));
   unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(f->partials.ptr);
-  QMCL_TRY(prefix_shard_summary(f, n, d_sum));
+  bool resolved = false;
+  if (me == 0 && n) {
+    QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, 0.0));
+    QMCL_TRY(prefix_exact_summary(f, d_sum));
+    resolved = true;
+  } else {
+    QMCL_TRY(prefix_shard_summary(f, n, d_sum));
+  }
   QMCL_TRY(shard_gather(f, d_sum, true, sizeof(Summary), summaries.data()));
   std::vector<double> &carry = *carry_out;
   carry.assign(G + 1, 0.0);
   std::vector<double> round(G);
-  bool resolved = false;
   for (int r = 0; r < G; ++r) {
-    if (prefix_apply_summary(carry[r], summaries[r].w, &carry[r + 1])) continue;
-    if (r == me) {
+    const bool known = prefix_apply_summary(carry[r], summaries[r].w, &carry[r + 1]);
+    // this rank's own walk starts as soon as its carry-in is exact: it then runs
+    // beside whatever rounds later shards still need
+    if (r == me && !resolved) {
       QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[r]));
       resolved = true;
+    }
+    if (known) continue;
+    // The last shard's carry-out is the grand total.  A caller that does not use it
+    // (low variance: the last shard owns every slot above its carry-in) is spared the
+    // round; with weights that add up to 1 that shard fails often - whether the sum
+    // reaches the next power of two at its very end is beyond any prediction.
+    if (r == G - 1 && !need_total) {
+      carry[G] = carry[G - 1];
+      continue;
     }
     QMCL_TRY(shard_gather(f, f->prefix_carry.ptr, true, sizeof(double), round.data()));
     carry[r + 1] = round[r];
@@ -416,7 +437,7 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
     return QMCL_OK;
   }
   std::vector<double> carry, count;
-  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count));
+  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count, /*need_total=*/false));
   struct Info { double count; };
   std::vector<Info> info(G);
   for (int r = 0; r < G; ++r) info[r].count = count[r];

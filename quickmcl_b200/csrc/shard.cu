@@ -137,6 +137,14 @@ qmcl_status qmcl_filter_shard_range(const qmcl_filter *f, uint64_t *first, uint6
   return QMCL_OK;
 }
 
+qmcl_status qmcl_filter_shard_stats(const qmcl_filter *f, uint64_t out[3]) {
+  if (!f || !out) return QMCL_ERR_INVALID_ARG;
+  out[0] = f->n_collectives;
+  out[1] = f->n_chain_rounds;
+  out[2] = f->n_rebalance_skipped;
+  return QMCL_OK;
+}
+
 void qmcl_shard_slice(uint64_t n, int rank, int size, uint64_t *first, uint64_t *count) {
   size_t a = 0, c = 0;
   if (size >= 1 && rank >= 0 && rank < size) shard_slice_of(n, rank, size, &a, &c);

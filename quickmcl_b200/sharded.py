@@ -20,7 +20,7 @@ from . import _abi
 from ._abi import check, ptr
 from .api import PARTICLE_DTYPE, Particle, ParticleFilter
 
-_DT = {0: torch.int32, 1: torch.int64, 2: torch.float64, 3: torch.uint8}
+_DT = {0: torch.int32, 1: torch.int64, 2: torch.float64}
 _OP = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -83,11 +83,14 @@ def _worker(rank, world, port, n, seed, errors):
             assert np.array_equal(b, -np.arange(5).astype(dt))
             assert np.array_equal(c, np.arange(5).astype(dt))
 
-        # bin occupancy bytes (QMCL_DT_U8), max-reduced
-        occ = np.zeros(9, np.uint8)
-        occ[rank::world] = rank + 1
-        assert st.allreduce(None, occ.ctypes.data, 9, 3, 2, None) == 0
-        assert np.array_equal(occ, np.array([(i % world) + 1 for i in range(9)], np.uint8))
+        # bin occupancy: 0/1 bytes summed four at a time as int32 words (cluster.cu, build_bins)
+        occ = np.zeros(12, np.uint8)
+        occ[rank::3] = 1
+        assert st.allreduce(None, occ.ctypes.data, 3, 0, 0, None) == 0
+        want_occ = np.zeros(12, np.uint8)
+        for r in range(world):
+            want_occ[r::3] += 1
+        assert np.array_equal(occ, want_occ) and np.array_equal(occ != 0, want_occ != 0)
 
         # ---- 2. sharded low-variance resampling against the oracle
         from oracle import binding as ob

@@ -332,3 +332,46 @@ def test_sharded_draws_without_any_weight_fail_like_the_reference():
         return f.num_particles(), f.get_estimated_pose()[0]
 
     assert sharded.run_local_shards(2, s.make_map, body, seed=3) == [(0, False), (0, False)]
+
+
+@pytest.mark.parametrize("total,max_rounds", [(0.9, 0), (1.0, 0)])
+def test_carry_chain_needs_no_rounds_for_single_crossings(total, max_rounds):
+    """Eight shards of a ramped weight array: the running sum crosses one power of two
+    well inside shards 1, 2 and 4 (at 21 %, 37 % and 62 % of the particles).  Those
+    shards publish the crossing
+    form of the closed-form summary and the first shard its exact carry-out, so the chain
+    is settled by the summaries' exchange alone - and the result is still the sequential
+    sum, slot for slot (checked against the oracle).  With weights that add up to 1 the
+    sum may or may not reach the next power of two at the very last particles, which no
+    prediction can know: the last shard then has no usable summary, but low-variance
+    resampling does not need its carry-out (the grand total) and skips the round."""
+    import ctypes as C
+    G, n = 8, 400_000
+    s = Setup(resample_type=0, particle_count_min=n, particle_count_max=n)
+    of = s.of
+    x, y, t = syn.uniform_cloud(s.occ, s.res, s.origin, n)
+    w = np.random.default_rng(5).uniform(0.9, 1.1, n) * (1.0 + 2.0 * np.arange(n) / n)
+    w *= total / w.sum()
+    start = q.make_particles(x, y, t, w)
+    of.set_particles(start.view(ob.PARTICLE_DTYPE))
+
+    def body(f, rank):
+        f.set_parameters(s.gpu_params())
+        set_block(f, rank, G, start)
+        f.set_rng(3, 5)
+        f.resample_and_cluster()
+        st = (C.c_uint64 * 3)()
+        check(f._L.qmcl_filter_shard_stats(f._h, st), "stats")
+        return local_particles(f), int(st[1])
+
+    res = sharded.run_local_shards(G, s.make_map, body, seed=3)
+    of.set_rng(3, 5)
+    of.resample_and_cluster()
+    want = of.get_particles()
+    got = assemble([r[0] for r in res])
+    for k in ("x", "y", "theta"):
+        assert np.array_equal(got[k], want[k]), k
+    rounds = {r[1] for r in res}
+    assert len(rounds) == 1                        # every rank walked the same chain
+    print("carry-chain rounds:", rounds)
+    assert rounds.pop() <= max_rounds
