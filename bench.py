@@ -358,6 +358,7 @@ class Harness:
 
     def step(self, host):
         f = self.f
+        self.cycles_run = getattr(self, "cycles_run", 0) + 1
         f.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
         if host:
             f.update_importance_from_observations(self.h_scan)
@@ -733,6 +734,13 @@ def run_b200(args, wl):
             one_gpu["speedup_of_this_run"] = one_gpu["ms_per_step"] / ms_per_step
             line["same_workload_on_one_gpu"] = one_gpu
         line["parity_vs_one_gpu"] = parity
+        if hasattr(h.f, "shard_stats"):
+            # counted over every cycle this filter ran (warm-up, timed, e2e and parity passes)
+            st = h.f.shard_stats()
+            cycles = max(1, getattr(h, "cycles_run", 0))
+            line["exchanges"] = dict(st, cycles=cycles,
+                                     collectives_per_cycle=st["collectives"] / cycles,
+                                     chain_rounds_per_cycle=st["chain_rounds"] / cycles)
     emit(line)
     h.close()
     if dist:

@@ -277,7 +277,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     hb[3] = prev_grid.x0 + prev_grid.nx - 1;
     hb[4] = prev_grid.y0 + prev_grid.ny - 1;
     hb[5] = prev_grid.t0 + prev_grid.nt - 1;
-  } else if (known_bbox && !sharded(f)) {
+  } else if (known_bbox) {  // (a sharded caller passes the union over all ranks)
     for (int d = 0; d < 6; ++d) hb[d] = known_bbox[d];
   } else {
     QMCL_TRY(launch_bin_bbox(f, x, y, t, n));

@@ -57,11 +57,16 @@ using namespace pfx;
 // Exclusive scan of the chunk sums by one block, offset by the carry-in.
 __global__ void __launch_bounds__(1024)
 prefix_scan_chunk_sums_kernel(const double *__restrict__ chunk_sum, size_t nc, double carry_in,
-                              double *__restrict__ approx_in, double *__restrict__ total_out) {
+                              double *__restrict__ approx_in, double *__restrict__ total_out,
+                              const double *__restrict__ carry_terms = nullptr, int n_terms = 0,
+                              int term_stride = 0) {
   __shared__ double warp_tot[32];
   __shared__ double chunk_total;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double carry = carry_in;
+  // sharded filters: the approximate totals of the shards before this one, as they
+  // came out of the exchange (device memory), added in rank order
+  for (int r = 0; r < n_terms; ++r) carry += carry_terms[static_cast<size_t>(r) * term_stride];
   for (size_t base = 0; base < nc; base += 1024) {
     const size_t i = base + threadIdx.x;
     const double v = (i < nc) ? chunk_sum[i] : 0.0;
@@ -318,6 +323,22 @@ qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double a
   QMCL_TRY(plan_prefix(f, n, &pl));
   prefix_scan_chunk_sums_kernel<<<1, 1024, 0, s>>>(pl.pb.chunk_sum, pl.nc, approx_carry_in,
                                                   pl.pb.approx_in, nullptr);
+  QMCL_LAUNCHED();
+  prefix_summaries_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.nc, pl.pb);
+  QMCL_LAUNCHED();
+  return QMCL_OK;
+}
+
+// The same with the approximate carry-in still on the device: the sum of
+// terms[0], terms[stride], ... (n_terms of them), e.g. the gathered shard totals.
+qmcl_status prefix_summaries_dev(qmcl_filter *f, const double *w, size_t n, const double *terms,
+                                 int n_terms, int stride) {
+  if (!n) return QMCL_OK;
+  cudaStream_t s = f->map->stream;
+  PrefixPlan pl;
+  QMCL_TRY(plan_prefix(f, n, &pl));
+  prefix_scan_chunk_sums_kernel<<<1, 1024, 0, s>>>(pl.pb.chunk_sum, pl.nc, 0.0, pl.pb.approx_in, nullptr,
+                                                  terms, n_terms, stride);
   QMCL_LAUNCHED();
   prefix_summaries_kernel<<<static_cast<unsigned>(pl.nt), 256, 0, s>>>(w, n, pl.nc, pl.pb);
   QMCL_LAUNCHED();

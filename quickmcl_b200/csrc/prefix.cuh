@@ -17,6 +17,8 @@ qmcl_status sequential_prefix(qmcl_filter *f, const double *w, size_t n, double 
 //   prefix_apply       : expand into out[]
 qmcl_status prefix_local_total(qmcl_filter *f, const double *w, size_t n);
 qmcl_status prefix_summaries(qmcl_filter *f, const double *w, size_t n, double approx_carry_in);
+qmcl_status prefix_summaries_dev(qmcl_filter *f, const double *w, size_t n, const double *terms,
+                                 int n_terms, int stride);
 qmcl_status prefix_resolve(qmcl_filter *f, const double *w, size_t n, double *out,
                            double carry_in);
 qmcl_status prefix_apply(qmcl_filter *f, const double *w, size_t n, double *out);

@@ -273,35 +273,58 @@ static qmcl_status resample_low_variance(qmcl_filter *f, const ParticleSet &in, 
   return QMCL_OK;
 }
 
+// What a shard tells the others before the chain: its approximate total, its particle
+// count and (optionally) the bin bounds of its particles.
+struct ShardInfo {
+  double approx_total, count;
+  int bbox[6];
+};
+static_assert(sizeof(ShardInfo) == 40, "ShardInfo is exchanged as raw bytes");
 __global__ void pack_info_kernel(const double *__restrict__ approx_total, double count,
-                                 double *__restrict__ out) {
-  out[0] = *approx_total;
-  out[1] = count;
+                                 const int *__restrict__ bbox, ShardInfo *__restrict__ out) {
+  out->approx_total = *approx_total;
+  out->count = count;
+  for (int d = 0; d < 6; ++d) out->bbox[d] = bbox ? bbox[d] : (d < 3 ? INT_MAX : INT_MIN);
+}
+// The summary's exchange carries the info block along: one host wait for both.
+struct ShardSummaryMsg {
+  unsigned long long w[kShardSummaryWords];
+  ShardInfo info;
+};
+__global__ void pack_summary_msg_kernel(const unsigned long long *__restrict__ summary,
+                                        const ShardInfo *__restrict__ info,
+                                        ShardSummaryMsg *__restrict__ out) {
+  for (int k = 0; k < kShardSummaryWords; ++k) out->w[k] = summary[k];
+  out->info = *info;
 }
 
 // The exact (sequentially rounded) running sum of a sharded weight array:
 // f->cdf[i] = global running sum after local particle i.  carry[r] = running
 // sum before shard r's first particle (carry[G] = grand total), the same bits
-// on every rank; count[r] = particles of shard r.
+// on every rank; count[r] = particles of shard r.  dev_bbox (optional): this
+// rank's bin bounds (6 ints, device); their union over the ranks -> bbox_union.
 qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
                                  std::vector<double> *carry_out, std::vector<double> *count_out,
-                                 bool need_total = true) {
+                                 bool need_total = true, const int *dev_bbox = nullptr,
+                                 int *bbox_union = nullptr) {
   cudaStream_t s = f->map->stream;
   const int G = f->n_shards, me = f->shard_rank;
   QMCL_TRY(f->cdf.ensure(n + 1));
   StageScope sc(f, QMCL_STAGE_CDF);
-  // approximate shard totals -> approximate carry-ins (binade guesses only)
-  struct Info { double approx_total; double count; };
-  std::vector<Info> info(G);
+  // approximate shard totals -> approximate carry-ins (binade guesses only).  The
+  // totals stay on the device: the summaries' kernel adds up the ones before this
+  // rank itself, and the host sees the block with the summaries' exchange.
   QMCL_TRY(prefix_local_total(f, w, n));
-  // (the count joins the total on the device: one exchange, one host wait)
-  QMCL_TRY(f->partials.ensure(8));
-  pack_info_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr + 1, static_cast<double>(n), f->partials.ptr);
+  QMCL_TRY(f->partials.ensure(32));
+  ShardInfo *d_info = reinterpret_cast<ShardInfo *>(f->partials.ptr);               // 5 doubles
+  unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(f->partials.ptr + 8);  // 7 words
+  ShardSummaryMsg *d_msg = reinterpret_cast<ShardSummaryMsg *>(f->partials.ptr + 16);     // 12 words
+  pack_info_kernel<<<1, 1, 0, s>>>(f->prefix_carry.ptr + 1, static_cast<double>(n), dev_bbox, d_info);
   QMCL_LAUNCHED();
-  QMCL_TRY(shard_gather(f, f->partials.ptr, true, sizeof(Info), info.data()));
-  double approx_in = 0.0;
-  for (int r = 0; r < me; ++r) approx_in += info[r].approx_total;
-  QMCL_TRY(prefix_summaries(f, w, n, approx_in));
+  void *d_all = nullptr;
+  QMCL_TRY(shard_gather_device(f, d_info, sizeof(ShardInfo), &d_all));
+  QMCL_TRY(prefix_summaries_dev(f, w, n, static_cast<const double *>(d_all), me,
+                                static_cast<int>(sizeof(ShardInfo) / sizeof(double))));
   // The exact carry, shard after shard.  A shard publishes a closed-form summary -
   // its particles all fall into one binade of the running sum, or the sum crosses
   // into the next binade once, at a predicted element - which every rank replays
@@ -309,10 +332,6 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   // resolves itself right away and publishes its exact carry-out instead.  Only
   // shards without either (two crossings, a failed prediction) cost a round of the
   // chain: at 8 ranks usually none (3-4 rounds before the crossing form existed).
-  struct Summary { unsigned long long w[kShardSummaryWords]; };
-  std::vector<Summary> summaries(G);
-  QMCL_TRY(f->partials.ensure(8));
-  unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(f->partials.ptr);
   bool resolved = false;
   if (me == 0 && n) {
     QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, 0.0));
@@ -321,12 +340,23 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   } else {
     QMCL_TRY(prefix_shard_summary(f, n, d_sum));
   }
-  QMCL_TRY(shard_gather(f, d_sum, true, sizeof(Summary), summaries.data()));
+  pack_summary_msg_kernel<<<1, 1, 0, s>>>(d_sum, d_info, d_msg);
+  QMCL_LAUNCHED();
+  std::vector<ShardSummaryMsg> msgs(G);
+  QMCL_TRY(shard_gather(f, d_msg, true, sizeof(ShardSummaryMsg), msgs.data()));
+  if (bbox_union) {
+    for (int d = 0; d < 6; ++d) bbox_union[d] = msgs[0].info.bbox[d];
+    for (int r = 1; r < G; ++r)
+      for (int d = 0; d < 3; ++d) {
+        bbox_union[d] = std::min(bbox_union[d], msgs[r].info.bbox[d]);
+        bbox_union[3 + d] = std::max(bbox_union[3 + d], msgs[r].info.bbox[3 + d]);
+      }
+  }
   std::vector<double> &carry = *carry_out;
   carry.assign(G + 1, 0.0);
   std::vector<double> round(G);
   for (int r = 0; r < G; ++r) {
-    const bool known = prefix_apply_summary(carry[r], summaries[r].w, &carry[r + 1]);
+    const bool known = prefix_apply_summary(carry[r], msgs[r].w, &carry[r + 1]);
     // this rank's own walk starts as soon as its carry-in is exact: it then runs
     // beside whatever rounds later shards still need
     if (r == me && !resolved) {
@@ -349,7 +379,7 @@ qmcl_status sharded_exact_prefix(qmcl_filter *f, const double *w, size_t n,
   if (!resolved) QMCL_TRY(prefix_resolve(f, w, n, f->cdf.ptr, carry[me]));
   QMCL_TRY(prefix_apply(f, w, n, f->cdf.ptr));
   count_out->resize(G);
-  for (int r = 0; r < G; ++r) (*count_out)[r] = info[r].count;
+  for (int r = 0; r < G; ++r) (*count_out)[r] = msgs[r].info.count;
   return QMCL_OK;
 }
 
@@ -437,7 +467,17 @@ static qmcl_status resample_low_variance_sharded(qmcl_filter *f, const ParticleS
     return QMCL_OK;
   }
   std::vector<double> carry, count;
-  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count, /*need_total=*/false));
+  // The new set only copies input particles, so the union of the input shards' bin
+  // bounds covers it: they ride along with the running sum's exchange and spare the
+  // clustering that follows an exchange (and a host wait) of its own.
+  QMCL_TRY(launch_bin_bbox(f, in.x.ptr, in.y.ptr, in.t.ptr, in.n));
+  int in_bbox[6];
+  QMCL_TRY(sharded_exact_prefix(f, in.w.ptr, in.n, &carry, &count, /*need_total=*/false, f->bbox.ptr,
+                                in_bbox));
+  if (in_bbox[0] <= in_bbox[3]) {
+    std::memcpy(f->bbox_hint, in_bbox, sizeof(in_bbox));
+    f->bbox_hint_valid = true;
+  }
   struct Info { double count; };
   std::vector<Info> info(G);
   for (int r = 0; r < G; ++r) info[r].count = count[r];

@@ -230,6 +230,13 @@ class ShardedParticleFilter(ParticleFilter):
               "qmcl_filter_shard_range")
         return a.value, b.value, c.value
 
+    def shard_stats(self):
+        """Exchange counters since creation: collectives enqueued, carry-chain rounds that
+        needed an exchange of their own, rebalancing all-to-alls skipped."""
+        st = (C.c_uint64 * 3)()
+        check(self._L.qmcl_filter_shard_stats(self._h, st), "qmcl_filter_shard_stats")
+        return {"collectives": int(st[0]), "chain_rounds": int(st[1]), "rebalances_skipped": int(st[2])}
+
     def set_particles(self, particles):
         """`particles` is the GLOBAL set (same array on every rank); each rank keeps its block."""
         particles = np.ascontiguousarray(particles)
