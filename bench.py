@@ -634,11 +634,20 @@ def run_b200(args, wl):
             h.step(False)
         tb = f.get_timing(reset=True)
         f.set_timing(0)
-        if rank == 0:
-            log("stage breakdown (device ms per step, CUDA events inside the library, multi-launch path):")
-            for k, (ms, cnt) in tb.items():
-                if cnt:
-                    log(f"  {k:15s} {ms / min(args.steps, 20):9.4f} ms  ({cnt / min(args.steps, 20):.1f} scopes/step)")
+        # every rank reports: what one rank books as a long exchange is another rank's longer stage
+        rows = [f"stage breakdown of rank {rank} (device ms per step, CUDA events inside the library, "
+                "multi-launch path):"]
+        for k, (ms, cnt) in tb.items():
+            if cnt:
+                rows.append(f"  {k:15s} {ms / min(args.steps, 20):9.4f} ms  ({cnt / min(args.steps, 20):.1f} scopes/step)")
+        if world > 1 and dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, rows)
+            if rank == 0:
+                for g in gathered:
+                    log("\n".join(g))
+        elif rank == 0:
+            log("\n".join(rows))
 
     n, scan = h.n, h.scan
     evals_job = n * len(scan)

@@ -18,6 +18,8 @@
 #include "cluster_dev.cuh"
 
 #include "scan.cuh"
+
+#include <cstdlib>
 #include "shard.cuh"
 
 namespace qmcl {
@@ -343,13 +345,22 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     // the per-bin counts are made on demand (qmcl_filter_copy_bins).
     const size_t words = (cells + 3) / 4;
     QMCL_TRY(f->occ8.ensure(4 * words));
-    QMCL_CUDA(cudaMemsetAsync(f->occ8.ptr, 0, 4 * words, s));
-    if (n) {
-      bin_mark_occupancy_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g,
-                                                               reinterpret_cast<unsigned *>(f->occ8.ptr));
-      QMCL_LAUNCHED();
+    // QMCL_BINS_SPLIT=1 (diagnostic): the marking is booked under the otherwise unused
+    // "kld" stage and the exchange under "tail" in the stage breakdown of a sharded run
+    static const bool split = std::getenv("QMCL_BINS_SPLIT") != nullptr;
+    {
+      StageScope sub(f, QMCL_STAGE_KLD, split ? 2 : 99);
+      QMCL_CUDA(cudaMemsetAsync(f->occ8.ptr, 0, 4 * words, s));
+      if (n) {
+        bin_mark_occupancy_kernel<<<div_up(n, 256), 256, 0, s>>>(x, y, t, n, bp, g,
+                                                                 reinterpret_cast<unsigned *>(f->occ8.ptr));
+        QMCL_LAUNCHED();
+      }
     }
-    QMCL_TRY(shard_allreduce(f, f->occ8.ptr, words, QMCL_DT_I32, QMCL_OP_SUM));
+    {
+      StageScope sub(f, QMCL_STAGE_TAIL, split ? 2 : 99);
+      QMCL_TRY(shard_allreduce(f, f->occ8.ptr, words, QMCL_DT_I32, QMCL_OP_SUM));
+    }
     n_all = f->global_n;
     QMCL_TRY(device_scan(s, OccupiedByte{f->occ8.ptr},
                          EmitBinOccupancy{f->table.ptr, f->bin_cell.ptr, f->bin_label.ptr}, cells,
@@ -457,6 +468,10 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
   }
   QMCL_TRY(flush_motion(f));
   QMCL_TRY(flush_sensor(f));
+  // A sharded filter exchanges the cluster weights below and needs the cluster count on
+  // the host for that: it waits for the counts here (a plain stream wait) instead of
+  // inside an exchange of its own.
+  if (sharded(f)) QMCL_TRY(settle(f));
   const ParticleSet &ps = f->cur();
   // every rank of a sharded filter must take the same branch here
   const size_t n_any = sharded(f) ? f->global_n : ps.n;
@@ -494,14 +509,10 @@ qmcl_status qmcl_filter_get_estimate(qmcl_filter *f, double pose[3], double cov[
     wmax_kernel<<<std::min<unsigned>(blocks, 2 * kSMs), 256, 0, s>>>(ps.w.ptr, ps.n, es);
     QMCL_LAUNCHED();
   }
-  if (sharded(f)) {
-    // Exchange: the fixed-point scale needs the largest weight of all shards.
-    std::vector<unsigned long long> all(f->n_shards);
-    QMCL_TRY(shard_gather(f, &es->wmax_bits, true, sizeof(unsigned long long), all.data()));
-    unsigned long long gmax = 0;
-    for (unsigned long long v : all) gmax = std::max(gmax, v);
-    QMCL_CUDA(copy_h2d(&es->wmax_bits, &gmax, sizeof(gmax), s));
-  }
+  // Exchange: the fixed-point scale needs the largest weight of all shards.  The bits of
+  // a non-negative double order like integers: an in-place integer maximum, consumed by
+  // the next kernel - no host wait.
+  if (sharded(f)) QMCL_TRY(shard_allreduce(f, &es->wmax_bits, 1, QMCL_DT_I64, QMCL_OP_MAX));
   if (ps.n) {
     cluster_weight_kernel<<<div_up(ps.n, 256), 256, 0, s>>>(
         ps.x.ptr, ps.y.ptr, ps.t.ptr, ps.w.ptr, ps.n, bp, f->grid, f->table.ptr, f->bin_label.ptr,

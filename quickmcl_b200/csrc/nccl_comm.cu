@@ -98,9 +98,24 @@ int cb_alltoallv(void *ctx, const void *dev_send, const uint64_t *send_bytes,
                  const uint64_t *recv_offsets, void *stream) {
   NcclCtx *c = static_cast<NcclCtx *>(ctx);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // What stays on this rank (the bulk of a rebalancing exchange) is a plain device copy,
+  // not a send to oneself through NCCL; peers with nothing to exchange are skipped, and a
+  // call without any remote traffic issues no NCCL operation at all.
+  const int me = c->rank;
+  if (send_bytes[me] && recv_bytes[me]) {
+    if (send_bytes[me] != recv_bytes[me]) return fail(ncclInvalidArgument, "alltoallv: self piece");
+    if (cudaMemcpyAsync(static_cast<char *>(dev_recv) + recv_offsets[me],
+                        static_cast<const char *>(dev_send) + send_offsets[me], send_bytes[me],
+                        cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(ncclUnhandledCudaError, "alltoallv: self copy");
+  }
+  bool remote = false;
+  for (int p = 0; p < c->size; ++p) remote |= p != me && (send_bytes[p] || recv_bytes[p]);
+  if (!remote) return 0;
   ncclResult_t r = nccl().GroupStart();
   if (r != ncclSuccess) return fail(r, "ncclGroupStart");
   for (int p = 0; p < c->size; ++p) {
+    if (p == me) continue;
     if (send_bytes[p]) {
       r = nccl().Send(static_cast<const char *>(dev_send) + send_offsets[p], send_bytes[p], ncclInt8, p,
                       c->comm, s);
