@@ -56,12 +56,12 @@ bin_count_kernel(const float *__restrict__ x, const float *__restrict__ y,
 __global__ void __launch_bounds__(256)
 cc_hook_kernel(const int32_t *__restrict__ table, const int32_t *__restrict__ bin_cell,
                size_t n_bins, const unsigned long long *__restrict__ n_bins_dev, BinGrid g,
-               BinParams bp, int32_t *__restrict__ parent) {
+               BinParams bp, int32_t *__restrict__ parent, bool linked_runs) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   // n_bins is a launch bound while the count is still on its way to the host
   if (n_bins_dev) n_bins = static_cast<size_t>(*n_bins_dev);
   if (tid >= n_bins) return;
-  cc_hook_bin(table, bin_cell, g, bp, parent, static_cast<int>(tid));
+  cc_hook_bin(table, bin_cell, g, bp, parent, static_cast<int>(tid), linked_runs);
 }
 
 __global__ void __launch_bounds__(256)
@@ -336,6 +336,10 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
   QMCL_TRY(f->bin_cluster.ensure(max_bins_local));
   QMCL_TRY(f->scan_tmp.ensure_zero(scan_tmp_words(cells) + 4));
   unsigned long long *d_total = &f->scalars.ptr->n_bins;  // stable: the labelling reads it
+  // QMCL_LINK_THETA=0 (A/B): the forest starts without the theta runs linked
+  static const bool link_theta = !(std::getenv("QMCL_LINK_THETA") && std::getenv("QMCL_LINK_THETA")[0] == '0');
+  const int link_nt = link_theta ? g.nt : 0;
+  f->bins_linked = link_nt > 0;
   if (sharded(f)) {
     // Exchange: bin OCCUPANCY, one 0/1 byte per cell - a quarter of the count table's
     // bytes.  The bytes are summed four at a time as int32 words: with at most 255
@@ -363,7 +367,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
     }
     n_all = f->global_n;
     QMCL_TRY(device_scan(s, OccupiedByte{f->occ8.ptr},
-                         EmitBinOccupancy{f->table.ptr, f->bin_cell.ptr, f->bin_label.ptr}, cells,
+                         EmitBinOccupancy{f->occ8.ptr, f->table.ptr, f->bin_cell.ptr, f->bin_label.ptr, link_nt}, cells,
                          f->scan_tmp.ptr, d_total));
     f->bin_counts_valid = false;
   } else {
@@ -373,7 +377,7 @@ qmcl_status build_bins(qmcl_filter *f, const float *x, const float *y, const flo
       QMCL_LAUNCHED();
     }
     QMCL_TRY(device_scan(s, OccupiedFlag{f->table.ptr},
-                         EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr},
+                         EmitBin{f->table.ptr, f->bin_cell.ptr, f->bin_count.ptr, f->bin_label.ptr, link_nt},
                          cells, f->scan_tmp.ptr, d_total));
     f->bin_counts_valid = true;
   }
@@ -407,9 +411,12 @@ qmcl_status label_clusters(qmcl_filter *f) {
     return QMCL_OK;
   }
   const BinParams bp = bin_params(f);
+  // the linked start of the forest is there once: after this pass it is flattened
+  const bool linked = f->bins_linked;
+  f->bins_linked = false;
   StageScope sc(f, QMCL_STAGE_LABEL);
   cc_hook_kernel<<<div_up(nb, 256), 256, 0, s>>>(f->table.ptr, f->bin_cell.ptr, nb, nb_dev, f->grid,
-                                                 bp, f->bin_label.ptr);
+                                                 bp, f->bin_label.ptr, linked);
   QMCL_LAUNCHED();
   cc_flatten_kernel<<<div_up(nb, 256), 256, 0, s>>>(f->bin_label.ptr, nb, nb_dev);
   QMCL_LAUNCHED();

@@ -122,14 +122,23 @@ struct OccupiedByte {
 // Compacted bin list from the occupancy bytes; every cell of the table is written
 // (cell -> bin id + 1, 0 for an empty cell), so the table needs no clearing.
 struct EmitBinOccupancy {
+  const uint8_t *occ;
   int32_t *table;
   int32_t *bin_cell;
   int32_t *parent;
-  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+  int nt;  // runs along theta start out linked (see EmitBin); 0: off
+  size_t run_next = ~static_cast<size_t>(0);
+  int32_t run_head = 0;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) {
     table[i] = flag ? static_cast<int32_t>(pos) + 1 : 0;
     if (!flag) return;
     bin_cell[pos] = static_cast<int32_t>(i);
-    parent[pos] = static_cast<int32_t>(pos);
+    const bool linked = nt > 0 && pos > 0 && (i % static_cast<size_t>(nt)) != 0 && occ[i - 1] != 0;
+    int32_t p = static_cast<int32_t>(pos);
+    if (linked) p = (i == run_next) ? run_head : p - 1;
+    if (!linked || i != run_next) run_head = static_cast<int32_t>(pos);
+    run_next = i + 1;
+    parent[pos] = p;
   }
 };
 // Per-bin particle counts of this rank's particles (table: cell -> bin id + 1).
@@ -152,16 +161,33 @@ struct OccupiedFlag {
   __device__ uint32_t operator()(size_t i) const { return table[i] > 0 ? 1u : 0u; }
 };
 // Writes the compacted bin list and turns the table into cell -> bin id + 1.
+// The forest starts with the runs along theta already linked: a bin whose predecessor
+// in its (x, y) column is occupied - the previous bin of the sorted list, one cell back
+// in memory - points at it.  That edge is part of the neighbour relation in either
+// reading of it (cc_hook_bin), the link keeps the forest's invariant (parent < self),
+// and on a dense grid (global localisation: 36 bins per column) it turns most of the
+// labelling's scattered unions into walks along consecutive memory.  nt = 0: off.
 struct EmitBin {
   int32_t *table;
   int32_t *bin_cell;
   int32_t *bin_count;
   int32_t *parent;
-  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) const {
+  int nt;
+  // the scan hands a thread its items in order: the bin at which the thread's current
+  // run began, so that the run's later bins point there directly (short chains)
+  size_t run_next = ~static_cast<size_t>(0);
+  int32_t run_head = 0;
+  __device__ void operator()(size_t i, uint32_t pos, uint32_t flag) {
     if (!flag) return;
     bin_cell[pos] = static_cast<int32_t>(i);
     bin_count[pos] = table[i];
-    parent[pos] = static_cast<int32_t>(pos);
+    // table[i - 1] is a count (> 0) or already that cell's bin id + 1 (> 0) when occupied
+    const bool linked = nt > 0 && pos > 0 && (i % static_cast<size_t>(nt)) != 0 && table[i - 1] != 0;
+    int32_t p = static_cast<int32_t>(pos);
+    if (linked) p = (i == run_next) ? run_head : p - 1;
+    if (!linked || i != run_next) run_head = static_cast<int32_t>(pos);
+    run_next = i + 1;
+    parent[pos] = p;
     table[i] = static_cast<int32_t>(pos) + 1;
   }
 };
@@ -269,9 +295,14 @@ static_assert(masks_ok(), "QMCL_HOOK_ADJ out of date");
 static_assert(adjacency_mask(0) == (1u << kCand) - 1, "A must be adjacent to every candidate");
 }  // namespace hook
 
+// linked_runs: the forest came with the theta runs linked (EmitBin).  A bin whose theta
+// predecessor is occupied, and whose hub A = (x-1, y, t) has an occupied predecessor
+// too, then needs no union of its own: the two predecessors were joined one step down
+// (by this rule or by their union), and each is linked to its successor.  On a dense
+// grid that leaves one union per pair of neighbouring runs instead of one per bin.
 __device__ __forceinline__ void cc_hook_bin(const int32_t *table, const int32_t *bin_cell,
                                             const BinGrid &g, const BinParams &bp, int32_t *parent,
-                                            int b) {
+                                            int b, bool linked_runs = false) {
   const int cell = bin_cell[b];
   const int it = cell % g.nt;
   const int iy = (cell / g.nt) % g.ny;
@@ -301,6 +332,9 @@ __device__ __forceinline__ void cc_hook_bin(const int32_t *table, const int32_t 
   v[0] = occupant(ix - 1, iy, kt0);
   v[1] = occupant(ix, iy - 1, kt0);
   if (v[0] > 0) {  // adjacent to every other candidate
+    if (linked_runs && it > 0 && kt0 - 1 >= bp.theta_lo && table[cell - 1] > 0 &&
+        occupant(ix - 1, iy, kt0 - 1) > 0)
+      return;
     uf_union(parent, b, v[0] - 1);
     return;
   }

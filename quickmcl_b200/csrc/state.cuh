@@ -283,6 +283,7 @@ struct qmcl_filter {
   qmcl::DevBuf<int32_t> bin_cell;     // bin -> dense cell index (ascending)
   qmcl::DevBuf<int32_t> bin_count;    // particles per bin
   qmcl::DevBuf<uint8_t> occ8;         // sharded filters: bin occupancy, one byte per cell (the exchanged form)
+  bool bins_linked = false;           // the labelling forest starts with the theta runs linked (build_bins)
   bool bin_counts_valid = true;       // false: bin_count is made on demand (qmcl_filter_copy_bins)
   qmcl::DevBuf<int32_t> bin_label;    // union-find parent, then component root
   qmcl::DevBuf<int32_t> bin_cluster;  // root bin -> dense cluster id
