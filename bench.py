@@ -619,6 +619,13 @@ def run_b200(args, wl):
             es = hs.timed_loop(True, max(5, st // 2), 2, 1000, flush)
             secondary[name] = hs.summary(ds, es)
             hs.close()
+        # the sharded workload on this one GPU: the like-for-like anchor of the N = 2/4/8 lines
+        # (those runs measure it again on rank 0, see `same_workload_on_one_gpu`)
+        hs = Harness(q, torch, "C4", local_rank, stream)
+        secondary["C4_one_gpu"] = hs.summary(hs.timed_loop(False, 5, 2, 0, flush), None)
+        hs.close()
+        del hs
+        torch.cuda.empty_cache()
         secondary["C5_field_rebuild"] = measure_field_rebuild(q, torch, stream)
         secondary["C5_batch"] = measure_batch(q, torch, stream)
     clocks = sampler.stop() if rank == 0 else None
