@@ -611,6 +611,16 @@ def run_b200(args, wl):
                                 and parity["particles"][0] == parity["particles"][1])
 
     secondary = None
+    if world > 1 and not args.no_secondary and args.workload == "C4":
+        # the KLD variant of the sharded workload ("C4 low_variance and kld at 16 M"):
+        # candidate draws enumerated on every rank, slot all-to-all, first-draw table min-allreduce
+        hk = Harness(q, torch, "C4K", local_rank, stream, dist=dist, transport=args.transport, sharded=True)
+        dk = hk.timed_loop(False, min(args.steps, 20), 3, 0, flush)
+        secondary = {"C4K": hk.summary(dk, None, world)}
+        secondary["C4K"]["kept_particles"] = int(hk.f.num_particles())
+        hk.close()
+        del hk
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_secondary and args.workload == "C2":
         secondary = {}
         for name, st, wu in (("C1", 50, 5), ("C3", 20, 3)):
