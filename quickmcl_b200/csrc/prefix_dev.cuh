@@ -348,7 +348,7 @@ QMCL_PHASE_FN void prefix_summaries_tile(const double *w, size_t n, size_t nc,
 // chunks whose summary cannot be used: the literal sequence of double
 // additions.  The warp stages the chunk in shared memory, lane 0 runs the
 // dependent chain (bound by the DADD latency, the loads are issued ahead in
-// groups of 16), the warp writes the result back coalesced: 1.8 us per chunk on
+// groups of 16), the warp writes the result back coalesced: 1.8-2.1 us per chunk on
 // the B200 (profiles/r2_resolve_trace.txt).  A closed-form variant that
 // re-summarised the lanes around the crossing inside this phase was tried twice;
 // on one latency-bound warp its ~1500 instructions took 4.4 us.
