@@ -290,7 +290,7 @@ qmcl_status qmcl_batch_update(qmcl_filter *const *filters, size_t n_filters, int
                               const size_t *n_points, int resample, double *poses_out,
                               double *covs_out, int *valid_out);
 
-/* The same cycle for n filters that live on ONE map handle, in four launches
+/* The same cycle for n filters that live on ONE map handle, in three launches
  * for the whole batch (motion + beam selection, sensor model, and the fused
  * tail with one block per filter) and one host wait.  The batch owns its
  * filters (seeds seed, seed + 1, ...); qmcl_batch_filter lends filter i for the

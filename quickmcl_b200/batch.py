@@ -112,7 +112,7 @@ class FilterBatch:
 
 class FusedBatch:
     """qmcl_batch: n independent filters on ONE map handle whose scan cycle
-    (laser_handler.cpp:243-276 per robot) runs as four launches for the whole batch —
+    (laser_handler.cpp:243-276 per robot) runs as three launches for the whole batch —
     deferred motion + beam selection, sensor model, and the fused tail with one block per
     filter (csrc/tail.cu) — and one host wait.  `filters[i]` is filter i for the per-filter
     calls (initialise, set_particles, getters)."""

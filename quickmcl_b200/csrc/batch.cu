@@ -78,7 +78,7 @@ qmcl_status qmcl_batch_update(qmcl_filter *const *filters, size_t n_filters, int
 
 
 // ------------------------------------------------------------- fused batch
-// n independent filters on ONE map handle, updated by four launches in all
+// n independent filters on ONE map handle, updated by three launches in all
 // (front, sensor, tail, one per stage with blockIdx.y / blockIdx.x = filter)
 // instead of ~28 launches and two host waits per filter.  A filter's tail runs
 // in a single block (BlockTeam, tail.cu), which is enough for the default-size
