@@ -22,7 +22,7 @@ roofline  the sensor-model kernel (K7), timed with CUDA events inside the
         (SURVEY.md 8d), against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the CPU oracle (a restatement of the reference's single-threaded
         implementation; the reference itself needs ROS/Eigen/Boost/PCL and
-        cannot be built here) timed on this host, one thread
+        cannot be built here as a whole) timed on this host, one thread
 --impl reference  times that CPU implementation on the same workload and
         prints the same line with "impl": "reference"
 
@@ -287,7 +287,7 @@ def run_reference(args, wl):
                          "field": "brushfire (the reference's own field build)",
                          "stage_ms": {k: v * 1e3 for k, v in stages.items()},
                          "note": "CPU restatement of the reference (oracle/); the reference is "
-                                 "single-threaded (main.cpp:90) and cannot be built here",
+                                 "single-threaded (main.cpp:90) and cannot be built here as a whole",
                          "all_cores": all_cores},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},

@@ -6,15 +6,23 @@
  * reference legs may load this library, and only as the checker or as the
  * timed CPU baseline.  The CUDA library (quickmcl_b200/csrc) never links it.
  *
- * The reference (/root/reference, QuickMCL 0.5.0) cannot be compiled in this
- * image (ROS, Eigen, Boost, PCL, gtest absent), so this is a dependency-free
- * restatement.  Every function cites the reference file:line it follows.
- * Parity pinning: the helpers are checked against all golden vectors of the
- * reference's own gtest suite (tests/test_oracle_golden.py).  The RNG-driven
- * stages (motion, resampling, init) are NOT pinned by any reference test
- * ("parity unpinned" for those): the reference draws from a private, unseeded
- * std::mt19937, so both this oracle and the CUDA path consume one shared
- * counter-based Philox4x32-10 stream instead (contract in DESIGN.md §RNG).
+ * The reference (/root/reference, QuickMCL 0.5.0) cannot be compiled as a whole
+ * in this image (ROS, Eigen, Boost, PCL, gtest absent), so this is a
+ * dependency-free restatement.  Every function cites the reference file:line
+ * it follows.
+ * Parity pinning: (1) the helpers are checked against all golden vectors of the
+ * reference's own gtest suite (tests/test_oracle_golden.py); (2) the parts of
+ * the reference that use Eigen only as a container - distance_calculator.cpp,
+ * particle.cpp, space_partitioning.cpp, scaled_map.h, low_pass_filter.h,
+ * utils.h - are compiled from where they lie into oracle/_ref/libqmcl_ref.so
+ * (oracle/Makefile target `ref`, oracle/ref_shim.cpp, stand-in headers in
+ * oracle/ref_stubs) and this oracle is held against them bit for bit on random
+ * inputs (tests/test_oracle_vs_ref.py).  The sensor model, the motion model,
+ * the resamplers' draws and initialisation are NOT pinned by any reference
+ * test and cannot be built that way ("parity unpinned" for those; the
+ * statistics have their golden vector only): the reference draws from a private, unseeded std::mt19937, so both
+ * this oracle and the CUDA path consume one shared counter-based Philox4x32-10
+ * stream instead (contract in DESIGN.md section 6).
  */
 #ifndef QMCL_ORACLE_H
 #define QMCL_ORACLE_H
