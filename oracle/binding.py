@@ -86,6 +86,8 @@ def lib():
         "orc_statistics_merge": (None, [pf64, pf64, C.c_int, pf64]),
         "orc_lowpass_run": (f64, [f64, pf64, sz, C.c_int]),
         "orc_philox4x32_10": (None, [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "orc_rng_words": (None, [u64, u32, u32, u64, sz, C.POINTER(u32)]),
+        "orc_normal_pairs": (None, [C.POINTER(u32), sz, pf64]),
         "orc_kld_limit": (u64, [u64, f64, f64, i32, i32]),
         "orc_map_create": (vp, []),
         "orc_map_destroy": (None, [vp]),
@@ -329,6 +331,27 @@ class OracleFilter:
 
     def last_total_weight(self):
         return self.L.orc_filter_last_total_weight(self.h)
+
+
+# purposes of the shared RNG contract (qmcl_oracle.cpp: enum Purpose)
+P_INIT, P_GLOBAL, P_MOTION, P_LV_OFFSET, P_DRAW, P_INJECT = 1, 2, 3, 4, 5, 6
+
+
+def rng_words(seed, step, purpose, count, first_index=0):
+    """The four Philox words of draws first_index .. first_index + count - 1: uint32 [count, 4]."""
+    out = np.zeros((count, 4), np.uint32)
+    if count:
+        lib().orc_rng_words(seed, step, purpose, first_index, count, _ptr(out, C.c_uint32))
+    return out
+
+
+def normal_pairs(words2):
+    """Box-Muller pairs as the motion model makes them of two words each: float64 [n, 2]."""
+    w = np.ascontiguousarray(words2, np.uint32).reshape(-1, 2)
+    out = np.zeros((len(w), 2), np.float64)
+    if len(w):
+        lib().orc_normal_pairs(_ptr(w, C.c_uint32), len(w), _ptr(out, C.c_double))
+    return out
 
 
 def project_scan(ranges, angle_min, angle_increment, range_min, range_max, mount=(0.0, 0.0, 0.0)):

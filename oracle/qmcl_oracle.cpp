@@ -936,6 +936,17 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2],
                        uint32_t out[4]) {
   philox(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
+void orc_rng_words(uint64_t seed, uint32_t step, uint32_t purpose,
+                   uint64_t first_index, size_t count, uint32_t *out4) {
+  Rng rng;
+  rng.seed = seed;
+  rng.step = step;
+  for (size_t i = 0; i < count; ++i) rng.draw(first_index + i, purpose, out4 + 4 * i);
+}
+void orc_normal_pairs(const uint32_t *words2, size_t count, double *out2) {
+  for (size_t i = 0; i < count; ++i)
+    normal_pair(words2[2 * i], words2[2 * i + 1], &out2[2 * i], &out2[2 * i + 1]);
+}
 uint64_t orc_kld_limit(uint64_t k, double eps, double z, int32_t nmin,
                        int32_t nmax) {
   return Bins::limit_for(k, 2 * eps, z, nmin, nmax);

@@ -108,6 +108,13 @@ void orc_statistics_merge(const double a[15], const double b[15],
 double orc_lowpass_run(double alpha, const double *xs, size_t n, int as_float);
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2],
                        uint32_t out[4]);
+/* The shared RNG contract, exposed for tests that replay the oracle's draws
+ * into the reference's own code (oracle/ref_shim.cpp): the four Philox words of
+ * draws first_index .. first_index + count - 1 for one (seed, step, purpose),
+ * and the Box-Muller pair the motion model makes of two words. */
+void orc_rng_words(uint64_t seed, uint32_t step, uint32_t purpose,
+                   uint64_t first_index, size_t count, uint32_t *out4);
+void orc_normal_pairs(const uint32_t *words2, size_t count, double *out2);
 uint64_t orc_kld_limit(uint64_t k, double eps, double z, int32_t nmin,
                        int32_t nmax);
 

@@ -1,32 +1,49 @@
 /*
  * ref_shim.cpp — C entry points over the REFERENCE's own code (oracle/_ref).
  *
- * TEST INFRASTRUCTURE ONLY.  This file is compiled together with a handful of the
- * reference's translation units, taken from where they lie under /root/reference
- * (never copied): distance_calculator.cpp, particle.cpp, pose_2d.cpp,
- * space_partitioning.cpp, plus its header-only scaled_map.h, low_pass_filter.h and
- * utils.h.  Those units use Eigen only as a container / for element-wise float
- * operations and ROS only for two message structs, so they build against the
- * stand-in headers in oracle/ref_stubs (see the note in ref_stubs/Eigen/Core).  The
- * result, oracle/_ref/libqmcl_ref.so, lets tests/test_oracle_vs_ref.py hold the
- * restated oracle against what the reference's statements actually compute, on
- * inputs far beyond the reference's own golden vectors: brushfire distance and
- * state maps of random occupancy grids, grid truncation, weights / N_eff / running
- * sum, the KLD bound as bins fill up, the bin keys and the cluster partition.
+ * TEST INFRASTRUCTURE ONLY.  This file is compiled together with the reference's
+ * translation units of the particle-filter path, taken from where they lie under
+ * /root/reference (never copied): distance_calculator.cpp, map_base.cpp,
+ * map_likelihood.cpp, odometry.cpp, particle.cpp, particle_filter.cpp, pose_2d.cpp,
+ * space_partitioning.cpp, statistics.cpp, plus the header-only scaled_map.h,
+ * low_pass_filter.h, random.h and utils.h.  Eigen, ROS and PCL are absent from this
+ * image; the units build against the stand-in headers in oracle/ref_stubs (what each
+ * stand-in restates is written at its top: Eigen/Core, Eigen/Geometry,
+ * Eigen/Eigenvalues, random).  The result, oracle/_ref/libqmcl_ref.so, lets
+ * tests/test_oracle_vs_ref.py hold the restated oracle against what the reference's
+ * statements actually compute, on inputs far beyond the reference's own golden
+ * vectors: brushfire distance and state maps, the likelihood table, the sensor
+ * model, the motion model, the three resamplers, KLD, clustering, the estimate and
+ * whole scan cycles.
  *
- * What is NOT here: the sensor model, the motion model, the resamplers, the
- * statistics - they need real Eigen numerics, PCL or the reference's private RNG.
+ * Randomness: the reference's engines are private and unseeded, so ref_stubs/random
+ * replaces std::mt19937 by an engine that reads a script (ref_script below).  The
+ * tests write into that script the very words the shared Philox contract (DESIGN.md
+ * section 6) hands the oracle for each draw, in the order the reference consumes them.
+ *
+ * This file is compiled with -fno-access-control: it reads and sets private members
+ * of the reference's classes (the likelihood table, the low-pass filters, the
+ * current particle set) where the reference has no accessor.
+ *
+ * Not built: laser.cpp (PCL conversion), pose_restore.cpp, the factories, the node.
  */
 #include "quickmcl/distance_calculator.h"
 #include "quickmcl/low_pass_filter.h"
+#include "quickmcl/map_likelihood.h"
+#include "quickmcl/odometry.h"
 #include "quickmcl/parameters.h"
 #include "quickmcl/particle.h"
+#include "quickmcl/particle_filter.h"
 #include "quickmcl/scaled_map.h"
 #include "quickmcl/space_partitioning.h"
+#include "quickmcl/statistics.h"
 #include "quickmcl/utils.h"
 
+#include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <stdexcept>
 #include <vector>
 
 namespace {
@@ -54,6 +71,38 @@ void from_collection(const quickmcl::ParticleCollection &c, PodParticle *p) {
   for (size_t i = 0; i < c.size(); ++i) p[i].weight = c[i].weight;
 }
 
+void from_collection_full(const quickmcl::ParticleCollection &c, PodParticle *p) {
+  for (size_t i = 0; i < c.size(); ++i) {
+    p[i].x = c[i].data.x;
+    p[i].y = c[i].data.y;
+    p[i].theta = c[i].data.theta;
+    p[i].pad = 0;
+    p[i].weight = c[i].weight;
+  }
+}
+
+quickmcl::LaserPointCloud to_cloud(const float *xy, size_t n) {
+  quickmcl::LaserPointCloud cloud;
+  cloud.points.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    cloud.points[i].x = xy[2 * i];
+    cloud.points[i].y = xy[2 * i + 1];
+  }
+  return cloud;
+}
+
+// the script the stand-in engines read (ref_stubs/random)
+std::vector<uint64_t> g_words;
+std::vector<double> g_normals;
+size_t g_word_pos = 0, g_normal_pos = 0;
+int g_underflow = 0;
+double g_last_seconds = 0;
+
+struct Stopwatch {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~Stopwatch() { g_last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 nav_msgs::OccupancyGrid make_grid(const int8_t *occ, uint32_t w, uint32_t h, float resolution) {
   nav_msgs::OccupancyGrid g;
   g.info.width = w;
@@ -61,6 +110,19 @@ nav_msgs::OccupancyGrid make_grid(const int8_t *occ, uint32_t w, uint32_t h, flo
   g.info.resolution = resolution;
   g.data.assign(occ, occ + static_cast<size_t>(w) * h);
   return g;
+}
+
+// distance_calculator.cpp:45-57 keeps one distance cache in a function-local static and
+// rebuilds it when the resolution changes or when the cached range is >= the requested
+// one - so a process that asks for a LARGER range than before at the same resolution is
+// handed the old, too small cache and reads past its end.  One process building maps with
+// different parameters is what these tests do and the node never does; a dummy request
+// at another resolution before every real one makes the next call rebuild.
+void forget_distance_cache() {
+  const int8_t cell = 0;
+  const nav_msgs::OccupancyGrid g = make_grid(&cell, 1, 1, 12345.0f);
+  quickmcl::MapContainer m;
+  quickmcl::compute_distance_map(12345.0f, g, &m);
 }
 
 }  // namespace
@@ -81,6 +143,7 @@ int ref_distance_cache(float resolution, float max_dist, float *out, size_t cap)
 void ref_distance_map(const int8_t *occ, uint32_t w, uint32_t h, float resolution, float max_dist, float *out) {
   const nav_msgs::OccupancyGrid g = make_grid(occ, w, h, resolution);
   quickmcl::MapContainer m;
+  forget_distance_cache();
   quickmcl::compute_distance_map(max_dist, g, &m);
   for (Eigen::Index r = 0; r < m.rows(); ++r)
     for (Eigen::Index c = 0; c < m.cols(); ++c) out[r * m.cols() + c] = m(r, c);
@@ -215,6 +278,247 @@ int ref_space_partitioning(const PodParticle *p, size_t n, int32_t particle_coun
     if (cluster_out) cluster_out[i] = sp.get_cluster_id(pose);
   }
   return sp.get_cluster_count();
+}
+
+// ----------------------------------------------------------------- the script
+uint64_t qmcl_ref_next_word(void) {
+  if (g_word_pos < g_words.size()) return g_words[g_word_pos++];
+  g_underflow = 1;
+  return 0;
+}
+double qmcl_ref_next_normal(void) {
+  if (g_normal_pos < g_normals.size()) return g_normals[g_normal_pos++];
+  g_underflow = 1;
+  return 0;
+}
+// replaces the script: `words` feed every uniform draw, `normals` every normal draw
+void ref_script(const uint64_t *words, size_t n_words, const double *normals, size_t n_normals) {
+  g_words.assign(words, words + n_words);
+  g_normals.assign(normals, normals + n_normals);
+  g_word_pos = g_normal_pos = 0;
+  g_underflow = 0;
+}
+// consumed[0] = words read, consumed[1] = normals read; returns 1 if a draw found the script empty
+int ref_script_state(uint64_t consumed[2]) {
+  consumed[0] = g_word_pos;
+  consumed[1] = g_normal_pos;
+  return g_underflow;
+}
+// wall-clock seconds of the last timed entry point (sensor update, resampling, cycle)
+double ref_last_seconds(void) { return g_last_seconds; }
+
+// ------------------------------------------------- MapLikelihood (+ MapBase)
+struct ref_map {
+  std::shared_ptr<quickmcl::MapLikelihood> map;
+};
+struct RefLikelihoodParams {  // = orc_likelihood_params
+  float z_hit, z_rand;
+  int32_t num_beams;
+  float max_laser_distance, max_obstacle_distance, sigma_hit;
+};
+
+// set_parameters (map_likelihood.cpp:39-48) then new_map (:50-61, map_base.cpp:29-56)
+ref_map *ref_map_create(const int8_t *occ, uint32_t w, uint32_t h, float resolution, double origin_x,
+                        double origin_y, const RefLikelihoodParams *p) {
+  quickmcl::Parameters::LikelihoodMap lp;
+  lp.z_hit = p->z_hit;
+  lp.z_rand = p->z_rand;
+  lp.num_beams = p->num_beams;
+  lp.max_laser_distance = p->max_laser_distance;
+  lp.max_obstacle_distance = p->max_obstacle_distance;
+  lp.sigma_hit = p->sigma_hit;
+  auto grid = std::make_shared<nav_msgs::OccupancyGrid>(make_grid(occ, w, h, resolution));
+  grid->info.origin.position.x = origin_x;
+  grid->info.origin.position.y = origin_y;
+  auto *m = new ref_map;
+  m->map = std::make_shared<quickmcl::MapLikelihood>();
+  m->map->set_parameters(lp);
+  forget_distance_cache();
+  m->map->new_map(grid);
+  return m;
+}
+void ref_map_destroy(ref_map *m) { delete m; }
+void ref_map_copy_field(const ref_map *m, float *out) {
+  const auto &f = m->map->likelihood_data;
+  std::memcpy(out, f.data(), sizeof(float) * static_cast<size_t>(f.rows() * f.cols()));
+}
+// replaces the likelihood table (same shape) so that two implementations can be
+// compared on one identical field
+void ref_map_set_field(ref_map *m, const float *field) {
+  auto &f = m->map->likelihood_data;
+  std::memcpy(f.data(), field, sizeof(float) * static_cast<size_t>(f.rows() * f.cols()));
+}
+void ref_map_copy_state(const ref_map *m, int8_t *out) {
+  const auto &s = m->map->map_state;
+  for (Eigen::Index r = 0; r < s.rows(); ++r)
+    for (Eigen::Index c = 0; c < s.cols(); ++c) out[r * s.cols() + c] = static_cast<int8_t>(s(r, c));
+}
+size_t ref_map_num_free(const ref_map *m) { return m->map->free_cells.size(); }
+void ref_map_copy_free_cells(const ref_map *m, int32_t *xy_out) {
+  const auto &fc = m->map->free_cells;
+  for (size_t i = 0; i < fc.size(); ++i) {
+    xy_out[2 * i] = fc[i](0);
+    xy_out[2 * i + 1] = fc[i](1);
+  }
+}
+int8_t ref_map_state_at(const ref_map *m, float x, float y) {
+  return static_cast<int8_t>(m->map->get_map_state_at(Eigen::Vector2f(x, y)));
+}
+double ref_map_probability_at(const ref_map *m, float x, float y) {
+  return m->map->get_probability_at(Eigen::Vector2f(x, y));
+}
+void ref_map_likelihood_grid(const ref_map *m, int8_t *out) {
+  const nav_msgs::OccupancyGrid g = m->map->get_likelihood_as_gridmap();
+  std::memcpy(out, g.data.data(), g.data.size());
+}
+// map_base.cpp:58-64; reads two words of the script (cell, heading)
+void ref_map_random_pose(const ref_map *m, float out[3]) {
+  const auto p = m->map->generate_random_pose();
+  out[0] = p.x;
+  out[1] = p.y;
+  out[2] = p.theta;
+}
+// map_likelihood.cpp:63-130: weights written into p, returns the total
+double ref_map_update_importance(const ref_map *m, const float *xy, size_t npoints, PodParticle *p, size_t n) {
+  const quickmcl::LaserPointCloud cloud = to_cloud(xy, npoints);
+  auto c = to_collection(p, n);
+  double total;
+  {
+    Stopwatch sw;
+    total = m->map->update_importance(cloud, &c);
+  }
+  from_collection(c, p);
+  return total;
+}
+
+// statistics.cpp: add every particle in order, optionally finalise;
+// out = {total_weight, sample_count, mean[4], covariance[9] row-major}
+void ref_statistics(const PodParticle *p, size_t n, int finalise, double out[15]) {
+  quickmcl::ParticleCloudStatistics st;
+  st.add(to_collection(p, n));
+  if (finalise) st.finalise();
+  out[0] = st.total_weight;
+  out[1] = static_cast<double>(st.sample_count);
+  for (int k = 0; k < 4; ++k) out[2 + k] = st.mean(k);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) out[6 + 3 * i + j] = st.covariance(i, j);
+}
+
+// odometry.cpp:44-102; reads three normals of the script per particle
+void ref_sample_odometry(const double odom_new[3], const double odom_old[3], PodParticle *p, size_t n,
+                         const float alpha[4]) {
+  auto c = to_collection(p, n);
+  std::mt19937 rng;
+  float a[4] = {alpha[0], alpha[1], alpha[2], alpha[3]};
+  quickmcl::sample_odometry(quickmcl::Odometry(odom_new[0], odom_new[1], odom_new[2]),
+                            quickmcl::Odometry(odom_old[0], odom_old[1], odom_old[2]), &c, &rng, a);
+  from_collection_full(c, p);
+}
+
+// ------------------------------------------------------------ ParticleFilter
+struct ref_filter {
+  std::shared_ptr<quickmcl::MapLikelihood> map;
+  std::unique_ptr<quickmcl::ParticleFilter> pf;
+};
+struct RefPfParams {  // = orc_pf_params
+  int32_t resample_type, particle_count_min, particle_count_max, resample_count;
+  double alpha_fast, alpha_slow, kld_epsilon, kld_z;
+  float res_xy, res_theta;
+};
+
+ref_filter *ref_filter_create(ref_map *m) {
+  auto *f = new ref_filter;
+  f->map = m->map;
+  f->pf.reset(new quickmcl::ParticleFilter(m->map));
+  return f;
+}
+void ref_filter_destroy(ref_filter *f) { delete f; }
+void ref_filter_set_params(ref_filter *f, const RefPfParams *p) {
+  quickmcl::Parameters::ParticleFilter pp;
+  pp.resample_type = p->resample_type == 0   ? quickmcl::ResampleType::low_variance
+                     : p->resample_type == 1 ? quickmcl::ResampleType::adaptive
+                                             : quickmcl::ResampleType::kld;
+  pp.particle_count_min = p->particle_count_min;
+  pp.particle_count_max = p->particle_count_max;
+  pp.resample_count = p->resample_count;
+  pp.alpha_fast = p->alpha_fast;
+  pp.alpha_slow = p->alpha_slow;
+  pp.kld_epsilon = p->kld_epsilon;
+  pp.kld_z = p->kld_z;
+  pp.space_partitioning_resolution_xy = p->res_xy;
+  pp.space_partitioning_resolution_theta = p->res_theta;
+  f->pf->set_parameters(pp);
+}
+// particle_filter.cpp:39-68; reads three normals per particle
+void ref_filter_initialise(ref_filter *f, const float pose[3], const float cov[9]) {
+  quickmcl::WeightedParticle::ParticleT::EigenMatrix c;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) c(i, j) = cov[3 * i + j];
+  f->pf->initialise(quickmcl::WeightedParticle::ParticleT(pose[0], pose[1], pose[2]), c);
+}
+// particle_filter.cpp:70-82; reads two words per particle
+void ref_filter_global_localization(ref_filter *f) { f->pf->global_localization(); }
+void ref_filter_handle_odometry(ref_filter *f, const double odom_new[3], const double odom_old[3],
+                                const float alpha[4]) {
+  float a[4] = {alpha[0], alpha[1], alpha[2], alpha[3]};
+  Stopwatch sw;
+  f->pf->handle_odometry(quickmcl::Odometry(odom_new[0], odom_new[1], odom_new[2]),
+                         quickmcl::Odometry(odom_old[0], odom_old[1], odom_old[2]), a);
+}
+void ref_filter_update_sensor(ref_filter *f, const float *xy, size_t npoints) {
+  const quickmcl::LaserPointCloud cloud = to_cloud(xy, npoints);
+  Stopwatch sw;
+  f->pf->update_importance_from_observations(cloud);
+}
+// returns 0, or 1 when the reference threw std::out_of_range: its low-variance walk
+// ran off the end of the set (particle_filter.cpp:229-235, the assert is compiled out in
+// Release and .at(i) throws)
+int ref_filter_resample_and_cluster(ref_filter *f) {
+  Stopwatch sw;
+  try {
+    f->pf->resample_and_cluster();
+  } catch (const std::out_of_range &) {
+    return 1;
+  }
+  return 0;
+}
+void ref_filter_cluster(ref_filter *f) { f->pf->cluster(); }
+int ref_filter_get_estimate(const ref_filter *f, double pose[3], double cov[9]) {
+  quickmcl::Pose2D<double> p(0, 0, 0);
+  Eigen::Matrix3d c = Eigen::Matrix3d::Zero();
+  bool ok;
+  {
+    Stopwatch sw;
+    ok = f->pf->get_estimated_pose(&p, &c);
+  }
+  if (!ok) return 0;
+  pose[0] = p.x;
+  pose[1] = p.y;
+  pose[2] = p.theta;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov[3 * i + j] = c(i, j);
+  return 1;
+}
+size_t ref_filter_num_particles(const ref_filter *f) { return f->pf->num_particles(); }
+void ref_filter_copy_particles(const ref_filter *f, PodParticle *out) {
+  from_collection_full(f->pf->get_particles(), out);
+}
+void ref_filter_set_particles(ref_filter *f, const PodParticle *p, size_t n) {
+  f->pf->data_sets[f->pf->current_data_set].particles = to_collection(p, n);
+}
+void ref_filter_get_lowpass(const ref_filter *f, double out[2]) {
+  out[0] = f->pf->w_slow.get();
+  out[1] = f->pf->w_fast.get();
+}
+void ref_filter_set_lowpass(ref_filter *f, double w_slow, double w_fast) {
+  f->pf->w_slow.reset(w_slow);
+  f->pf->w_fast.reset(w_fast);
+}
+int ref_filter_num_clusters(const ref_filter *f) { return f->pf->space_partitioning.get_cluster_count(); }
+// cluster id of every current particle (numbering follows the unordered_map: compare partitions)
+void ref_filter_cluster_ids(const ref_filter *f, int32_t *out) {
+  const auto &ps = f->pf->get_particles();
+  for (size_t i = 0; i < ps.size(); ++i) out[i] = f->pf->space_partitioning.get_cluster_id(ps[i].data);
 }
 
 }  // extern "C"

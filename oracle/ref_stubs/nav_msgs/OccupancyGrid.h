@@ -5,6 +5,7 @@
 #include <geometry_msgs/Pose.h>
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 namespace nav_msgs {
@@ -17,6 +18,7 @@ struct MapMetaData {
 };
 
 struct OccupancyGrid {
+  using ConstPtr = std::shared_ptr<const OccupancyGrid>;  // boost::shared_ptr in ROS
   MapMetaData info;
   std::vector<int8_t> data;  // row-major, -1 unknown, 0..100 occupancy
 };
