@@ -281,7 +281,7 @@ def test_low_variance_matches_reference(n, seed, short):
     _, _, p = weighted_cloud(occ, res, org, rm, om, n, seed)
     if not short:
         p["weight"] /= np.cumsum(p["weight"])[-1]
-        p["weight"][-1] += 1e-9  # the running sum reaches past every target
+        p["weight"][-1] += 1e-6  # the running sum reaches past every target
     assert low_variance_overruns(p, 33, seed) == short
     of.set_particles(p)
     rf.set_particles(p)
