@@ -20,9 +20,12 @@ e2e     the same step through the public API with HOST buffers: the scan is
 roofline  the sensor-model kernel (K7), timed with CUDA events inside the
         library on the launching stream, 4.02 algorithmic bytes per evaluation
         (SURVEY.md 8d), against MEASURED_PEAKS.json hbm_gbs
-cpu_baseline  the CPU oracle (a restatement of the reference's single-threaded
-        implementation; the reference itself needs ROS/Eigen/Boost/PCL and
-        cannot be built here as a whole) timed on this host, one thread
+cpu_baseline  the reference's own particle-filter sources (map_likelihood.cpp,
+        odometry.cpp, particle_filter.cpp ...), compiled into oracle/_ref from
+        where they lie against stand-in Eigen / ROS / PCL headers ("kind":
+        "reference"), timed on this host on one thread - the reference is
+        single-threaded (main.cpp:90).  Without that library: the CPU oracle,
+        a restatement of the same code ("kind": "port")
 --impl reference  times that CPU implementation on the same workload and
         prints the same line with "impl": "reference"
 
@@ -144,6 +147,199 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm
+def ref_cycle_seconds(wl, inputs, steps, warmup):
+    """Times the full update cycle of the REFERENCE'S OWN CODE (oracle/_ref: map_likelihood.cpp,
+    odometry.cpp, particle_filter.cpp ... compiled from /root/reference against stand-in
+    headers).  Its private random engines read a script (oracle/ref_stubs/random) that is
+    filled, untimed, with the draws of the shared Philox contract - popping a word is cheaper
+    than mt19937 + libstdc++'s normal_distribution, so this errs in the reference's favour.
+    Only the four calls of the cycle are timed.  Returns (seconds per step, evals per step,
+    per-stage seconds, notes)."""
+    from oracle import binding as ob
+    from oracle import ref_binding as rb
+    occ, res, origin, pose, scan, (x, y, t) = inputs
+    lp = dict(syn.NODE_LIKELIHOOD, num_beams=0)
+    rm = rb.RefMap(occ, res, origin, **lp)          # the reference's brushfire + table build
+    rf = rb.RefFilter(rm)
+    pfp = dict(wl["pf"])
+    rf.set_parameters(**pfp)
+    rtype = pfp.get("resample_type", 2)
+    n_slots = pfp.get("particle_count_max", 5000) if rtype == 2 else pfp.get("particle_count_min", 100)
+    n = len(x)
+    init = ob.make_particles(x, y, t, np.full(n, 1.0 / n))
+    stages = {"odometry": 0.0, "sensor": 0.0, "resample": 0.0, "estimate": 0.0}
+    overruns = 0
+    for it in range(warmup + steps):
+        rf.set_particles(init)
+        rf.set_lowpass(0.0, 0.0)
+        rb.script(normals=rb.motion_script(3, 10 + it, n))
+        t0 = time.perf_counter()
+        rf.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
+        t1 = time.perf_counter()
+        rf.update_importance_from_observations(scan)
+        t2 = time.perf_counter()
+        if rtype == 0:
+            rb.script(words=rb.low_variance_script(3, 11 + it))
+        else:
+            w_slow, w_fast = rf.lowpass()
+            w_diff = max(0.0, 1.0 - w_fast / w_slow) if w_slow else 0.0
+            rb.script(words=rb.draw_script(3, 11 + it, n_slots, w_diff)[0])
+        t3 = time.perf_counter()
+        ok = rf.resample_and_cluster()
+        t4 = time.perf_counter()
+        if not ok:
+            # the reference's low-variance walk ran off the end of the set and threw
+            # (particle_filter.cpp:229-235; weights sum to < 1 after the wall penalties): the
+            # resampling stage ends early, the estimate is timed on a valid set of the same size
+            overruns += it >= warmup
+            rf.set_particles(init)
+            rf.cluster()
+        t5 = time.perf_counter()
+        rf.get_estimated_pose()
+        t6 = time.perf_counter()
+        if it >= warmup:
+            stages["odometry"] += t1 - t0
+            stages["sensor"] += t2 - t1
+            stages["resample"] += t4 - t3
+            stages["estimate"] += t6 - t5
+    if rb.script_state()[2]:
+        raise RuntimeError("the reference drew more numbers than the script held")
+    stages = {k: v / steps for k, v in stages.items()}
+    notes = {"low_variance_overrun_steps": overruns} if overruns else {}
+    return sum(stages.values()), n * len(scan), stages, notes
+
+
+def with_deep_stack(fn, *args):
+    """Runs fn on a thread with a 1 GiB stack: the reference labels clusters by recursion, one
+    frame per bin (space_partitioning.cpp:101-128), and overflows the default 8 MiB stack on the
+    large connected bin sets of a global cloud of >= 1e5 particles (the node was never run there).
+    The stack is virtual memory; only the depth actually reached is touched."""
+    box = {}
+
+    def run():
+        try:
+            box["result"] = fn(*args)
+        except BaseException as e:  # handed to the caller below
+            box["error"] = e
+
+    old = threading.stack_size(1 << 30)
+    try:
+        th = threading.Thread(target=run)
+        th.start()
+        th.join()
+    finally:
+        threading.stack_size(old)
+    if "error" in box:
+        raise box["error"]
+    return box["result"]
+
+
+MAX_REFERENCE_CLUSTERS = 65000  # space_partitioning.h:59: ClusterId is uint16_t, 65535 = invalid
+
+
+def sampled_workload(wl, n_sample):
+    """The workload cut down to its first n_sample particles, particle-count bounds scaled alike."""
+    wl_s = dict(wl)
+    pf = dict(wl["pf"])
+    scale = n_sample / wl["particles"]
+    if scale < 1.0:
+        pf["particle_count_min"] = max(1, int(pf["particle_count_min"] * scale))
+        pf["particle_count_max"] = max(1, int(pf["particle_count_max"] * scale))
+    wl_s["pf"] = pf
+    return wl_s
+
+
+def sample_inputs(inputs, n_sample):
+    occ, res, origin, pose, scan, (x, y, t) = inputs
+    return occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])
+
+
+def reference_can_label(wl_s, inputs):
+    """The reference numbers clusters with uint16_t and treats 65535 as "none yet"
+    (space_partitioning.h:59-63): on a cloud with that many clusters its recursion never ends.
+    The oracle (no such limit) counts the clusters of the set before and after one cycle."""
+    from oracle import binding as ob
+    occ, res, origin, pose, scan, (x, y, t) = inputs
+    om = ob.OracleMap(**dict(syn.NODE_LIKELIHOOD, num_beams=0))
+    om.new_map(occ, res, origin, field_mode=ob.FIELD_BRUSHFIRE)
+    of = ob.OracleFilter(om, seed=3)
+    of.set_parameters(**wl_s["pf"])
+    n = len(x)
+    of.set_particles(ob.make_particles(x, y, t, np.full(n, 1.0 / n)))
+    of.cluster()
+    counts = [of.num_clusters()]
+    of.set_rng(3, 10)
+    of.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
+    of.update_importance_from_observations(scan)
+    of.resample_and_cluster()
+    counts.append(of.num_clusters())
+    return max(counts) < MAX_REFERENCE_CLUSTERS, max(counts)
+
+
+def run_ref_worker(args, wl):
+    """Child process of cpu_cycle(): times the compiled reference on a sample and prints one JSON
+    object.  A process of its own because the reference's code can take the process down (a stack
+    overflow cannot be caught) and must not take the bench line with it."""
+    n_sample = args.sample or wl["particles"]
+    wl_s = sampled_workload(wl, n_sample)
+    inputs = sample_inputs(make_inputs(wl), n_sample)
+    ok, clusters = reference_can_label(wl_s, inputs)
+    if not ok:
+        emit({"unusable": f"{clusters} clusters in this cloud: the reference's 16-bit cluster ids "
+                          f"(space_partitioning.h:59) cannot label them, its recursion does not end"})
+        return 0
+    sec, ev, stages, notes = with_deep_stack(ref_cycle_seconds, wl_s, inputs, args.steps, args.warmup)
+    emit({"sec": sec, "evals": ev, "stages": stages, "notes": notes, "clusters": clusters})
+    return 0
+
+
+def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup):
+    """The CPU baseline on the first n_sample particles of the workload: the compiled reference
+    (oracle/_ref, timed in a child process) when its library is there and the cloud is one it can
+    label, else the oracle port.  Returns (seconds per step, evals per step, per-stage seconds,
+    kind, note)."""
+    wl_s = sampled_workload(wl, n_sample)
+    inputs_s = sample_inputs(inputs, n_sample)
+    why_port = "oracle/_ref is not built"
+    if os.environ.get("QMCL_BENCH_CPU_PORT"):
+        why_port = "QMCL_BENCH_CPU_PORT is set"
+    else:
+        try:
+            from oracle import ref_binding as rb
+            if rb.available():
+                out = subprocess.run(
+                    [sys.executable, os.path.abspath(__file__), "--impl", "ref-worker", "--workload", wl_name,
+                     "--sample", str(n_sample), "--steps", str(steps), "--warmup", str(warmup)],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=900)
+                res = json.loads(out.stdout.decode().strip().splitlines()[-1]) if out.returncode == 0 else None
+                if res is None:
+                    why_port = f"the compiled reference ended with exit code {out.returncode} on this sample"
+                elif "unusable" in res:
+                    why_port = res["unusable"]
+                else:
+                    note = ("the reference's own sources (map_likelihood.cpp, odometry.cpp, "
+                            "particle_filter.cpp, space_partitioning.cpp, statistics.cpp ...) compiled into "
+                            "oracle/_ref against stand-in Eigen / ROS / PCL headers, -O3 -DNDEBUG like catkin "
+                            "Release; single-threaded like the node (main.cpp:90); random draws read from a "
+                            "script, which is cheaper than its mt19937; run on a 1 GiB stack because its "
+                            "cluster labelling recurses once per bin")
+                    if res["notes"]:
+                        note += f"; {res['notes']}"
+                    try:  # the oracle port on the same sample, for comparison with earlier rounds
+                        psec, pev, _ = cpu_cycle_seconds(wl_s, inputs_s, min(steps, 2), 1)
+                        note += (f"; the oracle port (kind 'port' of earlier rounds) on the same sample: "
+                                 f"{pev / psec:.4g} evals/s")
+                    except Exception as e:
+                        log(f"oracle port timing skipped ({type(e).__name__}: {e})")
+                    return res["sec"], res["evals"], res["stages"], "reference", note
+        except Exception as e:  # the baseline must never take the bench line with it
+            why_port = f"{type(e).__name__}: {e}"
+    log(f"CPU baseline: timing the oracle port ({why_port})")
+    sec, ev, stages = cpu_cycle_seconds(wl_s, inputs_s, steps, warmup)
+    return sec, ev, stages, "port", ("CPU restatement of the reference (oracle/); the reference is "
+                                     f"single-threaded (main.cpp:90); not the compiled reference: {why_port}")
+
+
 def cpu_cycle_seconds(wl, inputs, steps, warmup):
     """Times the CPU oracle's full update cycle; returns (seconds per step, evals per step,
     per-stage seconds)."""
@@ -258,16 +454,9 @@ def run_reference(args, wl):
     per_step = budget_evals / max(1, args.steps + args.warmup)
     n_sample = int(min(n_full, max(1000, per_step // max(1, len(inputs[4])))))
     occ, res, origin, pose, scan, (x, y, t) = inputs
-    wl_s = dict(wl)
-    pf = dict(wl["pf"])
     scale = n_sample / n_full
-    if scale < 1.0:
-        pf["particle_count_min"] = max(1, int(pf["particle_count_min"] * scale))
-        pf["particle_count_max"] = max(1, int(pf["particle_count_max"] * scale))
-    wl_s["pf"] = pf
-    sec, evals, stages = cpu_cycle_seconds(
-        wl_s, (occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])),
-        args.steps, args.warmup)
+    wl_s = sampled_workload(wl, n_sample)
+    sec, evals, stages, kind, note = cpu_cycle(wl, args.workload, inputs, n_sample, args.steps, args.warmup)
     value = evals / sec
     all_cores = cpu_all_cores(
         wl_s, (occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])))
@@ -282,12 +471,11 @@ def run_reference(args, wl):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, wl, len(scan)),
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": kind,
                          "sample": sample, "cpu": cpu_model(), "host_cores": os.cpu_count(),
                          "field": "brushfire (the reference's own field build)",
                          "stage_ms": {k: v * 1e3 for k, v in stages.items()},
-                         "note": "CPU restatement of the reference (oracle/); the reference is "
-                                 "single-threaded (main.cpp:90) and cannot be built here as a whole",
+                         "note": note,
                          "all_cores": all_cores},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -713,16 +901,10 @@ def run_b200(args, wl):
         # bounded CPU sample: a slice of the particle set, full cycle, one thread
         occ, res, origin, pose, _, (x, y, t) = h.inputs
         n_cpu = int(min(n, max(2000, 2.0e9 / 6 // len(scan))))
-        wl_s = dict(wl)
-        pf = dict(wl["pf"])
-        sc = n_cpu / n
-        if sc < 1.0:
-            pf["particle_count_min"] = max(1, int(pf["particle_count_min"] * sc))
-            pf["particle_count_max"] = max(1, int(pf["particle_count_max"] * sc))
-        wl_s["pf"] = pf
-        sec, ev, stages = cpu_cycle_seconds(
-            wl_s, (occ, res, origin, pose, scan, (x[:n_cpu], y[:n_cpu], t[:n_cpu])), 5, 1)
-        cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": "port",
+        wl_s = sampled_workload(wl, n_cpu)
+        sec, ev, stages, kind, note = cpu_cycle(
+            wl, args.workload, (occ, res, origin, pose, scan, (x, y, t)), n_cpu, 5, 1)
+        cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": kind, "note": note,
                "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
                          f"5 steps after 1 warm-up",
                "field": "brushfire (the reference's own field build; the GPU arm uses the exact EDT "
@@ -800,7 +982,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "ref-worker"])
+    ap.add_argument("--sample", type=int, default=0, help="ref-worker only: particles of the sample")
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--breakdown", action="store_true",
                     help="extra untimed pass with per-stage CUDA events, printed to stderr")
@@ -818,6 +1001,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
+    if args.impl == "ref-worker":
+        return run_ref_worker(args, wl)
     return run_b200(args, wl)
 
 

@@ -243,14 +243,17 @@ def draw_script(seed, step, n_slots, w_diff):
     rw = _word53(r[:, 2], r[:, 3])
     cell = (q[:, 1].astype(np.uint64) << np.uint64(32)) | q[:, 0].astype(np.uint64)
     head = q[:, 2].astype(np.uint64) << np.uint64(32)
-    words = []
-    for m in range(n_slots):
-        words.append(pw[m])
-        if inject[m]:
-            words.extend((cell[m], head[m]))
-        else:
-            words.append(rw[m])
-    return np.array(words, np.uint64), inject
+    # slot m holds 2 words (p, r) or 3 (p, cell, heading)
+    start = np.zeros(n_slots, np.int64)
+    if n_slots:
+        np.cumsum(2 + inject[:-1].astype(np.int64), out=start[1:])
+    words = np.zeros(int(2 * n_slots + inject.sum()), np.uint64)
+    words[start] = pw
+    keep = ~inject
+    words[start[keep] + 1] = rw[keep]
+    words[start[inject] + 1] = cell[inject]
+    words[start[inject] + 2] = head[inject]
+    return words, inject
 
 
 # ------------------------------------------------------------------ MapLikelihood / ParticleFilter
