@@ -293,7 +293,7 @@ def run_ref_worker(args, wl):
     return 0
 
 
-def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup):
+def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup, allow_ref=True):
     """The CPU baseline on the first n_sample particles of the workload: the compiled reference
     (oracle/_ref, timed in a child process) when its library is there and the cloud is one it can
     label, else the oracle port.  Returns (seconds per step, evals per step, per-stage seconds,
@@ -303,6 +303,8 @@ def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup):
     why_port = "oracle/_ref is not built"
     if os.environ.get("QMCL_BENCH_CPU_PORT"):
         why_port = "QMCL_BENCH_CPU_PORT is set"
+    elif not allow_ref:
+        why_port = "N > 1: the compiled reference is timed by the N = 1 line and by --impl reference"
     else:
         try:
             from oracle import ref_binding as rb
@@ -903,7 +905,7 @@ def run_b200(args, wl):
         n_cpu = int(min(n, max(2000, 2.0e9 / 6 // len(scan))))
         wl_s = sampled_workload(wl, n_cpu)
         sec, ev, stages, kind, note = cpu_cycle(
-            wl, args.workload, (occ, res, origin, pose, scan, (x, y, t)), n_cpu, 5, 1)
+            wl, args.workload, (occ, res, origin, pose, scan, (x, y, t)), n_cpu, 5, 1, allow_ref=(world == 1))
         cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": kind, "note": note,
                "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
                          f"5 steps after 1 warm-up",

@@ -6,23 +6,31 @@
  * reference legs may load this library, and only as the checker or as the
  * timed CPU baseline.  The CUDA library (quickmcl_b200/csrc) never links it.
  *
- * The reference (/root/reference, QuickMCL 0.5.0) cannot be compiled as a whole
- * in this image (ROS, Eigen, Boost, PCL, gtest absent), so this is a
- * dependency-free restatement.  Every function cites the reference file:line
- * it follows.
+ * The reference's own build (catkin / cmake, ROS, Eigen, Boost, PCL, gtest) cannot
+ * run in this image, so this is a dependency-free restatement of QuickMCL 0.5.0
+ * (/root/reference).  Every function cites the reference file:line it follows.
  * Parity pinning: (1) the helpers are checked against all golden vectors of the
- * reference's own gtest suite (tests/test_oracle_golden.py); (2) the parts of
- * the reference that use Eigen only as a container - distance_calculator.cpp,
- * particle.cpp, space_partitioning.cpp, scaled_map.h, low_pass_filter.h,
- * utils.h - are compiled from where they lie into oracle/_ref/libqmcl_ref.so
- * (oracle/Makefile target `ref`, oracle/ref_shim.cpp, stand-in headers in
- * oracle/ref_stubs) and this oracle is held against them bit for bit on random
- * inputs (tests/test_oracle_vs_ref.py).  The sensor model, the motion model,
- * the resamplers' draws and initialisation are NOT pinned by any reference
- * test and cannot be built that way ("parity unpinned" for those; the
- * statistics have their golden vector only): the reference draws from a private, unseeded std::mt19937, so both
- * this oracle and the CUDA path consume one shared counter-based Philox4x32-10
- * stream instead (contract in DESIGN.md section 6).
+ * reference's own gtest suite (tests/test_oracle_golden.py); (2) the reference's
+ * translation units of the path - distance_calculator, map_base, map_likelihood,
+ * odometry, particle, particle_filter, pose_2d, space_partitioning, statistics
+ * .cpp and the header-only parts - are compiled unmodified from where they lie
+ * into oracle/_ref/libqmcl_ref.so (oracle/Makefile target `ref`,
+ * oracle/ref_shim.cpp, stand-in Eigen / ROS / PCL headers and a scripted
+ * <random> in oracle/ref_stubs) and this oracle is held against them bit for
+ * bit on random inputs: field and state maps, grid truncation, weights, running
+ * sum, KLD bound, bins and clusters (tests/test_oracle_vs_ref.py), the sensor
+ * model, the motion model, the statistics, the three resamplers, global
+ * localisation and whole scan cycles (tests/test_oracle_vs_ref_filter.py).
+ * "Parity unpinned" remains for: ParticleFilter::initialise beyond T T^T =
+ * covariance (Eigen's eigen-solver and libstdc++'s normal_distribution decide
+ * the individual draws), the laser_geometry projection (third-party, absent),
+ * and the three pieces of Eigen's own arithmetic that the stand-in headers
+ * restate instead of running (Isometry2f product, the statistics' outer
+ * product, the packet exp() of the table build: DESIGN.md section 2).  The
+ * reference draws from private, unseeded std::mt19937 engines, so both this
+ * oracle and the CUDA path consume one shared counter-based Philox4x32-10
+ * stream instead (contract in DESIGN.md section 6); the tests replay that
+ * stream into the reference's engines.
  */
 #ifndef QMCL_ORACLE_H
 #define QMCL_ORACLE_H

@@ -1,10 +1,11 @@
 """Holds the CPU oracle against the REFERENCE'S OWN CODE where that code can be built here.
 
 oracle/_ref/libqmcl_ref.so is compiled (oracle/Makefile, target `ref`) from reference
-translation units where they lie under /root/reference - distance_calculator.cpp,
+translation units where they lie under /root/reference against stand-in headers for the
+libraries they use (oracle/ref_stubs).  This file covers distance_calculator.cpp,
 particle.cpp, pose_2d.cpp, space_partitioning.cpp and the header-only scaled_map.h,
-low_pass_filter.h, utils.h - against stand-in headers for the containers they use
-(oracle/ref_stubs).  These tests feed both sides inputs far beyond the reference's own
+low_pass_filter.h, utils.h; tests/test_oracle_vs_ref_filter.py covers the sensor model, the
+motion model, the statistics and the particle filter.  These tests feed both sides inputs far beyond the reference's own
 golden vectors (tests/test_oracle_golden.py) and ask for the same bits: brushfire
 distance and state maps of random grids, grid truncation, weights / N_eff / running-sum
 lookups, the KLD bound while bins fill up, bin keys and the cluster partition.
