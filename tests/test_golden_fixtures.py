@@ -12,7 +12,9 @@ from oracle import binding as ob
 from quickmcl_b200 import synthetic as syn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+# ref_*.npz are the reference-generated fixtures of tests/test_golden_ref_fixtures.py
+FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+                  if not os.path.basename(p).startswith("ref_"))
 RES_THETA = float(np.float32(math.pi / 18))
 
 
