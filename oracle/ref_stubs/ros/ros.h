@@ -3,3 +3,8 @@
 #pragma once
 
 #include <ros/console.h>
+
+namespace ros {
+// test_main.cpp of the reference's gtest suite calls this; there is no ROS master to talk to
+inline void init(int &, char **, const char *) {}
+}  // namespace ros

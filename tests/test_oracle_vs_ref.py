@@ -228,3 +228,60 @@ def test_kld_bound_bins_and_clusters_match_reference(name, res_xy, res_t):
     mine = np.array([olabels[index[tuple(k)]] for k in keys])
     pairs = set(zip(mine.tolist(), cluster.tolist()))
     assert len(pairs) == n_clusters == len({a for a, _ in pairs}) == len({b for _, b in pairs})
+
+
+# ------------------------------------------------------------------ the reference's own unit tests
+def test_reference_own_gtests_pass():
+    """The reference's test suite (/root/reference/test: 21 TESTs, the typed ones for float and double)
+    compiled against the same stand-in headers and reference sources as oracle/_ref, plus a stand-in
+    gtest / gmock (oracle/Makefile, target ref_gtests): the build of the reference the oracle is held
+    against passes the reference's own tests."""
+    import os
+    import subprocess
+    if not os.path.isdir(os.path.join(rb.REFERENCE_ROOT, "test", "quickmcl")):
+        pytest.skip("no reference tree")
+    here = os.path.dirname(rb.LIB_PATH)
+    out = subprocess.run(["make", "-s", "-C", os.path.dirname(here), "ref_gtests", f"REF={rb.REFERENCE_ROOT}"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    text = out.stdout.decode()
+    assert out.returncode == 0, text[-3000:]
+    assert "28 tests ran, 0 failed." in text
+    assert text.count("[       OK ]") == 28 and "FAILED" not in text
+
+
+def test_gtest_stand_in_reports_failures(tmp_path):
+    """Negative control for the stand-in gtest: wrong expectations must fail, 4-ULP ones must pass."""
+    import os
+    import subprocess
+    stubs = os.path.join(os.path.dirname(os.path.dirname(rb.LIB_PATH)), "ref_stubs")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include <gmock/gmock.h>
+#include <gtest/gtest.h>
+#include <cmath>
+#include <vector>
+struct P { double w; };
+TEST(Control, passes) {
+  EXPECT_FLOAT_EQ(1.0f, std::nextafter(std::nextafter(1.0f, 2.0f), 2.0f));
+  EXPECT_DOUBLE_EQ(0.1 + 0.2, 0.3);
+  EXPECT_EQ(3, 3u) << "never shown";
+  std::vector<P> v{{0.5}, {0.5}};
+  EXPECT_THAT(v, testing::Each(testing::Field(&P::w, testing::DoubleEq(0.5))));
+}
+TEST(Control, float_off_by_more_than_4_ulp) { EXPECT_FLOAT_EQ(1.0f, 1.000001f); }
+TEST(Control, nan_is_never_equal) { EXPECT_DOUBLE_EQ(std::nan(""), std::nan("")); }
+TEST(Control, each_field) {
+  std::vector<P> v{{0.5}, {0.25}};
+  EXPECT_THAT(v, testing::Each(testing::Field(&P::w, testing::DoubleEq(0.5))));
+}
+TEST(Control, plain) { EXPECT_EQ(1, 2) << "shown"; EXPECT_TRUE(false); EXPECT_FALSE(true); }
+int main(int argc, char **argv) { testing::InitGoogleTest(&argc, argv); return RUN_ALL_TESTS(); }
+''')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-w", "-I", stubs, "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE)
+    text = out.stdout.decode()
+    assert out.returncode == 1
+    assert "[       OK ] Control.passes" in text
+    assert text.count("[   FAILED ]") == 4 and "5 tests ran, 4 failed." in text
+    assert "shown" in text and "never shown" not in text
