@@ -81,6 +81,8 @@ def lib():
         "ref_map_update_importance": (f64, [vp, pf32, sz, pP, sz]),
         "ref_statistics": (None, [pP, sz, C.c_int, pf64]),
         "ref_sample_odometry": (None, [pf64, pf64, pP, sz, pf32]),
+        "ref_pose_restore": (C.c_int, [pf64, C.c_int, pf32, pf32, C.c_char_p, sz]),
+        "ref_pose_store": (C.c_int, [C.c_int, pf64, pf64, pf64, C.c_char_p, sz]),
         "ref_filter_create": (vp, [vp]),
         "ref_filter_destroy": (None, [vp]),
         "ref_filter_set_params": (None, [vp, pF]),
@@ -413,3 +415,27 @@ class RefFilter:
         if len(out):
             self.L.ref_filter_cluster_ids(self.h, _p(out, C.c_int32))
         return out
+
+
+# ------------------------------------------------------------------ PoseRestorer (pose_restore.cpp)
+def pose_restore(v=None):
+    """PoseRestorer::restore_pose with ~initial_pose = v (None: parameter absent).  Returns
+    (initialise calls, pose float32[3], covariance float32[3, 3], warning lines)."""
+    vals = np.ascontiguousarray([] if v is None else v, np.float64)
+    pose, cov = np.zeros(3, np.float32), np.zeros(9, np.float32)
+    buf = C.create_string_buffer(4096)
+    calls = lib().ref_pose_restore(_p(vals, C.c_double), -1 if v is None else len(vals), _p(pose, C.c_float),
+                                   _p(cov, C.c_float), buf, len(buf))
+    return calls, pose, cov.reshape(3, 3), [ln for ln in buf.value.decode().split("\n") if ln]
+
+
+def pose_store(ok, pose, cov):
+    """PoseRestorer::store_pose on a filter whose estimate is (ok, pose, cov).  Returns
+    (the stored ~initial_pose list or None, warning lines)."""
+    pose = np.ascontiguousarray(pose, np.float64)
+    cov = np.ascontiguousarray(cov, np.float64).reshape(9)
+    out = np.zeros(6)
+    buf = C.create_string_buffer(4096)
+    n = lib().ref_pose_store(int(bool(ok)), _p(pose, C.c_double), _p(cov, C.c_double), _p(out, C.c_double), buf,
+                             len(buf))
+    return (None if n < 0 else out[:n].tolist()), [ln for ln in buf.value.decode().split("\n") if ln]

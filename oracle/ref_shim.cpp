@@ -5,7 +5,7 @@
  * translation units of the particle-filter path, taken from where they lie under
  * /root/reference (never copied): distance_calculator.cpp, map_base.cpp,
  * map_likelihood.cpp, odometry.cpp, particle.cpp, particle_filter.cpp, pose_2d.cpp,
- * space_partitioning.cpp, statistics.cpp, plus the header-only scaled_map.h,
+ * pose_restore.cpp, space_partitioning.cpp, statistics.cpp, timer.cpp, plus the header-only scaled_map.h,
  * low_pass_filter.h, random.h and utils.h.  Eigen, ROS and PCL are absent from this
  * image; the units build against the stand-in headers in oracle/ref_stubs (what each
  * stand-in restates is written at its top: Eigen/Core, Eigen/Geometry,
@@ -28,7 +28,7 @@
  * The same sources and stand-ins also build the reference's own gtest suite
  * (oracle/Makefile, target ref_gtests): 28 of 28 cases pass.
  *
- * Not built: laser.cpp (PCL conversion), pose_restore.cpp, the factories, the node.
+ * Not built: laser.cpp (PCL conversion), the factories, the node.
  */
 #include "quickmcl/distance_calculator.h"
 #include "quickmcl/low_pass_filter.h"
@@ -37,10 +37,13 @@
 #include "quickmcl/parameters.h"
 #include "quickmcl/particle.h"
 #include "quickmcl/particle_filter.h"
+#include "quickmcl/pose_restore.h"
 #include "quickmcl/scaled_map.h"
 #include "quickmcl/space_partitioning.h"
 #include "quickmcl/statistics.h"
 #include "quickmcl/utils.h"
+
+#include <ros/console.h>
 
 #include <chrono>
 #include <cstdint>
@@ -522,6 +525,92 @@ int ref_filter_num_clusters(const ref_filter *f) { return f->pf->space_partition
 void ref_filter_cluster_ids(const ref_filter *f, int32_t *out) {
   const auto &ps = f->pf->get_particles();
   for (size_t i = 0; i < ps.size(); ++i) out[i] = f->pf->space_partitioning.get_cluster_id(ps[i].data);
+}
+
+// -------------------------------------------------------------- PoseRestorer
+namespace {
+// an IParticleFilter that records what PoseRestorer does with it
+struct RecordingFilter final : quickmcl::IParticleFilter {
+  bool has_estimate = false;
+  quickmcl::Pose2D<double> estimate{0, 0, 0};
+  Eigen::Matrix3d estimate_cov = Eigen::Matrix3d::Zero();
+  int initialise_calls = 0;
+  quickmcl::WeightedParticle::ParticleT init_pose{0, 0, 0};
+  quickmcl::WeightedParticle::ParticleT::EigenMatrix init_cov;
+  quickmcl::ParticleCollection none;
+
+  void initialise(const quickmcl::WeightedParticle::ParticleT &p,
+                  const quickmcl::WeightedParticle::ParticleT::EigenMatrix &c) override {
+    ++initialise_calls;
+    init_pose = p;
+    init_cov = c;
+  }
+  void global_localization() override {}
+  void handle_odometry(const quickmcl::Odometry &, const quickmcl::Odometry &, float[4]) override {}
+  void update_importance_from_observations(const quickmcl::LaserPointCloud &) override {}
+  void resample_and_cluster() override {}
+  void cluster() override {}
+  void set_parameters(const quickmcl::Parameters::ParticleFilter &) override {}
+  bool get_estimated_pose(quickmcl::Pose2D<double> *pose, Eigen::Matrix3d *cov) const override {
+    if (!has_estimate) return false;
+    *pose = estimate;
+    *cov = estimate_cov;
+    return true;
+  }
+  const quickmcl::ParticleCollection &get_particles() const override { return none; }
+  size_t num_particles() const override { return 0; }
+};
+
+size_t copy_warnings(char *out, size_t cap) {
+  std::string all;
+  for (const auto &line : ros::stand_in_warnings()) all += line + "\n";
+  ros::stand_in_warnings().clear();
+  if (out && cap) {
+    const size_t n = all.size() < cap - 1 ? all.size() : cap - 1;
+    std::memcpy(out, all.data(), n);
+    out[n] = 0;
+  }
+  return all.size();
+}
+}  // namespace
+
+// PoseRestorer::restore_pose (pose_restore.cpp:57-78).  n < 0: no ~initial_pose parameter.
+// Returns how often the filter was initialised; pose / cov = what it was initialised with;
+// warnings = the ROS_WARN lines, one per line.
+int ref_pose_restore(const double *v, int n, float pose_out[3], float cov_out[9], char *warnings, size_t cap) {
+  ros::stand_in_parameters().clear();
+  ros::stand_in_warnings().clear();
+  if (n >= 0) ros::stand_in_parameters()["initial_pose"] = std::vector<double>(v, v + n);
+  auto filter = std::make_shared<RecordingFilter>();
+  quickmcl::PoseRestorer restorer(ros::NodeHandle(), filter);
+  restorer.restore_pose();
+  pose_out[0] = filter->init_pose.x;
+  pose_out[1] = filter->init_pose.y;
+  pose_out[2] = filter->init_pose.theta;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov_out[3 * i + j] = filter->init_cov(i, j);
+  copy_warnings(warnings, cap);
+  return filter->initialise_calls;
+}
+
+// PoseRestorer::store_pose (pose_restore.cpp:37-55).  Returns the length of the stored
+// ~initial_pose vector (copied to out6), or -1 when nothing was stored.
+int ref_pose_store(int has_estimate, const double pose[3], const double cov[9], double out6[6], char *warnings,
+                   size_t cap) {
+  ros::stand_in_parameters().clear();
+  ros::stand_in_warnings().clear();
+  auto filter = std::make_shared<RecordingFilter>();
+  filter->has_estimate = has_estimate != 0;
+  filter->estimate = quickmcl::Pose2D<double>(pose[0], pose[1], pose[2]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) filter->estimate_cov(i, j) = cov[3 * i + j];
+  quickmcl::PoseRestorer restorer(ros::NodeHandle(), filter);
+  restorer.store_pose();
+  copy_warnings(warnings, cap);
+  const auto it = ros::stand_in_parameters().find("initial_pose");
+  if (it == ros::stand_in_parameters().end()) return -1;
+  for (size_t i = 0; i < it->second.size() && i < 6; ++i) out6[i] = it->second[i];
+  return static_cast<int>(it->second.size());
 }
 
 }  // extern "C"

@@ -432,3 +432,67 @@ def test_scan_cycles_match_reference(rtype, nmin, nmax):
             rf.cluster()
             of.cluster()
         compare_estimates(rf, of)
+
+
+# ------------------------------------------------------------------ pose_restore.cpp
+class RecordingFilter:
+    """What PoseCheckpoint needs of an IParticleFilter; remembers how it was initialised."""
+
+    def __init__(self, estimate=None):
+        self.estimate = estimate
+        self.initialised = []
+
+    def get_estimated_pose(self):
+        if self.estimate is None:
+            return False, np.zeros(3), np.zeros((3, 3))
+        return (True,) + self.estimate
+
+    def initialise(self, pose, cov):
+        self.initialised.append((np.asarray(pose), np.asarray(cov)))
+
+
+@pytest.mark.parametrize("stored", [
+    None,                                                   # no ~initial_pose: pose 0, identity covariance
+    [1.5, -2.25, 0.7, 0.04, 0.09, 0.01],                    # what store_pose wrote
+    [1.5, -2.25],                                           # short vector: the rest falls back
+    [float("nan"), 3.0, float("nan"), 0.2, float("nan"), float("nan")],
+    [],                                                     # present but empty
+    [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7],                    # longer than six: the tail is ignored
+    [1e-3 + 1e-12, 7.000000001, -3.14159265358979, 1e-9, 0.25, 0.01],   # values that round in float
+])
+def test_pose_checkpoint_restores_like_the_reference_pose_restorer(stored):
+    """quickmcl_b200.cycle.PoseCheckpoint against PoseRestorer::restore_pose itself
+    (pose_restore.cpp:57-97): the pose and the float covariance the filter is re-initialised
+    with, and the warnings, for missing, short, NaN and complete parameter vectors."""
+    from quickmcl_b200.cycle import PoseCheckpoint
+    calls, pose_ref, cov_ref, warn_ref = rb.pose_restore(stored)
+    rec = RecordingFilter()
+    cp = PoseCheckpoint(rec)
+    cp.restore(stored)
+    assert calls == 1 and len(rec.initialised) == 1
+    pose, cov = rec.initialised[0]
+    assert same_bits(np.asarray(pose, np.float32), pose_ref)
+    assert same_bits(np.asarray(cov, np.float32).reshape(3, 3), cov_ref)
+    assert cp.warnings == warn_ref
+
+
+@pytest.mark.parametrize("estimate", [
+    None,
+    (np.array([1.25, -0.5, 2.0]), np.array([[0.04, 0.01, 0.0], [0.01, 0.09, 0.0], [0.0, 0.0, 0.02]])),
+])
+def test_pose_checkpoint_stores_like_the_reference_pose_restorer(estimate):
+    """PoseRestorer::store_pose (pose_restore.cpp:37-55): six numbers, or nothing and a warning."""
+    from quickmcl_b200.cycle import PoseCheckpoint
+    if estimate is None:
+        stored_ref, warn_ref = rb.pose_store(False, np.zeros(3), np.zeros((3, 3)))
+    else:
+        stored_ref, warn_ref = rb.pose_store(True, *estimate)
+    cp = PoseCheckpoint(RecordingFilter(estimate))
+    assert cp.store() == stored_ref
+    assert cp.warnings == warn_ref
+    if estimate is not None:                      # and the round trip through both
+        _, pose_ref, cov_ref, _ = rb.pose_restore(stored_ref)
+        rec = RecordingFilter()
+        PoseCheckpoint(rec).restore(cp.store())
+        assert same_bits(np.asarray(rec.initialised[0][0], np.float32), pose_ref)
+        assert same_bits(np.asarray(rec.initialised[0][1], np.float32).reshape(3, 3), cov_ref)
