@@ -50,3 +50,53 @@ def test_host_cycle_matches_oracle_on_gpu():
     out = subprocess.run([SELFTEST], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_selftest ok" in out.stdout
+
+
+# ------------------------------------------------------------------ PoseCheckpoint vs the reference's PoseRestorer
+PROBE = os.path.join(ROOT, "tests", "host", "pose_checkpoint_probe")
+
+
+def _probe(*args):
+    build()
+    out = subprocess.check_output([PROBE] + [str(a) for a in args], text=True)
+    return {ln.split()[0]: ln.split()[1:] for ln in out.splitlines()}
+
+
+@pytest.mark.parametrize("stored", [
+    None, [1.5, -2.25, 0.7, 0.04, 0.09, 0.01], [1.5, -2.25], [float("nan"), 3.0, float("nan"), 0.2, float("nan")],
+    [], [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7], [1e-3 + 1e-12, 7.000000001, -3.14159265358979, 1e-9, 0.25, 0.01],
+])
+def test_cpp_pose_checkpoint_restores_like_the_reference_pose_restorer(stored):
+    """quickmcl_b200::PoseCheckpoint::restore (C++ host mirror) against the reference's own
+    PoseRestorer::restore_pose (pose_restore.cpp:57-97, compiled into oracle/_ref): the same
+    re-initialisation arguments bit for bit.  CPU only."""
+    import numpy as np
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built and no reference tree")
+    calls, pose_ref, cov_ref, _ = rb.pose_restore(stored)
+    if stored is None:
+        got = _probe("restore", "none")
+    elif not stored:
+        got = _probe("restore", "empty")
+    else:
+        got = _probe("restore", *[repr(float(v)) for v in stored])
+    assert int(got["calls"][0]) == calls == 1
+    pose = np.array([float.fromhex(v) for v in got["pose"]], np.float32)
+    cov = np.array([float.fromhex(v) for v in got["cov"]], np.float32).reshape(3, 3)
+    assert pose.tobytes() == pose_ref.tobytes()
+    assert cov.tobytes() == cov_ref.tobytes()
+
+
+def test_cpp_pose_checkpoint_stores_like_the_reference_pose_restorer():
+    import numpy as np
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built and no reference tree")
+    pose = np.array([1.25, -0.5, 2.0])
+    cov = np.array([[0.04, 0.01, 0.0], [0.01, 0.09, 0.0], [0.0, 0.0, 0.02]])
+    stored_ref, _ = rb.pose_store(True, pose, cov)
+    got = _probe("store", 1, *[repr(float(v)) for v in pose], *[repr(float(v)) for v in cov.reshape(9)])
+    assert [float.fromhex(v) for v in got["stored"][1:]] == stored_ref and int(got["stored"][0]) == 6
+    none_ref, _ = rb.pose_store(False, np.zeros(3), np.zeros((3, 3)))
+    assert none_ref is None and _probe("store", 0)["stored"] == ["0"]
