@@ -26,19 +26,36 @@ REFERENCE_ROOT = os.environ.get("QMCL_REFERENCE_ROOT", "/root/reference")
 _lib = None
 
 
+_available = None
+
+
 def available():
-    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "quickmcl")):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "ref", f"REF={REFERENCE_ROOT}"],
-                              stdout=subprocess.DEVNULL)
-    return os.path.exists(LIB_PATH)
+    """True when the library is there AND loads with every entry point this binding names (a
+    stale prebuilt file from an older build must make the tests skip, not error)."""
+    global _available
+    if _available is None:
+        if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "quickmcl")):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "ref", f"REF={REFERENCE_ROOT}"],
+                                  stdout=subprocess.DEVNULL)
+        _available = False
+        if os.path.exists(LIB_PATH):
+            try:
+                _load()
+                _available = True
+            except (OSError, AttributeError) as e:
+                print(f"oracle/_ref: {LIB_PATH} is not usable ({e})")
+    return _available
 
 
 def lib():
+    if _lib is None and not available():
+        raise RuntimeError("oracle/_ref/libqmcl_ref.so is missing or unusable and there is no reference tree to "
+                           "build it from")
+    return _lib
+
+
+def _load():
     global _lib
-    if _lib is not None:
-        return _lib
-    if not available():
-        raise RuntimeError("oracle/_ref/libqmcl_ref.so is missing and there is no reference tree to build it from")
     L = C.CDLL(LIB_PATH)
     f32, f64, i32, u32, u64, sz = C.c_float, C.c_double, C.c_int32, C.c_uint32, C.c_uint64, C.c_size_t
     pf32, pf64, pi32, pi8 = C.POINTER(f32), C.POINTER(f64), C.POINTER(i32), C.POINTER(C.c_int8)
