@@ -12,8 +12,8 @@
  * Parity pinning: (1) the helpers are checked against all golden vectors of the
  * reference's own gtest suite (tests/test_oracle_golden.py); (2) the reference's
  * translation units of the path - distance_calculator, map_base, map_likelihood,
- * odometry, particle, particle_filter, pose_2d, pose_restore, space_partitioning,
- * statistics, timer
+ * laser, odometry, particle, particle_filter, pose_2d, pose_restore,
+ * space_partitioning, statistics, timer and the node's laser_handler
  * .cpp and the header-only parts - are compiled unmodified from where they lie
  * into oracle/_ref/libqmcl_ref.so (oracle/Makefile target `ref`,
  * oracle/ref_shim.cpp, stand-in Eigen / ROS / PCL headers and a scripted

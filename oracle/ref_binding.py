@@ -12,6 +12,7 @@ timed CPU baseline.  The library is built in this container, where
 elsewhere the prebuilt file is loaded, and `available()` is False without one.
 """
 import ctypes as C
+import math
 import os
 import subprocess
 
@@ -100,6 +101,11 @@ def _load():
         "ref_sample_odometry": (None, [pf64, pf64, pP, sz, pf32]),
         "ref_pose_restore": (C.c_int, [pf64, C.c_int, pf32, pf32, C.c_char_p, sz]),
         "ref_pose_store": (C.c_int, [C.c_int, pf64, pf64, pf64, C.c_char_p, sz]),
+        "ref_cycle_create": (vp, [C.c_int, f32, f32, pf32, f64]),
+        "ref_cycle_destroy": (None, [vp]),
+        "ref_cycle_force_pose_reset": (None, [vp]),
+        "ref_cycle_set_particles_present": (None, [vp, C.c_int]),
+        "ref_cycle_on_scan": (sz, [vp, pf64, C.c_int, sz, f64, C.c_char_p, sz]),
         "ref_filter_create": (vp, [vp]),
         "ref_filter_destroy": (None, [vp]),
         "ref_filter_set_params": (None, [vp, pF]),
@@ -456,3 +462,33 @@ def pose_store(ok, pose, cov):
     n = lib().ref_pose_store(int(bool(ok)), _p(pose, C.c_double), _p(cov, C.c_double), _p(out, C.c_double), buf,
                              len(buf))
     return (None if n < 0 else out[:n].tolist()), [ln for ln in buf.value.decode().split("\n") if ln]
+
+
+# ------------------------------------------------------------------ LaserHandler::Impl::cloud_callback
+class RefScanCycle:
+    """The reference's LaserHandler (laser_handler.cpp) wired to recorders: on_scan() delivers one
+    point cloud to its callback and returns the log of what it did - IParticleFilter calls with
+    their arguments (doubles and floats as C hex floats), publish_* calls, "log: ..." lines."""
+
+    def __init__(self, resample_count=2, min_trans=0.2, min_rot=math.pi / 6, alpha=(0.05, 0.1, 0.02, 0.05),
+                 save_pose_period=0.0):
+        self.L = lib()
+        a = np.asarray(alpha, np.float32)
+        self.h = self.L.ref_cycle_create(resample_count, min_trans, min_rot, _p(a, C.c_float), save_pose_period)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_cycle_destroy(self.h)
+            self.h = None
+
+    def force_pose_reset(self):
+        self.L.ref_cycle_force_pose_reset(self.h)
+
+    def set_particles_present(self, present):
+        self.L.ref_cycle_set_particles_present(self.h, int(bool(present)))
+
+    def on_scan(self, odom, n_points, now=0.0, odom_ok=True):
+        o = np.asarray(odom, np.float64)
+        buf = C.create_string_buffer(1 << 14)
+        self.L.ref_cycle_on_scan(self.h, _p(o, C.c_double), int(bool(odom_ok)), n_points, now, buf, len(buf))
+        return [ln for ln in buf.value.decode().split("\n") if ln]

@@ -28,7 +28,8 @@
  * The same sources and stand-ins also build the reference's own gtest suite
  * (oracle/Makefile, target ref_gtests): 28 of 28 cases pass.
  *
- * Not built: laser.cpp (PCL conversion), the factories, the node.
+ * laser.cpp and the node's laser_handler.cpp are built too: see ref_shim_node.cpp.
+ * Not built: the factories and the rest of the node.
  */
 #include "quickmcl/distance_calculator.h"
 #include "quickmcl/low_pass_filter.h"

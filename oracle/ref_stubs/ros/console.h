@@ -23,6 +23,8 @@ inline std::vector<std::string> &stand_in_warnings() {
     qmcl_stand_in_stream << args;                  \
     ros::stand_in_warnings().push_back(qmcl_stand_in_stream.str()); \
   } while (0)
+#define ROS_ERROR(text) ros::stand_in_warnings().push_back(std::string("ERROR: ") + text)
+#define ROS_DEBUG(...) ((void)0)
 #define ROS_DEBUG_STREAM_NAMED(name, args) ((void)0)
 #define ROS_DEBUG_NAMED(...) ((void)0)
 #define ROS_INFO_NAMED(...) ((void)0)

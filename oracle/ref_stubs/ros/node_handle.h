@@ -2,6 +2,8 @@
 // backed by a process-wide table instead of a ROS master.  TEST INFRASTRUCTURE (oracle/_ref).
 #pragma once
 
+#include <ros/console.h>  // the real header brings the logging macros along
+
 #include <map>
 #include <memory>
 #include <string>

@@ -23,7 +23,10 @@ import numpy as np
 
 @dataclasses.dataclass
 class MotionModelParameters:
-    """Parameters::MotionModel (parameters.h:40-50); alpha as the node's cfg (QuickMCL.cfg:25-28)."""
+    """Parameters::MotionModel (parameters.h:40-50); alpha as the node's cfg (QuickMCL.cfg:25-28).
+    The reference keeps the two thresholds as floats and compares doubles with them
+    (laser_handler.cpp:207-209): on_scan rounds them to float32 before use, so 0.2 means
+    0.2f = 0.20000000298 here as it does there."""
     alpha: Sequence[float] = (0.05, 0.1, 0.02, 0.05)
     min_trans: float = 0.2
     min_rot: float = math.pi / 6
@@ -71,8 +74,9 @@ class ScanCycle:
             recompute = True
         diff = odom_new - self.odom_at_last_filter_run
         diff[2] = _normalise_angle(diff[2])
-        has_moved = (abs(diff[0]) > self.motion.min_trans or abs(diff[1]) > self.motion.min_trans
-                     or abs(diff[2]) > self.motion.min_rot)
+        min_trans = float(np.float32(self.motion.min_trans))
+        min_rot = float(np.float32(self.motion.min_rot))
+        has_moved = abs(diff[0]) > min_trans or abs(diff[1]) > min_trans or abs(diff[2]) > min_rot
         if not self.pose_reset and not has_moved:
             self._call("cluster")
             ok, pose, cov = self._call("get_estimated_pose")

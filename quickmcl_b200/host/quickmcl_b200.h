@@ -207,8 +207,8 @@ class ScanCycle {
 public:
   struct MotionModel {  // Parameters::MotionModel (parameters.h:40-50), the node's cfg defaults
     float alpha[4] = {0.05f, 0.1f, 0.02f, 0.05f};
-    double min_trans = 0.2;
-    double min_rot = 3.14159265358979323846 / 6;
+    float min_trans = 0.2f;  // floats like the reference's: doubles are compared with them (:207-209)
+    float min_rot = static_cast<float>(3.14159265358979323846 / 6);
   };
   struct Result {
     bool processed = false;            // false: "Skipping laser scan: haven't moved"

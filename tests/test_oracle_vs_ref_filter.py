@@ -496,3 +496,108 @@ def test_pose_checkpoint_stores_like_the_reference_pose_restorer(estimate):
         PoseCheckpoint(rec).restore(cp.store())
         assert same_bits(np.asarray(rec.initialised[0][0], np.float32), pose_ref)
         assert same_bits(np.asarray(rec.initialised[0][1], np.float32).reshape(3, 3), cov_ref)
+
+
+# ------------------------------------------------------------------ laser_handler.cpp
+class LoggingFilter:
+    """An IParticleFilter that only writes down how ScanCycle calls it, in the format of
+    oracle/ref_shim_node.cpp's recorder."""
+
+    def __init__(self):
+        self.log = []
+        self.present = False
+
+    def num_particles(self):
+        return 1 if self.present else 0
+
+    def global_localization(self):
+        self.log.append("global_localization")
+        self.present = True
+
+    def handle_odometry(self, odom_new, odom_old, alpha):
+        vals = [float(v) for v in odom_new] + [float(v) for v in odom_old] + [float(np.float32(a)) for a in alpha]
+        self.log.append("handle_odometry " + " ".join(v.hex() for v in vals))
+
+    def update_importance_from_observations(self, cloud):
+        self.log.append(f"update_importance_from_observations {len(cloud)}")
+
+    def resample_and_cluster(self):
+        self.log.append("resample_and_cluster")
+
+    def cluster(self):
+        self.log.append("cluster")
+
+    def get_estimated_pose(self):
+        return False, None, None
+
+
+def _canonical(lines):
+    """C's %a and Python's float.hex() spell the same number differently: compare values."""
+    out = []
+    for ln in lines:
+        head, *rest = ln.split(" ")
+        if head == "handle_odometry":
+            out.append((head, tuple(float.fromhex(v) for v in rest)))
+        else:
+            out.append((ln,))
+    return out
+
+
+@pytest.mark.parametrize("resample_count,seed", [(2, 0), (1, 1), (3, 2), (5, 3)])
+def test_scan_cycle_makes_the_calls_of_the_reference_laser_handler(resample_count, seed):
+    """quickmcl_b200.cycle.ScanCycle against LaserHandler::Impl::cloud_callback itself
+    (laser_handler.cpp:179-288, compiled into oracle/_ref with recorders for its collaborators):
+    for a random walk with stops, turns on the spot, jumps across +-pi, emptied particle sets and
+    pose resets, the same IParticleFilter calls with the same arguments, in the same order, and
+    the same recompute_transform flag handed to publish_estimated_pose."""
+    from quickmcl_b200.cycle import MotionModelParameters, ScanCycle
+    rng = np.random.default_rng(seed)
+    alpha = (0.05, 0.1, 0.02, 0.05)
+    min_trans, min_rot = 0.2, math.pi / 6          # the reference keeps them as floats; so does on_scan
+    ref = rb.RefScanCycle(resample_count, min_trans, min_rot, alpha)
+    lf = LoggingFilter()
+    cyc = ScanCycle(lf, MotionModelParameters(alpha=alpha, min_trans=min_trans, min_rot=min_rot),
+                    resample_count=resample_count)
+    odom = np.array([rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-math.pi, math.pi)])
+    kinds = ["stay", "creep", "drive", "turn", "wrap", "threshold"]
+    for step in range(120):
+        kind = kinds[rng.integers(len(kinds))]
+        if kind == "creep":
+            odom = odom + np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(-0.2, 0.2)])
+        elif kind == "drive":
+            odom = odom + np.array([rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(-0.3, 0.3)])
+        elif kind == "turn":
+            odom = odom + np.array([0.0, 0.0, rng.uniform(-1.5, 1.5)])
+        elif kind == "wrap":                      # odometry yaw jumps by a whole turn: no motion at all
+            odom = odom + np.array([0.0, 0.0, 2 * math.pi * rng.choice([-1, 1])])
+        elif kind == "threshold":                 # exactly on / next to the translation threshold
+            last = cyc.odom_at_last_filter_run if cyc.odom_at_last_filter_run is not None else odom
+            edge = float(np.float32(min_trans))
+            odom = np.array([last[0] + rng.choice([edge, np.nextafter(edge, 1.0), -edge, 0.2, -0.2]), last[1],
+                             last[2]])
+        if rng.random() < 0.08:
+            ref.force_pose_reset()
+            cyc.force_pose_reset()
+        if rng.random() < 0.1:                    # the filter lost every particle
+            ref.set_particles_present(False)
+            lf.present = False
+        n_points = int(rng.integers(0, 400))
+        lf.log.clear()
+        ref_lines = ref.on_scan(odom, n_points, now=float(step))
+        result = cyc.on_scan(odom, np.zeros((n_points, 2), np.float32))
+        ref_calls = [ln for ln in ref_lines if not ln.startswith(("publish_", "log: "))]
+        assert _canonical(ref_calls) == _canonical(lf.log), (step, kind)
+        publish = [ln for ln in ref_lines if ln.startswith("publish_estimated_pose")]
+        assert publish == ["publish_estimated_pose recompute" if result.recompute_transform
+                           else "publish_estimated_pose"], (step, kind)
+        assert ("log: No particles... Trying global localisation!" in ref_lines) == result.global_localization
+        assert result.processed == any(ln.startswith("handle_odometry") for ln in ref_lines)
+        assert result.resampled == ("resample_and_cluster" in ref_lines)
+
+
+def test_scan_cycle_reference_drops_the_scan_without_odometry():
+    """laser_handler.cpp:183-187: no odometry transform, nothing happens (the ROS-free ScanCycle is
+    handed the odometry by its caller, so this branch has no counterpart there)."""
+    ref = rb.RefScanCycle()
+    assert ref.on_scan((0.0, 0.0, 0.0), 10, odom_ok=False) == [
+        "log: ERROR: Failed to get odometry pose while handling laser"]
