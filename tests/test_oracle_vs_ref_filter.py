@@ -337,6 +337,32 @@ def test_kld_matches_reference(n, nmin, nmax, lowpass, eps, z, seed):
         compare_estimates(rf, of)
 
 
+def test_c2_shaped_kld_cycle_matches_reference_at_size():
+    """A C2-shaped cycle at a size the reference finishes in a second: 20 000 particles on a 400 x 400
+    map, every hit of a 1081-beam 270 degree scan, KLD: weights, total, kept set and estimate."""
+    occ, res, org, rm, om, rf, of = make_filters(2, 100, 20000, width=400, seed=1, num_beams=0)
+    pose = syn.pick_truth_pose(occ, res, org)
+    scan = syn.make_scan(occ, res, org, pose, 1081, 270.0)
+    n = 20000
+    x, y, t = syn.gaussian_cloud(pose, n)
+    start = ob.make_particles(x, y, t, np.full(n, 1.0 / n))
+    of.set_particles(start)
+    rf.set_particles(start)
+    of.set_rng(33, 0)
+    of.handle_odometry((0.25, 0.05, 0.1), (0.0, 0.0, 0.0), syn.NODE_ALPHA)
+    rb.script(normals=rb.motion_script(33, 0, n))
+    rf.handle_odometry((0.25, 0.05, 0.1), (0.0, 0.0, 0.0), syn.NODE_ALPHA)
+    compare_sets(rf.get_particles(), of.get_particles())
+    of.update_importance_from_observations(scan)
+    rf.update_importance_from_observations(scan)
+    compare_sets(rf.get_particles(), of.get_particles())
+    assert same_bits(rf.lowpass(), of.lowpass())
+    resample_both(rf, of, 2, 33, 1, tuple(of.lowpass()), 20000)
+    assert 100 < rf.num_particles() < 20000
+    compare_sets(rf.get_particles(), of.get_particles())
+    compare_estimates(rf, of)
+
+
 def test_zero_weight_input_is_left_alone_like_the_reference():
     """Both resamplers with a running sum return early on an all-zero input
     (particle_filter.cpp:255-259, :307-311)."""
