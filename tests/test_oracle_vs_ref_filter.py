@@ -337,13 +337,14 @@ def test_kld_matches_reference(n, nmin, nmax, lowpass, eps, z, seed):
         compare_estimates(rf, of)
 
 
-def test_c2_shaped_kld_cycle_matches_reference_at_size():
-    """A C2-shaped cycle at a size the reference finishes in a second: 20 000 particles on a 400 x 400
-    map, every hit of a 1081-beam 270 degree scan, KLD: weights, total, kept set and estimate."""
-    occ, res, org, rm, om, rf, of = make_filters(2, 100, 20000, width=400, seed=1, num_beams=0)
+@pytest.mark.parametrize("width,n", [(400, 20000), (2000, 100000)])
+def test_c2_kld_cycle_matches_reference_at_size(width, n):
+    """BASELINE.json's C2 itself (100 000 particles, 2000 x 2000 map at 5 cm, every hit of a 1081-beam
+    270 degree scan, KLD) and a smaller cut of it: one whole cycle of the compiled reference against the
+    oracle - moved poses, weights, total, kept set and estimate.  The reference does it in about a second."""
+    occ, res, org, rm, om, rf, of = make_filters(2, 100, n, width=width, seed=1, num_beams=0)
     pose = syn.pick_truth_pose(occ, res, org)
     scan = syn.make_scan(occ, res, org, pose, 1081, 270.0)
-    n = 20000
     x, y, t = syn.gaussian_cloud(pose, n)
     start = ob.make_particles(x, y, t, np.full(n, 1.0 / n))
     of.set_particles(start)
@@ -357,8 +358,8 @@ def test_c2_shaped_kld_cycle_matches_reference_at_size():
     rf.update_importance_from_observations(scan)
     compare_sets(rf.get_particles(), of.get_particles())
     assert same_bits(rf.lowpass(), of.lowpass())
-    resample_both(rf, of, 2, 33, 1, tuple(of.lowpass()), 20000)
-    assert 100 < rf.num_particles() < 20000
+    resample_both(rf, of, 2, 33, 1, tuple(of.lowpass()), n)
+    assert 100 < rf.num_particles() < n
     compare_sets(rf.get_particles(), of.get_particles())
     compare_estimates(rf, of)
 
