@@ -209,6 +209,77 @@ def ref_cycle_seconds(wl, inputs, steps, warmup):
     return sum(stages.values()), n * len(scan), stages, notes
 
 
+def ref_all_cores(wl, inputs, steps=3):
+    """The compiled reference on every host core at once: the particle set is cut into one slice per
+    thread, each slice runs its own full cycle on its own ParticleFilter (shared read-only map, a
+    script of its own).  NOT how the reference runs (it is single-threaded, main.cpp:90, and slices
+    resample independently); it bounds what its code could do on this host if it were parallelised
+    over particles.  Runs inside the ref-worker child."""
+    from oracle import binding as ob
+    from oracle import ref_binding as rb
+    occ, res, origin, pose, scan, (x, y, t) = inputs
+    threads_n = max(1, min(os.cpu_count() or 1, 64))
+    n = len(x)
+    per = n // threads_n
+    if per < 64:
+        return None
+    rm = rb.RefMap(occ, res, origin, **dict(syn.NODE_LIKELIHOOD, num_beams=0))
+    pfp = sampled_workload(dict(wl, particles=n), per)["pf"]
+    rtype = pfp.get("resample_type", 2)
+    n_slots = pfp.get("particle_count_max", 5000) if rtype == 2 else pfp.get("particle_count_min", 100)
+    jobs = []
+    for k in range(threads_n):
+        rf = rb.RefFilter(rm)
+        rf.set_parameters(**pfp)
+        sl = slice(k * per, (k + 1) * per)
+        init = ob.make_particles(x[sl], y[sl], t[sl], np.full(per, 1.0 / per))
+        # every draw of every step, prepared before the clock starts
+        scripts = [(rb.motion_script(3 + k, 10 + it, per),
+                    rb.low_variance_script(3 + k, 11 + it) if rtype == 0
+                    else rb.draw_script(3 + k, 11 + it, n_slots, 0.0)[0]) for it in range(steps + 1)]
+        jobs.append((rf, init, scripts))
+    barrier = threading.Barrier(threads_n + 1)
+    errors = []
+
+    def work(rf, init, scripts):
+        try:
+            for it, (normals, words) in enumerate(scripts):
+                rf.set_particles(init)
+                rf.set_lowpass(0.0, 0.0)
+                if it == 1:
+                    barrier.wait()   # the warm-up step is over everywhere: the clock starts
+                rb.script(words=words, normals=normals)
+                rf.handle_odometry(ODOM_NEW, ODOM_OLD, syn.NODE_ALPHA)
+                rf.update_importance_from_observations(scan)
+                if not rf.resample_and_cluster():
+                    rf.set_particles(init)
+                    rf.cluster()
+                rf.get_estimated_pose()
+        except BaseException as e:
+            errors.append(e)
+            barrier.abort()
+
+    old = threading.stack_size(256 << 20)
+    try:
+        ts = [threading.Thread(target=work, args=job) for job in jobs]
+        for th in ts:
+            th.start()
+    finally:
+        threading.stack_size(old)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for th in ts:
+        th.join()
+    sec = (time.perf_counter() - t0) / steps
+    if errors:
+        raise errors[0]
+    return {"value": threads_n * per * len(scan) / sec, "unit": "evals/s", "cores": threads_n, "kind": "reference",
+            "sample": f"{threads_n} threads x {per} particles x {len(scan)} beams, independent full cycles per "
+                      f"slice, {steps} steps after 1 warm-up",
+            "note": "the reference's own compiled code, one ParticleFilter per thread; not reference behaviour "
+                    "(the reference is single-threaded); an upper bound for a particle-parallel host"}
+
+
 def with_deep_stack(fn, *args):
     """Runs fn on a thread with a 1 GiB stack: the reference labels clusters by recursion, one
     frame per bin (space_partitioning.cpp:101-128), and overflows the default 8 MiB stack on the
@@ -289,7 +360,12 @@ def run_ref_worker(args, wl):
                           f"(space_partitioning.h:59) cannot label them, its recursion does not end"})
         return 0
     sec, ev, stages, notes = with_deep_stack(ref_cycle_seconds, wl_s, inputs, args.steps, args.warmup)
-    emit({"sec": sec, "evals": ev, "stages": stages, "notes": notes, "clusters": clusters})
+    all_cores = None
+    try:
+        all_cores = ref_all_cores(wl_s, inputs)
+    except Exception as e:
+        log(f"all-cores run of the compiled reference skipped ({type(e).__name__}: {e})")
+    emit({"sec": sec, "evals": ev, "stages": stages, "notes": notes, "clusters": clusters, "all_cores": all_cores})
     return 0
 
 
@@ -297,7 +373,7 @@ def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup, allow_ref=True):
     """The CPU baseline on the first n_sample particles of the workload: the compiled reference
     (oracle/_ref, timed in a child process) when its library is there and the cloud is one it can
     label, else the oracle port.  Returns (seconds per step, evals per step, per-stage seconds,
-    kind, note)."""
+    kind, note, extra keys for the cpu_baseline object)."""
     wl_s = sampled_workload(wl, n_sample)
     inputs_s = sample_inputs(inputs, n_sample)
     why_port = "oracle/_ref is not built"
@@ -333,13 +409,14 @@ def cpu_cycle(wl, wl_name, inputs, n_sample, steps, warmup, allow_ref=True):
                                  f"{pev / psec:.4g} evals/s")
                     except Exception as e:
                         log(f"oracle port timing skipped ({type(e).__name__}: {e})")
-                    return res["sec"], res["evals"], res["stages"], "reference", note
+                    extra = {"all_cores_reference": res["all_cores"]} if res.get("all_cores") else {}
+                    return res["sec"], res["evals"], res["stages"], "reference", note, extra
         except Exception as e:  # the baseline must never take the bench line with it
             why_port = f"{type(e).__name__}: {e}"
     log(f"CPU baseline: timing the oracle port ({why_port})")
     sec, ev, stages = cpu_cycle_seconds(wl_s, inputs_s, steps, warmup)
     return sec, ev, stages, "port", ("CPU restatement of the reference (oracle/); the reference is "
-                                     f"single-threaded (main.cpp:90); not the compiled reference: {why_port}")
+                                     f"single-threaded (main.cpp:90); not the compiled reference: {why_port}"), {}
 
 
 def cpu_cycle_seconds(wl, inputs, steps, warmup):
@@ -462,7 +539,7 @@ def run_reference(args, wl):
     occ, res, origin, pose, scan, (x, y, t) = inputs
     scale = n_sample / n_full
     wl_s = sampled_workload(wl, n_sample)
-    sec, evals, stages, kind, note = cpu_cycle(wl, args.workload, inputs, n_sample, args.steps, args.warmup)
+    sec, evals, stages, kind, note, extra = cpu_cycle(wl, args.workload, inputs, n_sample, args.steps, args.warmup)
     value = evals / sec
     all_cores = cpu_all_cores(
         wl_s, (occ, res, origin, pose, scan, (x[:n_sample], y[:n_sample], t[:n_sample])))
@@ -482,7 +559,7 @@ def run_reference(args, wl):
                          "field": "brushfire (the reference's own field build)",
                          "stage_ms": {k: v * 1e3 for k, v in stages.items()},
                          "note": note,
-                         "all_cores": all_cores},
+                         "all_cores": all_cores, **extra},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -908,9 +985,9 @@ def run_b200(args, wl):
         occ, res, origin, pose, _, (x, y, t) = h.inputs
         n_cpu = int(min(n, max(2000, 2.0e9 / 6 // len(scan))))
         wl_s = sampled_workload(wl, n_cpu)
-        sec, ev, stages, kind, note = cpu_cycle(
+        sec, ev, stages, kind, note, extra = cpu_cycle(
             wl, args.workload, (occ, res, origin, pose, scan, (x, y, t)), n_cpu, 5, 1, allow_ref=(world == 1))
-        cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": kind, "note": note,
+        cpu = {"value": ev / sec, "unit": "evals/s", "cores": 1, "kind": kind, "note": note, **extra,
                "sample": f"{n_cpu} of {n} particles x {len(scan)} beams, full update cycle, "
                          f"5 steps after 1 warm-up",
                "field": "brushfire (the reference's own field build; the GPU arm uses the exact EDT "

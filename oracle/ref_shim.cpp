@@ -99,11 +99,12 @@ quickmcl::LaserPointCloud to_cloud(const float *xy, size_t n) {
 }
 
 // the script the stand-in engines read (ref_stubs/random)
-std::vector<uint64_t> g_words;
-std::vector<double> g_normals;
-size_t g_word_pos = 0, g_normal_pos = 0;
-int g_underflow = 0;
-double g_last_seconds = 0;
+// (per thread: bench.py times one reference filter per host thread, each with its own script)
+thread_local std::vector<uint64_t> g_words;
+thread_local std::vector<double> g_normals;
+thread_local size_t g_word_pos = 0, g_normal_pos = 0;
+thread_local int g_underflow = 0;
+thread_local double g_last_seconds = 0;
 
 struct Stopwatch {
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();

@@ -45,6 +45,8 @@ def test_reference_arm_times_the_compiled_reference():
     cb = check_line(run_arm())
     assert cb["kind"] == "reference"
     assert "oracle port" in cb["note"]          # the port's rate on the same sample rides along
+    if cb.get("all_cores_reference"):           # one reference filter per host thread (>= 64 particles each)
+        assert cb["all_cores_reference"]["kind"] == "reference" and cb["all_cores_reference"]["value"] > 0
 
 
 def test_reference_arm_falls_back_to_the_oracle_port():
