@@ -4,7 +4,8 @@
  * TEST INFRASTRUCTURE ONLY.  This file is compiled together with the reference's
  * translation units of the particle-filter path, taken from where they lie under
  * /root/reference (never copied): distance_calculator.cpp, map_base.cpp,
- * map_likelihood.cpp, odometry.cpp, particle.cpp, particle_filter.cpp, pose_2d.cpp,
+ * map_factory.cpp, map_likelihood.cpp, odometry.cpp, particle.cpp, particle_filter.cpp,
+ * particle_filter_factory.cpp, pose_2d.cpp,
  * pose_restore.cpp, space_partitioning.cpp, statistics.cpp, timer.cpp, plus the header-only scaled_map.h,
  * low_pass_filter.h, random.h and utils.h.  Eigen, ROS and PCL are absent from this
  * image; the units build against the stand-in headers in oracle/ref_stubs (what each
@@ -29,15 +30,17 @@
  * (oracle/Makefile, target ref_gtests): 28 of 28 cases pass.
  *
  * laser.cpp and the node's laser_handler.cpp are built too: see ref_shim_node.cpp.
- * Not built: the factories and the rest of the node.
+ * Not built: the rest of the node (main, publishing, tf_reader, commands, parameter_manager).
  */
 #include "quickmcl/distance_calculator.h"
 #include "quickmcl/low_pass_filter.h"
+#include "quickmcl/map_factory.h"
 #include "quickmcl/map_likelihood.h"
 #include "quickmcl/odometry.h"
 #include "quickmcl/parameters.h"
 #include "quickmcl/particle.h"
 #include "quickmcl/particle_filter.h"
+#include "quickmcl/particle_filter_factory.h"
 #include "quickmcl/pose_restore.h"
 #include "quickmcl/scaled_map.h"
 #include "quickmcl/space_partitioning.h"
@@ -339,7 +342,8 @@ ref_map *ref_map_create(const int8_t *occ, uint32_t w, uint32_t h, float resolut
   grid->info.origin.position.x = origin_x;
   grid->info.origin.position.y = origin_y;
   auto *m = new ref_map;
-  m->map = std::make_shared<quickmcl::MapLikelihood>();
+  // through the reference's factory, as main.cpp does (map_factory.cpp:23-26)
+  m->map = std::dynamic_pointer_cast<quickmcl::MapLikelihood>(quickmcl::create_likelihood_map());
   m->map->set_parameters(lp);
   forget_distance_cache();
   m->map->new_map(grid);
@@ -426,7 +430,7 @@ void ref_sample_odometry(const double odom_new[3], const double odom_old[3], Pod
 // ------------------------------------------------------------ ParticleFilter
 struct ref_filter {
   std::shared_ptr<quickmcl::MapLikelihood> map;
-  std::unique_ptr<quickmcl::ParticleFilter> pf;
+  std::shared_ptr<quickmcl::ParticleFilter> pf;
 };
 struct RefPfParams {  // = orc_pf_params
   int32_t resample_type, particle_count_min, particle_count_max, resample_count;
@@ -437,7 +441,8 @@ struct RefPfParams {  // = orc_pf_params
 ref_filter *ref_filter_create(ref_map *m) {
   auto *f = new ref_filter;
   f->map = m->map;
-  f->pf.reset(new quickmcl::ParticleFilter(m->map));
+  // through the reference's factory (particle_filter_factory.cpp:23-27)
+  f->pf = std::dynamic_pointer_cast<quickmcl::ParticleFilter>(quickmcl::create_particle_filter(m->map));
   return f;
 }
 void ref_filter_destroy(ref_filter *f) { delete f; }
